@@ -1,0 +1,224 @@
+/*
+ * openkitchen_b200.h -- C ABI of the B200-native batched step loop for OpenKitchen's racing
+ * environment.  This is the drop-in boundary: plain pointers and sizes, no C++/torch types.
+ *
+ * The reference has no FFI layer; its seam is the C++ class surface of Environment/ and the
+ * pybind module.  Each entry point below names the reference interface it replaces (file:line
+ * relative to the reference repo root).  The C++ shim (openkitchen_b200/shim/) and the pybind
+ * module (openkitchen_b200/pybind/) are written on top of exactly these functions; see
+ * INTEGRATION.md for the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 (OK_SUCCESS) or a negative OkStatus; nothing throws or aborts
+ *     across the ABI; ok_last_error() returns a thread-local message for the last failure;
+ *   - `stream` arguments are cudaStream_t passed as void* (NULL = the legacy default stream);
+ *     launches are asynchronous on that stream and never synchronise the device;
+ *   - pointers named d_* are DEVICE pointers, h_* are HOST pointers;
+ *   - agent buffers are owned by the OkEnv and stay valid until ok_alloc_agents is called again
+ *     or the env is destroyed (borrowed by callers -- this is what DLPack exports);
+ *   - one OkEnv per GPU; an env is thread-compatible (external synchronisation per env).
+ */
+#ifndef OPENKITCHEN_B200_H
+#define OPENKITCHEN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OK_ABI_VERSION 1
+
+typedef enum OkStatus {
+    OK_SUCCESS            = 0,
+    OK_ERR_INVALID_ARG    = -1,
+    OK_ERR_CUDA           = -2,
+    OK_ERR_IO             = -3,
+    OK_ERR_STATE          = -4, /* e.g. stepping before ok_alloc_agents */
+    OK_ERR_CAPACITY       = -5, /* a track does not fit the shared-memory staging area */
+    OK_ERR_NO_DEVICE      = -6
+} OkStatus;
+
+/* Agent::MovementMode, Environment/Agent.h:20-25 (MANUAL is keyboard input: not supported) */
+typedef enum OkMovementMode { OK_MOVE_VELOCITY = 0, OK_MOVE_ACCELERATION = 1 } OkMovementMode;
+
+/* App-side progress/reward definitions */
+typedef enum OkRewardMode {
+    OK_REWARD_NONE           = 0,
+    OK_REWARD_Q_PROGRESS     = 1, /* RLRacers/Q_Learning/QAgent.hpp:150-168 */
+    OK_REWARD_CMAES_PROGRESS = 2, /* CovarianceMatrixAdaptationEvolution/main_eigen.cpp:147-163 */
+    OK_REWARD_CONSTANT       = 3, /* RLRacers/PPO/ppo_sim.cpp:76 */
+    OK_REWARD_DISPLACEMENT   = 4, /* RLRacers/ReinforceContinuous/reinforce_sim.cpp:59-73 */
+    OK_REWARD_MIN_RAY        = 5, /* RLRacers/Deep_Q_Learning/DQAgent.hpp:161-180 */
+    OK_REWARD_TRACK_INDEX    = 6, /* EvolutionaryRacer/MiscUtils.hpp:64-71 */
+    OK_REWARD_LANE_CENTER    = 7  /* WorldModelVaeRnn/main.cpp:336-342 */
+} OkRewardMode;
+
+typedef enum OkRaycastMode {
+    OK_RAYCAST_GRID  = 0, /* uniform-grid broadphase (default) */
+    OK_RAYCAST_BRUTE = 1  /* every ray x every segment, the reference's loop (CollisionChecker.cu:51-66) */
+} OkRaycastMode;
+
+/* Device buffers exported by ok_get_buffer.  N = agents, R = rays per agent. */
+typedef enum OkBuffer {
+    OK_BUF_POS_X = 0,    /* f32[N]     Agent::pos_.x                         Agent.h:56 */
+    OK_BUF_POS_Y,        /* f32[N]     Agent::pos_.y */
+    OK_BUF_ROT,          /* f32[N]     Agent::rot_ (degrees, never wrapped)  Agent.h:59 */
+    OK_BUF_SPEED,        /* f32[N]     Agent::speed_                         Agent.h:57 */
+    OK_BUF_ACCEL,        /* f32[N]     Agent::acceleration_                  Agent.h:58 */
+    OK_BUF_ACT_THROTTLE, /* f32[N]     Agent::current_action_.throttle_delta Agent.h:78 */
+    OK_BUF_ACT_STEER,    /* f32[N]     Agent::current_action_.steering_delta */
+    OK_BUF_CRASHED,      /* u8[N]      Agent::crashed_                       Agent.h:72 */
+    OK_BUF_TIMED_OUT,    /* u8[N]      Agent::timed_out_                     Agent.h:74 */
+    OK_BUF_DONE,         /* u8[N]      Agent::isDone()                       Agent.cpp:138-144 */
+    OK_BUF_SS_CTR,       /* u32[N]     DisplacementStats::displacement_ctr   Environment.h:23 */
+    OK_BUF_SS_X,         /* f32[N]     DisplacementStats::init_pos.x         Environment.h:25 */
+    OK_BUF_SS_Y,         /* f32[N]     DisplacementStats::init_pos.y */
+    OK_BUF_TRACK_ID,     /* i32[N]     which track the agent drives on */
+    OK_BUF_HIT_ABS,      /* f32[N,R,2] Ray_::hit_x/hit_y (window coords)     Typedefs.h:96-97 */
+    OK_BUF_HIT_REL,      /* f32[N,R,2] Agent::sensor_hits_                   Agent.h:76 */
+    OK_BUF_OBS,          /* f32[N,R]   sensor_hits_[i].norm()/sensor_range   PPOAgent.hpp:68-76 */
+    OK_BUF_HIT_SEG,      /* i32[N,R]   index of the hit segment in TrackSegments order, -1 = none */
+    OK_BUF_HIT_T,        /* f32[N,R]   ray parameter of the hit (min_t of CollisionChecker.cu:49) */
+    OK_BUF_MIN_DIST2,    /* f32[N]     min_dist2 of CollisionChecker.cu:150 */
+    OK_BUF_NEAREST_IDX,  /* i32[N]     RaceTrack::findNearestTrackIndexBruteForce(pos_) */
+    OK_BUF_PREV_IDX,     /* i32[N]     prev_track_idx_ of the progress rewards */
+    OK_BUF_REWARD,       /* f32[N]     per-tick reward of OkConfig::reward_mode */
+    OK_BUF_FITNESS,      /* f32[N]     accumulated fitness (CMA-ES / lane-centre modes) */
+    OK_BUF_RESET_PT,     /* i32[N]     centre-line index of the agent's last reset */
+    OK_BUF_START_X,      /* f32[N]     pose at the start of the episode */
+    OK_BUF_START_Y,      /* f32[N] */
+    OK_BUF_COUNT
+} OkBuffer;
+
+typedef enum OkDType { OK_DTYPE_F32 = 0, OK_DTYPE_I32 = 1, OK_DTYPE_U32 = 2, OK_DTYPE_U8 = 3 } OkDType;
+
+/* Track geometry arrays readable through ok_track_copy (host side, reference layout). */
+typedef enum OkTrackArray {
+    OK_TRACK_X = 0,     /* f32[P]   RaceTrack::track_data_points_.x_m (after fit-to-window) */
+    OK_TRACK_Y,         /* f32[P] */
+    OK_TRACK_W_RIGHT,   /* f32[P]   w_tr_right_m (clamped, scaled) */
+    OK_TRACK_W_LEFT,    /* f32[P] */
+    OK_TRACK_HEADING,   /* f32[P]   RaceTrack::headings_ (degrees) */
+    OK_TRACK_LEFT_INNER,  /* f32[P,2] RaceTrack::left_bound_inner_ */
+    OK_TRACK_LEFT_OUTER,  /* f32[P,2] */
+    OK_TRACK_RIGHT_INNER, /* f32[P,2] */
+    OK_TRACK_RIGHT_OUTER, /* f32[P,2] */
+    OK_TRACK_SEGMENTS     /* f32[S,4] Segment2d in TrackSegments order, S = 4(P-1)+4 */
+} OkTrackArray;
+
+/* Constants the reference bakes in at compile time; defaults = reference values. */
+typedef struct OkConfig {
+    int32_t  device;               /* CUDA device ordinal */
+    int32_t  movement_mode;        /* OkMovementMode; Agent.h:80 default VELOCITY */
+    int32_t  reward_mode;          /* OkRewardMode */
+    int32_t  raycast_mode;         /* OkRaycastMode */
+    int32_t  auto_reset;           /* !=0: a crashed agent is reset at the start of the next step
+                                      (GuidedCostLearning/test.cpp:102-111) to centre-line index
+                                      (last_reset + auto_reset_stride) mod P, with a zero action */
+    int32_t  auto_reset_stride;    /* 97 */
+    float    sensor_range;         /* Agent::kSensorRange 200        Agent.h:10 */
+    float    speed_limit;          /* Agent::kSpeedLimit 100         Agent.h:11 */
+    float    dt;                   /* kDt 0.016                      Agent.cpp:84,110 */
+    float    collision_dist2;      /* 2.0 (strict <)                 CollisionChecker.cu:167 */
+    float    sensor_offset;        /* Agent::sensor_offset_ 0        Agent.h:61 */
+    uint32_t standstill_period;    /* DisplacementStats::kPeriod 200 Environment.h:19 */
+    float    standstill_threshold; /* kDisplamentThreshold 20        Environment.h:20 */
+    float    grid_cell;            /* broadphase cell size in px (16) */
+    int32_t  reserved[4];
+} OkConfig;
+
+typedef struct OkTrackInfo {
+    int32_t n_points;
+    int32_t n_segments;
+    int32_t grid_nx, grid_ny;
+    int32_t grid_items;   /* total (cell, segment) registrations */
+    int32_t blob_bytes;   /* bytes staged into shared memory for this track */
+    float   grid_x0, grid_y0, grid_cell;
+} OkTrackInfo;
+
+typedef struct OkEnv OkEnv;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int         ok_abi_version(void);
+const char *ok_last_error(void);
+void        ok_config_default(OkConfig *cfg);
+/* Environment::Environment (Environment.cpp:42-62) minus raylib/visualizer/screen grabber. */
+int  ok_create(const OkConfig *cfg, OkEnv **out);
+void ok_destroy(OkEnv *env);
+
+/* ---- tracks: RaceTrack ctor chain (RaceTrack.cpp:3-14,127-307) + TrackSegments (TrackSegments.cu:6-76)
+ *      + broadphase grid build + device upload. Must precede ok_alloc_agents. -------------------- */
+/* the four raw CSV columns x_m,y_m,w_tr_right_m,w_tr_left_m (before clamp/scale) */
+int ok_add_track(OkEnv *env, const float *h_x_m, const float *h_y_m, const float *h_w_right, const float *h_w_left,
+                 int32_t n_points, int32_t *track_id_out);
+/* RaceTrack::getTrackDataFromCsv, RaceTrack.cpp:127-164 */
+int ok_load_track_csv(OkEnv *env, const char *path, int32_t *track_id_out);
+int ok_num_tracks(const OkEnv *env);
+int ok_track_info(const OkEnv *env, int32_t track_id, OkTrackInfo *out);
+/* copies min(count, available) elements of the named array to h_out; returns elements available */
+int64_t ok_track_copy(const OkEnv *env, int32_t track_id, int32_t which /*OkTrackArray*/, float *h_out, int64_t count);
+
+/* ---- agents -------------------------------------------------------------------------------- */
+/* replaces `std::vector<Agent*>` + CollisionChecker ctor (CollisionChecker.cu:76-86).  All agents
+ * have `rays` rays (the reference assumes agents[0]'s count, CollisionChecker.cu:82) with angles
+ * h_ray_deg[rays] relative to heading (Agent::sensor_ray_angles_).  h_track_id may be NULL (all on
+ * track 0).  Every agent starts reset at RaceTrack::kStartingIdx (RaceTrack.h:18). Agents on the
+ * same track should be contiguous for best performance. */
+int     ok_alloc_agents(OkEnv *env, int64_t n_agents, int32_t rays, const float *h_ray_deg, const int32_t *h_track_id);
+int64_t ok_num_agents(const OkEnv *env);
+int32_t ok_num_rays(const OkEnv *env);
+
+/* Environment::resetAgent (Environment.cpp:79-122) + Agent::reset (Agent.cpp:123-135) with the
+ * random draws made explicit: agent d_agent_idx[k] (NULL = k) goes to centre-line index d_pt_idx[k];
+ * d_lane_alpha (nullable) = the lane lerp alpha of Environment.cpp:107-114; d_heading_off (nullable)
+ * = the heading offset of Environment.cpp:88-101.  Device pointers, asynchronous on `stream`. */
+int ok_reset_agents(OkEnv *env, const int64_t *d_agent_idx, const int32_t *d_pt_idx, const float *d_lane_alpha,
+                    const float *d_heading_off, int64_t n, void *stream);
+/* same with HOST arrays (staged through an internal buffer; synchronises `stream`) */
+int ok_reset_agents_host(OkEnv *env, const int64_t *h_agent_idx, const int32_t *h_pt_idx, const float *h_lane_alpha,
+                         const float *h_heading_off, int64_t n, void *stream);
+
+/* ---- the tick ------------------------------------------------------------------------------ */
+/* CollisionChecker::checkCollision (CollisionChecker.cu:96-100,113-174): lidar + crash flag on the
+ * current poses, no movement. */
+int ok_cast_rays(OkEnv *env, void *stream);
+/* Environment::step stages 1-2 (Environment.cpp:125-146) + the app-side progress/reward/done:
+ * one fused kernel.  d_act_* (nullable) are copied into the ACT_* buffers first; NULL = step with
+ * the actions already stored there (what Agent::updateAction wrote). */
+int ok_launch_step(OkEnv *env, const float *d_act_throttle, const float *d_act_steer, void *stream);
+/* k consecutive ticks whose actions come from the counter-based Philox4x32-10 stream of
+ * SURVEY.md 8(d) (key = seed, counter = (agent, first_step + i)), generated inside the step kernel. */
+int ok_launch_steps_random(OkEnv *env, uint64_t first_step, int32_t k, uint32_t seed, void *stream);
+/* write the Philox actions for `step` into the ACT_* buffers without stepping */
+int ok_fill_random_actions(OkEnv *env, uint64_t step, uint32_t seed, void *stream);
+
+/* End-to-end host call (what the C++ shim's Environment::step and the reference-facing plugin
+ * use): H2D of the two action arrays, one tick, D2H of obs / reward / done / crashed (each
+ * nullable), then a stream synchronise.  Host buffers should be pinned (ok_host_alloc). */
+int ok_step_host(OkEnv *env, const float *h_act_throttle, const float *h_act_steer, float *h_obs, float *h_reward,
+                 uint8_t *h_done, void *stream);
+int ok_host_alloc(void **h_ptr, size_t bytes); /* cudaMallocHost */
+int ok_host_free(void *h_ptr);
+
+/* ---- buffers ------------------------------------------------------------------------------- */
+/* device pointer, shape (shape[1] = 0 for per-agent vectors; shape[2] = 2 for the xy buffers) and
+ * OkDType of an agent buffer: the DLPack export of the Python layer is built from this. */
+int ok_get_buffer(OkEnv *env, int32_t which /*OkBuffer*/, void **d_ptr, int64_t shape[3], int32_t *dtype);
+/* convenience copies (synchronise `stream`) */
+int ok_read_buffer(OkEnv *env, int32_t which, void *h_dst, size_t bytes, void *stream);
+int ok_write_buffer(OkEnv *env, int32_t which, const void *h_src, size_t bytes, void *stream);
+int ok_sync(OkEnv *env, void *stream);
+
+/* ---- introspection (bench / profiling) ----------------------------------------------------- */
+typedef struct OkLaunchStats {
+    uint64_t kernel_launches; /* kernels launched by this env since creation */
+    int32_t  grid_blocks, block_threads, smem_bytes, tiles;
+} OkLaunchStats;
+int ok_launch_stats(const OkEnv *env, OkLaunchStats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPENKITCHEN_B200_H */

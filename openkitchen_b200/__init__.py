@@ -1,0 +1,26 @@
+"""openkitchen_b200 -- B200-native batched step loop for OpenKitchen's racing environment.
+
+Only what the hot path needs: ``csrc/`` (sm_100a kernels + the C ABI of include/openkitchen_b200.h),
+this ctypes front-end, the drop-in C++ shim (``shim/``) and the pybind module (``pybind/``).
+"""
+from ._capi import (  # noqa: F401
+    BUF,
+    BUFFERS,
+    LIB_PATH,
+    MOVE_ACCELERATION,
+    MOVE_VELOCITY,
+    RAYCAST_BRUTE,
+    RAYCAST_GRID,
+    REWARD_CMAES_PROGRESS,
+    REWARD_CONSTANT,
+    REWARD_DISPLACEMENT,
+    REWARD_LANE_CENTER,
+    REWARD_MIN_RAY,
+    REWARD_NONE,
+    REWARD_Q_PROGRESS,
+    REWARD_TRACK_INDEX,
+    OkError,
+)
+from .env import Env, pinned_array, ray_fan, track_columns, track_names, write_track_csv  # noqa: F401
+
+__version__ = "0.1.0"

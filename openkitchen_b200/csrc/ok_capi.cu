@@ -1,0 +1,761 @@
+// ok_capi.cu -- implementation of the C ABI (include/openkitchen_b200.h) over the sm_100a kernels.
+// Host side of the product: owns device memory, builds the tile table, launches.  No CPU
+// fallback exists: without a CUDA device every compute entry point returns OK_ERR_NO_DEVICE.
+#include "../../include/openkitchen_b200.h"
+
+#include "ok_kernels.cuh"
+#include "ok_track.hpp"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace
+{
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define OK_CUDA(expr)                                                                                                  \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t err__ = (expr);                                                                                    \
+        if (err__ != cudaSuccess)                                                                                      \
+            return fail(OK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__));                           \
+    } while (0)
+
+struct DeviceGuard
+{
+    int  prev{-1};
+    bool active{false};
+    explicit DeviceGuard(int dev)
+    {
+        if (dev >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != dev)
+        {
+            cudaSetDevice(dev);
+            active = true;
+        }
+    }
+    ~DeviceGuard()
+    {
+        if (active)
+            cudaSetDevice(prev);
+    }
+};
+
+constexpr int kBlock = 512;
+
+struct BufferDesc
+{
+    int32_t dtype;
+    int32_t per_ray; // 0: [N], 1: [N,R], 2: [N,R,2]
+};
+
+BufferDesc describe(int which)
+{
+    switch (which)
+    {
+    case OK_BUF_CRASHED:
+    case OK_BUF_TIMED_OUT:
+    case OK_BUF_DONE: return {OK_DTYPE_U8, 0};
+    case OK_BUF_SS_CTR: return {OK_DTYPE_U32, 0};
+    case OK_BUF_TRACK_ID:
+    case OK_BUF_NEAREST_IDX:
+    case OK_BUF_PREV_IDX:
+    case OK_BUF_RESET_PT: return {OK_DTYPE_I32, 0};
+    case OK_BUF_HIT_ABS:
+    case OK_BUF_HIT_REL: return {OK_DTYPE_F32, 2};
+    case OK_BUF_OBS:
+    case OK_BUF_HIT_T: return {OK_DTYPE_F32, 1};
+    case OK_BUF_HIT_SEG: return {OK_DTYPE_I32, 1};
+    default: return {OK_DTYPE_F32, 0};
+    }
+}
+
+size_t dtype_size(int32_t dt)
+{
+    return dt == OK_DTYPE_U8 ? 1 : 4;
+}
+} // namespace
+
+struct OkEnv
+{
+    OkConfig               cfg{};
+    bool                   has_device{false};
+    int                    num_sms{0};
+    size_t                 max_blob{0};
+    std::vector<ok::Track> tracks;
+    // device track arena
+    uint8_t      *d_arena{nullptr};
+    ok::TrackRef *d_track_refs{nullptr};
+    size_t        arena_bytes{0};
+    size_t        max_blob_used{0};
+    bool          arena_dirty{true};
+    // agents
+    int64_t              n_agents{0};
+    int32_t              rays{0};
+    uint8_t             *d_slab{nullptr};
+    void                *d_buf[OK_BUF_COUNT]{};
+    float               *d_ray_deg{nullptr};
+    ok::Tile            *d_tiles{nullptr};
+    int32_t              n_tiles{0};
+    int32_t              lanes_per_agent{32};
+    std::vector<int32_t> h_track_id;
+    // staging for the *_host entry points
+    uint8_t *d_stage{nullptr};
+    size_t   stage_bytes{0};
+    // stats
+    uint64_t launches{0};
+    int32_t  grid{0};
+    size_t   smem{0};
+};
+
+namespace
+{
+size_t buffer_bytes(const OkEnv *e, int which)
+{
+    const BufferDesc d = describe(which);
+    size_t           n = static_cast<size_t>(e->n_agents);
+    if (d.per_ray >= 1)
+        n *= static_cast<size_t>(e->rays);
+    if (d.per_ray == 2)
+        n *= 2;
+    return n * dtype_size(d.dtype);
+}
+
+void free_agents(OkEnv *e)
+{
+    if (e->d_slab)
+        cudaFree(e->d_slab);
+    if (e->d_ray_deg)
+        cudaFree(e->d_ray_deg);
+    if (e->d_tiles)
+        cudaFree(e->d_tiles);
+    e->d_slab = nullptr, e->d_ray_deg = nullptr, e->d_tiles = nullptr;
+    for (auto &b : e->d_buf)
+        b = nullptr;
+    e->n_agents = 0, e->rays = 0, e->n_tiles = 0;
+}
+
+int ensure_arena(OkEnv *e)
+{
+    if (!e->arena_dirty)
+        return OK_SUCCESS;
+    if (e->d_arena)
+        cudaFree(e->d_arena);
+    if (e->d_track_refs)
+        cudaFree(e->d_track_refs);
+    e->d_arena = nullptr, e->d_track_refs = nullptr;
+    std::vector<ok::TrackRef> refs;
+    size_t                    total = 0;
+    e->max_blob_used                = 0;
+    for (auto &t : e->tracks)
+    {
+        ok::TrackRef r{};
+        r.offset = total;
+        r.bytes  = static_cast<uint32_t>(t.blob.size());
+        refs.push_back(r);
+        total += (t.blob.size() + 127) / 128 * 128;
+        e->max_blob_used = std::max(e->max_blob_used, t.blob.size());
+    }
+    std::vector<uint8_t> host(total, 0);
+    for (size_t i = 0; i < e->tracks.size(); ++i)
+        std::memcpy(host.data() + refs[i].offset, e->tracks[i].blob.data(), e->tracks[i].blob.size());
+    OK_CUDA(cudaMalloc(&e->d_arena, std::max<size_t>(total, 128)));
+    OK_CUDA(cudaMalloc(&e->d_track_refs, sizeof(ok::TrackRef) * std::max<size_t>(refs.size(), 1)));
+    OK_CUDA(cudaMemcpy(e->d_arena, host.data(), total, cudaMemcpyHostToDevice));
+    OK_CUDA(cudaMemcpy(e->d_track_refs, refs.data(), sizeof(ok::TrackRef) * refs.size(), cudaMemcpyHostToDevice));
+    e->arena_bytes = total;
+    e->arena_dirty = false;
+    e->smem        = (e->max_blob_used + 127) / 128 * 128;
+    OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<kBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(e->smem)));
+    return OK_SUCCESS;
+}
+
+ok::StepParams base_params(OkEnv *e)
+{
+    ok::StepParams p{};
+    p.x         = static_cast<float *>(e->d_buf[OK_BUF_POS_X]);
+    p.y         = static_cast<float *>(e->d_buf[OK_BUF_POS_Y]);
+    p.rot       = static_cast<float *>(e->d_buf[OK_BUF_ROT]);
+    p.speed     = static_cast<float *>(e->d_buf[OK_BUF_SPEED]);
+    p.accel     = static_cast<float *>(e->d_buf[OK_BUF_ACCEL]);
+    p.act_thr   = static_cast<float *>(e->d_buf[OK_BUF_ACT_THROTTLE]);
+    p.act_steer = static_cast<float *>(e->d_buf[OK_BUF_ACT_STEER]);
+    p.crashed   = static_cast<uint8_t *>(e->d_buf[OK_BUF_CRASHED]);
+    p.timed_out = static_cast<uint8_t *>(e->d_buf[OK_BUF_TIMED_OUT]);
+    p.done      = static_cast<uint8_t *>(e->d_buf[OK_BUF_DONE]);
+    p.ss_ctr    = static_cast<uint32_t *>(e->d_buf[OK_BUF_SS_CTR]);
+    p.ss_x      = static_cast<float *>(e->d_buf[OK_BUF_SS_X]);
+    p.ss_y      = static_cast<float *>(e->d_buf[OK_BUF_SS_Y]);
+    p.track_id  = static_cast<int32_t *>(e->d_buf[OK_BUF_TRACK_ID]);
+    p.hit_abs   = static_cast<float *>(e->d_buf[OK_BUF_HIT_ABS]);
+    p.hit_rel   = static_cast<float *>(e->d_buf[OK_BUF_HIT_REL]);
+    p.obs       = static_cast<float *>(e->d_buf[OK_BUF_OBS]);
+    p.hit_t     = static_cast<float *>(e->d_buf[OK_BUF_HIT_T]);
+    p.min_dist2 = static_cast<float *>(e->d_buf[OK_BUF_MIN_DIST2]);
+    p.hit_seg   = static_cast<int32_t *>(e->d_buf[OK_BUF_HIT_SEG]);
+    p.nearest   = static_cast<int32_t *>(e->d_buf[OK_BUF_NEAREST_IDX]);
+    p.prev      = static_cast<int32_t *>(e->d_buf[OK_BUF_PREV_IDX]);
+    p.reward    = static_cast<float *>(e->d_buf[OK_BUF_REWARD]);
+    p.fitness   = static_cast<float *>(e->d_buf[OK_BUF_FITNESS]);
+    p.reset_pt  = static_cast<int32_t *>(e->d_buf[OK_BUF_RESET_PT]);
+    p.start_x   = static_cast<float *>(e->d_buf[OK_BUF_START_X]);
+    p.start_y   = static_cast<float *>(e->d_buf[OK_BUF_START_Y]);
+    p.ray_deg   = e->d_ray_deg;
+    p.arena     = e->d_arena;
+    p.tracks    = e->d_track_refs;
+    p.tiles     = e->d_tiles;
+    p.n_tiles   = e->n_tiles;
+    p.rays      = e->rays;
+    p.lanes_per_agent   = e->lanes_per_agent;
+    p.movement_mode     = e->cfg.movement_mode;
+    p.reward_mode       = e->cfg.reward_mode;
+    p.raycast_mode      = e->cfg.raycast_mode;
+    p.auto_reset        = e->cfg.auto_reset;
+    p.auto_reset_stride = e->cfg.auto_reset_stride;
+    p.sensor_range      = e->cfg.sensor_range;
+    p.speed_limit       = e->cfg.speed_limit;
+    p.dt                = e->cfg.dt;
+    p.collision_dist2   = e->cfg.collision_dist2;
+    p.sensor_offset     = e->cfg.sensor_offset;
+    p.standstill_thr2   = e->cfg.standstill_threshold * e->cfg.standstill_threshold; // Environment.cpp:26
+    p.standstill_period = e->cfg.standstill_period;
+    return p;
+}
+
+int check_ready(OkEnv *e)
+{
+    if (!e)
+        return fail(OK_ERR_INVALID_ARG, "env is NULL");
+    if (!e->has_device)
+        return fail(OK_ERR_NO_DEVICE, "this env was created without a CUDA device (device = -1): no compute entry point is available");
+    if (e->n_agents <= 0)
+        return fail(OK_ERR_STATE, "ok_alloc_agents has not been called");
+    return OK_SUCCESS;
+}
+
+int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
+{
+    int rc = ensure_arena(e);
+    if (rc)
+        return rc;
+    p.arena  = e->d_arena;
+    p.tracks = e->d_track_refs;
+    ok::step_kernel<kBlock><<<e->grid, kBlock, e->smem, s>>>(p);
+    OK_CUDA(cudaGetLastError());
+    e->launches++;
+    return OK_SUCCESS;
+}
+} // namespace
+
+extern "C"
+{
+int ok_abi_version(void)
+{
+    return OK_ABI_VERSION;
+}
+
+const char *ok_last_error(void)
+{
+    return g_last_error.c_str();
+}
+
+void ok_config_default(OkConfig *c)
+{
+    if (!c)
+        return;
+    std::memset(c, 0, sizeof *c);
+    c->device               = 0;
+    c->movement_mode        = OK_MOVE_VELOCITY;
+    c->reward_mode          = OK_REWARD_NONE;
+    c->raycast_mode         = OK_RAYCAST_GRID;
+    c->auto_reset           = 0;
+    c->auto_reset_stride    = 97;
+    c->sensor_range         = 200.0f;
+    c->speed_limit          = 100.0f;
+    c->dt                   = static_cast<float>(0.016);
+    c->collision_dist2      = 2.0f;
+    c->sensor_offset        = 0.0f;
+    c->standstill_period    = 200u;
+    c->standstill_threshold = 20.0f;
+    c->grid_cell            = 16.0f;
+}
+
+int ok_create(const OkConfig *cfg, OkEnv **out)
+{
+    if (!out)
+        return fail(OK_ERR_INVALID_ARG, "out is NULL");
+    *out = nullptr;
+    OkConfig c;
+    if (cfg)
+        c = *cfg;
+    else
+        ok_config_default(&c);
+    if (c.movement_mode != OK_MOVE_VELOCITY && c.movement_mode != OK_MOVE_ACCELERATION)
+        return fail(OK_ERR_INVALID_ARG, "movement_mode must be VELOCITY or ACCELERATION");
+    if (c.reward_mode < OK_REWARD_NONE || c.reward_mode > OK_REWARD_LANE_CENTER)
+        return fail(OK_ERR_INVALID_ARG, "unknown reward_mode");
+    if (c.raycast_mode != OK_RAYCAST_GRID && c.raycast_mode != OK_RAYCAST_BRUTE)
+        return fail(OK_ERR_INVALID_ARG, "unknown raycast_mode");
+    if (!(c.grid_cell >= 1.0f && c.grid_cell <= 512.0f))
+        return fail(OK_ERR_INVALID_ARG, "grid_cell must be in [1, 512] px");
+    auto e = new OkEnv();
+    e->cfg = c;
+    if (c.device >= 0)
+    {
+        int         count = 0;
+        cudaError_t err   = cudaGetDeviceCount(&count);
+        if (err != cudaSuccess || count <= 0 || c.device >= count)
+        {
+            delete e;
+            return fail(OK_ERR_NO_DEVICE, std::string("no usable CUDA device ") + std::to_string(c.device) + " (" +
+                                              (err != cudaSuccess ? cudaGetErrorString(err) : "device count 0") +
+                                              "); there is no CPU fallback");
+        }
+        DeviceGuard g(c.device);
+        int         sms = 0, optin = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c.device);
+        cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device);
+        e->has_device = true;
+        e->num_sms    = sms;
+        e->max_blob   = optin > 2048 ? static_cast<size_t>(optin) - 1024 : 0;
+    }
+    else
+    {
+        e->max_blob = 227 * 1024 - 1024; // host-only env: tracks can be built and inspected, nothing else
+    }
+    *out = e;
+    return OK_SUCCESS;
+}
+
+void ok_destroy(OkEnv *e)
+{
+    if (!e)
+        return;
+    if (e->has_device)
+    {
+        DeviceGuard g(e->cfg.device);
+        free_agents(e);
+        if (e->d_arena)
+            cudaFree(e->d_arena);
+        if (e->d_track_refs)
+            cudaFree(e->d_track_refs);
+        if (e->d_stage)
+            cudaFree(e->d_stage);
+    }
+    delete e;
+}
+
+int ok_add_track(OkEnv *e, const float *x, const float *y, const float *wr, const float *wl, int32_t n, int32_t *id_out)
+{
+    if (!e)
+        return fail(OK_ERR_INVALID_ARG, "env is NULL");
+    ok::Track   t;
+    std::string err;
+    if (!ok::build_track(x, y, wr, wl, n, e->cfg.grid_cell, e->max_blob, t, err))
+        return fail(err.find("fit") != std::string::npos ? OK_ERR_CAPACITY : OK_ERR_INVALID_ARG, err);
+    e->tracks.push_back(std::move(t));
+    e->arena_dirty = true;
+    if (id_out)
+        *id_out = static_cast<int32_t>(e->tracks.size()) - 1;
+    return OK_SUCCESS;
+}
+
+int ok_load_track_csv(OkEnv *e, const char *path, int32_t *id_out)
+{
+    if (!e || !path)
+        return fail(OK_ERR_INVALID_ARG, "env or path is NULL");
+    std::vector<float> cols[4];
+    std::string        err;
+    if (!ok::read_track_csv(path, cols, err))
+        return fail(OK_ERR_IO, err);
+    return ok_add_track(e, cols[0].data(), cols[1].data(), cols[2].data(), cols[3].data(),
+                        static_cast<int32_t>(cols[0].size()), id_out);
+}
+
+int ok_num_tracks(const OkEnv *e)
+{
+    return e ? static_cast<int>(e->tracks.size()) : 0;
+}
+
+int ok_track_info(const OkEnv *e, int32_t id, OkTrackInfo *out)
+{
+    if (!e || !out || id < 0 || id >= static_cast<int32_t>(e->tracks.size()))
+        return fail(OK_ERR_INVALID_ARG, "bad track id");
+    const ok::Track &t = e->tracks[id];
+    out->n_points      = t.n_points();
+    out->n_segments    = t.n_segments();
+    out->grid_nx       = t.grid_nx;
+    out->grid_ny       = t.grid_ny;
+    out->grid_items    = static_cast<int32_t>(t.items.size());
+    out->blob_bytes    = static_cast<int32_t>(t.blob.size());
+    out->grid_x0       = t.grid_x0;
+    out->grid_y0       = t.grid_y0;
+    out->grid_cell     = t.cell;
+    return OK_SUCCESS;
+}
+
+int64_t ok_track_copy(const OkEnv *e, int32_t id, int32_t which, float *h_out, int64_t count)
+{
+    if (!e || id < 0 || id >= static_cast<int32_t>(e->tracks.size()))
+        return fail(OK_ERR_INVALID_ARG, "bad track id");
+    const ok::Track          &t = e->tracks[id];
+    const std::vector<float> *v = nullptr;
+    switch (which)
+    {
+    case OK_TRACK_X: v = &t.x; break;
+    case OK_TRACK_Y: v = &t.y; break;
+    case OK_TRACK_W_RIGHT: v = &t.w_right; break;
+    case OK_TRACK_W_LEFT: v = &t.w_left; break;
+    case OK_TRACK_HEADING: v = &t.heading; break;
+    case OK_TRACK_LEFT_INNER: v = &t.left_inner; break;
+    case OK_TRACK_LEFT_OUTER: v = &t.left_outer; break;
+    case OK_TRACK_RIGHT_INNER: v = &t.right_inner; break;
+    case OK_TRACK_RIGHT_OUTER: v = &t.right_outer; break;
+    case OK_TRACK_SEGMENTS: v = &t.segments; break;
+    default: return fail(OK_ERR_INVALID_ARG, "unknown track array");
+    }
+    if (h_out && count > 0)
+        std::memcpy(h_out, v->data(), sizeof(float) * static_cast<size_t>(std::min<int64_t>(count, v->size())));
+    return static_cast<int64_t>(v->size());
+}
+
+int ok_alloc_agents(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, const int32_t *h_track_id)
+{
+    if (!e)
+        return fail(OK_ERR_INVALID_ARG, "env is NULL");
+    if (!e->has_device)
+        return fail(OK_ERR_NO_DEVICE, "this env was created without a CUDA device (device = -1)");
+    if (n <= 0 || rays <= 0 || !h_ray_deg)
+        return fail(OK_ERR_INVALID_ARG, "n_agents and rays must be positive and ray angles given");
+    if (rays > 4096)
+        return fail(OK_ERR_INVALID_ARG, "at most 4096 rays per agent");
+    if (e->tracks.empty())
+        return fail(OK_ERR_STATE, "add at least one track before allocating agents");
+    for (int64_t i = 0; h_track_id && i < n; ++i)
+        if (h_track_id[i] < 0 || h_track_id[i] >= static_cast<int32_t>(e->tracks.size()))
+            return fail(OK_ERR_INVALID_ARG, "track id out of range for agent " + std::to_string(i));
+    DeviceGuard g(e->cfg.device);
+    free_agents(e);
+    e->n_agents = n;
+    e->rays     = rays;
+    int lpa     = 1;
+    while (lpa < rays && lpa < 32)
+        lpa <<= 1;
+    e->lanes_per_agent = lpa;
+
+    // one slab, 256-byte aligned sub-buffers
+    size_t offs[OK_BUF_COUNT], total = 0;
+    for (int b = 0; b < OK_BUF_COUNT; ++b)
+    {
+        offs[b] = total;
+        total += (buffer_bytes(e, b) + 255) / 256 * 256;
+    }
+    OK_CUDA(cudaMalloc(&e->d_slab, total));
+    OK_CUDA(cudaMemset(e->d_slab, 0, total));
+    for (int b = 0; b < OK_BUF_COUNT; ++b)
+        e->d_buf[b] = e->d_slab + offs[b];
+    OK_CUDA(cudaMalloc(&e->d_ray_deg, sizeof(float) * rays));
+    OK_CUDA(cudaMemcpy(e->d_ray_deg, h_ray_deg, sizeof(float) * rays, cudaMemcpyHostToDevice));
+    e->h_track_id.assign(static_cast<size_t>(n), 0);
+    if (h_track_id)
+        std::copy(h_track_id, h_track_id + n, e->h_track_id.begin());
+    OK_CUDA(cudaMemcpy(e->d_buf[OK_BUF_TRACK_ID], e->h_track_id.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+    OK_CUDA(cudaMemset(e->d_buf[OK_BUF_HIT_SEG], 0xff, buffer_bytes(e, OK_BUF_HIT_SEG))); // -1 = no hit yet
+
+    // tiles: maximal runs of one track, cut into one-pass pieces
+    const int             per_pass = (kBlock / 32) * (32 / lpa);
+    std::vector<ok::Tile> tiles;
+    for (int64_t i = 0; i < n;)
+    {
+        int64_t j = i;
+        while (j < n && e->h_track_id[j] == e->h_track_id[i])
+            ++j;
+        for (int64_t b = i; b < j; b += per_pass)
+        {
+            ok::Tile t{};
+            t.track = e->h_track_id[i];
+            t.begin = b;
+            t.count = static_cast<int32_t>(std::min<int64_t>(per_pass, j - b));
+            tiles.push_back(t);
+        }
+        i = j;
+    }
+    e->n_tiles = static_cast<int32_t>(tiles.size());
+    OK_CUDA(cudaMalloc(&e->d_tiles, sizeof(ok::Tile) * tiles.size()));
+    OK_CUDA(cudaMemcpy(e->d_tiles, tiles.data(), sizeof(ok::Tile) * tiles.size(), cudaMemcpyHostToDevice));
+    e->grid = std::max(1, std::min(e->num_sms, e->n_tiles));
+
+    // every agent starts where `Environment::resetAgent(agent, false)` puts it: RaceTrack::kStartingIdx
+    std::vector<int32_t> pt(static_cast<size_t>(n));
+    for (int64_t i = 0; i < n; ++i)
+        pt[i] = e->tracks[e->h_track_id[i]].n_points() > 3 ? 3 : 0;
+    return ok_reset_agents_host(e, nullptr, pt.data(), nullptr, nullptr, n, nullptr);
+}
+
+int64_t ok_num_agents(const OkEnv *e)
+{
+    return e ? e->n_agents : 0;
+}
+
+int32_t ok_num_rays(const OkEnv *e)
+{
+    return e ? e->rays : 0;
+}
+
+int ok_reset_agents(OkEnv *e, const int64_t *d_agent_idx, const int32_t *d_pt_idx, const float *d_lane_alpha,
+                    const float *d_heading_off, int64_t n, void *stream)
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    if (n <= 0)
+        return OK_SUCCESS;
+    if (!d_pt_idx)
+        return fail(OK_ERR_INVALID_ARG, "pt_idx is NULL");
+    DeviceGuard g(e->cfg.device);
+    rc = ensure_arena(e);
+    if (rc)
+        return rc;
+    ok::StepParams  p = base_params(e);
+    ok::ResetParams r{d_agent_idx, d_pt_idx, d_lane_alpha, d_heading_off, n, e->n_agents};
+    const int       threads = 128;
+    const int       blocks  = static_cast<int>((n + threads - 1) / threads);
+    ok::reset_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(p, r);
+    OK_CUDA(cudaGetLastError());
+    e->launches++;
+    return OK_SUCCESS;
+}
+
+int ok_reset_agents_host(OkEnv *e, const int64_t *h_agent_idx, const int32_t *h_pt_idx, const float *h_lane_alpha,
+                         const float *h_heading_off, int64_t n, void *stream)
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    if (n <= 0)
+        return OK_SUCCESS;
+    if (!h_pt_idx)
+        return fail(OK_ERR_INVALID_ARG, "pt_idx is NULL");
+    DeviceGuard  g(e->cfg.device);
+    cudaStream_t s    = static_cast<cudaStream_t>(stream);
+    const size_t need = static_cast<size_t>(n) * (8 + 4 + 4 + 4) + 64;
+    if (need > e->stage_bytes)
+    {
+        if (e->d_stage)
+            cudaFree(e->d_stage);
+        e->d_stage = nullptr, e->stage_bytes = 0;
+        OK_CUDA(cudaMalloc(&e->d_stage, need));
+        e->stage_bytes = need;
+    }
+    int64_t *d_ai = reinterpret_cast<int64_t *>(e->d_stage);
+    int32_t *d_pt = reinterpret_cast<int32_t *>(e->d_stage + 8 * static_cast<size_t>(n));
+    float   *d_la = reinterpret_cast<float *>(e->d_stage + 12 * static_cast<size_t>(n));
+    float   *d_ho = reinterpret_cast<float *>(e->d_stage + 16 * static_cast<size_t>(n));
+    if (h_agent_idx)
+        OK_CUDA(cudaMemcpyAsync(d_ai, h_agent_idx, 8 * static_cast<size_t>(n), cudaMemcpyHostToDevice, s));
+    OK_CUDA(cudaMemcpyAsync(d_pt, h_pt_idx, 4 * static_cast<size_t>(n), cudaMemcpyHostToDevice, s));
+    if (h_lane_alpha)
+        OK_CUDA(cudaMemcpyAsync(d_la, h_lane_alpha, 4 * static_cast<size_t>(n), cudaMemcpyHostToDevice, s));
+    if (h_heading_off)
+        OK_CUDA(cudaMemcpyAsync(d_ho, h_heading_off, 4 * static_cast<size_t>(n), cudaMemcpyHostToDevice, s));
+    rc = ok_reset_agents(e, h_agent_idx ? d_ai : nullptr, d_pt, h_lane_alpha ? d_la : nullptr,
+                         h_heading_off ? d_ho : nullptr, n, stream);
+    if (rc)
+        return rc;
+    OK_CUDA(cudaStreamSynchronize(s));
+    return OK_SUCCESS;
+}
+
+int ok_cast_rays(OkEnv *e, void *stream)
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    DeviceGuard    g(e->cfg.device);
+    ok::StepParams p = base_params(e);
+    p.do_move        = 0;
+    return launch_step(e, p, static_cast<cudaStream_t>(stream));
+}
+
+int ok_launch_step(OkEnv *e, const float *d_thr, const float *d_steer, void *stream)
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    if ((d_thr == nullptr) != (d_steer == nullptr))
+        return fail(OK_ERR_INVALID_ARG, "pass both action arrays or neither");
+    DeviceGuard    g(e->cfg.device);
+    ok::StepParams p = base_params(e);
+    p.do_move        = 1;
+    p.ext_thr        = d_thr;
+    p.ext_steer      = d_steer;
+    return launch_step(e, p, static_cast<cudaStream_t>(stream));
+}
+
+int ok_launch_steps_random(OkEnv *e, uint64_t first_step, int32_t k, uint32_t seed, void *stream)
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    DeviceGuard    g(e->cfg.device);
+    ok::StepParams p = base_params(e);
+    p.do_move        = 1;
+    p.action_source  = 1;
+    p.seed           = seed;
+    for (int32_t i = 0; i < k; ++i)
+    {
+        p.step = first_step + static_cast<uint64_t>(i);
+        rc     = launch_step(e, p, static_cast<cudaStream_t>(stream));
+        if (rc)
+            return rc;
+    }
+    return OK_SUCCESS;
+}
+
+int ok_fill_random_actions(OkEnv *e, uint64_t step, uint32_t seed, void *stream)
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    DeviceGuard    g(e->cfg.device);
+    ok::StepParams p = base_params(e);
+    p.step           = step;
+    p.seed           = seed;
+    const int threads = 256;
+    const int blocks  = static_cast<int>((e->n_agents + threads - 1) / threads);
+    ok::fill_actions_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(p, e->n_agents);
+    OK_CUDA(cudaGetLastError());
+    e->launches++;
+    return OK_SUCCESS;
+}
+
+int ok_step_host(OkEnv *e, const float *h_thr, const float *h_steer, float *h_obs, float *h_reward, uint8_t *h_done,
+                 void *stream)
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    if ((h_thr == nullptr) != (h_steer == nullptr))
+        return fail(OK_ERR_INVALID_ARG, "pass both action arrays or neither");
+    DeviceGuard  g(e->cfg.device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t n = static_cast<size_t>(e->n_agents);
+    if (h_thr)
+    {
+        OK_CUDA(cudaMemcpyAsync(e->d_buf[OK_BUF_ACT_THROTTLE], h_thr, 4 * n, cudaMemcpyHostToDevice, s));
+        OK_CUDA(cudaMemcpyAsync(e->d_buf[OK_BUF_ACT_STEER], h_steer, 4 * n, cudaMemcpyHostToDevice, s));
+    }
+    ok::StepParams p = base_params(e);
+    p.do_move        = 1;
+    rc               = launch_step(e, p, s);
+    if (rc)
+        return rc;
+    if (h_obs)
+        OK_CUDA(cudaMemcpyAsync(h_obs, e->d_buf[OK_BUF_OBS], buffer_bytes(e, OK_BUF_OBS), cudaMemcpyDeviceToHost, s));
+    if (h_reward)
+        OK_CUDA(cudaMemcpyAsync(h_reward, e->d_buf[OK_BUF_REWARD], 4 * n, cudaMemcpyDeviceToHost, s));
+    if (h_done)
+        OK_CUDA(cudaMemcpyAsync(h_done, e->d_buf[OK_BUF_DONE], n, cudaMemcpyDeviceToHost, s));
+    OK_CUDA(cudaStreamSynchronize(s));
+    return OK_SUCCESS;
+}
+
+int ok_host_alloc(void **h_ptr, size_t bytes)
+{
+    if (!h_ptr)
+        return fail(OK_ERR_INVALID_ARG, "h_ptr is NULL");
+    OK_CUDA(cudaMallocHost(h_ptr, bytes));
+    return OK_SUCCESS;
+}
+
+int ok_host_free(void *h_ptr)
+{
+    OK_CUDA(cudaFreeHost(h_ptr));
+    return OK_SUCCESS;
+}
+
+int ok_get_buffer(OkEnv *e, int32_t which, void **d_ptr, int64_t shape[3], int32_t *dtype)
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    if (which < 0 || which >= OK_BUF_COUNT)
+        return fail(OK_ERR_INVALID_ARG, "unknown buffer id");
+    const BufferDesc d = describe(which);
+    if (d_ptr)
+        *d_ptr = e->d_buf[which];
+    if (shape)
+    {
+        shape[0] = e->n_agents;
+        shape[1] = d.per_ray >= 1 ? e->rays : 0;
+        shape[2] = d.per_ray == 2 ? 2 : 0;
+    }
+    if (dtype)
+        *dtype = d.dtype;
+    return OK_SUCCESS;
+}
+
+int ok_read_buffer(OkEnv *e, int32_t which, void *h_dst, size_t bytes, void *stream)
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    if (which < 0 || which >= OK_BUF_COUNT || !h_dst)
+        return fail(OK_ERR_INVALID_ARG, "bad buffer id or NULL destination");
+    if (bytes > buffer_bytes(e, which))
+        return fail(OK_ERR_INVALID_ARG, "read larger than the buffer");
+    DeviceGuard  g(e->cfg.device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    OK_CUDA(cudaMemcpyAsync(h_dst, e->d_buf[which], bytes, cudaMemcpyDeviceToHost, s));
+    OK_CUDA(cudaStreamSynchronize(s));
+    return OK_SUCCESS;
+}
+
+int ok_write_buffer(OkEnv *e, int32_t which, const void *h_src, size_t bytes, void *stream)
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    if (which < 0 || which >= OK_BUF_COUNT || !h_src)
+        return fail(OK_ERR_INVALID_ARG, "bad buffer id or NULL source");
+    if (which == OK_BUF_TRACK_ID)
+        return fail(OK_ERR_INVALID_ARG, "track ids are fixed by ok_alloc_agents (the tile table depends on them)");
+    if (bytes > buffer_bytes(e, which))
+        return fail(OK_ERR_INVALID_ARG, "write larger than the buffer");
+    DeviceGuard  g(e->cfg.device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    OK_CUDA(cudaMemcpyAsync(e->d_buf[which], h_src, bytes, cudaMemcpyHostToDevice, s));
+    OK_CUDA(cudaStreamSynchronize(s));
+    return OK_SUCCESS;
+}
+
+int ok_sync(OkEnv *e, void *stream)
+{
+    if (!e || !e->has_device)
+        return fail(OK_ERR_NO_DEVICE, "no device");
+    DeviceGuard g(e->cfg.device);
+    OK_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return OK_SUCCESS;
+}
+
+int ok_launch_stats(const OkEnv *e, OkLaunchStats *out)
+{
+    if (!e || !out)
+        return fail(OK_ERR_INVALID_ARG, "NULL argument");
+    out->kernel_launches = e->launches;
+    out->grid_blocks     = e->grid;
+    out->block_threads   = kBlock;
+    out->smem_bytes      = static_cast<int32_t>(e->smem);
+    out->tiles           = e->n_tiles;
+    return OK_SUCCESS;
+}
+}

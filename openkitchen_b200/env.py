@@ -1,0 +1,216 @@
+"""Thin object wrapper over the C ABI: one :class:`Env` per GPU.
+
+This layer holds no algorithm: every method is one call into ``libopenkitchen_b200.so``.  numpy
+arrays cross the boundary as HOST buffers (``*_host`` / read / write entry points); device pointers
+are exposed as integers for the torch / DLPack layer in :mod:`openkitchen_b200.batch_env`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _capi
+from ._capi import BUF, OkConfig, OkLaunchStats, OkTrackInfo, check
+
+_NP_DTYPES = {_capi.DTYPE_F32: np.float32, _capi.DTYPE_I32: np.int32, _capi.DTYPE_U32: np.uint32, _capi.DTYPE_U8: np.uint8}
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "tracks_f32.npz")
+
+
+def _vp(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def track_names():
+    """Names of the 23 racetrack-database tracks packed in data/tracks_f32.npz (sorted)."""
+    with np.load(_DATA) as z:
+        return [str(n) for n in z["__names__"]]
+
+
+def track_columns(name: str):
+    """The four raw CSV columns (x_m, y_m, w_tr_right_m, w_tr_left_m) of a packed track, binary32."""
+    with np.load(_DATA) as z:
+        a = z[name]
+    return a[0].copy(), a[1].copy(), a[2].copy(), a[3].copy()
+
+
+def write_track_csv(name: str, path: str):
+    """Re-emit a packed track in the reference's CSV format (%.9g round-trips binary32 through stof)."""
+    x, y, wr, wl = track_columns(name)
+    with open(path, "w") as f:
+        f.write("# x_m,y_m,w_tr_right_m,w_tr_left_m\n")
+        for i in range(len(x)):
+            f.write("%.9g,%.9g,%.9g,%.9g\n" % (x[i], y[i], wr[i], wl[i]))
+
+
+def ray_fan(n_rays: int) -> np.ndarray:
+    """Evenly spaced fan -70..70 deg in binary32: the generator of main_torch.cpp:26-34."""
+    if n_rays == 1:
+        return np.zeros(1, dtype=np.float32)
+    i = np.arange(n_rays, dtype=np.int32).astype(np.float32)
+    return (np.float32(-70.0) + (i * np.float32(140.0)) / np.float32(n_rays - 1)).astype(np.float32)
+
+
+class Env:
+    """Owns one ``OkEnv``.  ``device=-1`` builds a host-only env (tracks can be built and inspected)."""
+
+    def __init__(self, device: int = 0, **cfg):
+        self.lib = _capi.load()
+        c = OkConfig()
+        self.lib.ok_config_default(C.byref(c))
+        c.device = device
+        for k, v in cfg.items():
+            if not hasattr(c, k):
+                raise AttributeError(f"OkConfig has no field {k}")
+            setattr(c, k, v)
+        self.cfg = c
+        h = C.c_void_p()
+        check(self.lib.ok_create(C.byref(c), C.byref(h)))
+        self.h = h
+        self.n = 0
+        self.rays = 0
+
+    # ---- lifetime -----------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.ok_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- tracks -------------------------------------------------------------------------
+    def add_track(self, cols) -> int:
+        x, y, wr, wl = (np.ascontiguousarray(c, dtype=np.float32) for c in cols)
+        tid = C.c_int32(-1)
+        check(self.lib.ok_add_track(self.h, _vp(x), _vp(y), _vp(wr), _vp(wl), len(x), C.byref(tid)))
+        return tid.value
+
+    def add_named_track(self, name: str) -> int:
+        return self.add_track(track_columns(name))
+
+    def load_track_csv(self, path: str) -> int:
+        tid = C.c_int32(-1)
+        check(self.lib.ok_load_track_csv(self.h, path.encode(), C.byref(tid)))
+        return tid.value
+
+    def num_tracks(self) -> int:
+        return self.lib.ok_num_tracks(self.h)
+
+    def track_info(self, t: int) -> OkTrackInfo:
+        info = OkTrackInfo()
+        check(self.lib.ok_track_info(self.h, t, C.byref(info)))
+        return info
+
+    def track_array(self, t: int, name: str) -> np.ndarray:
+        which = _capi.TRACK_ARRAYS[name]
+        n = check(self.lib.ok_track_copy(self.h, t, which, None, 0))
+        out = np.empty(n, dtype=np.float32)
+        check(self.lib.ok_track_copy(self.h, t, which, _vp(out), n))
+        if name in ("li", "lo", "ri", "ro"):
+            return out.reshape(-1, 2)
+        if name == "segments":
+            return out.reshape(-1, 4)
+        return out
+
+    # ---- agents -------------------------------------------------------------------------
+    def alloc_agents(self, n: int, ray_deg, track_id=None):
+        ray_deg = np.ascontiguousarray(ray_deg, dtype=np.float32)
+        tid = None if track_id is None else np.ascontiguousarray(track_id, dtype=np.int32)
+        if tid is not None and len(tid) != n:
+            raise ValueError("track_id must have one entry per agent")
+        check(self.lib.ok_alloc_agents(self.h, n, len(ray_deg), _vp(ray_deg), _vp(tid)))
+        self.n, self.rays = n, len(ray_deg)
+
+    def reset(self, agent_idx, pt_idx, lane_alpha=None, heading_off=None, stream=None):
+        """Host-array reset (Environment::resetAgent with explicit draws)."""
+        ai = None if agent_idx is None else np.ascontiguousarray(agent_idx, dtype=np.int64)
+        pt = np.ascontiguousarray(pt_idx, dtype=np.int32)
+        la = None if lane_alpha is None else np.ascontiguousarray(lane_alpha, dtype=np.float32)
+        ho = None if heading_off is None else np.ascontiguousarray(heading_off, dtype=np.float32)
+        check(self.lib.ok_reset_agents_host(self.h, _vp(ai), _vp(pt), _vp(la), _vp(ho), len(pt), stream))
+
+    def reset_device(self, d_agent_idx, d_pt_idx, d_lane_alpha, d_heading_off, n, stream=None):
+        check(self.lib.ok_reset_agents(self.h, d_agent_idx, d_pt_idx, d_lane_alpha, d_heading_off, n, stream))
+
+    # ---- the tick -----------------------------------------------------------------------
+    def cast_rays(self, stream=None):
+        check(self.lib.ok_cast_rays(self.h, stream))
+
+    def launch_step(self, d_thr=None, d_steer=None, stream=None):
+        check(self.lib.ok_launch_step(self.h, d_thr, d_steer, stream))
+
+    def launch_steps_random(self, first_step: int, k: int, seed: int = 0x0C17C4E2, stream=None):
+        check(self.lib.ok_launch_steps_random(self.h, first_step, k, seed, stream))
+
+    def fill_random_actions(self, step: int, seed: int = 0x0C17C4E2, stream=None):
+        check(self.lib.ok_fill_random_actions(self.h, step, seed, stream))
+
+    def step_host(self, thr=None, steer=None, obs=None, reward=None, done=None, stream=None):
+        """End-to-end tick with HOST buffers (H2D actions, kernel, D2H results, sync)."""
+        check(self.lib.ok_step_host(self.h, _vp(thr), _vp(steer), _vp(obs), _vp(reward), _vp(done), stream))
+
+    def sync(self, stream=None):
+        check(self.lib.ok_sync(self.h, stream))
+
+    # ---- buffers ------------------------------------------------------------------------
+    def buffer_info(self, name: str):
+        """(device pointer, shape tuple, numpy dtype) of an agent buffer."""
+        ptr, shape, dt = C.c_void_p(), (C.c_int64 * 3)(), C.c_int32()
+        check(self.lib.ok_get_buffer(self.h, BUF[name], C.byref(ptr), shape, C.byref(dt)))
+        shp = tuple(int(s) for s in shape if s > 0)
+        return ptr.value, shp, _NP_DTYPES[dt.value]
+
+    def read(self, name: str, stream=None) -> np.ndarray:
+        _, shp, dt = self.buffer_info(name)
+        out = np.empty(shp, dtype=dt)
+        check(self.lib.ok_read_buffer(self.h, BUF[name], _vp(out), out.nbytes, stream))
+        return out
+
+    def write(self, name: str, arr, stream=None):
+        _, shp, dt = self.buffer_info(name)
+        a = np.ascontiguousarray(arr, dtype=dt)
+        if a.shape != shp:
+            raise ValueError(f"{name}: expected shape {shp}, got {a.shape}")
+        check(self.lib.ok_write_buffer(self.h, BUF[name], _vp(a), a.nbytes, stream))
+
+    def launch_stats(self) -> OkLaunchStats:
+        s = OkLaunchStats()
+        check(self.lib.ok_launch_stats(self.h, C.byref(s)))
+        return s
+
+
+def pinned_array(shape, dtype) -> np.ndarray:
+    """numpy array over cudaMallocHost memory (for the end-to-end path); freed when collected."""
+    lib = _capi.load()
+    nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    check(lib.ok_host_alloc(C.byref(p), max(nbytes, 1)))
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib.ok_host_free(self.ptr)
+            except Exception:
+                pass
+
+    _OWNERS[id(buf)] = _Owner(p)  # keep alive as long as the module (simple and safe for benches)
+    return arr
+
+
+_OWNERS = {}

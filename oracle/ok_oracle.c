@@ -575,6 +575,7 @@ int oko_alloc_agents(OkoEnv *e, int64_t n, int rays, const float *ray_deg, const
     memcpy(e->ray_deg, ray_deg, sizeof(float) * (size_t)rays);
     for (int i = 0; i < OKO_BUF_COUNT; ++i)
         e->buf[i] = calloc(1, buf_bytes(e, i) + 16);
+    memset(e->buf[OKO_BUF_HIT_SEG], 0xff, buf_bytes(e, OKO_BUF_HIT_SEG)); /* -1: no hit recorded yet */
     int32_t *tid = (int32_t *)e->buf[OKO_BUF_TRACK_ID];
     for (int64_t i = 0; i < n; ++i) {
         tid[i] = track_id ? track_id[i] : 0;
@@ -757,6 +758,7 @@ static void cast_one(OkoEnv *e, int64_t a)
     F32(e, OKO_BUF_MIN_DIST2)[a] = min_dist2;
     if (min_dist2 < e->cfg.collision_dist2) /* CollisionChecker.cu:167-171 */
         U8(e, OKO_BUF_CRASHED)[a] = 1;
+    U8(e, OKO_BUF_DONE)[a] = U8(e, OKO_BUF_CRASHED)[a]; /* Agent::isDone, Agent.cpp:138-144 */
 }
 
 /* App-side progress / reward / done after env.step(); see the mode enum for the sources. */

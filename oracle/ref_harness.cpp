@@ -513,7 +513,7 @@ int okr_alloc_agents(OkrEnv *e, int64_t n, int rays, const float *ray_deg, const
             bytes = static_cast<size_t>(n) * rays * 8;
         if (i == OKO_BUF_OBS || i == OKO_BUF_HIT_SEG || i == OKO_BUF_HIT_T)
             bytes = static_cast<size_t>(n) * rays * 4;
-        e->buf[i].assign(bytes + 16, 0);
+        e->buf[i].assign(bytes + 16, i == OKO_BUF_HIT_SEG ? 0xff : 0);
     }
     for (int64_t i = 0; i < n; ++i)
     {
