@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/s and ray-casts/s of the batched step loop on B200 (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 1000 --warmup 100            # our arm (N>1: under torchrun)
+    python bench.py --impl reference --steps K --warmup W          # the reference CPU arm
+
+Workload (BASELINE.json configs[2], the shape the 1e10 ray-casts/s target is quoted on): 65,536
+agents spread over all 23 tracks, 32 rays each, random (Philox) actions, VELOCITY mode, crashed
+agents auto-reset, CMA-ES progress reward (nearest centre-line index every tick).  A "step" is one
+tick of every agent.  At N GPUs every rank owns its own 65,536-agent slice (weak scaling, no
+data-path collective: agents never interact).
+
+Timing: W warm-up ticks, then K ticks each bracketed by CUDA events on the launching stream with an
+L2 flush (a 256 MiB memset) between ticks; ms_per_step = mean event time, max over ranks.  The
+`e2e` number drives the same tick through ok_step_host with pinned HOST buffers (H2D actions, D2H
+obs/reward/done inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_AGENTS = 65536
+N_RAYS = 32
+SEED = 0x0C17C4E2
+BYTES_PER_AGENT_STEP = 92 + 8 * N_RAYS  # 348 B at R = 32
+WORKLOAD = "C3: 65536 agents over 23 tracks x 32 rays, random actions, auto-reset, progress reward"
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_workload(ok, env_or_oracle, n_agents, is_oracle=False):
+    """tracks + agents + deterministic reset of SURVEY 8(d); identical for the product and the oracle"""
+    names = ok.track_names()
+    pts_per_track = []
+    for nm in names:
+        cols = ok.track_columns(nm)
+        if is_oracle:
+            env_or_oracle.add_track(cols)
+        else:
+            env_or_oracle.add_track(cols)
+        pts_per_track.append(len(cols[0]))
+    nt = len(names)
+    tid = (np.arange(n_agents, dtype=np.int64) * nt // n_agents).astype(np.int32)  # contiguous per track
+    env_or_oracle.alloc_agents(n_agents, ok.ray_fan(N_RAYS), tid)
+    ids = np.arange(n_agents, dtype=np.uint64)
+    pts = ((ids * np.uint64(2654435761)) % np.uint64(2**32) % np.asarray(pts_per_track, dtype=np.uint64)[tid]).astype(np.int32)
+    env_or_oracle.reset(None, pts)
+    return tid
+
+
+def cpu_reference_run(steps, warmup, budget_s, n_cap=N_AGENTS):
+    """Times the reference CPU implementation (oracle/_ref when built, else the C port) with every
+    host thread on a bounded sample of the workload.  Returns (agent_steps_per_s, info dict)."""
+    import openkitchen_b200 as ok
+    from oracle import api as oapi
+
+    kind = "reference" if oapi.have_ref() else "port"
+    cfg = dict(movement_mode=0, reward_mode=2, auto_reset=1)
+    # calibration tick on a small sample to size the run
+    cal = oapi.Oracle(kind, **cfg)
+    cores = cal.max_threads()
+    cal.set_threads(cores)
+    n_cal = 23 * 8
+    build_workload(ok, cal, n_cal, is_oracle=True)
+    cal.fill_random_actions(0, SEED)
+    cal.step()
+    t0 = time.perf_counter()
+    for s in range(1, 4):
+        cal.fill_random_actions(s, SEED)
+        cal.step()
+    rate = 3 * n_cal / (time.perf_counter() - t0)
+    cal.close()
+    total_ticks = max(1, steps + warmup)
+    n = int(min(n_cap, max(23, rate * budget_s / total_ticks)))
+    n = max(23, (n // 23) * 23)
+    ora = oapi.Oracle(kind, **cfg)
+    ora.set_threads(cores)
+    build_workload(ok, ora, n, is_oracle=True)
+    for s in range(warmup):
+        ora.fill_random_actions(s, SEED)
+        ora.step()
+    t0 = time.perf_counter()
+    for s in range(warmup, warmup + steps):
+        ora.fill_random_actions(s, SEED)
+        ora.step()
+    dt = time.perf_counter() - t0
+    ora.close()
+    value = n * steps / dt
+    info = {"value": value, "unit": "agent-steps/s", "cores": cores, "kind": kind,
+            "sample": f"{n} agents (same 23-track mix, ray fan, Philox actions, auto-reset) x {steps} ticks after {warmup} warm-up, {dt:.1f} s"}
+    return value, dt, info
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, dt, info = cpu_reference_run(args.steps, args.warmup, budget_s=90.0)
+    line = {
+        "impl": "reference", "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s",
+        "ray_casts_per_sec": value * N_RAYS, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "note": "CPU arm: each step is one tick of a bounded agent sample"},
+        "cpu_baseline": info,
+        "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--agents", type=int, default=N_AGENTS, help="agents per GPU (default: the BASELINE workload)")
+    ap.add_argument("--raycast", default="grid", choices=["grid", "brute"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed ticks")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+
+    import openkitchen_b200 as ok
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: openkitchen_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    n = args.agents
+    env = ok.Env(device=local, movement_mode=ok.MOVE_VELOCITY, reward_mode=ok.REWARD_CMAES_PROGRESS, auto_reset=1,
+                 raycast_mode=ok.RAYCAST_GRID if args.raycast == "grid" else ok.RAYCAST_BRUTE)
+    build_workload(ok, env, n)
+    stream = torch.cuda.current_stream()
+    sp = stream.cuda_stream
+    flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    # every rank steps a different slice of the global agent id space: offset the Philox step counter per rank
+    step0 = rank * 10_000_000
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident arm ----------------------------------------------------------------
+    for s in range(args.warmup):
+        env.launch_steps_random(step0 + s, 1, SEED, sp)
+    barrier()
+    launches0 = env.launch_stats().kernel_launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        if flush is not None:
+            flush.zero_()
+        starts[i].record(stream)
+        env.launch_steps_random(step0 + args.warmup + i, 1, SEED, sp)
+        stops[i].record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop() if rank == 0 else None
+    launches = env.launch_stats().kernel_launches - launches0
+    ms = np.array([a.elapsed_time(b) for a, b in zip(starts, stops)], dtype=np.float64)
+    ms_per_step = float(ms.mean())
+    crashed_frac = float(env.read("crashed", sp).mean())
+
+    # ---- end-to-end arm: HOST buffers through ok_step_host ---------------------------------------
+    e2e_steps = max(10, min(args.steps, 200))
+    thr = ok.pinned_array((e2e_steps, n), np.float32)
+    steer = ok.pinned_array((e2e_steps, n), np.float32)
+    rng = np.random.default_rng(1234 + rank)
+    thr[:] = rng.random((e2e_steps, n), dtype=np.float32) * 100.0
+    steer[:] = rng.random((e2e_steps, n), dtype=np.float32) * 10.0 - 5.0
+    obs = ok.pinned_array((n, N_RAYS), np.float32)
+    rew = ok.pinned_array((n,), np.float32)
+    done = ok.pinned_array((n,), np.uint8)
+    for i in range(3):
+        env.step_host(thr[i], steer[i], obs, rew, done, sp)
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    tw = time.perf_counter()
+    for i in range(e2e_steps):
+        env.step_host(thr[i], steer[i], obs, rew, done, sp)
+    e1.record(stream)
+    barrier()
+    tw = time.perf_counter() - tw
+    e2e_ms = max(e0.elapsed_time(e1), 1e3 * tw) / e2e_steps  # host-synchronous path: the wall clock is the honest one
+    h2d = 2 * 4 * n
+    d2h = n * N_RAYS * 4 + n * 4 + n
+
+    # ---- max over ranks ------------------------------------------------------------------------
+    if dist is not None:
+        t = torch.tensor([ms_per_step, e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        total_agents = n * world
+        value = total_agents / (ms_per_step * 1e-3)
+        peak, peak_src = peak_hbm()
+        achieved = n * BYTES_PER_AGENT_STEP / (ms_per_step * 1e-3) / 1e9  # per GPU, GB/s
+        line = {
+            "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s",
+            "ray_casts_per_sec": value * N_RAYS,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "agents_per_gpu": n, "rays": N_RAYS, "tracks": 23, "raycast": args.raycast,
+                       "l2": "flushed between timed ticks (256 MiB memset)" if flush is not None else "not flushed",
+                       "parallelism": f"agent-sharded x{world}, no data-path collective",
+                       "crashed_fraction_at_end": crashed_frac, "wall_s_timed_region": t_wall},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": n * BYTES_PER_AGENT_STEP,
+                         "note": "latency/issue-bound path: see profiles/ for the FP32-issue and L1/shared numbers"},
+            "e2e": {"value": total_agents / (e2e_ms * 1e-3), "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            try:
+                _, _, info = cpu_reference_run(steps=10, warmup=2, budget_s=20.0)
+                line["cpu_baseline"] = info
+            except Exception as ex:  # the bench line must still print
+                line["cpu_baseline"] = {"value": None, "unit": "agent-steps/s", "cores": None, "kind": "port",
+                                        "sample": f"failed: {ex}"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

