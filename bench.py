@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--agents", type=int, default=N_AGENTS, help="agents per GPU (default: the BASELINE workload)")
     ap.add_argument("--raycast", default="grid", choices=["grid", "brute"])
+    ap.add_argument("--cell", type=float, default=0.0, help="broadphase cell size in px (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed ticks")
     args = ap.parse_args()
@@ -210,8 +211,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     n = args.agents
+    extra = {"grid_cell": args.cell} if args.cell > 0 else {}
     env = ok.Env(device=local, movement_mode=ok.MOVE_VELOCITY, reward_mode=ok.REWARD_CMAES_PROGRESS, auto_reset=1,
-                 raycast_mode=ok.RAYCAST_GRID if args.raycast == "grid" else ok.RAYCAST_BRUTE)
+                 raycast_mode=ok.RAYCAST_GRID if args.raycast == "grid" else ok.RAYCAST_BRUTE, **extra)
     build_workload(ok, env, n)
     stream = torch.cuda.current_stream()
     sp = stream.cuda_stream
@@ -292,7 +294,7 @@ def main():
             "ray_casts_per_sec": value * N_RAYS,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "agents_per_gpu": n, "rays": N_RAYS, "tracks": 23, "raycast": args.raycast,
+            "config": {"workload": WORKLOAD, "agents_per_gpu": n, "rays": N_RAYS, "tracks": 23, "raycast": args.raycast, "grid_cell_px": float(env.cfg.grid_cell),
                        "l2": "flushed between timed ticks (256 MiB memset)" if flush is not None else "not flushed",
                        "parallelism": f"agent-sharded x{world}, no data-path collective",
                        "crashed_fraction_at_end": crashed_frac, "wall_s_timed_region": t_wall},

@@ -125,7 +125,7 @@ typedef struct OkConfig {
     float    sensor_offset;        /* Agent::sensor_offset_ 0        Agent.h:61 */
     uint32_t standstill_period;    /* DisplacementStats::kPeriod 200 Environment.h:19 */
     float    standstill_threshold; /* kDisplamentThreshold 20        Environment.h:20 */
-    float    grid_cell;            /* broadphase cell size in px (16) */
+    float    grid_cell;            /* broadphase cell size in px (8) */
     int32_t  reserved[4];
 } OkConfig;
 

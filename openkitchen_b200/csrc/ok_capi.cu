@@ -286,7 +286,7 @@ void ok_config_default(OkConfig *c)
     c->sensor_offset        = 0.0f;
     c->standstill_period    = 200u;
     c->standstill_threshold = 20.0f;
-    c->grid_cell            = 16.0f;
+    c->grid_cell            = 8.0f;
 }
 
 int ok_create(const OkConfig *cfg, OkEnv **out)

@@ -81,7 +81,8 @@ struct StepParams
 struct TrackView
 {
     const float4   *seg;
-    const uint16_t *cells;
+    const uint2    *words;  // {occupancy bits, occupied-cell rank} per 32 cells
+    const uint16_t *starts; // item offsets of the occupied cells
     const uint16_t *items;
     const float2   *pts;
     const float    *widths;
@@ -95,7 +96,8 @@ __device__ __forceinline__ TrackView make_view(const uint8_t *blob)
     const TrackHeader *h = reinterpret_cast<const TrackHeader *>(blob);
     TrackView          v;
     v.seg      = reinterpret_cast<const float4 *>(blob + h->off_segments);
-    v.cells    = reinterpret_cast<const uint16_t *>(blob + h->off_cells);
+    v.words    = reinterpret_cast<const uint2 *>(blob + h->off_words);
+    v.starts   = reinterpret_cast<const uint16_t *>(blob + h->off_starts);
     v.items    = reinterpret_cast<const uint16_t *>(blob + h->off_items);
     v.pts      = reinterpret_cast<const float2 *>(blob + h->off_points);
     v.widths   = reinterpret_cast<const float *>(blob + h->off_widths);
@@ -171,16 +173,17 @@ __device__ __forceinline__ void test_segment(const float4 sg, const int idx, con
     const float    ey    = fsub(sg.y, oy);
     const float    denom = fsub(fmul(dx, sg.w), fmul(dy, sg.z));
     const float    sn    = fsub(fmul(ex, dy), fmul(ey, dx));
-    const float    tn    = fsub(fmul(ex, sg.w), fmul(ey, sg.z));
     const uint32_t db    = __float_as_uint(denom);
     const uint32_t adb   = db & 0x7fffffffu;
-    if (adb < 0x322BCC77u) // fabsf(denom) < 1e-8f: parallel
+    const uint32_t sgn   = db & 0x80000000u;
+    const float    ad    = __uint_as_float(adb);
+    const float    b     = __uint_as_float(__float_as_uint(sn) ^ sgn);
+    // most candidates end here: parallel (fabsf(denom) < 1e-8f), or the ray's line misses the segment
+    if ((adb < 0x322BCC77u) | (b > ad) | (b < -0x1p-22f))
         return;
-    const uint32_t sgn = db & 0x80000000u;
-    const float    ad  = __uint_as_float(adb);
-    const float    b   = __uint_as_float(__float_as_uint(sn) ^ sgn);
-    const float    a   = __uint_as_float(__float_as_uint(tn) ^ sgn);
-    if ((b > ad) | (b < -0x1p-22f) | (a < -0x1p-22f))
+    const float tn = fsub(fmul(ex, sg.w), fmul(ey, sg.z));
+    const float a  = __uint_as_float(__float_as_uint(tn) ^ sgn);
+    if (a < -0x1p-22f)
         return;
     const float lim = fmul(ad, min_t);
     if ((lim >= 0x1p-100f) & (a > fmul(lim, 1.00000047683715820312f)))
@@ -262,31 +265,52 @@ __device__ __forceinline__ void cast_ray_grid(const TrackView &tv, float ox, flo
         tmy = (tv.gy0 + (iy + (dy > 0.0f ? 1 : 0)) * tv.cell - oy) * inv_dy;
         tdy = tv.cell * fabsf(inv_dy);
     }
+    // One loop, one unit of work per trip: a lane either tests the next segment of its current cell
+    // or moves to the next cell.  (A cell loop around a segment loop leaves most lanes idle: the
+    // 32 rays of a fan sit in cells with very different populations -- measured 5.7 active lanes.)
+    uint32_t k = 0, k_end = 0;
+    {
+        const int   c = iy * tv.nx + ix;
+        const uint2 w = tv.words[c >> 5];
+        if ((w.x >> (c & 31)) & 1u)
+        {
+            const uint32_t r = w.y + __popc(w.x & ((1u << (c & 31)) - 1u));
+            k = tv.starts[r], k_end = tv.starts[r + 1];
+        }
+    }
     for (;;)
     {
-        const int      c   = iy * tv.nx + ix;
-        const uint32_t beg = tv.cells[c], end = tv.cells[c + 1];
-        for (uint32_t k = beg; k < end; ++k)
+        if (k < k_end)
         {
-            const int i = tv.items[k];
+            const int i = tv.items[k++];
             test_segment(tv.seg[i], i, ox, oy, dx, dy, min_t, best);
-        }
-        const float t_next = fminf(tmx, tmy);
-        if (!(t_next <= fminf(min_t + OK_DDA_SLACK, t1)))
-            break;
-        if (tmx < tmy)
-        {
-            ix += sx;
-            tmx += tdx;
-            if (static_cast<unsigned>(ix) >= static_cast<unsigned>(tv.nx))
-                break;
         }
         else
         {
-            iy += sy;
-            tmy += tdy;
-            if (static_cast<unsigned>(iy) >= static_cast<unsigned>(tv.ny))
+            const float t_next = fminf(tmx, tmy);
+            if (!(t_next <= fminf(min_t + OK_DDA_SLACK, t1)))
                 break;
+            if (tmx < tmy)
+            {
+                ix += sx;
+                tmx += tdx;
+                if (static_cast<unsigned>(ix) >= static_cast<unsigned>(tv.nx))
+                    break;
+            }
+            else
+            {
+                iy += sy;
+                tmy += tdy;
+                if (static_cast<unsigned>(iy) >= static_cast<unsigned>(tv.ny))
+                    break;
+            }
+            const int   c = iy * tv.nx + ix;
+            const uint2 w = tv.words[c >> 5];
+            if ((w.x >> (c & 31)) & 1u)
+            {
+                const uint32_t r = w.y + __popc(w.x & ((1u << (c & 31)) - 1u));
+                k = tv.starts[r], k_end = tv.starts[r + 1];
+            }
         }
     }
 }

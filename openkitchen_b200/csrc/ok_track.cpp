@@ -129,7 +129,7 @@ bool build_grid(Track &t, float cell, std::string &err)
     if (t.grid_ny < 1)
         t.grid_ny = 1;
     const int64_t n_cells = static_cast<int64_t>(t.grid_nx) * t.grid_ny;
-    if (n_cells + 1 > 65535 * 4)
+    if (n_cells > (1 << 22))
     {
         err = "grid has too many cells";
         return false;
@@ -157,23 +157,38 @@ bool build_grid(Track &t, float cell, std::string &err)
                     lists[static_cast<size_t>(iy) * t.grid_nx + ix].push_back(static_cast<uint16_t>(s));
             }
     }
-    size_t total = 0;
+    size_t total = 0, occupied = 0;
     for (auto &l : lists)
+    {
         total += l.size();
-    if (total > 65535)
+        occupied += l.empty() ? 0 : 1;
+    }
+    if (total > 65535 || occupied > 65535)
     {
         err = "too many (cell, segment) registrations for 16-bit offsets";
         return false;
     }
-    t.cell_start.assign(static_cast<size_t>(n_cells) + 1, 0);
+    // Sparse cell table: one occupancy bit per cell, 32 cells per word, each word paired with the
+    // number of occupied cells before it; item offsets exist only for occupied cells.  An empty
+    // cell -- most of what a ray crosses -- costs one shared-memory word and a bit test.
+    const int64_t n_words = (n_cells + 31) / 32;
+    t.cell_words.assign(static_cast<size_t>(n_words) * 2, 0);
+    t.cell_starts.clear();
     t.items.clear();
     t.items.reserve(total);
+    uint32_t rank = 0;
     for (int64_t c = 0; c < n_cells; ++c)
     {
-        t.cell_start[c] = static_cast<uint16_t>(t.items.size());
+        if ((c & 31) == 0)
+            t.cell_words[2 * (c >> 5) + 1] = rank;
+        if (lists[c].empty())
+            continue;
+        t.cell_words[2 * (c >> 5)] |= 1u << (c & 31);
+        t.cell_starts.push_back(static_cast<uint16_t>(t.items.size()));
         t.items.insert(t.items.end(), lists[c].begin(), lists[c].end());
+        ++rank;
     }
-    t.cell_start[n_cells] = static_cast<uint16_t>(t.items.size());
+    t.cell_starts.push_back(static_cast<uint16_t>(t.items.size()));
     return true;
 }
 
@@ -198,10 +213,10 @@ void pack_blob(Track &t)
     t.blob.assign(sizeof(TrackHeader), 0);
     TrackHeader h{};
     h.n_points = n, h.n_segments = ns, h.grid_nx = t.grid_nx, h.grid_ny = t.grid_ny;
-    h.n_items = static_cast<int32_t>(t.items.size());
     h.grid_x0 = t.grid_x0, h.grid_y0 = t.grid_y0, h.cell = t.cell, h.inv_cell = 1.0f / t.cell;
     h.off_segments = static_cast<uint32_t>(append_section(t.blob, seg4.data(), seg4.size()));
-    h.off_cells    = static_cast<uint32_t>(append_section(t.blob, t.cell_start.data(), t.cell_start.size()));
+    h.off_words    = static_cast<uint32_t>(append_section(t.blob, t.cell_words.data(), t.cell_words.size()));
+    h.off_starts   = static_cast<uint32_t>(append_section(t.blob, t.cell_starts.data(), t.cell_starts.size()));
     h.off_items    = static_cast<uint32_t>(append_section(t.blob, t.items.data(), t.items.size()));
     h.off_points   = static_cast<uint32_t>(append_section(t.blob, pts.data(), pts.size()));
     h.off_widths   = static_cast<uint32_t>(append_section(t.blob, widths.data(), widths.size()));

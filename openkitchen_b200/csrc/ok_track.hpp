@@ -23,13 +23,13 @@ struct TrackHeader
     int32_t  n_segments;
     int32_t  grid_nx;
     int32_t  grid_ny;
-    int32_t  n_items;
     float    grid_x0;
     float    grid_y0;
     float    cell;
     float    inv_cell;
     uint32_t off_segments; // float4 {x1, y1, x2-x1, y2-y1}[n_segments], TrackSegments order
-    uint32_t off_cells;    // uint16 cell_start[nx*ny + 1]
+    uint32_t off_words;    // uint2 {occupancy bits of 32 cells, #occupied cells before this word}[ceil(nx*ny/32)]
+    uint32_t off_starts;   // uint16 item offset per OCCUPIED cell (+1 sentinel), in cell order
     uint32_t off_items;    // uint16 segment index [n_items]
     uint32_t off_points;   // float2 centre line [n_points]
     uint32_t off_widths;   // float  w_left + w_right [n_points]
@@ -46,8 +46,9 @@ struct Track
     std::vector<float> segments;                                         // x1,y1,x2,y2 per segment
     // broadphase
     int32_t               grid_nx{0}, grid_ny{0};
-    float                 grid_x0{0}, grid_y0{0}, cell{16.f};
-    std::vector<uint16_t> cell_start, items;
+    float                 grid_x0{0}, grid_y0{0}, cell{8.f};
+    std::vector<uint32_t> cell_words; // pairs {occupancy bits, occupied-cell rank} per 32 cells
+    std::vector<uint16_t> cell_starts, items;
     // staged form
     std::vector<uint8_t> blob;
 
