@@ -7,7 +7,9 @@
 #include "ok_track.hpp"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -49,7 +51,8 @@ struct DeviceGuard
     }
 };
 
-constexpr int kBlock = 512;
+constexpr int kBlock = 1024;
+constexpr int kMaxBatchAgents = 128;
 
 struct BufferDesc
 {
@@ -105,7 +108,10 @@ struct OkEnv
     float               *d_ray_deg{nullptr};
     ok::Tile            *d_tiles{nullptr};
     int32_t              n_tiles{0};
-    int32_t              lanes_per_agent{32};
+    int32_t              batch_agents{0};
+    uint16_t            *d_ray_order{nullptr};
+    int32_t             *d_sched{nullptr};
+    int                  smem_optin{0};
     std::vector<int32_t> h_track_id;
     // staging for the *_host entry points
     uint8_t *d_stage{nullptr};
@@ -137,7 +143,11 @@ void free_agents(OkEnv *e)
         cudaFree(e->d_ray_deg);
     if (e->d_tiles)
         cudaFree(e->d_tiles);
-    e->d_slab = nullptr, e->d_ray_deg = nullptr, e->d_tiles = nullptr;
+    if (e->d_ray_order)
+        cudaFree(e->d_ray_order);
+    if (e->d_sched)
+        cudaFree(e->d_sched);
+    e->d_slab = nullptr, e->d_ray_deg = nullptr, e->d_tiles = nullptr, e->d_ray_order = nullptr, e->d_sched = nullptr;
     for (auto &b : e->d_buf)
         b = nullptr;
     e->n_agents = 0, e->rays = 0, e->n_tiles = 0;
@@ -173,9 +183,6 @@ int ensure_arena(OkEnv *e)
     OK_CUDA(cudaMemcpy(e->d_track_refs, refs.data(), sizeof(ok::TrackRef) * refs.size(), cudaMemcpyHostToDevice));
     e->arena_bytes = total;
     e->arena_dirty = false;
-    e->smem        = (e->max_blob_used + 127) / 128 * 128;
-    OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<kBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 static_cast<int>(e->smem)));
     return OK_SUCCESS;
 }
 
@@ -215,7 +222,10 @@ ok::StepParams base_params(OkEnv *e)
     p.tiles     = e->d_tiles;
     p.n_tiles   = e->n_tiles;
     p.rays      = e->rays;
-    p.lanes_per_agent   = e->lanes_per_agent;
+    p.batch_agents      = e->batch_agents;
+    p.smem_blob_bytes   = static_cast<uint32_t>((e->max_blob_used + 127) / 128 * 128);
+    p.ray_order         = e->d_ray_order;
+    p.sched             = e->d_sched;
     p.movement_mode     = e->cfg.movement_mode;
     p.reward_mode       = e->cfg.reward_mode;
     p.raycast_mode      = e->cfg.raycast_mode;
@@ -326,6 +336,7 @@ int ok_create(const OkConfig *cfg, OkEnv **out)
         cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c.device);
         e->has_device = true;
         e->num_sms    = sms;
+        e->smem_optin = optin;
         e->max_blob   = optin > 2048 ? static_cast<size_t>(optin) - 1024 : 0;
     }
     else
@@ -358,6 +369,8 @@ int ok_add_track(OkEnv *e, const float *x, const float *y, const float *wr, cons
 {
     if (!e)
         return fail(OK_ERR_INVALID_ARG, "env is NULL");
+    if (e->n_agents > 0)
+        return fail(OK_ERR_STATE, "add every track before ok_alloc_agents (the batch size depends on the largest track)");
     ok::Track   t;
     std::string err;
     if (!ok::build_track(x, y, wr, wl, n, e->cfg.grid_cell, e->max_blob, t, err))
@@ -436,8 +449,8 @@ int ok_alloc_agents(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, c
         return fail(OK_ERR_NO_DEVICE, "this env was created without a CUDA device (device = -1)");
     if (n <= 0 || rays <= 0 || !h_ray_deg)
         return fail(OK_ERR_INVALID_ARG, "n_agents and rays must be positive and ray angles given");
-    if (rays > 4096)
-        return fail(OK_ERR_INVALID_ARG, "at most 4096 rays per agent");
+    if (rays > 1024)
+        return fail(OK_ERR_INVALID_ARG, "at most 1024 rays per agent");
     if (e->tracks.empty())
         return fail(OK_ERR_STATE, "add at least one track before allocating agents");
     for (int64_t i = 0; h_track_id && i < n; ++i)
@@ -447,10 +460,28 @@ int ok_alloc_agents(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, c
     free_agents(e);
     e->n_agents = n;
     e->rays     = rays;
-    int lpa     = 1;
-    while (lpa < rays && lpa < 32)
-        lpa <<= 1;
-    e->lanes_per_agent = lpa;
+    int rc0 = ensure_arena(e);
+    if (rc0)
+        return rc0;
+    // batch = the agents a CTA keeps in flight: as many as fit behind the largest staged track
+    {
+        const size_t blob  = (e->max_blob_used + 127) / 128 * 128;
+        const size_t avail = static_cast<size_t>(e->smem_optin) > blob + 1024 ? e->smem_optin - blob - 1024 : 0;
+        const size_t per   = ok::batch_smem_bytes(1, rays);
+        int64_t      a     = static_cast<int64_t>(avail / per);
+        int          cap   = kMaxBatchAgents;
+        if (const char *env = std::getenv("OK_BATCH_AGENTS"))
+            cap = std::max(1, std::atoi(env));
+        a = std::min<int64_t>(a, cap);
+        // small populations: spread over all SMs rather than filling a few batches
+        a = std::min<int64_t>(a, std::max<int64_t>(1, (n + e->num_sms - 1) / std::max(1, e->num_sms)));
+        if (a < 1)
+            return fail(OK_ERR_CAPACITY, "shared memory cannot hold one agent's rays next to the largest track");
+        e->batch_agents = static_cast<int32_t>(a);
+        e->smem         = blob + ok::batch_smem_bytes(e->batch_agents, rays);
+        OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<kBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(e->smem)));
+    }
 
     // one slab, 256-byte aligned sub-buffers
     size_t offs[OK_BUF_COUNT], total = 0;
@@ -471,8 +502,21 @@ int ok_alloc_agents(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, c
     OK_CUDA(cudaMemcpy(e->d_buf[OK_BUF_TRACK_ID], e->h_track_id.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
     OK_CUDA(cudaMemset(e->d_buf[OK_BUF_HIT_SEG], 0xff, buffer_bytes(e, OK_BUF_HIT_SEG))); // -1 = no hit yet
 
-    // tiles: maximal runs of one track, cut into one-pass pieces
-    const int             per_pass = (kBlock / 32) * (32 / lpa);
+    // pool order of the rays: by |angle|, the fan's centre (long) rays first
+    {
+        std::vector<uint16_t> order(rays);
+        for (int i = 0; i < rays; ++i)
+            order[i] = static_cast<uint16_t>(i);
+        std::stable_sort(order.begin(), order.end(),
+                         [&](uint16_t x, uint16_t y) { return std::fabs(h_ray_deg[x]) < std::fabs(h_ray_deg[y]); });
+        OK_CUDA(cudaMalloc(&e->d_ray_order, sizeof(uint16_t) * rays));
+        OK_CUDA(cudaMemcpy(e->d_ray_order, order.data(), sizeof(uint16_t) * rays, cudaMemcpyHostToDevice));
+        OK_CUDA(cudaMalloc(&e->d_sched, sizeof(int32_t) * 2));
+        OK_CUDA(cudaMemset(e->d_sched, 0, sizeof(int32_t) * 2));
+    }
+
+    // tiles: maximal runs of one track, cut into batches
+    const int             per_pass = e->batch_agents;
     std::vector<ok::Tile> tiles;
     for (int64_t i = 0; i < n;)
     {

@@ -64,7 +64,10 @@ struct StepParams
     const Tile    *tiles;
     int32_t        n_tiles;
     int32_t        rays;
-    int32_t        lanes_per_agent; // LPA
+    int32_t        batch_agents;    // agents per tile (shared-memory scratch is sized for this many)
+    uint32_t       smem_blob_bytes; // offset of the batch scratch behind the staged track
+    const uint16_t *ray_order;      // ray indices sorted by |angle|: pool order, long (central) rays first
+    int32_t       *sched;           // {next tile, CTAs finished}: dynamic tile scheduler
     // this launch
     const float *ext_thr, *ext_steer; // nullable: actions supplied by the caller
     int32_t      action_source;       // 0 stored/ext, 1 philox
@@ -213,106 +216,119 @@ __device__ __forceinline__ void cast_ray_brute(const TrackView &tv, float ox, fl
 // Exactness w.r.t. the brute-force loop is argued in DESIGN.md: segments are registered with a
 // kGridMargin inflation that dominates every rounding error of this walk, and the per-pair
 // arithmetic is the same function as above.
+//
+// The walk is a resumable state machine (begin / unit) because rays are NOT bound to lanes: the
+// work per ray is heavy tailed (mean 18 units, 1 ray in 32 needs 65+), so a lane that finishes
+// its ray pulls the next one from a CTA-wide pool (see step_kernel phase 2).
 #define OK_DDA_SLACK 0.5f
-__device__ __forceinline__ void cast_ray_grid(const TrackView &tv, float ox, float oy, float dx, float dy, float range,
-                                              float &min_t, int &best)
+struct RayWalk
 {
-    min_t = range;
-    best  = -1;
+    float    ox, oy, dx, dy;
+    float    min_t, t1;
+    float    tmx, tmy, tdx, tdy;
+    int      ix, iy, best;
+    uint32_t k, k_end;
+};
+
+__device__ __forceinline__ void open_cell(const TrackView &tv, RayWalk &w)
+{
+    const int   c    = w.iy * tv.nx + w.ix;
+    const uint2 word = tv.words[c >> 5];
+    if ((word.x >> (c & 31)) & 1u)
+    {
+        const uint32_t r = word.y + __popc(word.x & ((1u << (c & 31)) - 1u));
+        w.k = tv.starts[r], w.k_end = tv.starts[r + 1];
+    }
+}
+
+// returns false when the ray cannot hit anything (result stays min_t = range, best = -1)
+__device__ __forceinline__ bool walk_begin(const TrackView &tv, RayWalk &w, float ox, float oy, float dx, float dy,
+                                           float range)
+{
+    w.ox = ox, w.oy = oy, w.dx = dx, w.dy = dy;
+    w.min_t = range;
+    w.best  = -1;
+    w.k = 0, w.k_end = 0;
     // a non-finite ray fails the reference predicate on every segment
     if (!(fabsf(ox) <= FLT_MAX && fabsf(oy) <= FLT_MAX && fabsf(dx) <= FLT_MAX && fabsf(dy) <= FLT_MAX))
-        return;
+        return false;
     const float gx1 = tv.gx0 + tv.nx * tv.cell;
     const float gy1 = tv.gy0 + tv.ny * tv.cell;
     float       t0 = 0.0f, t1 = range + OK_DDA_SLACK;
     float       inv_dx = 0.0f, inv_dy = 0.0f;
     if (dx != 0.0f)
     {
-        inv_dx         = 1.0f / dx;
+        inv_dx         = __fdividef(1.0f, dx); // traversal only: any error here is covered by kGridMargin
         const float ta = (tv.gx0 - ox) * inv_dx, tb = (gx1 - ox) * inv_dx;
         t0 = fmaxf(t0, fminf(ta, tb));
         t1 = fminf(t1, fmaxf(ta, tb));
     }
     else if (ox < tv.gx0 || ox > gx1)
-        return;
+        return false;
     if (dy != 0.0f)
     {
-        inv_dy         = 1.0f / dy;
+        inv_dy         = __fdividef(1.0f, dy);
         const float ta = (tv.gy0 - oy) * inv_dy, tb = (gy1 - oy) * inv_dy;
         t0 = fmaxf(t0, fminf(ta, tb));
         t1 = fminf(t1, fmaxf(ta, tb));
     }
     else if (oy < tv.gy0 || oy > gy1)
-        return;
+        return false;
     if (!(t0 <= t1))
-        return; // the ray does not reach the grid within range
+        return false; // the ray does not reach the grid within range
+    w.t1 = t1;
 
     const float px = ox + t0 * dx, py = oy + t0 * dy; // entry point
     int         ix = static_cast<int>(floorf((px - tv.gx0) * tv.inv_cell));
     int         iy = static_cast<int>(floorf((py - tv.gy0) * tv.inv_cell));
     ix             = min(max(ix, 0), tv.nx - 1);
     iy             = min(max(iy, 0), tv.ny - 1);
-    const int   sx = dx > 0.0f ? 1 : -1, sy = dy > 0.0f ? 1 : -1;
     const float inf = __int_as_float(0x7f800000);
-    float       tmx = inf, tmy = inf, tdx = inf, tdy = inf;
+    w.tmx = inf, w.tmy = inf, w.tdx = inf, w.tdy = inf;
     if (dx != 0.0f)
     {
-        tmx = (tv.gx0 + (ix + (dx > 0.0f ? 1 : 0)) * tv.cell - ox) * inv_dx;
-        tdx = tv.cell * fabsf(inv_dx);
+        w.tmx = (tv.gx0 + (ix + (dx > 0.0f ? 1 : 0)) * tv.cell - ox) * inv_dx;
+        w.tdx = tv.cell * fabsf(inv_dx);
     }
     if (dy != 0.0f)
     {
-        tmy = (tv.gy0 + (iy + (dy > 0.0f ? 1 : 0)) * tv.cell - oy) * inv_dy;
-        tdy = tv.cell * fabsf(inv_dy);
+        w.tmy = (tv.gy0 + (iy + (dy > 0.0f ? 1 : 0)) * tv.cell - oy) * inv_dy;
+        w.tdy = tv.cell * fabsf(inv_dy);
     }
-    // One loop, one unit of work per trip: a lane either tests the next segment of its current cell
-    // or moves to the next cell.  (A cell loop around a segment loop leaves most lanes idle: the
-    // 32 rays of a fan sit in cells with very different populations -- measured 5.7 active lanes.)
-    uint32_t k = 0, k_end = 0;
+    w.ix = ix, w.iy = iy;
+    open_cell(tv, w);
+    return true;
+}
+
+// one unit of work: test the next segment of the current cell, or step to the next cell.
+// returns false when the walk is over.
+__device__ __forceinline__ bool walk_unit(const TrackView &tv, RayWalk &w)
+{
+    if (w.k < w.k_end)
     {
-        const int   c = iy * tv.nx + ix;
-        const uint2 w = tv.words[c >> 5];
-        if ((w.x >> (c & 31)) & 1u)
-        {
-            const uint32_t r = w.y + __popc(w.x & ((1u << (c & 31)) - 1u));
-            k = tv.starts[r], k_end = tv.starts[r + 1];
-        }
+        const int i = tv.items[w.k++];
+        test_segment(tv.seg[i], i, w.ox, w.oy, w.dx, w.dy, w.min_t, w.best);
+        return true;
     }
-    for (;;)
+    const float t_next = fminf(w.tmx, w.tmy);
+    if (!(t_next <= fminf(w.min_t + OK_DDA_SLACK, w.t1)))
+        return false;
+    if (w.tmx < w.tmy)
     {
-        if (k < k_end)
-        {
-            const int i = tv.items[k++];
-            test_segment(tv.seg[i], i, ox, oy, dx, dy, min_t, best);
-        }
-        else
-        {
-            const float t_next = fminf(tmx, tmy);
-            if (!(t_next <= fminf(min_t + OK_DDA_SLACK, t1)))
-                break;
-            if (tmx < tmy)
-            {
-                ix += sx;
-                tmx += tdx;
-                if (static_cast<unsigned>(ix) >= static_cast<unsigned>(tv.nx))
-                    break;
-            }
-            else
-            {
-                iy += sy;
-                tmy += tdy;
-                if (static_cast<unsigned>(iy) >= static_cast<unsigned>(tv.ny))
-                    break;
-            }
-            const int   c = iy * tv.nx + ix;
-            const uint2 w = tv.words[c >> 5];
-            if ((w.x >> (c & 31)) & 1u)
-            {
-                const uint32_t r = w.y + __popc(w.x & ((1u << (c & 31)) - 1u));
-                k = tv.starts[r], k_end = tv.starts[r + 1];
-            }
-        }
+        w.ix += w.dx > 0.0f ? 1 : -1;
+        w.tmx += w.tdx;
+        if (static_cast<unsigned>(w.ix) >= static_cast<unsigned>(tv.nx))
+            return false;
     }
+    else
+    {
+        w.iy += w.dy > 0.0f ? 1 : -1;
+        w.tmy += w.tdy;
+        if (static_cast<unsigned>(w.iy) >= static_cast<unsigned>(tv.ny))
+            return false;
+    }
+    open_cell(tv, w);
+    return true;
 }
 
 // RaceTrack::findNearestTrackIndexBruteForce (RaceTrack.cpp:16-31), cooperatively by the `lpa`
@@ -350,30 +366,67 @@ __device__ __forceinline__ int nearest_index(const TrackView &tv, float qx, floa
 // ---------------------------------------------------------------------------------------------
 // the tick
 // ---------------------------------------------------------------------------------------------
+// per-agent scratch in shared memory while its batch is in flight
+struct AgentRec
+{
+    float    ox, oy, rc, rs; // lidar origin, cos/sin of the heading
+    float    rot, x, y;      // pose after the move
+    float    rx, ry;         // where a reset put the agent (FLAG_RESET)
+    int      min_d2_bits;    // running min of the squared hit norms (as int: all values are >= +0)
+    uint32_t flags;
+    int32_t  pad;
+};
+static_assert(sizeof(AgentRec) == 48, "AgentRec layout");
+enum : uint32_t
+{
+    kFlagCrashed = 1u,
+    kFlagTimedOut = 2u,
+    kFlagReset = 4u
+};
+
+__host__ __device__ inline size_t batch_smem_bytes(int agents, int rays)
+{ // AgentRec + per ray {float2 dir, float t, int seg}
+    return static_cast<size_t>(agents) * (sizeof(AgentRec) + 16u * static_cast<size_t>(rays));
+}
+
+constexpr int kRefillThreshold = 8; // a warp refills its idle lanes from the pool once this many are idle
+
 template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(const StepParams p)
 {
-    extern __shared__ __align__(128) uint8_t blob[];
+    extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t         bar;
+    __shared__ int                           s_tile, s_pool;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = kBlock / 32;
-    const int lpa = p.lanes_per_agent, sub = lane & (lpa - 1), grp = lane / lpa, groups = 32 / lpa;
+    const int     R      = p.rays;
+
+    uint8_t  *blob    = smem;
+    AgentRec *recs    = reinterpret_cast<AgentRec *>(smem + p.smem_blob_bytes);
+    float2   *dirs    = reinterpret_cast<float2 *>(recs + p.batch_agents);
+    float    *out_t   = reinterpret_cast<float *>(dirs + static_cast<size_t>(p.batch_agents) * R);
+    int      *out_seg = reinterpret_cast<int *>(out_t + static_cast<size_t>(p.batch_agents) * R);
 
     if (tid == 0)
         mbar_init(&bar, 1);
     __syncthreads();
 
-    const int tile_begin = static_cast<int>((static_cast<int64_t>(blockIdx.x) * p.n_tiles) / gridDim.x);
-    const int tile_end   = static_cast<int>((static_cast<int64_t>(blockIdx.x + 1) * p.n_tiles) / gridDim.x);
-    int       staged = -1;
-    uint32_t  phase  = 0;
+    int      staged = -1;
+    uint32_t phase  = 0;
+    const float inv_R = 1.0f / static_cast<float>(R);
 
-    for (int tile = tile_begin; tile < tile_end; ++tile)
+    for (;;)
     {
+        // ---- dynamic tile scheduler: tiles are batches of same-track agents, in agent order ----
+        if (tid == 0)
+            s_tile = atomicAdd(p.sched, 1);
+        __syncthreads(); // also: everyone is done with the previous batch and its track
+        const int tile = s_tile;
+        if (tile >= p.n_tiles)
+            break;
         const Tile tl = p.tiles[tile];
         if (tl.track != staged)
         {
-            __syncthreads(); // everyone is done with the previous track
             if (tid == 0)
             {
                 const TrackRef tr = p.tracks[tl.track];
@@ -385,23 +438,21 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
             phase ^= 1u;
             staged = tl.track;
         }
-        const TrackView tv = make_view(blob);
+        const TrackView tv       = make_view(blob);
+        const int       count    = tl.count;
+        const int       n_rays   = count * R;
+        const float     inv_cnt  = 1.0f / static_cast<float>(count);
 
-        // warp w serves agents (w*groups + grp) + j*(kWarps*groups) of the tile; the trip count is
-        // warp-uniform so the shuffles below always see all 32 lanes
-        const int per_pass = kWarps * groups;
-        for (int base = 0; base < tl.count; base += per_pass)
+        // =====================================================================================
+        // phase 1 -- one thread per agent: optional reset, kinematics, standstill (Environment.cpp:128-143)
+        // =====================================================================================
+        if (tid < count)
         {
-            const int     local = base + warp * groups + grp;
-            const bool    valid = local < tl.count;
-            const int64_t a     = tl.begin + (valid ? local : 0);
-
-            // ---- load ----
-            float   x = p.x[a], y = p.y[a], rot = p.rot[a], speed = p.speed[a], accel = p.accel[a];
-            bool    crashed = p.crashed[a] != 0, timed_out = p.timed_out[a] != 0;
-            float   fitness = p.fitness[a];
-            int32_t prev    = p.prev[a];
-
+            const int64_t a = tl.begin + tid;
+            float    x = p.x[a], y = p.y[a], rot = p.rot[a], speed = p.speed[a], accel = p.accel[a];
+            bool     crashed = p.crashed[a] != 0, timed_out = p.timed_out[a] != 0;
+            uint32_t flags = 0;
+            float    rx = 0.0f, ry = 0.0f;
             if (p.do_move)
             {
                 float thr, steer;
@@ -432,46 +483,26 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
                     thr   = p.act_thr[a];
                     steer = p.act_steer[a];
                 }
-
-                // ---- optional reset of a crashed agent before the tick (GuidedCostLearning/test.cpp:102-111):
-                //      Environment::resetAgent + Agent::reset, Environment.cpp:103-121 / Agent.cpp:123-135 ----
-                const bool do_reset = p.auto_reset && crashed; // uniform within the agent's lanes
-                if (__any_sync(0xffffffffu, do_reset))
+                // app-side reset of a crashed agent before the tick (GuidedCostLearning/test.cpp:102-111):
+                // Environment::resetAgent + Agent::reset, Environment.cpp:103-121 / Agent.cpp:123-135.
+                // prev / nearest / fitness are finalised in phase 4 (they need a centre-line search).
+                if (p.auto_reset && crashed)
                 {
-                    int32_t pt = 0;
-                    float   rx = x, ry = y;
-                    if (do_reset)
-                    {
-                        pt = static_cast<int32_t>((static_cast<int64_t>(p.reset_pt[a]) + p.auto_reset_stride) % tv.n_pts);
-                        const float2 c = tv.pts[pt];
-                        rx = c.x, ry = c.y;
-                    }
-                    float     d2;
-                    const int near0 = nearest_index(tv, rx, ry, sub, lpa, d2); // all lanes take part
-                    if (do_reset)
-                    {
-                        x = rx, y = ry, rot = tv.headings[pt];
-                        accel = 0.0f, speed = 0.0f;
-                        crashed = false, timed_out = false;
-                        thr = 0.0f, steer = 0.0f; // Agent::reset zeroes current_action_
-                        prev    = near0;
-                        fitness = 0.0f;
-                        if (valid && sub == 0)
-                        {
-                            p.reset_pt[a] = pt;
-                            p.start_x[a]  = rx;
-                            p.start_y[a]  = ry;
-                            p.nearest[a]  = near0;
-                        }
-                    }
+                    const int32_t pt =
+                        static_cast<int32_t>((static_cast<int64_t>(p.reset_pt[a]) + p.auto_reset_stride) % tv.n_pts);
+                    const float2 c = tv.pts[pt];
+                    x = c.x, y = c.y, rot = tv.headings[pt];
+                    accel = 0.0f, speed = 0.0f;
+                    crashed = false, timed_out = false;
+                    thr = 0.0f, steer = 0.0f; // Agent::reset zeroes current_action_
+                    rx = x, ry = y;
+                    flags |= kFlagReset;
+                    p.reset_pt[a] = pt;
+                    p.start_x[a]  = x;
+                    p.start_y[a]  = y;
                 }
-                if (valid && sub == 0)
-                {
-                    p.act_thr[a]   = thr;
-                    p.act_steer[a] = steer;
-                }
-
-                // ---- 1) kinematics + standstill, Environment.cpp:128-143 ----
+                p.act_thr[a]   = thr;
+                p.act_steer[a] = steer;
                 if (!crashed)
                 {
                     rot = fadd(rot, steer);
@@ -490,18 +521,14 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
                     sincosf(fmul(OK_DEG2RAD, rot), ms, mc);
                     x = fadd(x, fmul(fmul(mc, speed), p.dt));
                     y = fadd(y, fmul(fmul(ms, speed), p.dt));
-
                     // checkAndUpdateStandstill, Environment.cpp:16-39
                     uint32_t ctr = p.ss_ctr[a];
                     bool     out = false;
                     if (ctr == 0)
                     {
-                        if (valid && sub == 0)
-                        {
-                            p.ss_x[a] = x;
-                            p.ss_y[a] = y;
-                        }
-                        ctr = 1;
+                        p.ss_x[a] = x;
+                        p.ss_y[a] = y;
+                        ctr       = 1;
                     }
                     else if (ctr >= p.standstill_period)
                     {
@@ -511,141 +538,289 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
                     }
                     else
                         ++ctr;
-                    if (valid && sub == 0)
-                        p.ss_ctr[a] = ctr;
+                    p.ss_ctr[a] = ctr;
                     if (out)
                     {
                         crashed   = true;
                         timed_out = true;
                     }
                 }
+                p.x[a] = x, p.y[a] = y, p.rot[a] = rot, p.speed[a] = speed, p.accel[a] = accel;
+                p.timed_out[a] = timed_out;
             }
-
-            // ---- 2) lidar: pack (CollisionChecker.cu:115-128), cast (:37-71), unpack (:144-172) ----
+            // lidar origin, CollisionChecker.cu:121-124
             float rs, rc;
             sincosf(fmul(OK_DEG2RAD, rot), rs, rc);
-            const float ox   = fadd(x, fmul(p.sensor_offset, rc));
-            const float oy   = fadd(y, fmul(p.sensor_offset, rs));
-            const bool  live = !crashed;
-            float       min_d2 = fmul(p.sensor_range, p.sensor_range);
-            for (int r0 = 0; r0 < p.rays; r0 += lpa)
+            AgentRec rec;
+            rec.ox = fadd(x, fmul(p.sensor_offset, rc));
+            rec.oy = fadd(y, fmul(p.sensor_offset, rs));
+            rec.rc = rc, rec.rs = rs, rec.rot = rot, rec.x = x, rec.y = y, rec.rx = rx, rec.ry = ry;
+            rec.min_d2_bits = __float_as_int(fmul(p.sensor_range, p.sensor_range));
+            rec.flags       = flags | (crashed ? kFlagCrashed : 0u) | (timed_out ? kFlagTimedOut : 0u);
+            rec.pad         = 0;
+            recs[tid]       = rec;
+        }
+        if (tid == 0)
+            s_pool = 0;
+        __syncthreads();
+
+        // =====================================================================================
+        // phase 1b -- one thread per ray: direction (cosf/sinf of CollisionChecker.cu:47-48)
+        // =====================================================================================
+        for (int q = tid; q < n_rays; q += kBlock)
+        {
+            const int al = __float2int_rz((static_cast<float>(q) + 0.5f) * inv_R);
+            const int r  = q - al * R;
+            float     s, c;
+            sincosf(fmul(OK_DEG2RAD, fadd(recs[al].rot, p.ray_deg[r])), s, c);
+            dirs[q] = make_float2(c, s);
+        }
+        __syncthreads();
+
+        // =====================================================================================
+        // phase 2 -- the casts.  Rays are pulled from a CTA-wide pool: a warp refills its idle lanes
+        // (warp-aggregated atomic on the pool cursor) whenever kRefillThreshold of them are idle, so
+        // the long rays of the heavy tail do not hold 31 lanes hostage.  The pool is ordered
+        // ray-major with the fan's centre rays first (p.ray_order): those are the long ones.
+        // =====================================================================================
+        if (p.raycast_mode == 0)
+        {
+            RayWalk w;
+            int     mine      = -1; // pool slot this lane is working on (index into dirs / out_*), -1 = idle
+            bool    exhausted = false;
+            for (;;)
             {
-                const int     r      = r0 + sub;
-                const bool    has    = valid && r < p.rays;
-                const int64_t ri     = a * p.rays + (has ? r : 0);
-                float2        hit;
-                if (live)
+                const unsigned idle = __ballot_sync(0xffffffffu, mine < 0);
+                if (idle == 0xffffffffu && exhausted)
+                    break;
+                if (!exhausted && (__popc(idle) >= kRefillThreshold))
                 {
-                    float dx, dy;
-                    sincosf(fmul(OK_DEG2RAD, fadd(rot, p.ray_deg[has ? r : 0])), dy, dx);
-                    float min_t;
-                    int   best;
-                    if (p.raycast_mode == 0)
-                        cast_ray_grid(tv, ox, oy, dx, dy, p.sensor_range, min_t, best);
-                    else
-                        cast_ray_brute(tv, ox, oy, dx, dy, p.sensor_range, min_t, best);
-                    hit.x = fadd(ox, fmul(min_t, dx));
-                    hit.y = fadd(oy, fmul(min_t, dy));
-                    if (has)
+                    int base = 0;
+                    if (lane == 0)
+                        base = atomicAdd(&s_pool, __popc(idle));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (base + __popc(idle) >= n_rays)
+                        exhausted = true;
+                    if (mine < 0)
                     {
-                        reinterpret_cast<float2 *>(p.hit_abs)[ri] = hit;
-                        p.hit_t[ri]                               = min_t;
-                        p.hit_seg[ri]                             = best;
+                        const int q = base + __popc(idle & ((1u << lane) - 1u));
+                        if (q < n_rays)
+                        {
+                            // pool order -> (agent, ray): ray-major, centre rays first
+                            const int rank = __float2int_rz((static_cast<float>(q) + 0.5f) * inv_cnt);
+                            const int al   = q - rank * count;
+                            const int r    = p.ray_order[rank];
+                            const int slot = al * R + r;
+                            const AgentRec &rec = recs[al];
+                            if (rec.flags & kFlagCrashed)
+                            { // inactive ray: the kernel leaves its stale hit alone (CollisionChecker.cu:44)
+                                out_seg[slot] = -2;
+                            }
+                            else
+                            {
+                                const float2 d = dirs[slot];
+                                if (walk_begin(tv, w, rec.ox, rec.oy, d.x, d.y, p.sensor_range))
+                                    mine = slot;
+                                else
+                                {
+                                    out_t[slot]   = w.min_t;
+                                    out_seg[slot] = w.best;
+                                }
+                            }
+                        }
                     }
+                }
+                if (mine >= 0)
+                {
+                    if (!walk_unit(tv, w))
+                    {
+                        out_t[mine]   = w.min_t;
+                        out_seg[mine] = w.best;
+                        mine          = -1;
+                    }
+                }
+            }
+        }
+        else
+        { // OK_RAYCAST_BRUTE: every segment in ascending order, the reference's own loop
+            for (int q = tid; q < n_rays; q += kBlock)
+            {
+                const int       al  = __float2int_rz((static_cast<float>(q) + 0.5f) * inv_R);
+                const AgentRec &rec = recs[al];
+                if (rec.flags & kFlagCrashed)
+                {
+                    out_seg[q] = -2;
+                    continue;
+                }
+                const float2 d = dirs[q];
+                float        min_t;
+                int          best;
+                cast_ray_brute(tv, rec.ox, rec.oy, d.x, d.y, p.sensor_range, min_t, best);
+                out_t[q]   = min_t;
+                out_seg[q] = best;
+            }
+        }
+        __syncthreads();
+
+        // =====================================================================================
+        // phase 3 -- one thread per ray: hit point, unpack (CollisionChecker.cu:68-69,152-165), outputs
+        // =====================================================================================
+        for (int q0 = 0; q0 < n_rays; q0 += kBlock)
+        {
+            const int  q   = q0 + tid;
+            const bool has = q < n_rays;
+            float      sq  = __int_as_float(0x7f800000);
+            int        al  = 0;
+            if (has)
+            {
+                al                  = __float2int_rz((static_cast<float>(q) + 0.5f) * inv_R);
+                const AgentRec &rec = recs[al];
+                const int64_t   gi  = tl.begin * R + q;
+                const int       seg = out_seg[q];
+                float2          hit;
+                if (seg != -2)
+                {
+                    const float2 d = dirs[q];
+                    const float  t = out_t[q];
+                    hit.x          = fadd(rec.ox, fmul(t, d.x));
+                    hit.y          = fadd(rec.oy, fmul(t, d.y));
+                    reinterpret_cast<float2 *>(p.hit_abs)[gi] = hit;
+                    p.hit_t[gi]                               = t;
+                    p.hit_seg[gi]                             = seg;
                 }
                 else
-                    hit = reinterpret_cast<const float2 *>(p.hit_abs)[ri]; // stale hits of a crashed agent
-                const float xt = fsub(hit.x, ox), yt = fsub(hit.y, oy);
+                    hit = reinterpret_cast<const float2 *>(p.hit_abs)[gi]; // stale hit of a crashed agent
+                const float xt = fsub(hit.x, rec.ox), yt = fsub(hit.y, rec.oy);
                 float2      rel;
-                rel.x          = fsub(fmul(xt, rc), fmul(yt, rs));
-                rel.y          = fadd(fmul(xt, rs), fmul(yt, rc));
-                const float sq = fadd(fmul(rel.x, rel.x), fmul(rel.y, rel.y));
-                if (has)
-                {
-                    reinterpret_cast<float2 *>(p.hit_rel)[ri] = rel;
-                    p.obs[ri]                                 = __fdiv_rn(__fsqrt_rn(sq), p.sensor_range);
-                    if (sq < min_d2)
-                        min_d2 = sq;
-                }
+                rel.x = fsub(fmul(xt, rec.rc), fmul(yt, rec.rs));
+                rel.y = fadd(fmul(xt, rec.rs), fmul(yt, rec.rc));
+                sq    = fadd(fmul(rel.x, rel.x), fmul(rel.y, rel.y));
+                reinterpret_cast<float2 *>(p.hit_rel)[gi] = rel;
+                p.obs[gi] = __fdiv_rn(__fsqrt_rn(sq), p.sensor_range);
             }
-            for (int o = lpa >> 1; o > 0; o >>= 1)
-                min_d2 = fminf(min_d2, __shfl_xor_sync(0xffffffffu, min_d2, o));
-            if (min_d2 < p.collision_dist2)
-                crashed = true;
+            // min_dist2 of CollisionChecker.cu:150,162-165: `if (sq < min) min = sq` skips NaN, and so
+            // does a signed-int min over the bit patterns of values >= +0 (a NaN made here is 0x7fffffff)
+            if ((R & 31) == 0)
+            { // a warp's 32 rays belong to one agent: reduce in registers, one atomic per warp
+                float m = (sq == sq) ? sq : __int_as_float(0x7f800000);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                    m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                if (has && lane == 0)
+                    atomicMin(&recs[al].min_d2_bits, __float_as_int(m));
+            }
+            else if (has && sq == sq)
+                atomicMin(&recs[al].min_d2_bits, __float_as_int(sq));
+        }
+        __syncthreads();
 
-            // ---- app side: progress / reward / done ----
-            const int mode      = p.reward_mode;
-            const bool need_idx = mode == 1 || mode == 2 || mode == 6 || mode == 7;
-            int32_t   near      = 0;
-            float     near_d2   = 0.0f;
-            if (need_idx && p.do_move)
-                near = nearest_index(tv, x, y, sub, lpa, near_d2);
-            if (valid && sub == 0)
+        // =====================================================================================
+        // phase 4 -- one warp per agent: crash flag, centre-line search, progress / reward / done
+        // =====================================================================================
+        {
+            const int  mode     = p.reward_mode;
+            const bool need_idx = p.do_move && (mode == 1 || mode == 2 || mode == 6 || mode == 7);
+            for (int al = warp; al < count; al += kWarps)
             {
-                if (p.do_move)
-                {
-                    float reward = 0.0f;
-                    switch (mode)
-                    {
-                    case 1: // QAgent.hpp:150-168
-                        if (crashed)
-                            reward = -200.0f;
-                        else
-                        {
-                            const int32_t prog = near - prev;
-                            prev               = near;
-                            const int32_t ab = prog < 0 ? -prog : prog, len = tv.n_pts;
-                            reward = static_cast<float>(ab > (len / 2) ? len - ab : ab);
-                        }
-                        break;
-                    case 2: // main_eigen.cpp:147-163
-                        if (!crashed)
-                        {
-                            const int32_t prog = near - prev;
-                            prev               = near;
-                            reward             = static_cast<float>(prog < 0 ? -prog : prog);
-                            fitness            = fadd(fitness, reward);
-                        }
-                        else if (timed_out)
-                            fitness = 0.0f;
-                        break;
-                    case 3: reward = 1.0f; break; // ppo_sim.cpp:76
-                    case 4:                       // ReinforceContinuous/reinforce_sim.cpp:59-73
-                    {
-                        const float ddx = fsub(x, p.start_x[a]), ddy = fsub(y, p.start_y[a]);
-                        reward = crashed ? -5.0f : __fsqrt_rn(fadd(fmul(ddx, ddx), fmul(ddy, ddy)));
-                        break;
-                    }
-                    case 5: // DQAgent.hpp:161-180: min over rays of norm(), which is sqrt of the min squared norm
-                    {
-                        const float m = __fsqrt_rn(min_d2);
-                        reward        = crashed ? -200.0f : (p.sensor_range > m ? m : p.sensor_range);
-                        break;
-                    }
-                    case 6: reward = static_cast<float>(near); break; // MiscUtils.hpp:64-71
-                    case 7:                                           // WorldModelVaeRnn/main.cpp:336-342
-                        if (!crashed)
-                        {
-                            reward  = fsub(1.0f, __fdiv_rn(__fsqrt_rn(near_d2), tv.widths[near])); // RaceTrack.cpp:53-72
-                            fitness = fadd(fitness, reward);
-                        }
-                        else if (timed_out)
-                            fitness = 0.0f;
-                        break;
-                    default: break;
-                    }
-                    p.x[a] = x, p.y[a] = y, p.rot[a] = rot, p.speed[a] = speed, p.accel[a] = accel;
-                    p.timed_out[a] = timed_out;
-                    p.reward[a]    = reward;
-                    p.fitness[a]   = fitness;
-                    p.prev[a]      = prev;
-                    if (need_idx)
-                        p.nearest[a] = near;
+                const AgentRec rec = recs[al];
+                const int64_t  a   = tl.begin + al;
+                const float    min_d2 = __int_as_float(rec.min_d2_bits);
+                bool           crashed = (rec.flags & kFlagCrashed) != 0;
+                const bool     timed_out = (rec.flags & kFlagTimedOut) != 0;
+                if (min_d2 < p.collision_dist2) // CollisionChecker.cu:167-171
+                    crashed = true;
+                int32_t prev = 0, near = 0;
+                float   fitness = 0.0f, near_d2 = 0.0f;
+                if (rec.flags & kFlagReset)
+                { // prev_track_idx_ = nearest index of the post-reset pose (main_eigen.cpp:121-130)
+                    float d2;
+                    prev = nearest_index(tv, rec.rx, rec.ry, lane, 32, d2);
+                    near = prev;
                 }
-                p.crashed[a]   = crashed;
-                p.done[a]      = crashed; // Agent::isDone, Agent.cpp:138-144 (completed_ is never set)
-                p.min_dist2[a] = min_d2;
+                else if (p.do_move)
+                {
+                    prev    = p.prev[a];
+                    fitness = p.fitness[a];
+                }
+                if (need_idx)
+                    near = nearest_index(tv, rec.x, rec.y, lane, 32, near_d2);
+                if (lane == 0)
+                {
+                    if (p.do_move)
+                    {
+                        float reward = 0.0f;
+                        switch (mode)
+                        {
+                        case 1: // QAgent.hpp:150-168
+                            if (crashed)
+                                reward = -200.0f;
+                            else
+                            {
+                                const int32_t prog = near - prev;
+                                prev               = near;
+                                const int32_t ab = prog < 0 ? -prog : prog, len = tv.n_pts;
+                                reward = static_cast<float>(ab > (len / 2) ? len - ab : ab);
+                            }
+                            break;
+                        case 2: // main_eigen.cpp:147-163
+                            if (!crashed)
+                            {
+                                const int32_t prog = near - prev;
+                                prev               = near;
+                                reward             = static_cast<float>(prog < 0 ? -prog : prog);
+                                fitness            = fadd(fitness, reward);
+                            }
+                            else if (timed_out)
+                                fitness = 0.0f;
+                            break;
+                        case 3: reward = 1.0f; break; // ppo_sim.cpp:76
+                        case 4:                       // ReinforceContinuous/reinforce_sim.cpp:59-73
+                        {
+                            const float ddx = fsub(rec.x, p.start_x[a]), ddy = fsub(rec.y, p.start_y[a]);
+                            reward = crashed ? -5.0f : __fsqrt_rn(fadd(fmul(ddx, ddx), fmul(ddy, ddy)));
+                            break;
+                        }
+                        case 5: // DQAgent.hpp:161-180: min over rays of norm() == sqrt of the min squared norm
+                        {
+                            const float m = __fsqrt_rn(min_d2);
+                            reward        = crashed ? -200.0f : (p.sensor_range > m ? m : p.sensor_range);
+                            break;
+                        }
+                        case 6: reward = static_cast<float>(near); break; // MiscUtils.hpp:64-71
+                        case 7:                                           // WorldModelVaeRnn/main.cpp:336-342
+                            if (!crashed)
+                            {
+                                reward  = fsub(1.0f, __fdiv_rn(__fsqrt_rn(near_d2), tv.widths[near])); // RaceTrack.cpp:53-72
+                                fitness = fadd(fitness, reward);
+                            }
+                            else if (timed_out)
+                                fitness = 0.0f;
+                            break;
+                        default: break;
+                        }
+                        p.reward[a]  = reward;
+                        p.fitness[a] = fitness;
+                        p.prev[a]    = prev;
+                        if (need_idx || (rec.flags & kFlagReset))
+                            p.nearest[a] = near;
+                    }
+                    p.crashed[a]   = crashed;
+                    p.done[a]      = crashed; // Agent::isDone, Agent.cpp:138-144 (completed_ is never set)
+                    p.min_dist2[a] = min_d2;
+                }
             }
+        }
+    }
+
+    // last CTA out re-arms the tile scheduler for the next launch on this stream
+    if (tid == 0)
+    {
+        __threadfence();
+        if (atomicAdd(p.sched + 1, 1) == static_cast<int>(gridDim.x) - 1)
+        {
+            p.sched[0] = 0;
+            p.sched[1] = 0;
+            __threadfence();
         }
     }
 }
