@@ -52,7 +52,7 @@ struct DeviceGuard
 };
 
 constexpr int kBlock = 1024;
-constexpr int kMaxBatchAgents = 128;
+constexpr int kMaxBatchAgents = 256;
 
 struct BufferDesc
 {
@@ -515,24 +515,35 @@ int ok_alloc_agents(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, c
         OK_CUDA(cudaMemset(e->d_sched, 0, sizeof(int32_t) * 2));
     }
 
-    // tiles: maximal runs of one track, cut into batches
-    const int             per_pass = e->batch_agents;
-    std::vector<ok::Tile> tiles;
+    // tiles: maximal runs of one track, cut into batches.  Guided self-scheduling: CTAs pull tiles in
+    // list order, so full-size batches come first and a tail of quarter-size ones (about half a big
+    // batch per SM) evens out the finish.
+    const int     big   = e->batch_agents;
+    const int     small = std::max(1, big / 4);
+    const int64_t tail_agents = std::min<int64_t>(n / 2, static_cast<int64_t>(e->num_sms) * big / 2);
+    std::vector<ok::Tile> tiles, tail;
     for (int64_t i = 0; i < n;)
     {
         int64_t j = i;
         while (j < n && e->h_track_id[j] == e->h_track_id[i])
             ++j;
-        for (int64_t b = i; b < j; b += per_pass)
+        // this run's share of the small-tile tail
+        const int64_t run_tail = (j - i) * tail_agents / n;
+        const int64_t split    = j - run_tail;
+        for (int64_t b = i; b < j;)
         {
-            ok::Tile t{};
+            const bool    in_tail = b >= split;
+            const int64_t lim     = in_tail ? j : split;
+            ok::Tile      t{};
             t.track = e->h_track_id[i];
             t.begin = b;
-            t.count = static_cast<int32_t>(std::min<int64_t>(per_pass, j - b));
-            tiles.push_back(t);
+            t.count = static_cast<int32_t>(std::min<int64_t>(in_tail ? small : big, lim - b));
+            (in_tail ? tail : tiles).push_back(t);
+            b += t.count;
         }
         i = j;
     }
+    tiles.insert(tiles.end(), tail.begin(), tail.end());
     e->n_tiles = static_cast<int32_t>(tiles.size());
     OK_CUDA(cudaMalloc(&e->d_tiles, sizeof(ok::Tile) * tiles.size()));
     OK_CUDA(cudaMemcpy(e->d_tiles, tiles.data(), sizeof(ok::Tile) * tiles.size(), cudaMemcpyHostToDevice));

@@ -191,10 +191,17 @@ __device__ __forceinline__ void test_segment(const float4 sg, const int idx, con
     const float lim = fmul(ad, min_t);
     if ((lim >= 0x1p-100f) & (a > fmul(lim, 1.00000047683715820312f)))
         return;
-    // literal predicate of the reference
-    const float t = __fdiv_rn(tn, denom);
-    const float s = __fdiv_rn(sn, denom);
-    if ((t >= 0.0f) && (s >= 0.0f) && (s <= 1.0f) && ((t < min_t) || ((t == min_t) && (idx > best))))
+    // literal predicate of the reference.  The s test needs no division when b >= 0: b <= ad holds here
+    // and both are finite, so RN(b/ad) lies in [0,1].  (b in [-2^-22, 0) or a non-finite denominator
+    // still take the division.)
+    const float t    = __fdiv_rn(tn, denom);
+    bool        s_ok = (b >= 0.0f) & (adb < 0x7f800000u);
+    if (!s_ok)
+    {
+        const float s = __fdiv_rn(sn, denom);
+        s_ok          = (s >= 0.0f) && (s <= 1.0f);
+    }
+    if (s_ok && (t >= 0.0f) && ((t < min_t) || ((t == min_t) && (idx > best))))
     {
         min_t = t;
         best  = idx;
@@ -385,11 +392,12 @@ enum : uint32_t
 };
 
 __host__ __device__ inline size_t batch_smem_bytes(int agents, int rays)
-{ // AgentRec + per ray {float2 dir, float t, int seg}
-    return static_cast<size_t>(agents) * (sizeof(AgentRec) + 16u * static_cast<size_t>(rays));
+{ // AgentRec + per ray float2 direction
+    return static_cast<size_t>(agents) * (sizeof(AgentRec) + 8u * static_cast<size_t>(rays));
 }
 
-constexpr int kRefillThreshold = 8; // a warp refills its idle lanes from the pool once this many are idle
+constexpr int kRefillThreshold     = 8; // a warp refills its idle lanes from the pool once this many are idle
+constexpr int kUnitsPerRefillCheck = 4; // units of work between two looks at the pool
 
 template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(const StepParams p)
 {
@@ -404,8 +412,6 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
     uint8_t  *blob    = smem;
     AgentRec *recs    = reinterpret_cast<AgentRec *>(smem + p.smem_blob_bytes);
     float2   *dirs    = reinterpret_cast<float2 *>(recs + p.batch_agents);
-    float    *out_t   = reinterpret_cast<float *>(dirs + static_cast<size_t>(p.batch_agents) * R);
-    int      *out_seg = reinterpret_cast<int *>(out_t + static_cast<size_t>(p.batch_agents) * R);
 
     if (tid == 0)
         mbar_init(&bar, 1);
@@ -583,10 +589,11 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
         // the long rays of the heavy tail do not hold 31 lanes hostage.  The pool is ordered
         // ray-major with the fan's centre rays first (p.ray_order): those are the long ones.
         // =====================================================================================
+        const int64_t ray_base = tl.begin * R; // global index of the batch's first ray
         if (p.raycast_mode == 0)
         {
             RayWalk w;
-            int     mine      = -1; // pool slot this lane is working on (index into dirs / out_*), -1 = idle
+            int     mine      = -1; // batch-local ray (agent * R + ray) this lane is working on, -1 = idle
             bool    exhausted = false;
             for (;;)
             {
@@ -612,31 +619,33 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
                             const int r    = p.ray_order[rank];
                             const int slot = al * R + r;
                             const AgentRec &rec = recs[al];
-                            if (rec.flags & kFlagCrashed)
-                            { // inactive ray: the kernel leaves its stale hit alone (CollisionChecker.cu:44)
-                                out_seg[slot] = -2;
-                            }
-                            else
+                            // a crashed agent's rays are inactive: the kernel leaves their stale hits alone
+                            // (CollisionChecker.cu:44)
+                            if (!(rec.flags & kFlagCrashed))
                             {
                                 const float2 d = dirs[slot];
                                 if (walk_begin(tv, w, rec.ox, rec.oy, d.x, d.y, p.sensor_range))
                                     mine = slot;
                                 else
                                 {
-                                    out_t[slot]   = w.min_t;
-                                    out_seg[slot] = w.best;
+                                    p.hit_t[ray_base + slot]   = w.min_t;
+                                    p.hit_seg[ray_base + slot] = w.best;
                                 }
                             }
                         }
                     }
                 }
-                if (mine >= 0)
+#pragma unroll
+                for (int u = 0; u < kUnitsPerRefillCheck; ++u)
                 {
-                    if (!walk_unit(tv, w))
+                    if (mine >= 0)
                     {
-                        out_t[mine]   = w.min_t;
-                        out_seg[mine] = w.best;
-                        mine          = -1;
+                        if (!walk_unit(tv, w))
+                        {
+                            p.hit_t[ray_base + mine]   = w.min_t;
+                            p.hit_seg[ray_base + mine] = w.best;
+                            mine                       = -1;
+                        }
                     }
                 }
             }
@@ -648,16 +657,13 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
                 const int       al  = __float2int_rz((static_cast<float>(q) + 0.5f) * inv_R);
                 const AgentRec &rec = recs[al];
                 if (rec.flags & kFlagCrashed)
-                {
-                    out_seg[q] = -2;
                     continue;
-                }
                 const float2 d = dirs[q];
                 float        min_t;
                 int          best;
                 cast_ray_brute(tv, rec.ox, rec.oy, d.x, d.y, p.sensor_range, min_t, best);
-                out_t[q]   = min_t;
-                out_seg[q] = best;
+                p.hit_t[ray_base + q]   = min_t;
+                p.hit_seg[ray_base + q] = best;
             }
         }
         __syncthreads();
@@ -675,18 +681,15 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
             {
                 al                  = __float2int_rz((static_cast<float>(q) + 0.5f) * inv_R);
                 const AgentRec &rec = recs[al];
-                const int64_t   gi  = tl.begin * R + q;
-                const int       seg = out_seg[q];
+                const int64_t   gi  = ray_base + q;
                 float2          hit;
-                if (seg != -2)
+                if (!(rec.flags & kFlagCrashed))
                 {
                     const float2 d = dirs[q];
-                    const float  t = out_t[q];
+                    const float  t = p.hit_t[gi]; // written in phase 2 by whichever lane cast this ray
                     hit.x          = fadd(rec.ox, fmul(t, d.x));
                     hit.y          = fadd(rec.oy, fmul(t, d.y));
                     reinterpret_cast<float2 *>(p.hit_abs)[gi] = hit;
-                    p.hit_t[gi]                               = t;
-                    p.hit_seg[gi]                             = seg;
                 }
                 else
                     hit = reinterpret_cast<const float2 *>(p.hit_abs)[gi]; // stale hit of a crashed agent

@@ -185,6 +185,17 @@ bool build_grid(Track &t, float cell, std::string &err)
             continue;
         t.cell_words[2 * (c >> 5)] |= 1u << (c & 31);
         t.cell_starts.push_back(static_cast<uint16_t>(t.items.size()));
+        // inner boundaries first: from inside the lane they are hit before the outer ones 3 px behind
+        // them, which then fail the cheap "beyond the current hit" screen (any order is exact)
+        std::stable_sort(lists[c].begin(), lists[c].end(), [&](uint16_t p, uint16_t q) {
+            auto outer = [&](uint16_t s) {
+                const int32_t chain = t.n_points() - 1;
+                if (s < 4 * chain)
+                    return (s / chain) & 1; // chains LI, LO, RI, RO
+                return (s - 4 * chain) >= 2 ? 1 : 0; // closures LI, RI, LO, RO
+            };
+            return outer(p) < outer(q);
+        });
         t.items.insert(t.items.end(), lists[c].begin(), lists[c].end());
         ++rank;
     }
