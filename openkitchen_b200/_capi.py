@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libopenkitchen_b200.so")
+LIB_PATH = os.environ.get("OK_B200_LIB") or os.path.join(_HERE, "lib", "libopenkitchen_b200.so")
 
 OK_SUCCESS = 0
 OK_ERR_INVALID_ARG, OK_ERR_CUDA, OK_ERR_IO, OK_ERR_STATE, OK_ERR_CAPACITY, OK_ERR_NO_DEVICE = -1, -2, -3, -4, -5, -6

@@ -511,8 +511,8 @@ int ok_alloc_agents(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, c
                          [&](uint16_t x, uint16_t y) { return std::fabs(h_ray_deg[x]) < std::fabs(h_ray_deg[y]); });
         OK_CUDA(cudaMalloc(&e->d_ray_order, sizeof(uint16_t) * rays));
         OK_CUDA(cudaMemcpy(e->d_ray_order, order.data(), sizeof(uint16_t) * rays, cudaMemcpyHostToDevice));
-        OK_CUDA(cudaMalloc(&e->d_sched, sizeof(int32_t) * 2));
-        OK_CUDA(cudaMemset(e->d_sched, 0, sizeof(int32_t) * 2));
+        OK_CUDA(cudaMalloc(&e->d_sched, sizeof(int32_t) * 512));
+        OK_CUDA(cudaMemset(e->d_sched, 0, sizeof(int32_t) * 512));
     }
 
     // tiles: maximal runs of one track, cut into batches.  Guided self-scheduling: CTAs pull tiles in

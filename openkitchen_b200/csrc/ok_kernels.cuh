@@ -85,7 +85,7 @@ struct TrackView
 {
     const float4   *seg;
     const uint2    *words;  // {occupancy bits, occupied-cell rank} per 32 cells
-    const uint16_t *starts; // item offsets of the occupied cells
+    const uint32_t *starts; // per occupied cell: first item | (one past the last) << 16
     const uint16_t *items;
     const float2   *pts;
     const float    *widths;
@@ -100,7 +100,7 @@ __device__ __forceinline__ TrackView make_view(const uint8_t *blob)
     TrackView          v;
     v.seg      = reinterpret_cast<const float4 *>(blob + h->off_segments);
     v.words    = reinterpret_cast<const uint2 *>(blob + h->off_words);
-    v.starts   = reinterpret_cast<const uint16_t *>(blob + h->off_starts);
+    v.starts   = reinterpret_cast<const uint32_t *>(blob + h->off_starts);
     v.items    = reinterpret_cast<const uint16_t *>(blob + h->off_items);
     v.pts      = reinterpret_cast<const float2 *>(blob + h->off_points);
     v.widths   = reinterpret_cast<const float *>(blob + h->off_widths);
@@ -159,19 +159,42 @@ __device__ __forceinline__ void fence_proxy_async()
 // (smallest valid t, HIGHEST index among the segments attaining it): an order-independent rule,
 // which lets the broadphase visit candidates in any order.  `best` is that index (-1 = none).
 //
-// Two IEEE divisions per pair is the reference's cost; here a pair is first screened with
-// comparisons on the numerators that are SUFFICIENT for the reference's predicate to fail
-// (proofs in DESIGN.md "exact early rejection"); only survivors evaluate the literal predicate.
-//   a = tn*sign(denom), b = sn*sign(denom), ad = |denom|, so t = a/ad, s = b/ad as real numbers.
-//   b > ad              => RN(s) > 1            (RN(b/ad) <= 1 iff b <= ad for floats b, ad)
-//   b < -2^-22          => RN(s) <= -2^-149 < 0 (|b/ad| > 2^-150 because ad < 2^128)
-//   a < -2^-22          => RN(t) < 0            (same)
-//   a > RN(RN(ad*m)*(1+2^-21)), RN(ad*m) >= 2^-100 => RN(t) > m (m = current min_t)
-// NaN operands fail every screen and reach the literal predicate, which rejects them.
+// Two IEEE divisions per pair is the reference's cost.  Here:
+//  (1) a pair is first screened with comparisons on the numerators that are SUFFICIENT for the
+//      reference's predicate to fail (proofs in DESIGN.md "exact early rejection").  With
+//      a = tn*sign(denom), b = sn*sign(denom), ad = |denom| (t = a/ad, s = b/ad as reals):
+//        b > ad              => RN(s) > 1            (RN(b/ad) <= 1 iff b <= ad for floats b, ad)
+//        b < -2^-22          => RN(s) <= -2^-149 < 0 (|b/ad| > 2^-150 because ad < 2^128)
+//        a < -2^-22          => RN(t) < 0            (same)
+//        a > RN(RN(ad*m)*(1+2^-18)), RN(ad*m) >= 2^-100 => RN(t) > m(1+2^-21) >= incumbent
+//  (2) the survivors (real crossings in front of the ray) are ranked on an APPROXIMATE quotient
+//      tq = a * rcp(ad), |tq - RN(a/ad)| <= 2^-21 RN(a/ad): a candidate more than 2^-18 (relative)
+//      away from the incumbent is decided without a division; only a candidate inside that band --
+//      a near-tie -- is evaluated literally, against the incumbent's exact t.  The running value m
+//      is therefore "exact t, or within 2^-21 of it"; the exact t of the winner is recomputed once
+//      per ray in phase 3 (exact_t) from the same expression.
+// NaN / non-finite operands fail every shortcut and reach the literal predicate, which rejects them.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void test_segment(const float4 sg, const int idx, const float ox, const float oy,
-                                             const float dx, const float dy, float &min_t, int &best)
+enum : uint32_t
 {
+    kWalkApprox  = 1u, // the running minimum is an approximate quotient (see test_segment)
+    kWalkLaValid = 2u, // the look-ahead found the next occupied cell
+    kWalkLaDone  = 4u  // the look-ahead ran past the limit: no further cell
+};
+
+__device__ __forceinline__ float exact_t(const float4 sg, const float ox, const float oy, const float dx, const float dy)
+{
+    const float ex    = fsub(sg.x, ox);
+    const float ey    = fsub(sg.y, oy);
+    const float denom = fsub(fmul(dx, sg.w), fmul(dy, sg.z));
+    const float tn    = fsub(fmul(ex, sg.w), fmul(ey, sg.z));
+    return __fdiv_rn(tn, denom);
+}
+
+__device__ __forceinline__ void test_segment(const float4 *segs, const int idx, const float ox, const float oy,
+                                             const float dx, const float dy, float &m, int &best, uint32_t &flags)
+{
+    const float4   sg    = segs[idx];
     const float    ex    = fsub(sg.x, ox);
     const float    ey    = fsub(sg.y, oy);
     const float    denom = fsub(fmul(dx, sg.w), fmul(dy, sg.z));
@@ -188,34 +211,50 @@ __device__ __forceinline__ void test_segment(const float4 sg, const int idx, con
     const float a  = __uint_as_float(__float_as_uint(tn) ^ sgn);
     if (a < -0x1p-22f)
         return;
-    const float lim = fmul(ad, min_t);
-    if ((lim >= 0x1p-100f) & (a > fmul(lim, 1.00000047683715820312f)))
+    const float lim = fmul(ad, m);
+    if ((lim >= 0x1p-100f) & (a > fmul(lim, 1.000003814697265625f))) // 1 + 2^-18
         return;
-    // literal predicate of the reference.  The s test needs no division when b >= 0: b <= ad holds here
-    // and both are finite, so RN(b/ad) lies in [0,1].  (b in [-2^-22, 0) or a non-finite denominator
-    // still take the division.)
-    const float t    = __fdiv_rn(tn, denom);
+    // comfortably inside every edge: s in [0,1] needs no division (b in [0, ad], finite), t > 0
+    if ((b >= 0.0f) & (adb < 0x5d800000u /* 2^60 */) & (a >= 0x1p-60f))
+    {
+        const float tq = __fdividef(a, ad);
+        if (tq > fmul(m, 1.000003814697265625f))
+            return;
+        if (tq < fmul(m, 0.999996185302734375f)) // 1 - 2^-18
+        {
+            m    = tq;
+            best = idx;
+            flags |= kWalkApprox;
+            return;
+        }
+    }
+    // literal predicate of the reference, against the incumbent's exact t
+    if (flags & kWalkApprox)
+        m = exact_t(segs[best], ox, oy, dx, dy);
+    flags &= ~kWalkApprox;
+    const float t = __fdiv_rn(tn, denom);
     bool        s_ok = (b >= 0.0f) & (adb < 0x7f800000u);
     if (!s_ok)
     {
         const float s = __fdiv_rn(sn, denom);
         s_ok          = (s >= 0.0f) && (s <= 1.0f);
     }
-    if (s_ok && (t >= 0.0f) && ((t < min_t) || ((t == min_t) && (idx > best))))
+    if (s_ok && (t >= 0.0f) && ((t < m) || ((t == m) && (idx > best))))
     {
-        min_t = t;
-        best  = idx;
+        m    = t;
+        best = idx;
     }
 }
 
-// every segment, ascending: the reference's own loop (OK_RAYCAST_BRUTE)
-__device__ __forceinline__ void cast_ray_brute(const TrackView &tv, float ox, float oy, float dx, float dy, float range,
-                                               float &min_t, int &best)
+// every segment, ascending: the reference's own loop (OK_RAYCAST_BRUTE); returns the hit index
+__device__ __forceinline__ int cast_ray_brute(const TrackView &tv, float ox, float oy, float dx, float dy, float range)
 {
-    min_t = range;
-    best  = -1;
+    float    m     = range;
+    int      best  = -1;
+    uint32_t flags = 0;
     for (int i = 0; i < tv.n_seg; ++i)
-        test_segment(tv.seg[i], i, ox, oy, dx, dy, min_t, best);
+        test_segment(tv.seg, i, ox, oy, dx, dy, m, best, flags);
+    return best;
 }
 
 // Uniform-grid broadphase: 2-D DDA over the cells the ray crosses, testing the segments
@@ -225,71 +264,78 @@ __device__ __forceinline__ void cast_ray_brute(const TrackView &tv, float ox, fl
 // arithmetic is the same function as above.
 //
 // The walk is a resumable state machine (begin / unit) because rays are NOT bound to lanes: the
-// work per ray is heavy tailed (mean 18 units, 1 ray in 32 needs 65+), so a lane that finishes
+// work per ray is heavy tailed (mean ~20 units, 1 ray in 32 needs 65+), so a lane that finishes
 // its ray pulls the next one from a CTA-wide pool (see step_kernel phase 2).
+//
+// The grid carries a ring of empty cells around the clip box, so the walk needs no bounds checks:
+// it stops at t1, the parameter at which the ray leaves the clip box (or its range).
 #define OK_DDA_SLACK 0.5f
 struct RayWalk
 {
     float    ox, oy, dx, dy;
     float    min_t, t1;
     float    tmx, tmy, tdx, tdy;
-    int      ix, iy, best;
-    uint32_t k, k_end;
+    int      c, best;  // look-ahead cell (row-major index), incumbent segment
+    uint32_t k, k_end; // items of the cell being tested
+    uint32_t la_se;    // items of the look-ahead cell (first | end << 16), valid with kWalkLaValid
+    float    la_t;     // ray parameter at which the look-ahead cell is entered
+    uint32_t flags;
 };
 
-__device__ __forceinline__ void open_cell(const TrackView &tv, RayWalk &w)
+// item range of cell c, or 0 (empty range) when the cell is unoccupied
+__device__ __forceinline__ uint32_t cell_items(const TrackView &tv, int c)
 {
-    const int   c    = w.iy * tv.nx + w.ix;
     const uint2 word = tv.words[c >> 5];
-    if ((word.x >> (c & 31)) & 1u)
-    {
-        const uint32_t r = word.y + __popc(word.x & ((1u << (c & 31)) - 1u));
-        w.k = tv.starts[r], w.k_end = tv.starts[r + 1];
-    }
+    if (!((word.x >> (c & 31)) & 1u))
+        return 0u;
+    const uint32_t r = word.y + __popc(word.x & ((1u << (c & 31)) - 1u));
+    return tv.starts[r]; // first item | (one past the last item) << 16
 }
 
-// returns false when the ray cannot hit anything (result stays min_t = range, best = -1)
+// returns false when the ray cannot hit anything (result stays best = -1)
 __device__ __forceinline__ bool walk_begin(const TrackView &tv, RayWalk &w, float ox, float oy, float dx, float dy,
                                            float range)
 {
     w.ox = ox, w.oy = oy, w.dx = dx, w.dy = dy;
     w.min_t = range;
     w.best  = -1;
+    w.flags = 0;
     w.k = 0, w.k_end = 0;
     // a non-finite ray fails the reference predicate on every segment
     if (!(fabsf(ox) <= FLT_MAX && fabsf(oy) <= FLT_MAX && fabsf(dx) <= FLT_MAX && fabsf(dy) <= FLT_MAX))
         return false;
-    const float gx1 = tv.gx0 + tv.nx * tv.cell;
-    const float gy1 = tv.gy0 + tv.ny * tv.cell;
+    // clip box = the grid without its one-cell ring (every segment lies >= 1 px inside it)
+    const float bx0 = tv.gx0 + tv.cell, by0 = tv.gy0 + tv.cell;
+    const float bx1 = tv.gx0 + (tv.nx - 1) * tv.cell, by1 = tv.gy0 + (tv.ny - 1) * tv.cell;
     float       t0 = 0.0f, t1 = range + OK_DDA_SLACK;
     float       inv_dx = 0.0f, inv_dy = 0.0f;
     if (dx != 0.0f)
     {
         inv_dx         = __fdividef(1.0f, dx); // traversal only: any error here is covered by kGridMargin
-        const float ta = (tv.gx0 - ox) * inv_dx, tb = (gx1 - ox) * inv_dx;
+        const float ta = (bx0 - ox) * inv_dx, tb = (bx1 - ox) * inv_dx;
         t0 = fmaxf(t0, fminf(ta, tb));
         t1 = fminf(t1, fmaxf(ta, tb));
     }
-    else if (ox < tv.gx0 || ox > gx1)
+    else if (ox < bx0 || ox > bx1)
         return false;
     if (dy != 0.0f)
     {
         inv_dy         = __fdividef(1.0f, dy);
-        const float ta = (tv.gy0 - oy) * inv_dy, tb = (gy1 - oy) * inv_dy;
+        const float ta = (by0 - oy) * inv_dy, tb = (by1 - oy) * inv_dy;
         t0 = fmaxf(t0, fminf(ta, tb));
         t1 = fminf(t1, fmaxf(ta, tb));
     }
-    else if (oy < tv.gy0 || oy > gy1)
+    else if (oy < by0 || oy > by1)
         return false;
     if (!(t0 <= t1))
-        return false; // the ray does not reach the grid within range
+        return false; // the ray does not reach the clip box within range
     w.t1 = t1;
 
     const float px = ox + t0 * dx, py = oy + t0 * dy; // entry point
     int         ix = static_cast<int>(floorf((px - tv.gx0) * tv.inv_cell));
     int         iy = static_cast<int>(floorf((py - tv.gy0) * tv.inv_cell));
-    ix             = min(max(ix, 0), tv.nx - 1);
-    iy             = min(max(iy, 0), tv.ny - 1);
+    ix             = min(max(ix, 1), tv.nx - 2);
+    iy             = min(max(iy, 1), tv.ny - 2);
     const float inf = __int_as_float(0x7f800000);
     w.tmx = inf, w.tmy = inf, w.tdx = inf, w.tdy = inf;
     if (dx != 0.0f)
@@ -302,39 +348,61 @@ __device__ __forceinline__ bool walk_begin(const TrackView &tv, RayWalk &w, floa
         w.tmy = (tv.gy0 + (iy + (dy > 0.0f ? 1 : 0)) * tv.cell - oy) * inv_dy;
         w.tdy = tv.cell * fabsf(inv_dy);
     }
-    w.ix = ix, w.iy = iy;
-    open_cell(tv, w);
+    w.c = iy * tv.nx + ix;
+    const uint32_t se = cell_items(tv, w.c);
+    w.k = se & 0xffffu, w.k_end = se >> 16;
     return true;
 }
 
-// one unit of work: test the next segment of the current cell, or step to the next cell.
-// returns false when the walk is over.
+// One unit of work = one DDA step of the LOOK-AHEAD (towards the next occupied cell) and one segment
+// test in the CURRENT cell, so both halves of the code keep most lanes busy (a lane that alternates
+// "step" and "test" units leaves each half of the warp's instruction stream half empty).  The
+// look-ahead may run past the eventual hit; its cell is only adopted if it still starts within
+// min_t + slack when the current cell is used up, so the set of tested cells is the one the plain
+// walk would visit.  Returns false when the walk is over.
 __device__ __forceinline__ bool walk_unit(const TrackView &tv, RayWalk &w)
 {
+    if (!(w.flags & (kWalkLaValid | kWalkLaDone)))
+    {
+        const bool  step_x = w.tmx < w.tmy;
+        const float t_next = step_x ? w.tmx : w.tmy;
+        if (!(t_next <= fminf(w.min_t + OK_DDA_SLACK, w.t1)))
+            w.flags |= kWalkLaDone;
+        else
+        {
+            const int dcx = w.dx > 0.0f ? 1 : -1;
+            const int dcy = w.dy > 0.0f ? tv.nx : -tv.nx;
+            w.c += step_x ? dcx : dcy;
+            if (static_cast<unsigned>(w.c) >= static_cast<unsigned>(tv.nx * tv.ny))
+                return false; // cannot happen (see above); keeps a rounding surprise from reading out of bounds
+            w.tmx += step_x ? w.tdx : 0.0f;
+            w.tmy += step_x ? 0.0f : w.tdy;
+            const uint32_t se = cell_items(tv, w.c);
+            if (se)
+            {
+                w.la_se = se;
+                w.la_t  = t_next;
+                w.flags |= kWalkLaValid;
+            }
+        }
+    }
+    if (w.k >= w.k_end)
+    {
+        if (w.flags & kWalkLaValid)
+        {
+            if (!(w.la_t <= w.min_t + OK_DDA_SLACK))
+                return false;
+            w.k = w.la_se & 0xffffu, w.k_end = w.la_se >> 16;
+            w.flags &= ~kWalkLaValid;
+        }
+        else if (w.flags & kWalkLaDone)
+            return false;
+    }
     if (w.k < w.k_end)
     {
         const int i = tv.items[w.k++];
-        test_segment(tv.seg[i], i, w.ox, w.oy, w.dx, w.dy, w.min_t, w.best);
-        return true;
+        test_segment(tv.seg, i, w.ox, w.oy, w.dx, w.dy, w.min_t, w.best, w.flags);
     }
-    const float t_next = fminf(w.tmx, w.tmy);
-    if (!(t_next <= fminf(w.min_t + OK_DDA_SLACK, w.t1)))
-        return false;
-    if (w.tmx < w.tmy)
-    {
-        w.ix += w.dx > 0.0f ? 1 : -1;
-        w.tmx += w.tdx;
-        if (static_cast<unsigned>(w.ix) >= static_cast<unsigned>(tv.nx))
-            return false;
-    }
-    else
-    {
-        w.iy += w.dy > 0.0f ? 1 : -1;
-        w.tmy += w.tdy;
-        if (static_cast<unsigned>(w.iy) >= static_cast<unsigned>(tv.ny))
-            return false;
-    }
-    open_cell(tv, w);
     return true;
 }
 
@@ -396,8 +464,10 @@ __host__ __device__ inline size_t batch_smem_bytes(int agents, int rays)
     return static_cast<size_t>(agents) * (sizeof(AgentRec) + 8u * static_cast<size_t>(rays));
 }
 
-constexpr int kRefillThreshold     = 8; // a warp refills its idle lanes from the pool once this many are idle
-constexpr int kUnitsPerRefillCheck = 4; // units of work between two looks at the pool
+#ifndef OK_UNITS
+#define OK_UNITS 4
+#endif
+constexpr int kUnitsPerRefill = OK_UNITS; // units of work a lane does between two looks at the pool
 
 template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(const StepParams p)
 {
@@ -592,57 +662,49 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
         const int64_t ray_base = tl.begin * R; // global index of the batch's first ray
         if (p.raycast_mode == 0)
         {
+            // No warp-level primitive in this loop on purpose: every lane fetches and retires on its own
+            // (one shared-memory atomic per ray), so nothing depends on the lanes of a warp being converged
+            // inside this heavily divergent code.  (A vote-based, warp-aggregated refill with the unit loop
+            // unrolled hung on sm_100a / CUDA 12.9: lanes left the loop on different trips.)
             RayWalk w;
-            int     mine      = -1; // batch-local ray (agent * R + ray) this lane is working on, -1 = idle
-            bool    exhausted = false;
+            int     mine = -1;   // batch-local ray (agent * R + ray) this lane is working on, -1 = idle
+            bool    more = true; // the pool may still hold rays
             for (;;)
             {
-                const unsigned idle = __ballot_sync(0xffffffffu, mine < 0);
-                if (idle == 0xffffffffu && exhausted)
-                    break;
-                if (!exhausted && (__popc(idle) >= kRefillThreshold))
+                if (mine < 0)
                 {
-                    int base = 0;
-                    if (lane == 0)
-                        base = atomicAdd(&s_pool, __popc(idle));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (base + __popc(idle) >= n_rays)
-                        exhausted = true;
-                    if (mine < 0)
+                    if (!more)
+                        break;
+                    const int q = atomicAdd(&s_pool, 1);
+                    if (q >= n_rays)
+                        more = false;
+                    else
                     {
-                        const int q = base + __popc(idle & ((1u << lane) - 1u));
-                        if (q < n_rays)
+                        // pool order -> (agent, ray): ray-major, centre rays first
+                        const int rank = __float2int_rz((static_cast<float>(q) + 0.5f) * inv_cnt);
+                        const int al   = q - rank * count;
+                        const int r    = p.ray_order[rank];
+                        const int slot = al * R + r;
+                        const AgentRec &rec = recs[al];
+                        // a crashed agent's rays are inactive: the kernel leaves their stale hits alone
+                        // (CollisionChecker.cu:44)
+                        if (!(rec.flags & kFlagCrashed))
                         {
-                            // pool order -> (agent, ray): ray-major, centre rays first
-                            const int rank = __float2int_rz((static_cast<float>(q) + 0.5f) * inv_cnt);
-                            const int al   = q - rank * count;
-                            const int r    = p.ray_order[rank];
-                            const int slot = al * R + r;
-                            const AgentRec &rec = recs[al];
-                            // a crashed agent's rays are inactive: the kernel leaves their stale hits alone
-                            // (CollisionChecker.cu:44)
-                            if (!(rec.flags & kFlagCrashed))
-                            {
-                                const float2 d = dirs[slot];
-                                if (walk_begin(tv, w, rec.ox, rec.oy, d.x, d.y, p.sensor_range))
-                                    mine = slot;
-                                else
-                                {
-                                    p.hit_t[ray_base + slot]   = w.min_t;
-                                    p.hit_seg[ray_base + slot] = w.best;
-                                }
-                            }
+                            const float2 d = dirs[slot];
+                            if (walk_begin(tv, w, rec.ox, rec.oy, d.x, d.y, p.sensor_range))
+                                mine = slot;
+                            else
+                                p.hit_seg[ray_base + slot] = -1;
                         }
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < kUnitsPerRefillCheck; ++u)
+#pragma unroll 1
+                for (int u = 0; u < kUnitsPerRefill; ++u)
                 {
                     if (mine >= 0)
                     {
                         if (!walk_unit(tv, w))
-                        {
-                            p.hit_t[ray_base + mine]   = w.min_t;
+                        { // only the index travels: phase 3 recomputes the winner's exact t
                             p.hit_seg[ray_base + mine] = w.best;
                             mine                       = -1;
                         }
@@ -658,12 +720,8 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
                 const AgentRec &rec = recs[al];
                 if (rec.flags & kFlagCrashed)
                     continue;
-                const float2 d = dirs[q];
-                float        min_t;
-                int          best;
-                cast_ray_brute(tv, rec.ox, rec.oy, d.x, d.y, p.sensor_range, min_t, best);
-                p.hit_t[ray_base + q]   = min_t;
-                p.hit_seg[ray_base + q] = best;
+                const float2 d          = dirs[q];
+                p.hit_seg[ray_base + q] = cast_ray_brute(tv, rec.ox, rec.oy, d.x, d.y, p.sensor_range);
             }
         }
         __syncthreads();
@@ -685,9 +743,12 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
                 float2          hit;
                 if (!(rec.flags & kFlagCrashed))
                 {
-                    const float2 d = dirs[q];
-                    const float  t = p.hit_t[gi]; // written in phase 2 by whichever lane cast this ray
-                    hit.x          = fadd(rec.ox, fmul(t, d.x));
+                    const float2 d   = dirs[q];
+                    const int    seg = p.hit_seg[gi]; // written in phase 2 by whichever lane cast this ray
+                    // min_t of CollisionChecker.cu:49-66: the winner's t by the reference's expression
+                    const float t = seg >= 0 ? exact_t(tv.seg[seg], rec.ox, rec.oy, d.x, d.y) : p.sensor_range;
+                    p.hit_t[gi]   = t;
+                    hit.x         = fadd(rec.ox, fmul(t, d.x));
                     hit.y          = fadd(rec.oy, fmul(t, d.y));
                     reinterpret_cast<float2 *>(p.hit_abs)[gi] = hit;
                 }

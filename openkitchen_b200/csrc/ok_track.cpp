@@ -120,14 +120,16 @@ bool build_grid(Track &t, float cell, std::string &err)
             lo_y = std::min(lo_y, py), hi_y = std::max(hi_y, py);
         }
     t.cell    = cell;
-    t.grid_x0 = std::floor(static_cast<float>(lo_x) - 1.0f);
-    t.grid_y0 = std::floor(static_cast<float>(lo_y) - 1.0f);
-    t.grid_nx = static_cast<int32_t>(std::ceil((hi_x + 1.0 - t.grid_x0) / cell));
-    t.grid_ny = static_cast<int32_t>(std::ceil((hi_y + 1.0 - t.grid_y0) / cell));
-    if (t.grid_nx < 1)
-        t.grid_nx = 1;
-    if (t.grid_ny < 1)
-        t.grid_ny = 1;
+    // the segments' box grown by 1 px is the device's clip box; one more ring of (empty) cells around
+    // it lets the DDA run without bounds checks
+    const float in_x0 = std::floor(static_cast<float>(lo_x) - 1.0f);
+    const float in_y0 = std::floor(static_cast<float>(lo_y) - 1.0f);
+    const int32_t in_nx = std::max<int32_t>(1, static_cast<int32_t>(std::ceil((hi_x + 1.0 - in_x0) / cell)));
+    const int32_t in_ny = std::max<int32_t>(1, static_cast<int32_t>(std::ceil((hi_y + 1.0 - in_y0) / cell)));
+    t.grid_x0 = in_x0 - cell;
+    t.grid_y0 = in_y0 - cell;
+    t.grid_nx = in_nx + 2;
+    t.grid_ny = in_ny + 2;
     const int64_t n_cells = static_cast<int64_t>(t.grid_nx) * t.grid_ny;
     if (n_cells > (1 << 22))
     {
@@ -184,7 +186,7 @@ bool build_grid(Track &t, float cell, std::string &err)
         if (lists[c].empty())
             continue;
         t.cell_words[2 * (c >> 5)] |= 1u << (c & 31);
-        t.cell_starts.push_back(static_cast<uint16_t>(t.items.size()));
+        const size_t first_item = t.items.size();
         // inner boundaries first: from inside the lane they are hit before the outer ones 3 px behind
         // them, which then fail the cheap "beyond the current hit" screen (any order is exact)
         std::stable_sort(lists[c].begin(), lists[c].end(), [&](uint16_t p, uint16_t q) {
@@ -197,9 +199,9 @@ bool build_grid(Track &t, float cell, std::string &err)
             return outer(p) < outer(q);
         });
         t.items.insert(t.items.end(), lists[c].begin(), lists[c].end());
+        t.cell_starts.push_back(static_cast<uint32_t>(first_item) | (static_cast<uint32_t>(t.items.size()) << 16));
         ++rank;
     }
-    t.cell_starts.push_back(static_cast<uint16_t>(t.items.size()));
     return true;
 }
 

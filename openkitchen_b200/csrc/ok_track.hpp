@@ -29,7 +29,7 @@ struct TrackHeader
     float    inv_cell;
     uint32_t off_segments; // float4 {x1, y1, x2-x1, y2-y1}[n_segments], TrackSegments order
     uint32_t off_words;    // uint2 {occupancy bits of 32 cells, #occupied cells before this word}[ceil(nx*ny/32)]
-    uint32_t off_starts;   // uint16 item offset per OCCUPIED cell (+1 sentinel), in cell order
+    uint32_t off_starts;   // uint32 per OCCUPIED cell, in cell order: first item | (one past the last) << 16
     uint32_t off_items;    // uint16 segment index [n_items]
     uint32_t off_points;   // float2 centre line [n_points]
     uint32_t off_widths;   // float  w_left + w_right [n_points]
@@ -48,7 +48,8 @@ struct Track
     int32_t               grid_nx{0}, grid_ny{0};
     float                 grid_x0{0}, grid_y0{0}, cell{8.f};
     std::vector<uint32_t> cell_words; // pairs {occupancy bits, occupied-cell rank} per 32 cells
-    std::vector<uint16_t> cell_starts, items;
+    std::vector<uint32_t> cell_starts; // per occupied cell: first item | (one past the last) << 16
+    std::vector<uint16_t> items;
     // staged form
     std::vector<uint8_t> blob;
 
