@@ -32,6 +32,16 @@ def make_pair(track_names, n, rays_or_fan, kind="port", grouped=True, **cfg):
     return env, ora, tid
 
 
+def same_bits(a, b):
+    """elementwise: identical bits, except that any NaN equals any NaN"""
+    a, b = np.asarray(a), np.asarray(b)
+    if a.shape != b.shape:
+        return np.zeros(1, dtype=bool)
+    if a.dtype == np.float32:
+        return (a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))
+    return a == b
+
+
 def assert_same(env, ora, names=ALL_BUFS, ctx=""):
     for name in names:
         a, b = env.read(name), ora.buffer(name)
