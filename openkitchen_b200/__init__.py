@@ -24,3 +24,11 @@ from ._capi import (  # noqa: F401
 from .env import Env, pinned_array, ray_fan, track_columns, track_names, write_track_csv  # noqa: F401
 
 __version__ = "0.1.0"
+
+
+def __getattr__(name):  # BatchEnv needs torch; keep the ctypes layer importable without it
+    if name == "BatchEnv":
+        from .batch_env import BatchEnv
+
+        return BatchEnv
+    raise AttributeError(name)

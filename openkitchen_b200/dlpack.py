@@ -1,0 +1,93 @@
+"""Zero-copy DLPack export of OkEnv device buffers (no compiled extension needed).
+
+A ``DLManagedTensor`` is built with ctypes around the device pointer that ``ok_get_buffer`` returns and
+wrapped in a ``PyCapsule`` named ``"dltensor"``; ``torch.from_dlpack`` (or any DLPack consumer) adopts it.
+The capsule's deleter drops a reference on the owning :class:`~openkitchen_b200.env.Env`, so a tensor keeps
+its env -- and therefore the memory -- alive.  Layout follows dlpack.h v0.8 (the ABI torch consumes).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+kDLCUDA = 2
+kDLInt, kDLUInt, kDLFloat = 0, 1, 2
+
+
+class DLDevice(C.Structure):
+    _fields_ = [("device_type", C.c_int32), ("device_id", C.c_int32)]
+
+
+class DLDataType(C.Structure):
+    _fields_ = [("code", C.c_uint8), ("bits", C.c_uint8), ("lanes", C.c_uint16)]
+
+
+class DLTensor(C.Structure):
+    _fields_ = [
+        ("data", C.c_void_p),
+        ("device", DLDevice),
+        ("ndim", C.c_int32),
+        ("dtype", DLDataType),
+        ("shape", C.POINTER(C.c_int64)),
+        ("strides", C.POINTER(C.c_int64)),
+        ("byte_offset", C.c_uint64),
+    ]
+
+
+class DLManagedTensor(C.Structure):
+    pass
+
+
+_DELETER = C.CFUNCTYPE(None, C.POINTER(DLManagedTensor))
+DLManagedTensor._fields_ = [("dl_tensor", DLTensor), ("manager_ctx", C.c_void_p), ("deleter", _DELETER)]
+
+_CODES = {np.dtype(np.float32): (kDLFloat, 32), np.dtype(np.int32): (kDLInt, 32), np.dtype(np.uint32): (kDLUInt, 32),
+          np.dtype(np.uint8): (kDLUInt, 8)}
+
+_live = {}  # id -> (managed tensor, shape array, owner): everything the consumer may still touch
+
+C.pythonapi.PyCapsule_New.restype = C.py_object
+C.pythonapi.PyCapsule_New.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+
+
+@_DELETER
+def _release(managed_ptr):
+    _live.pop(C.addressof(managed_ptr.contents), None)
+
+
+def to_capsule(ptr: int, shape, dtype, device_id: int, owner):
+    """DLPack capsule over ``ptr`` (device memory on CUDA device ``device_id``), keeping ``owner`` alive."""
+    code, bits = _CODES[np.dtype(dtype)]
+    shp = (C.c_int64 * len(shape))(*shape)
+    m = DLManagedTensor()
+    m.dl_tensor.data = ptr
+    m.dl_tensor.device = DLDevice(kDLCUDA, device_id)
+    m.dl_tensor.ndim = len(shape)
+    m.dl_tensor.dtype = DLDataType(code, bits, 1)
+    m.dl_tensor.shape = shp
+    m.dl_tensor.strides = None  # compact row-major
+    m.dl_tensor.byte_offset = 0
+    m.manager_ctx = None
+    m.deleter = _release
+    _live[C.addressof(m)] = (m, shp, owner)
+    return C.pythonapi.PyCapsule_New(C.addressof(m), b"dltensor", None)
+
+
+class DeviceBuffer:
+    """``__dlpack__`` provider for one OkEnv buffer (what ``torch.from_dlpack`` expects)."""
+
+    def __init__(self, env, name: str):
+        self.env, self.name = env, name
+        self.ptr, self.shape, self.dtype = env.buffer_info(name)
+
+    def __dlpack__(self, stream=None, **_):
+        return to_capsule(self.ptr, self.shape, self.dtype, int(self.env.cfg.device), self.env)
+
+    def __dlpack_device__(self):
+        return (kDLCUDA, int(self.env.cfg.device))
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": tuple(self.shape), "typestr": np.dtype(self.dtype).str, "data": (self.ptr, False), "version": 3,
+                "strides": None}
