@@ -147,6 +147,10 @@ void        ok_config_default(OkConfig *cfg);
 /* Environment::Environment (Environment.cpp:42-62) minus raylib/visualizer/screen grabber. */
 int  ok_create(const OkConfig *cfg, OkEnv **out);
 void ok_destroy(OkEnv *env);
+/* change the per-tick constants of a live env (everything except `device` and `grid_cell`, which are fixed
+ * at creation): e.g. Agent::setMovementMode (Agent.h:46-49), the reward definition, auto-reset */
+int  ok_update_config(OkEnv *env, const OkConfig *cfg);
+int  ok_get_config(const OkEnv *env, OkConfig *out);
 
 /* ---- tracks: RaceTrack ctor chain (RaceTrack.cpp:3-14,127-307) + TrackSegments (TrackSegments.cu:6-76)
  *      + broadphase grid build + device upload. Must precede ok_alloc_agents. -------------------- */

@@ -86,6 +86,8 @@ SIGNATURES = {
     "ok_config_default": (None, [C.POINTER(OkConfig)]),
     "ok_create": (C.c_int, [C.POINTER(OkConfig), C.POINTER(_P)]),
     "ok_destroy": (None, [_P]),
+    "ok_update_config": (C.c_int, [_P, C.POINTER(OkConfig)]),
+    "ok_get_config": (C.c_int, [_P, C.POINTER(OkConfig)]),
     "ok_add_track": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "ok_load_track_csv": (C.c_int, [_P, C.c_char_p, C.POINTER(C.c_int32)]),
     "ok_num_tracks": (C.c_int, [_P]),

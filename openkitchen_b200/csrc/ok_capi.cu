@@ -347,6 +347,31 @@ int ok_create(const OkConfig *cfg, OkEnv **out)
     return OK_SUCCESS;
 }
 
+int ok_update_config(OkEnv *e, const OkConfig *cfg)
+{
+    if (!e || !cfg)
+        return fail(OK_ERR_INVALID_ARG, "NULL argument");
+    if (cfg->movement_mode != OK_MOVE_VELOCITY && cfg->movement_mode != OK_MOVE_ACCELERATION)
+        return fail(OK_ERR_INVALID_ARG, "movement_mode must be VELOCITY or ACCELERATION");
+    if (cfg->reward_mode < OK_REWARD_NONE || cfg->reward_mode > OK_REWARD_LANE_CENTER)
+        return fail(OK_ERR_INVALID_ARG, "unknown reward_mode");
+    if (cfg->raycast_mode != OK_RAYCAST_GRID && cfg->raycast_mode != OK_RAYCAST_BRUTE)
+        return fail(OK_ERR_INVALID_ARG, "unknown raycast_mode");
+    OkConfig c   = *cfg;
+    c.device     = e->cfg.device;
+    c.grid_cell  = e->cfg.grid_cell;
+    e->cfg       = c;
+    return OK_SUCCESS;
+}
+
+int ok_get_config(const OkEnv *e, OkConfig *out)
+{
+    if (!e || !out)
+        return fail(OK_ERR_INVALID_ARG, "NULL argument");
+    *out = e->cfg;
+    return OK_SUCCESS;
+}
+
 void ok_destroy(OkEnv *e)
 {
     if (!e)

@@ -89,6 +89,14 @@ class Env:
     def __exit__(self, *a):
         self.close()
 
+    def update_config(self, **cfg):
+        """change per-tick constants of the live env (movement_mode, reward_mode, auto_reset, ...)"""
+        for k, v in cfg.items():
+            if not hasattr(self.cfg, k) or k in ("device", "grid_cell"):
+                raise AttributeError(f"cannot update {k}")
+            setattr(self.cfg, k, v)
+        check(self.lib.ok_update_config(self.h, C.byref(self.cfg)))
+
     # ---- tracks -------------------------------------------------------------------------
     def add_track(self, cols) -> int:
         x, y, wr, wl = (np.ascontiguousarray(c, dtype=np.float32) for c in cols)

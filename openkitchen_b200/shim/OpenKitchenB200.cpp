@@ -1,0 +1,344 @@
+// OpenKitchenB200.cpp -- see OpenKitchenB200.hpp.  Everything here is a thin host adapter over the C ABI.
+#include "OpenKitchenB200.hpp"
+
+#include "../../include/openkitchen_b200.h"
+
+#include <algorithm>
+#include <cctype>
+#include <limits>
+
+namespace
+{
+[[noreturn]] void raise(const char *what)
+{
+    throw std::runtime_error(std::string(what) + ": " + ok_last_error());
+}
+
+void must(int rc, const char *what)
+{
+    if (rc < 0)
+        raise(what);
+}
+
+std::string upper_stem(const std::string &path)
+{ // RaceTrack::getTrackName, RaceTrack.cpp:116-125
+    const size_t slash = path.rfind('/'), dot = path.rfind('.');
+    std::string  s     = path.substr(slash == std::string::npos ? 0 : slash + 1,
+                                     (dot == std::string::npos ? path.size() : dot) - (slash == std::string::npos ? 0 : slash + 1));
+    std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return std::toupper(c); });
+    return s;
+}
+
+std::vector<float> track_array(const OkEnv *env, int id, int which)
+{
+    const int64_t n = ok_track_copy(env, id, which, nullptr, 0);
+    if (n < 0)
+        raise("ok_track_copy");
+    std::vector<float> v(static_cast<size_t>(n));
+    ok_track_copy(env, id, which, v.data(), n);
+    return v;
+}
+
+std::vector<Vec2d> as_points(const std::vector<float> &flat)
+{
+    std::vector<Vec2d> out(flat.size() / 2);
+    for (size_t i = 0; i < out.size(); ++i)
+        out[i] = Vec2d{flat[2 * i], flat[2 * i + 1]};
+    return out;
+}
+} // namespace
+
+// ---- Agent -------------------------------------------------------------------------------------------
+Agent::Agent(Vec2d start_pos, float start_rot, int16_t id) : pos_{start_pos}, rot_{start_rot}, id_{id}
+{
+    // default fan: -70..70 in steps of 10 degrees (Agent.cpp:8-19)
+    for (int deg = -70; deg <= 70; deg += 10)
+        sensor_ray_angles_.push_back(static_cast<float>(deg));
+}
+
+void Agent::reset(const Vec2d &reset_pos, const float reset_rot)
+{ // Agent.cpp:123-135
+    pos_            = reset_pos;
+    rot_            = reset_rot;
+    acceleration_   = 0.F;
+    speed_          = 0.F;
+    crashed_        = false;
+    timed_out_      = false;
+    completed_      = false;
+    current_action_ = Action{0.F, 0.F};
+}
+
+void Agent::move()
+{
+    throw std::logic_error("Agent::move(): kinematics run on the device inside Environment::step()");
+}
+
+// ---- RaceTrack ---------------------------------------------------------------------------------------
+RaceTrack::RaceTrack(const OkEnv *env, int track_id, const std::string &name) : track_name_{name}
+{
+    fill(env, track_id);
+}
+
+RaceTrack::RaceTrack(const std::string &track_csv_path) : track_name_{upper_stem(track_csv_path)}
+{
+    OkConfig cfg;
+    ok_config_default(&cfg);
+    cfg.device = -1; // host-only: geometry without a GPU
+    OkEnv *env = nullptr;
+    must(ok_create(&cfg, &env), "ok_create");
+    int32_t id = -1;
+    if (ok_load_track_csv(env, track_csv_path.c_str(), &id) < 0)
+    {
+        ok_destroy(env);
+        raise("ok_load_track_csv");
+    }
+    fill(env, id);
+    ok_destroy(env);
+}
+
+void RaceTrack::fill(const OkEnv *env, int id)
+{
+    track_data_points_.x_m          = track_array(env, id, OK_TRACK_X);
+    track_data_points_.y_m          = track_array(env, id, OK_TRACK_Y);
+    track_data_points_.w_tr_right_m = track_array(env, id, OK_TRACK_W_RIGHT);
+    track_data_points_.w_tr_left_m  = track_array(env, id, OK_TRACK_W_LEFT);
+    headings_                       = track_array(env, id, OK_TRACK_HEADING);
+    left_bound_inner_               = as_points(track_array(env, id, OK_TRACK_LEFT_INNER));
+    left_bound_outer_               = as_points(track_array(env, id, OK_TRACK_LEFT_OUTER));
+    right_bound_inner_              = as_points(track_array(env, id, OK_TRACK_RIGHT_INNER));
+    right_bound_outer_              = as_points(track_array(env, id, OK_TRACK_RIGHT_OUTER));
+    start_line_                     = {right_bound_outer_.front(), right_bound_outer_.back()};
+    finish_line_                    = {left_bound_outer_.front(), left_bound_outer_.back()};
+    const std::vector<float> s      = track_array(env, id, OK_TRACK_SEGMENTS);
+    segments_.resize(s.size() / 4);
+    for (size_t i = 0; i < segments_.size(); ++i)
+        segments_[i] = Segment2d{s[4 * i], s[4 * i + 1], s[4 * i + 2], s[4 * i + 3]};
+}
+
+size_t RaceTrack::findNearestTrackIndexBruteForce(const Vec2d &q) const
+{ // RaceTrack.cpp:16-31: strict '<' keeps the lowest index among ties
+    float  best = std::numeric_limits<float>::max();
+    size_t at   = 0;
+    for (size_t i = 0; i < track_data_points_.x_m.size(); ++i)
+    {
+        const float d = q.distanceSquared({track_data_points_.x_m[i], track_data_points_.y_m[i]});
+        if (d < best)
+        {
+            best = d;
+            at   = i;
+        }
+    }
+    return at;
+}
+
+float RaceTrack::getNearestDistanceToTrackBoundary(const Vec2d &q) const
+{ // RaceTrack.cpp:33-51
+    float best = std::numeric_limits<float>::max();
+    for (size_t i = 0; i < left_bound_inner_.size(); ++i)
+    {
+        best = std::min(best, q.distanceSquared(left_bound_inner_[i]));
+        best = std::min(best, q.distanceSquared(right_bound_inner_[i]));
+    }
+    return std::sqrt(best);
+}
+
+float RaceTrack::getDistanceToLaneCenter(const Vec2d &q) const
+{ // RaceTrack.cpp:53-72
+    const size_t i = findNearestTrackIndexBruteForce(q);
+    const float  d = q.distanceSquared({track_data_points_.x_m[i], track_data_points_.y_m[i]});
+    return std::sqrt(d) / (track_data_points_.w_tr_left_m[i] + track_data_points_.w_tr_right_m[i]);
+}
+
+// ---- Environment -------------------------------------------------------------------------------------
+Environment::Environment(const std::string &race_track_path, const std::vector<Agent *> &agents, const bool draw_rays,
+                         const bool hidden_window)
+    : draw_rays_(draw_rays)
+{
+    if (agents.empty())
+        throw std::invalid_argument("Environment needs at least one agent");
+    OkConfig cfg;
+    ok_config_default(&cfg);
+    cfg.movement_mode = agents[0]->movement_mode_ == Agent::MovementMode::ACCELERATION ? OK_MOVE_ACCELERATION : OK_MOVE_VELOCITY;
+    cfg.sensor_offset = agents[0]->sensor_offset_;
+    cfg.sensor_range  = agents[0]->sensor_range_;
+    must(ok_create(&cfg, &ok_), "ok_create");
+    int32_t track = -1;
+    if (ok_load_track_csv(ok_, race_track_path.c_str(), &track) < 0)
+    {
+        ok_destroy(ok_);
+        ok_ = nullptr;
+        raise("ok_load_track_csv");
+    }
+    race_track_     = std::make_unique<RaceTrack>(ok_, track, upper_stem(race_track_path));
+    track_segments_ = std::make_unique<TrackSegments>(*race_track_);
+    visualizer_     = std::make_unique<env::Visualizer>(hidden_window);
+    screen_grabber_ = std::make_unique<ScreenGrabber>(kScreenWidth, kScreenHeight);
+    agents_         = agents;
+    displacement_stats_.resize(agents.size());
+
+    // the reference sizes everything from agents[0]'s fan (CollisionChecker.cu:82) and silently assumes the
+    // others match; here a mismatch is an error
+    const auto &fan = agents[0]->sensor_ray_angles_;
+    for (const Agent *a : agents)
+        if (a->sensor_ray_angles_ != fan)
+        {
+            ok_destroy(ok_);
+            ok_ = nullptr;
+            throw std::invalid_argument("all agents of one Environment must share one sensor_ray_angles_ fan");
+        }
+    if (ok_alloc_agents(ok_, static_cast<int64_t>(agents.size()), static_cast<int32_t>(fan.size()), fan.data(), nullptr) < 0)
+    {
+        ok_destroy(ok_);
+        ok_ = nullptr;
+        raise("ok_alloc_agents");
+    }
+    collision_checker_ = std::make_unique<CollisionChecker>(this);
+    collision_checker_->rays_.assign(agents.size() * fan.size(), Ray_{});
+    for (auto &v : f_)
+        v.resize(agents.size());
+    for (auto &v : b_)
+        v.resize(agents.size());
+    ctr_.resize(agents.size());
+    hits_.resize(agents.size() * fan.size() * 2);
+    hit_abs_.resize(agents.size() * fan.size() * 2);
+}
+
+Environment::~Environment()
+{
+    if (ok_)
+        ok_destroy(ok_);
+}
+
+int32_t Environment::pickRandomResetTrackIdx() const
+{ // Environment.cpp:74-77 (GetRandomValue(0, n-1) -> a seedable generator)
+    std::uniform_int_distribution<int32_t> d(0, static_cast<int32_t>(race_track_->track_data_points_.x_m.size()) - 1);
+    return d(rng_);
+}
+
+void Environment::resetAgent(Agent *agent, const bool pick_random_point, const bool randomize_lane, const bool randomize_heading)
+{ // Environment.cpp:79-122.  The virtual Agent::reset is what derived agents hook, so the reset happens on
+  // the host object; the new pose reaches the device with the next step()'s upload.
+    const int32_t idx = pick_random_point ? pickRandomResetTrackIdx() : static_cast<int32_t>(RaceTrack::kStartingIdx);
+    float         heading_offset = 0.F;
+    if (pick_random_point && randomize_heading)
+    {
+        std::uniform_int_distribution<int> d(0, 45);
+        const float                        mag = static_cast<float>(d(rng_)) + 45.F;
+        heading_offset                         = (heading_ctr_++ % 2 == 0) ? -mag : mag;
+    }
+    Vec2d start;
+    if (pick_random_point && randomize_lane)
+    {
+        std::uniform_int_distribution<int> d(10, 90);
+        const float                        alpha = static_cast<float>(d(rng_)) / 100.F;
+        const Vec2d                        l = race_track_->left_bound_inner_[idx], r = race_track_->right_bound_inner_[idx];
+        start = Vec2d{l.x * alpha + r.x * (1.F - alpha), l.y * alpha + r.y * (1.F - alpha)};
+    }
+    else
+        start = Vec2d{race_track_->track_data_points_.x_m[idx], race_track_->track_data_points_.y_m[idx]};
+    agent->reset(start, race_track_->headings_[idx] + heading_offset);
+}
+
+void Environment::upload()
+{
+    const size_t n = agents_.size();
+    for (size_t i = 0; i < n; ++i)
+    {
+        const Agent *a = agents_[i];
+        f_[0][i] = a->pos_.x, f_[1][i] = a->pos_.y, f_[2][i] = a->rot_, f_[3][i] = a->speed_, f_[4][i] = a->acceleration_;
+        f_[5][i] = a->current_action_.throttle_delta, f_[6][i] = a->current_action_.steering_delta;
+        b_[0][i] = a->crashed_, b_[1][i] = a->timed_out_;
+        ctr_[i]  = displacement_stats_[i].displacement_ctr;
+        f_[7][i] = displacement_stats_[i].init_pos.x;
+    }
+    static const int kF[7] = {OK_BUF_POS_X, OK_BUF_POS_Y, OK_BUF_ROT, OK_BUF_SPEED, OK_BUF_ACCEL, OK_BUF_ACT_THROTTLE, OK_BUF_ACT_STEER};
+    for (int k = 0; k < 7; ++k)
+        must(ok_write_buffer(ok_, kF[k], f_[k].data(), 4 * n, nullptr), "ok_write_buffer");
+    must(ok_write_buffer(ok_, OK_BUF_CRASHED, b_[0].data(), n, nullptr), "ok_write_buffer");
+    must(ok_write_buffer(ok_, OK_BUF_TIMED_OUT, b_[1].data(), n, nullptr), "ok_write_buffer");
+    must(ok_write_buffer(ok_, OK_BUF_SS_CTR, ctr_.data(), 4 * n, nullptr), "ok_write_buffer");
+    must(ok_write_buffer(ok_, OK_BUF_SS_X, f_[7].data(), 4 * n, nullptr), "ok_write_buffer");
+    for (size_t i = 0; i < n; ++i)
+        f_[7][i] = displacement_stats_[i].init_pos.y;
+    must(ok_write_buffer(ok_, OK_BUF_SS_Y, f_[7].data(), 4 * n, nullptr), "ok_write_buffer");
+}
+
+void Environment::download(bool moved)
+{
+    const size_t n = agents_.size(), R = agents_[0]->sensor_ray_angles_.size();
+    static const int kF[5] = {OK_BUF_POS_X, OK_BUF_POS_Y, OK_BUF_ROT, OK_BUF_SPEED, OK_BUF_ACCEL};
+    if (moved)
+        for (int k = 0; k < 5; ++k)
+            must(ok_read_buffer(ok_, kF[k], f_[k].data(), 4 * n, nullptr), "ok_read_buffer");
+    must(ok_read_buffer(ok_, OK_BUF_CRASHED, b_[0].data(), n, nullptr), "ok_read_buffer");
+    must(ok_read_buffer(ok_, OK_BUF_TIMED_OUT, b_[1].data(), n, nullptr), "ok_read_buffer");
+    must(ok_read_buffer(ok_, OK_BUF_HIT_REL, hits_.data(), 4 * hits_.size(), nullptr), "ok_read_buffer");
+    must(ok_read_buffer(ok_, OK_BUF_HIT_ABS, hit_abs_.data(), 4 * hit_abs_.size(), nullptr), "ok_read_buffer");
+    if (moved)
+    {
+        must(ok_read_buffer(ok_, OK_BUF_SS_CTR, ctr_.data(), 4 * n, nullptr), "ok_read_buffer");
+        must(ok_read_buffer(ok_, OK_BUF_SS_X, f_[5].data(), 4 * n, nullptr), "ok_read_buffer");
+        must(ok_read_buffer(ok_, OK_BUF_SS_Y, f_[6].data(), 4 * n, nullptr), "ok_read_buffer");
+    }
+    for (size_t i = 0; i < n; ++i)
+    {
+        Agent *a = agents_[i];
+        if (moved)
+        {
+            a->pos_ = Vec2d{f_[0][i], f_[1][i]};
+            a->rot_ = f_[2][i], a->speed_ = f_[3][i], a->acceleration_ = f_[4][i];
+            DisplacementStats &ds = displacement_stats_[i];
+            ds.displacement_ctr   = ctr_[i];
+            ds.init_pos           = Vec2d{f_[5][i], f_[6][i]};
+            ds.displacement_timed_out = b_[1][i] != 0;
+        }
+        a->crashed_   = b_[0][i] != 0;
+        a->timed_out_ = b_[1][i] != 0;
+        a->sensor_hits_.resize(R);
+        for (size_t r = 0; r < R; ++r)
+        {
+            const size_t k      = i * R + r;
+            a->sensor_hits_[r]  = Vec2d{hits_[2 * k], hits_[2 * k + 1]};
+            Ray_ &ray           = collision_checker_->rays_[k];
+            ray.x               = a->pos_.x + a->sensor_offset_ * std::cos(kDeg2Rad * a->rot_);
+            ray.y               = a->pos_.y + a->sensor_offset_ * std::sin(kDeg2Rad * a->rot_);
+            ray.angle           = kDeg2Rad * (a->rot_ + a->sensor_ray_angles_[r]);
+            ray.hit_x           = hit_abs_[2 * k];
+            ray.hit_y           = hit_abs_[2 * k + 1];
+            ray.active          = !a->crashed_;
+        }
+    }
+}
+
+void Environment::run(bool move)
+{
+    // Agent::setMovementMode may be called at any time (Agent.h:46-49); the reference reads it per move()
+    OkConfig cfg;
+    must(ok_get_config(ok_, &cfg), "ok_get_config");
+    const int mode = agents_[0]->movement_mode_ == Agent::MovementMode::ACCELERATION ? OK_MOVE_ACCELERATION : OK_MOVE_VELOCITY;
+    for (const Agent *a : agents_)
+    {
+        if (a->movement_mode_ == Agent::MovementMode::MANUAL)
+            throw std::logic_error("MovementMode::MANUAL (keyboard) is not supported");
+        if ((a->movement_mode_ == Agent::MovementMode::ACCELERATION ? OK_MOVE_ACCELERATION : OK_MOVE_VELOCITY) != mode)
+            throw std::logic_error("all agents of one Environment must use the same MovementMode");
+    }
+    if (cfg.movement_mode != mode)
+    {
+        cfg.movement_mode = mode;
+        must(ok_update_config(ok_, &cfg), "ok_update_config");
+    }
+    upload();
+    must(move ? ok_launch_step(ok_, nullptr, nullptr, nullptr) : ok_cast_rays(ok_, nullptr), "launch");
+    download(move);
+}
+
+void Environment::step()
+{ // Environment.cpp:125-149 minus the render
+    run(true);
+}
+
+void CollisionChecker::checkCollision()
+{
+    env_->run(false);
+}

@@ -100,3 +100,24 @@ def test_grid_registers_every_segment_with_margin():
                 px, py = s[0] + u * (s[2] - s[0]), s[1] + u * (s[3] - s[1])
                 ix, iy = int((px - x0) // c), int((py - y0) // c)
                 assert 1 <= ix <= info.grid_nx - 2 and 1 <= iy <= info.grid_ny - 2
+
+
+def test_shim_and_pybind_build_and_fail_loudly_without_gpu(tmp_path):
+    """the drop-in layers compile against the C ABI; without a device they raise, they do not fall back"""
+    import subprocess
+
+    lib = os.path.dirname(_capi.LIB_PATH)
+    assert os.path.exists(os.path.join(lib, "libopenkitchen_shim.so"))
+    csv = tmp_path / "Monza.csv"
+    ok.write_track_csv("Monza", str(csv))
+    try:
+        ok.Env(device=0).close()
+        pytest.skip("a GPU is present: covered by tests/test_gpu_shim.py")
+    except ok.OkError:
+        pass
+    r = subprocess.run([os.path.join(lib, "ok_shim_example"), str(csv), "3", "2"], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+    import open_kitchen_pybind as okp
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        okp.Environment(str(csv))
