@@ -158,6 +158,42 @@ def cpu_reference_run(steps, warmup, budget_s, n_cap=N_AGENTS):
     return value, dt, info
 
 
+def ref_cuda_kernel_baseline(ok, n=4096, iters=30):
+    """Secondary baseline: the reference's REAL CollisionChecker (its CUDA kernel + per-step Ray_ H2D/D2H memcpys +
+    host pack/unpack loops, CollisionChecker.cu:113-174) compiled unchanged for sm_100a, on this GPU, at BASELINE
+    config 1's shape (4,096 agents x 32 rays on Silverstone; the reference's uint16_t loop caps it below 65,536)."""
+    import ctypes as C
+    import tempfile
+
+    lib = os.path.join(ROOT, "oracle", "_ref", "libokref_cuda.so")
+    if not os.path.exists(lib):
+        return None
+    ref = C.CDLL(lib)
+    ref.okc_create.restype = C.c_void_p
+    ref.okc_create.argtypes = [C.c_char_p, C.c_int64, C.c_int, C.c_void_p]
+    ref.okc_set_poses.argtypes = [C.c_void_p] * 5
+    ref.okc_time_checks.restype = C.c_double
+    ref.okc_time_checks.argtypes = [C.c_void_p, C.c_int]
+    ref.okc_destroy.argtypes = [C.c_void_p]
+    fan = ok.ray_fan(N_RAYS)
+    with tempfile.TemporaryDirectory() as d:
+        csv = os.path.join(d, "Silverstone.csv")
+        ok.write_track_csv("Silverstone", csv)
+        env = ok.Env(device=-1)
+        t = env.add_named_track("Silverstone")
+        tx, ty, th = env.track_array(t, "x"), env.track_array(t, "y"), env.track_array(t, "heading")
+        idx = (np.arange(n, dtype=np.int64) * 2654435761 % 2**32 % len(tx)).astype(np.int64)
+        x, y, rot = tx[idx].copy(), ty[idx].copy(), th[idx].copy()
+        h = ref.okc_create(csv.encode(), n, N_RAYS, fan.ctypes.data_as(C.c_void_p))
+        ref.okc_set_poses(h, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), rot.ctypes.data_as(C.c_void_p), None)
+        ref.okc_time_checks(h, 3)
+        sec = ref.okc_time_checks(h, iters)
+        ref.okc_destroy(h)
+    return {"what": "reference CollisionChecker::checkCollision (raycast + memcpys + host loops only, no kinematics), sm_100a build",
+            "agents": n, "rays": N_RAYS, "track": "Silverstone", "ms_per_check": 1e3 * sec / iters,
+            "ray_casts_per_sec": n * N_RAYS * iters / sec}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -307,6 +343,10 @@ def main():
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if world == 1 and not args.no_cpu:
+            try:
+                line["ref_cuda_kernel"] = ref_cuda_kernel_baseline(ok)
+            except Exception as ex:
+                line["ref_cuda_kernel"] = {"error": str(ex)}
             try:
                 _, _, info = cpu_reference_run(steps=10, warmup=2, budget_s=20.0)
                 line["cpu_baseline"] = info

@@ -221,6 +221,9 @@ typedef struct OkLaunchStats {
     int32_t  grid_blocks, block_threads, smem_bytes, tiles;
 } OkLaunchStats;
 int ok_launch_stats(const OkEnv *env, OkLaunchStats *out);
+/* evaluates the kernels' sincosf (the glibc-2.39 restatement, ok_math.cuh) on `n` host floats: lets a test
+ * compare the DEVICE function with libm / the oracle directly (tests/test_gpu_math.py) */
+int ok_eval_sincosf(OkEnv *env, const float *h_in, float *h_sin, float *h_cos, int64_t n);
 
 #ifdef __cplusplus
 }

@@ -110,6 +110,7 @@ SIGNATURES = {
     "ok_write_buffer": (C.c_int, [_P, C.c_int32, _P, C.c_size_t, _P]),
     "ok_sync": (C.c_int, [_P, _P]),
     "ok_launch_stats": (C.c_int, [_P, C.POINTER(OkLaunchStats)]),
+    "ok_eval_sincosf": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
 }
 
 _lib = None

@@ -51,7 +51,10 @@ struct DeviceGuard
     }
 };
 
-constexpr int kBlock = 1024;
+#ifndef OK_BLOCK
+#define OK_BLOCK 1024
+#endif
+constexpr int kBlock = OK_BLOCK;
 constexpr int kMaxBatchAgents = 256;
 
 struct BufferDesc
@@ -491,7 +494,7 @@ int ok_alloc_agents(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, c
     // batch = the agents a CTA keeps in flight: as many as fit behind the largest staged track
     {
         const size_t blob  = (e->max_blob_used + 127) / 128 * 128;
-        const size_t avail = static_cast<size_t>(e->smem_optin) > blob + 1024 ? e->smem_optin - blob - 1024 : 0;
+        const size_t avail = static_cast<size_t>(e->smem_optin) > blob + 4096 ? e->smem_optin - blob - 4096 : 0;
         const size_t per   = ok::batch_smem_bytes(1, rays);
         int64_t      a     = static_cast<int64_t>(avail / per);
         int          cap   = kMaxBatchAgents;
@@ -824,6 +827,30 @@ int ok_sync(OkEnv *e, void *stream)
         return fail(OK_ERR_NO_DEVICE, "no device");
     DeviceGuard g(e->cfg.device);
     OK_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return OK_SUCCESS;
+}
+
+int ok_eval_sincosf(OkEnv *e, const float *h_in, float *h_sin, float *h_cos, int64_t n)
+{
+    if (!e || !e->has_device)
+        return fail(OK_ERR_NO_DEVICE, "no device");
+    if (!h_in || !h_sin || !h_cos || n <= 0)
+        return fail(OK_ERR_INVALID_ARG, "bad arguments");
+    DeviceGuard g(e->cfg.device);
+    float      *d = nullptr;
+    OK_CUDA(cudaMalloc(&d, sizeof(float) * 3 * static_cast<size_t>(n)));
+    cudaError_t err = cudaMemcpy(d, h_in, sizeof(float) * n, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess)
+    {
+        ok::sincosf_kernel<<<static_cast<unsigned>((n + 255) / 256), 256>>>(d, d + n, d + 2 * n, n);
+        e->launches++;
+        err = cudaMemcpy(h_sin, d + n, sizeof(float) * n, cudaMemcpyDeviceToHost);
+        if (err == cudaSuccess)
+            err = cudaMemcpy(h_cos, d + 2 * n, sizeof(float) * n, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    if (err != cudaSuccess)
+        return fail(OK_ERR_CUDA, cudaGetErrorString(err));
     return OK_SUCCESS;
 }
 

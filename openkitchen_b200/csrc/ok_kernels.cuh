@@ -207,6 +207,10 @@ __device__ __forceinline__ void test_segment(const float4 *segs, const int idx, 
     // most candidates end here: parallel (fabsf(denom) < 1e-8f), or the ray's line misses the segment
     if ((adb < 0x322BCC77u) | (b > ad) | (b < -0x1p-22f))
         return;
+    // a segment registered in two cells along the ray comes back: it already is the incumbent (the literal
+    // rule `idx > best` would reject it anyway, after two divisions)
+    if (idx == best)
+        return;
     const float tn = fsub(fmul(ex, sg.w), fmul(ey, sg.z));
     const float a  = __uint_as_float(__float_as_uint(tn) ^ sgn);
     if (a < -0x1p-22f)
@@ -465,13 +469,14 @@ __host__ __device__ inline size_t batch_smem_bytes(int agents, int rays)
 }
 
 #ifndef OK_UNITS
-#define OK_UNITS 4
+#define OK_UNITS 8
 #endif
 constexpr int kUnitsPerRefill = OK_UNITS; // units of work a lane does between two looks at the pool
 
 template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(const StepParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint16_t                      s_order[1024]; // pool order of the rays (p.ray_order)
     __shared__ __align__(8) uint64_t         bar;
     __shared__ int                           s_tile, s_pool;
 
@@ -485,6 +490,8 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
 
     if (tid == 0)
         mbar_init(&bar, 1);
+    for (int i = tid; i < R; i += kBlock)
+        s_order[i] = p.ray_order[i];
     __syncthreads();
 
     int      staged = -1;
@@ -683,7 +690,7 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
                         // pool order -> (agent, ray): ray-major, centre rays first
                         const int rank = __float2int_rz((static_cast<float>(q) + 0.5f) * inv_cnt);
                         const int al   = q - rank * count;
-                        const int r    = p.ray_order[rank];
+                        const int r    = s_order[rank];
                         const int slot = al * R + r;
                         const AgentRec &rec = recs[al];
                         // a crashed agent's rays are inactive: the kernel leaves their stale hits alone
@@ -958,6 +965,17 @@ __global__ void reset_kernel(const StepParams p, const ResetParams r)
     p.nearest[a]  = near;
     p.fitness[a]  = 0.0f;
     p.reward[a]   = 0.0f;
+}
+
+__global__ void sincosf_kernel(const float *in, float *s_out, float *c_out, int64_t n)
+{
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    float s, c;
+    sincosf(in[i], s, c);
+    s_out[i] = s;
+    c_out[i] = c;
 }
 
 __global__ void fill_actions_kernel(const StepParams p, int64_t n)

@@ -192,6 +192,13 @@ class Env:
             raise ValueError(f"{name}: expected shape {shp}, got {a.shape}")
         check(self.lib.ok_write_buffer(self.h, BUF[name], _vp(a), a.nbytes, stream))
 
+    def eval_sincosf(self, x):
+        """the device sincosf on host floats -> (sin, cos); for tests of the arithmetic model"""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        s, c = np.empty_like(x), np.empty_like(x)
+        check(self.lib.ok_eval_sincosf(self.h, _vp(x), _vp(s), _vp(c), x.size))
+        return s, c
+
     def launch_stats(self) -> OkLaunchStats:
         s = OkLaunchStats()
         check(self.lib.ok_launch_stats(self.h, C.byref(s)))
