@@ -274,6 +274,12 @@ __device__ __forceinline__ int cast_ray_brute(const TrackView &tv, float ox, flo
 // The grid carries a ring of empty cells around the clip box, so the walk needs no bounds checks:
 // it stops at t1, the parameter at which the ray leaves the clip box (or its range).
 #define OK_DDA_SLACK 0.5f
+#ifndef OK_LA_STEPS
+#define OK_LA_STEPS 2
+#endif
+#ifndef OK_TESTS
+#define OK_TESTS 3
+#endif
 struct RayWalk
 {
     float    ox, oy, dx, dy;
@@ -364,8 +370,8 @@ __device__ __forceinline__ bool walk_begin(const TrackView &tv, RayWalk &w, floa
 // look-ahead may run past the eventual hit; its cell is only adopted if it still starts within
 // min_t + slack when the current cell is used up, so the set of tested cells is the one the plain
 // walk would visit.  Returns false when the walk is over.
-__device__ __forceinline__ bool walk_unit(const TrackView &tv, RayWalk &w)
-{
+__device__ __forceinline__ bool walk_look_ahead(const TrackView &tv, RayWalk &w)
+{ // one DDA step of the look-ahead; false = the walk left the grid (cannot happen, see walk_begin)
     if (!(w.flags & (kWalkLaValid | kWalkLaDone)))
     {
         const bool  step_x = w.tmx < w.tmy;
@@ -378,7 +384,7 @@ __device__ __forceinline__ bool walk_unit(const TrackView &tv, RayWalk &w)
             const int dcy = w.dy > 0.0f ? tv.nx : -tv.nx;
             w.c += step_x ? dcx : dcy;
             if (static_cast<unsigned>(w.c) >= static_cast<unsigned>(tv.nx * tv.ny))
-                return false; // cannot happen (see above); keeps a rounding surprise from reading out of bounds
+                return false; // keeps a rounding surprise from reading out of bounds
             w.tmx += step_x ? w.tdx : 0.0f;
             w.tmy += step_x ? 0.0f : w.tdy;
             const uint32_t se = cell_items(tv, w.c);
@@ -390,6 +396,15 @@ __device__ __forceinline__ bool walk_unit(const TrackView &tv, RayWalk &w)
             }
         }
     }
+    return true;
+}
+
+__device__ __forceinline__ bool walk_unit(const TrackView &tv, RayWalk &w)
+{
+#pragma unroll
+    for (int rep = 0; rep < OK_LA_STEPS; ++rep)
+        if (!walk_look_ahead(tv, w))
+            return false;
     if (w.k >= w.k_end)
     {
         if (w.flags & kWalkLaValid)
@@ -402,11 +417,13 @@ __device__ __forceinline__ bool walk_unit(const TrackView &tv, RayWalk &w)
         else if (w.flags & kWalkLaDone)
             return false;
     }
-    if (w.k < w.k_end)
-    {
-        const int i = tv.items[w.k++];
-        test_segment(tv.seg, i, w.ox, w.oy, w.dx, w.dy, w.min_t, w.best, w.flags);
-    }
+#pragma unroll
+    for (int rep = 0; rep < OK_TESTS; ++rep)
+        if (w.k < w.k_end)
+        {
+            const int i = tv.items[w.k++];
+            test_segment(tv.seg, i, w.ox, w.oy, w.dx, w.dy, w.min_t, w.best, w.flags);
+        }
     return true;
 }
 
@@ -469,7 +486,7 @@ __host__ __device__ inline size_t batch_smem_bytes(int agents, int rays)
 }
 
 #ifndef OK_UNITS
-#define OK_UNITS 8
+#define OK_UNITS 4
 #endif
 constexpr int kUnitsPerRefill = OK_UNITS; // units of work a lane does between two looks at the pool
 
