@@ -198,6 +198,14 @@ int ok_launch_steps_random(OkEnv *env, uint64_t first_step, int32_t k, uint32_t 
 /* write the Philox actions for `step` into the ACT_* buffers without stepping */
 int ok_fill_random_actions(OkEnv *env, uint64_t step, uint32_t seed, void *stream);
 
+/* The EvolutionaryRacer policy for the whole population: GeneticAgent::updateAction +
+ * Network::infer (EvolutionaryRacer/GeneticAgent.hpp:37-50, Network.hpp:119-155).  Agent i has its own weights
+ * d_w1[i] (f32 [R+2][hidden], inputs speed/100, normalizeAngleDeg(rot)/360, hits/200) and d_w2[i] (f32 [hidden][6]);
+ * hidden = relu(x W1), out = sigmoid(hidden W2), actions decoded with the 0.5 activation limit into the ACT_*
+ * buffers.  hidden <= 32.  One warp per agent; the kernel streams the weights once (HBM bound: 4*(R+2+6)*hidden
+ * bytes per agent). */
+int ok_genetic_policy(OkEnv *env, const float *d_w1, const float *d_w2, int32_t hidden, void *stream);
+
 /* End-to-end host call (what the C++ shim's Environment::step and the reference-facing plugin
  * use): H2D of the two action arrays, one tick, D2H of obs / reward / done / crashed (each
  * nullable), then a stream synchronise.  Host buffers should be pinned (ok_host_alloc). */

@@ -721,6 +721,24 @@ int ok_fill_random_actions(OkEnv *e, uint64_t step, uint32_t seed, void *stream)
     return OK_SUCCESS;
 }
 
+int ok_genetic_policy(OkEnv *e, const float *d_w1, const float *d_w2, int32_t hidden, void *stream)
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    if (!d_w1 || !d_w2 || hidden < 1 || hidden > 32)
+        return fail(OK_ERR_INVALID_ARG, "weights must be given and 1 <= hidden <= 32");
+    DeviceGuard    g(e->cfg.device);
+    ok::StepParams p = base_params(e);
+    const int      threads = 256;
+    const int64_t  blocks  = (e->n_agents * 32 + threads - 1) / threads;
+    ok::genetic_policy_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        p, d_w1, d_w2, hidden, e->n_agents);
+    OK_CUDA(cudaGetLastError());
+    e->launches++;
+    return OK_SUCCESS;
+}
+
 int ok_step_host(OkEnv *e, const float *h_thr, const float *h_steer, float *h_obs, float *h_reward, uint8_t *h_done,
                  void *stream)
 {

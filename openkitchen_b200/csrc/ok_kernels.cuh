@@ -984,6 +984,88 @@ __global__ void reset_kernel(const StepParams p, const ResetParams r)
     p.reward[a]   = 0.0f;
 }
 
+// GeneticAgent::updateAction + Network::infer for every agent (EvolutionaryRacer/GeneticAgent.hpp:37-50,
+// Network.hpp:119-155).  One warp per agent, lane j = hidden unit j.  The weights are streamed exactly once with
+// coalesced row reads (W1 row i = `hidden` consecutive floats), so the kernel is HBM bound:
+// 4*(R+2)*hidden + 4*hidden*6 bytes per agent (4,800 B at R = 32, hidden = 30).
+__global__ void genetic_policy_kernel(const StepParams p, const float *__restrict__ w1, const float *__restrict__ w2,
+                                      int hidden, int64_t n_agents)
+{
+    const int     lane = threadIdx.x & 31;
+    const int64_t a    = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (a >= n_agents)
+        return;
+    const int    R      = p.rays;
+    const int    inputs = R + 2;
+    const float *W1     = w1 + a * inputs * hidden;
+    const float *W2     = w2 + a * hidden * 6;
+    // inputs, Network.hpp:125-132
+    float rot = p.rot[a];
+    int   guard = 0;
+    while (rot < 360.0f && guard++ < 100000) // normalizeAngleDeg, Utils.h:3-14
+        rot = fadd(rot, 360.0f);
+    while (rot >= 360.0f && guard++ < 200000)
+        rot = fsub(rot, 360.0f);
+    const float in0 = __fdiv_rn(p.speed[a], p.speed_limit);
+    const float in1 = __fdiv_rn(rot, 360.0f);
+    const bool  unit = lane < hidden;
+    float       acc  = 0.0f;
+    if (unit)
+    {
+        acc = fmul(in0, W1[lane]);
+        acc = fadd(acc, fmul(in1, W1[hidden + lane]));
+    }
+    for (int r0 = 0; r0 < R; r0 += 32)
+    { // 32 lidar inputs at a time: one coalesced read, then broadcast one by one
+        const float mine = (r0 + lane < R) ? p.obs[a * R + r0 + lane] : 0.0f;
+        const int   cnt  = min(32, R - r0);
+        int         k    = 0;
+        for (; k + 8 <= cnt; k += 8)
+        { // 8 independent row loads in flight per lane
+            float wv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                wv[u] = unit ? W1[(2 + r0 + k + u) * hidden + lane] : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                acc = fadd(acc, fmul(__shfl_sync(0xffffffffu, mine, k + u), wv[u]));
+        }
+        for (; k < cnt; ++k)
+        {
+            const float x = __shfl_sync(0xffffffffu, mine, k);
+            if (unit)
+                acc = fadd(acc, fmul(x, W1[(2 + r0 + k) * hidden + lane]));
+        }
+    }
+    const float h = unit ? fmaxf(acc, 0.0f) : 0.0f; // relu
+    float       o[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        o[k] = unit ? fmul(h, W2[lane * 6 + k]) : 0.0f;
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1)
+            o[k] = fadd(o[k], __shfl_xor_sync(0xffffffffu, o[k], s));
+    if (lane == 0)
+    {
+        bool on[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+            on[k] = __fdiv_rn(1.0f, fadd(1.0f, expf(-o[k]))) > 0.5f; // sigmoid > kOutputActivationLim
+        // GeneticAgent.hpp:37-50
+        float thr = 0.0f, st = 0.0f;
+        thr = fadd(thr, on[0] ? 0.3f : 0.0f);
+        thr = fadd(thr, on[1] ? -0.3f : 0.0f);
+        st  = fadd(st, on[2] ? 1.0f : 0.0f);
+        st  = fadd(st, on[3] ? 4.0f : 0.0f);
+        st  = fadd(st, on[4] ? -1.0f : 0.0f);
+        st  = fadd(st, on[5] ? -4.0f : 0.0f);
+        p.act_thr[a]   = thr;
+        p.act_steer[a] = st;
+    }
+}
+
 __global__ void sincosf_kernel(const float *in, float *s_out, float *c_out, int64_t n)
 {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;

@@ -164,6 +164,10 @@ class Env:
     def fill_random_actions(self, step: int, seed: int = 0x0C17C4E2, stream=None):
         check(self.lib.ok_fill_random_actions(self.h, step, seed, stream))
 
+    def genetic_policy(self, d_w1, d_w2, hidden: int, stream=None):
+        """per-agent shallow MLP -> ACT_* buffers (device weight pointers)"""
+        check(self.lib.ok_genetic_policy(self.h, d_w1, d_w2, hidden, stream))
+
     def step_host(self, thr=None, steer=None, obs=None, reward=None, done=None, stream=None):
         """End-to-end tick with HOST buffers (H2D actions, kernel, D2H results, sync)."""
         check(self.lib.ok_step_host(self.h, _vp(thr), _vp(steer), _vp(obs), _vp(reward), _vp(done), stream))

@@ -82,6 +82,35 @@ def c2():
     ms_env = timed(lambda: env.step(), 300)
     report("C2 4096-agent genetic population, Silverstone, 32 rays, per-agent MLP (torch.bmm) + tick", n, rays, ms,
            {"ms_env_only": ms_env})
+    from openkitchen_b200.genetic import GeneticPopulation
+
+    pop = GeneticPopulation(n, rays, generator=g)
+
+    def tick2():
+        pop.act(env)   # ok_genetic_policy: one warp per agent, weights streamed once
+        env.step()
+
+    ms2 = timed(tick2, 300)
+    ms_pol = timed(lambda: pop.act(env), 300)
+    report("C2 4096-agent genetic population, Silverstone, 32 rays, per-agent MLP (ok_genetic_policy kernel) + tick", n, rays, ms2,
+           {"ms_policy_only": ms_pol, "policy_weight_bytes": n * (rays + 2 + 6) * 30 * 4})
+    # the policy kernel at a size where HBM, not launch latency, is the bound
+    nb = 262144
+    big = ok.BatchEnv(["Silverstone"], nb, rays=rays, movement_mode=ok.MOVE_ACCELERATION)
+    pb = GeneticPopulation(nb, rays, generator=g)
+    big.cast_rays()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    evs = []
+    for _ in range(20):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); pb.act(big); e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    msb = float(np.median([a.elapsed_time(b) for a, b in evs[3:]]))
+    bytes_ = nb * ((rays + 2 + 6) * 30 * 4 + rays * 4 + 8 + 8)
+    report("policy kernel alone, 262,144 agents (L2 flushed)", nb, rays, msb,
+           {"algorithmic_bytes": bytes_, "GBps": bytes_ / (msb * 1e-3) / 1e9, "frac_of_measured_hbm_6553": bytes_ / (msb * 1e-3) / 1e9 / 6553.3})
 
 
 def c4():
