@@ -269,6 +269,23 @@ int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
 }
 } // namespace
 
+namespace
+{
+// device-visible alias of a pinned (cudaMallocHost / cudaHostRegister) host pointer, or nullptr if pageable
+template <typename T> T *pinned_alias(T *h)
+{
+    if (!h)
+        return nullptr;
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return at.type == cudaMemoryTypeHost ? static_cast<T *>(at.devicePointer) : nullptr;
+}
+} // namespace
+
 extern "C"
 {
 int ok_abi_version(void)
@@ -750,21 +767,37 @@ int ok_step_host(OkEnv *e, const float *h_thr, const float *h_steer, float *h_ob
     DeviceGuard  g(e->cfg.device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const size_t n = static_cast<size_t>(e->n_agents);
-    if (h_thr)
-    {
-        OK_CUDA(cudaMemcpyAsync(e->d_buf[OK_BUF_ACT_THROTTLE], h_thr, 4 * n, cudaMemcpyHostToDevice, s));
-        OK_CUDA(cudaMemcpyAsync(e->d_buf[OK_BUF_ACT_STEER], h_steer, 4 * n, cudaMemcpyHostToDevice, s));
-    }
     ok::StepParams p = base_params(e);
     p.do_move        = 1;
-    rc               = launch_step(e, p, s);
+    // Pinned buffers are used in place: the kernel reads the actions and writes obs / reward / done straight
+    // through the host mapping, so both transfers overlap the tick.  Pageable buffers fall back to staged copies.
+    const float *a_thr = pinned_alias(h_thr), *a_steer = pinned_alias(h_steer);
+    if (h_thr)
+    {
+        if (a_thr && a_steer)
+        {
+            p.ext_thr   = a_thr;
+            p.ext_steer = a_steer;
+        }
+        else
+        {
+            OK_CUDA(cudaMemcpyAsync(e->d_buf[OK_BUF_ACT_THROTTLE], h_thr, 4 * n, cudaMemcpyHostToDevice, s));
+            OK_CUDA(cudaMemcpyAsync(e->d_buf[OK_BUF_ACT_STEER], h_steer, 4 * n, cudaMemcpyHostToDevice, s));
+        }
+    }
+    // only the lidar goes through the mapping (full 128-byte warp stores); reward / done are one element per warp,
+    // which would be 2 tiny PCIe writes per agent -- a 0.3 MB copy after the kernel is cheaper
+    p.host_obs    = pinned_alias(h_obs);
+    p.host_reward = nullptr;
+    p.host_done   = nullptr;
+    rc            = launch_step(e, p, s);
     if (rc)
         return rc;
-    if (h_obs)
+    if (h_obs && !p.host_obs)
         OK_CUDA(cudaMemcpyAsync(h_obs, e->d_buf[OK_BUF_OBS], buffer_bytes(e, OK_BUF_OBS), cudaMemcpyDeviceToHost, s));
-    if (h_reward)
+    if (h_reward && !p.host_reward)
         OK_CUDA(cudaMemcpyAsync(h_reward, e->d_buf[OK_BUF_REWARD], 4 * n, cudaMemcpyDeviceToHost, s));
-    if (h_done)
+    if (h_done && !p.host_done)
         OK_CUDA(cudaMemcpyAsync(h_done, e->d_buf[OK_BUF_DONE], n, cudaMemcpyDeviceToHost, s));
     OK_CUDA(cudaStreamSynchronize(s));
     return OK_SUCCESS;

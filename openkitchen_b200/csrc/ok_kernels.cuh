@@ -74,6 +74,10 @@ struct StepParams
     uint32_t     seed;
     uint64_t     step;
     int32_t      do_move;             // 0: ok_cast_rays
+    // optional mirrors in PINNED HOST memory (ok_step_host): the kernel stores results over PCIe as they are
+    // produced, so the device->host transfer overlaps the tick instead of following it
+    float   *host_obs, *host_reward;
+    uint8_t *host_done;
     // configuration
     int32_t  movement_mode, reward_mode, raycast_mode, auto_reset, auto_reset_stride;
     float    sensor_range, speed_limit, dt, collision_dist2, sensor_offset, standstill_thr2;
@@ -784,7 +788,10 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
                 rel.y = fadd(fmul(xt, rec.rs), fmul(yt, rec.rc));
                 sq    = fadd(fmul(rel.x, rel.x), fmul(rel.y, rel.y));
                 reinterpret_cast<float2 *>(p.hit_rel)[gi] = rel;
-                p.obs[gi] = __fdiv_rn(__fsqrt_rn(sq), p.sensor_range);
+                const float ob = __fdiv_rn(__fsqrt_rn(sq), p.sensor_range);
+                p.obs[gi]      = ob;
+                if (p.host_obs)
+                    p.host_obs[gi] = ob;
             }
             // min_dist2 of CollisionChecker.cu:150,162-165: `if (sq < min) min = sq` skips NaN, and so
             // does a signed-int min over the bit patterns of values >= +0 (a NaN made here is 0x7fffffff)
@@ -887,6 +894,8 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
                         default: break;
                         }
                         p.reward[a]  = reward;
+                        if (p.host_reward)
+                            p.host_reward[a] = reward;
                         p.fitness[a] = fitness;
                         p.prev[a]    = prev;
                         if (need_idx || (rec.flags & kFlagReset))
@@ -894,6 +903,8 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
                     }
                     p.crashed[a]   = crashed;
                     p.done[a]      = crashed; // Agent::isDone, Agent.cpp:138-144 (completed_ is never set)
+                    if (p.host_done)
+                        p.host_done[a] = crashed;
                     p.min_dist2[a] = min_d2;
                 }
             }
