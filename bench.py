@@ -227,7 +227,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--agents", type=int, default=N_AGENTS, help="agents per GPU (default: the BASELINE workload)")
-    ap.add_argument("--raycast", default="grid", choices=["grid", "brute"])
+    ap.add_argument("--raycast", default="beam", choices=["beam", "grid", "brute"])
+    ap.add_argument("--beam-cell", type=float, default=0.0, help="beam table start-cell size in px (0 = library default)")
+    ap.add_argument("--beam-bins", type=int, default=0, help="beam table direction bins (0 = library default)")
     ap.add_argument("--cell", type=float, default=0.0, help="broadphase cell size in px (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed ticks")
@@ -257,9 +259,18 @@ def main():
 
     n = args.agents
     extra = {"grid_cell": args.cell} if args.cell > 0 else {}
+    if args.beam_cell > 0:
+        extra["beam_cell"] = args.beam_cell
+    if args.beam_bins > 0:
+        extra["beam_bins"] = args.beam_bins
+    mode = {"beam": ok.RAYCAST_BEAM, "grid": ok.RAYCAST_GRID, "brute": ok.RAYCAST_BRUTE}[args.raycast]
     env = ok.Env(device=local, movement_mode=ok.MOVE_VELOCITY, reward_mode=ok.REWARD_CMAES_PROGRESS, auto_reset=1,
-                 raycast_mode=ok.RAYCAST_GRID if args.raycast == "grid" else ok.RAYCAST_BRUTE, **extra)
+                 raycast_mode=mode, **extra)
+    t_build = time.perf_counter()
     build_workload(ok, env, n)
+    env.cast_rays(None)  # first launch uploads the track arena (and builds the beam tables): outside every timed region
+    env.sync()
+    t_build = time.perf_counter() - t_build
     stream = torch.cuda.current_stream()
     sp = stream.cuda_stream
     flush = None if args.no_flush else torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
@@ -340,6 +351,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "agents_per_gpu": n, "rays": N_RAYS, "tracks": 23, "raycast": args.raycast, "grid_cell_px": float(env.cfg.grid_cell),
+                       "beam_cell_px": float(env.cfg.beam_cell), "beam_bins": int(env.cfg.beam_bins), "setup_s": t_build,
                        "l2": "flushed between timed ticks (256 MiB memset)" if flush is not None else "not flushed",
                        "parallelism": f"agent-sharded x{world}, no data-path collective",
                        "crashed_fraction_at_end": crashed_frac, "wall_s_timed_region": t_wall},

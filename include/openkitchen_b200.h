@@ -56,8 +56,10 @@ typedef enum OkRewardMode {
 } OkRewardMode;
 
 typedef enum OkRaycastMode {
-    OK_RAYCAST_GRID  = 0, /* uniform-grid broadphase (default) */
-    OK_RAYCAST_BRUTE = 1  /* every ray x every segment, the reference's loop (CollisionChecker.cu:51-66) */
+    OK_RAYCAST_GRID  = 0, /* uniform-grid broadphase: DDA walk over 8 px cells */
+    OK_RAYCAST_BRUTE = 1, /* every ray x every segment, the reference's loop (CollisionChecker.cu:51-66) */
+    OK_RAYCAST_BEAM  = 2  /* precomputed (start cell, direction bin) candidate lists, grid walk only for the rays a
+                             list cannot decide; same results as the two modes above */
 } OkRaycastMode;
 
 /* Device buffers exported by ok_get_buffer.  N = agents, R = rays per agent. */
@@ -126,7 +128,9 @@ typedef struct OkConfig {
     uint32_t standstill_period;    /* DisplacementStats::kPeriod 200 Environment.h:19 */
     float    standstill_threshold; /* kDisplamentThreshold 20        Environment.h:20 */
     float    grid_cell;            /* broadphase cell size in px (8) */
-    int32_t  reserved[4];
+    float    beam_cell;            /* OK_RAYCAST_BEAM: start-cell size in px (8); 0 = default */
+    int32_t  beam_bins;            /* OK_RAYCAST_BEAM: direction bins, a power of two (64); 0 = default */
+    int32_t  reserved[2];
 } OkConfig;
 
 typedef struct OkTrackInfo {
@@ -147,7 +151,7 @@ void        ok_config_default(OkConfig *cfg);
 /* Environment::Environment (Environment.cpp:42-62) minus raylib/visualizer/screen grabber. */
 int  ok_create(const OkConfig *cfg, OkEnv **out);
 void ok_destroy(OkEnv *env);
-/* change the per-tick constants of a live env (everything except `device` and `grid_cell`, which are fixed
+/* change the per-tick constants of a live env (everything except `device`, `grid_cell` and `beam_*`, which are fixed
  * at creation): e.g. Agent::setMovementMode (Agent.h:46-49), the reward definition, auto-reset */
 int  ok_update_config(OkEnv *env, const OkConfig *cfg);
 int  ok_get_config(const OkEnv *env, OkConfig *out);
@@ -232,6 +236,15 @@ int ok_launch_stats(const OkEnv *env, OkLaunchStats *out);
 /* evaluates the kernels' sincosf (the glibc-2.39 restatement, ok_math.cuh) on `n` host floats: lets a test
  * compare the DEVICE function with libm / the oracle directly (tests/test_gpu_math.py) */
 int ok_eval_sincosf(OkEnv *env, const float *h_in, float *h_sin, float *h_cos, int64_t n);
+
+/* OK_RAYCAST_BEAM's candidate table, host side (no device needed; built on first use, ok_beam.hpp): the
+ * segments a ray starting at (x, y) with direction `angle_rad` can reach within *d_complete px, nearest first.
+ * Copies min(count, capacity) indices to h_items and returns count; -1 = the start cell is not covered (the
+ * kernel then uses the grid walk); other negative values are OkStatus errors.  Test / inspection hook. */
+int32_t ok_beam_lookup(OkEnv *env, int32_t track_id, float x, float y, float angle_rad, uint16_t *h_items,
+                       int32_t capacity, float *d_complete);
+/* size of the track's beam table in bytes (builds it if needed) */
+int64_t ok_beam_table_bytes(OkEnv *env, int32_t track_id);
 
 #ifdef __cplusplus
 }

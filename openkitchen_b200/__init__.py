@@ -9,6 +9,7 @@ from ._capi import (  # noqa: F401
     LIB_PATH,
     MOVE_ACCELERATION,
     MOVE_VELOCITY,
+    RAYCAST_BEAM,
     RAYCAST_BRUTE,
     RAYCAST_GRID,
     REWARD_CMAES_PROGRESS,

@@ -17,7 +17,7 @@ OK_ERR_INVALID_ARG, OK_ERR_CUDA, OK_ERR_IO, OK_ERR_STATE, OK_ERR_CAPACITY, OK_ER
 MOVE_VELOCITY, MOVE_ACCELERATION = 0, 1
 REWARD_NONE, REWARD_Q_PROGRESS, REWARD_CMAES_PROGRESS, REWARD_CONSTANT = 0, 1, 2, 3
 REWARD_DISPLACEMENT, REWARD_MIN_RAY, REWARD_TRACK_INDEX, REWARD_LANE_CENTER = 4, 5, 6, 7
-RAYCAST_GRID, RAYCAST_BRUTE = 0, 1
+RAYCAST_GRID, RAYCAST_BRUTE, RAYCAST_BEAM = 0, 1, 2
 
 BUFFERS = [
     "pos_x", "pos_y", "rot", "speed", "accel", "act_throttle", "act_steer",
@@ -50,7 +50,9 @@ class OkConfig(C.Structure):
         ("standstill_period", C.c_uint32),
         ("standstill_threshold", C.c_float),
         ("grid_cell", C.c_float),
-        ("reserved", C.c_int32 * 4),
+        ("beam_cell", C.c_float),
+        ("beam_bins", C.c_int32),
+        ("reserved", C.c_int32 * 2),
     ]
 
 
@@ -112,6 +114,8 @@ SIGNATURES = {
     "ok_sync": (C.c_int, [_P, _P]),
     "ok_launch_stats": (C.c_int, [_P, C.POINTER(OkLaunchStats)]),
     "ok_eval_sincosf": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
+    "ok_beam_lookup": (C.c_int32, [_P, C.c_int32, C.c_float, C.c_float, C.c_float, _P, C.c_int32, C.POINTER(C.c_float)]),
+    "ok_beam_table_bytes": (C.c_int64, [_P, C.c_int32]),
 }
 
 _lib = None

@@ -1,0 +1,457 @@
+// ok_beam.cpp -- see ok_beam.hpp.  Host code, binary64 geometry.
+#include "ok_beam.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <thread>
+
+namespace ok
+{
+namespace
+{
+struct V2
+{
+    double x, y;
+};
+inline double cross(const V2 &a, const V2 &b)
+{
+    return a.x * b.y - a.y * b.x;
+}
+
+// convex hull (counter-clockwise, no collinear points) of at most 8 points; returns the vertex count
+int convex_hull8(V2 *pts, int n, V2 *out)
+{
+    std::sort(pts, pts + n, [](const V2 &a, const V2 &b) { return a.x < b.x || (a.x == b.x && a.y < b.y); });
+    int k = 0;
+    for (int i = 0; i < n; ++i)
+    {
+        while (k >= 2 && cross({out[k - 1].x - out[k - 2].x, out[k - 1].y - out[k - 2].y},
+                               {pts[i].x - out[k - 2].x, pts[i].y - out[k - 2].y}) <= 0)
+            --k;
+        out[k++] = pts[i];
+    }
+    for (int i = n - 2, lo = k + 1; i >= 0; --i)
+    {
+        while (k >= lo && cross({out[k - 1].x - out[k - 2].x, out[k - 1].y - out[k - 2].y},
+                                {pts[i].x - out[k - 2].x, pts[i].y - out[k - 2].y}) <= 0)
+            --k;
+        out[k++] = pts[i];
+    }
+    return k > 1 ? k - 1 : k;
+}
+
+// keeps the part of the convex polygon with cross(n, v) >= 0
+int clip_half_plane(const V2 *poly, int m, const V2 &n, V2 *out)
+{
+    int k = 0;
+    for (int i = 0; i < m; ++i)
+    {
+        const V2     a = poly[i], b = poly[(i + 1) % m];
+        const double fa = cross(n, a), fb = cross(n, b);
+        if (fa >= 0)
+            out[k++] = a;
+        if ((fa >= 0) != (fb >= 0))
+        {
+            const double t = fa / (fa - fb);
+            out[k++]       = {a.x + t * (b.x - a.x), a.y + t * (b.y - a.y)};
+        }
+    }
+    return k;
+}
+
+// distance from the origin to a convex polygon (counter-clockwise), 0 when the origin is inside
+double origin_distance(const V2 *poly, int m)
+{
+    if (m == 0)
+        return 1e300;
+    if (m == 1)
+        return std::hypot(poly[0].x, poly[0].y);
+    bool   inside = m >= 3;
+    double best   = 1e300;
+    for (int i = 0; i < m; ++i)
+    {
+        const V2 a = poly[i], b = poly[(i + 1) % m];
+        const V2 e = {b.x - a.x, b.y - a.y};
+        if (cross(e, {-a.x, -a.y}) < 0)
+            inside = false;
+        const double l2 = e.x * e.x + e.y * e.y;
+        double       t  = l2 > 0 ? (-(a.x * e.x) - a.y * e.y) / l2 : 0.0;
+        t               = std::min(1.0, std::max(0.0, t));
+        best            = std::min(best, std::hypot(a.x + t * e.x, a.y + t * e.y));
+    }
+    return inside ? 0.0 : best;
+}
+
+double point_segment_distance(double px, double py, double ax, double ay, double bx, double by)
+{
+    const double ex = bx - ax, ey = by - ay, l2 = ex * ex + ey * ey;
+    double       t  = l2 > 0 ? ((px - ax) * ex + (py - ay) * ey) / l2 : 0.0;
+    t               = std::min(1.0, std::max(0.0, t));
+    return std::hypot(ax + t * ex - px, ay + t * ey - py);
+}
+
+struct Cand
+{
+    double  lb;               // lower bound of the distance from any point of the cell to the segment
+    int32_t seg;
+    int32_t b_first, b_count; // direction bins the segment can be seen in from the cell (conservative)
+    int32_t hull;             // index into Scratch::hulls, -1 = not computed yet
+};
+
+struct HullRec
+{
+    int n;
+    V2  v[9];
+};
+
+struct Row
+{
+    std::vector<uint32_t> meta;  // per bin: count | dq << 16
+    std::vector<uint32_t> first; // per bin: first item of the bin within `items` (multiple of 4)
+    std::vector<uint16_t> items; // chunks of 4
+};
+
+struct Scratch
+{
+    std::vector<Cand>                                    cands;
+    std::vector<std::vector<int32_t>>                    by_bin;
+    std::vector<HullRec>                                 hulls;
+    std::vector<double>                                  sample_hit, dcomp;
+    std::vector<std::pair<float, uint16_t>>              list;
+};
+
+struct Builder
+{
+    const Track &t;
+    BeamConfig   cfg;
+    double       x0, y0, h, rb;
+    int32_t      nx, ny, nb;
+    double       dth;
+    std::vector<V2> edge_lo, edge_hi; // widened cone edges of every bin
+    std::vector<V2> sample_dir;       // 2 * nb sample directions (bin edges and bin centres)
+    std::vector<V2> seg_mid;          // per segment: midpoint
+    std::vector<double> seg_half;     // per segment: half length
+
+    void build_row(int32_t cx, int32_t cy, Row &row, Scratch &sc) const
+    {
+        const int32_t ns = t.n_segments();
+        const double  m  = kBeamCellMargin;
+        const double  bx0 = x0 + cx * h - m, bx1 = x0 + (cx + 1) * h + m;
+        const double  by0 = y0 + cy * h - m, by1 = y0 + (cy + 1) * h + m;
+        const double  ccx = 0.5 * (bx0 + bx1), ccy = 0.5 * (by0 + by1);
+        const double  half_diag = 0.5 * std::hypot(bx1 - bx0, by1 - by0);
+        const double  two_pi = 2.0 * M_PI, dbin = two_pi / nb;
+        // candidates: segments within reach, with a lower bound of their distance from the cell and the
+        // direction bins they can be seen in.  For p in the cell and q on the segment, q - p lies in the disc
+        // of radius (half_diag + half length) around (midpoint - cell centre).
+        auto &cands = sc.cands;
+        cands.clear();
+        for (int32_t s = 0; s < ns; ++s)
+        {
+            const double vx = seg_mid[s].x - ccx, vy = seg_mid[s].y - ccy;
+            const double dist = std::hypot(vx, vy), rho = half_diag + seg_half[s];
+            if (dist - rho > rb)
+                continue;
+            const float *g = &t.segments[4 * static_cast<size_t>(s)];
+            const double d = point_segment_distance(ccx, ccy, g[0], g[1], g[2], g[3]) - half_diag;
+            if (d > rb)
+                continue;
+            Cand c{std::max(0.0, d), s, 0, nb, -1};
+            if (dist > rho * 1.0000001)
+            {
+                const double phi = std::atan2(vy, vx), alpha = std::asin(std::min(1.0, rho / dist)) + 2.0 * dth;
+                const double f_lo = std::floor((phi - alpha) / dbin), f_hi = std::floor((phi + alpha) / dbin);
+                c.b_count = static_cast<int32_t>(std::min<double>(nb, f_hi - f_lo + 1.0));
+                c.b_first = static_cast<int32_t>(std::fmod(std::fmod(f_lo, nb) + nb, nb));
+            }
+            cands.push_back(c);
+        }
+        std::sort(cands.begin(), cands.end(), [](const Cand &a, const Cand &b) { return a.lb < b.lb || (a.lb == b.lb && a.seg < b.seg); });
+        sc.by_bin.resize(nb);
+        for (auto &v : sc.by_bin)
+            v.clear();
+        for (size_t i = 0; i < cands.size(); ++i)
+            for (int32_t k = 0; k < cands[i].b_count; ++k)
+                sc.by_bin[(cands[i].b_first + k) % nb].push_back(static_cast<int32_t>(i));
+
+        // completeness distance per bin from sample rays: the four corners and the centre of the cell, the bin's
+        // two edges and its centre.  Misses count as "beyond the range".
+        const double ox[5] = {bx0, bx1, bx0, bx1, ccx}, oy[5] = {by0, by0, by1, by1, ccy};
+        sc.sample_hit.assign(static_cast<size_t>(2 * nb), 0.0);
+        for (int32_t j = 0; j < 2 * nb; ++j)
+        {
+            const V2 d   = sample_dir[j];
+            double   far = 0.0;
+            for (int o = 0; o < 5; ++o)
+            {
+                double best = 2.0 * rb; // miss
+                for (const int32_t ci : sc.by_bin[j >> 1])
+                {
+                    const Cand &c = cands[ci];
+                    if (c.lb > best)
+                        break;
+                    const float *g  = &t.segments[4 * static_cast<size_t>(c.seg)];
+                    const double sx = static_cast<double>(g[2]) - g[0], sy = static_cast<double>(g[3]) - g[1];
+                    const double den = d.x * sy - d.y * sx;
+                    if (std::fabs(den) < 1e-12)
+                        continue;
+                    const double ex = g[0] - ox[o], ey = g[1] - oy[o];
+                    const double tt = (ex * sy - ey * sx) / den, ss = (ex * d.y - ey * d.x) / den;
+                    if (tt >= 0 && tt < best && ss >= 0 && ss <= 1)
+                        best = tt;
+                }
+                far = std::max(far, best);
+            }
+            sc.sample_hit[j] = far;
+        }
+        sc.dcomp.resize(nb);
+        for (int32_t b = 0; b < nb; ++b)
+        {
+            const double far =
+                std::max(sc.sample_hit[2 * b], std::max(sc.sample_hit[2 * b + 1], sc.sample_hit[(2 * b + 2) % (2 * nb)]));
+            double d = far + 1.0;
+            if (far >= cfg.range || d >= rb)
+                d = rb;
+            sc.dcomp[b] = d;
+        }
+
+        // exact membership: distance from the origin to (S (+) -C) clipped to the bin's cone
+        sc.hulls.clear();
+        row.meta.assign(nb, 0);
+        row.first.assign(nb, 0);
+        row.items.clear();
+        for (int32_t b = 0; b < nb; ++b)
+        {
+            auto &l = sc.list;
+            l.clear();
+            const double dc = sc.dcomp[b];
+            for (const int32_t ci : sc.by_bin[b])
+            {
+                Cand &c = cands[ci];
+                if (c.lb > dc)
+                    break;
+                if (c.hull < 0)
+                {
+                    const float *g = &t.segments[4 * static_cast<size_t>(c.seg)];
+                    V2           pts[8];
+                    int          np = 0;
+                    for (int e = 0; e < 2; ++e)
+                        for (int k = 0; k < 4; ++k)
+                            pts[np++] = {g[2 * e] - ((k & 1) ? bx1 : bx0), g[2 * e + 1] - ((k & 2) ? by1 : by0)};
+                    HullRec hr;
+                    hr.n   = convex_hull8(pts, np, hr.v);
+                    c.hull = static_cast<int32_t>(sc.hulls.size());
+                    sc.hulls.push_back(hr);
+                }
+                const HullRec &hr = sc.hulls[c.hull];
+                V2             c1[12], c2[14];
+                const int      n1  = clip_half_plane(hr.v, hr.n, edge_lo[b], c1);
+                const V2       neg = {-edge_hi[b].x, -edge_hi[b].y};
+                const int      n2  = clip_half_plane(c1, n1, neg, c2);
+                const double   d   = origin_distance(c2, n2);
+                if (d <= dc)
+                    l.push_back({static_cast<float>(d), static_cast<uint16_t>(c.seg)});
+            }
+            std::sort(l.begin(), l.end());
+            size_t count = std::min<size_t>(l.size(), 65535);
+            double d     = dc;
+            if (count < l.size())
+                d = std::max(0.0, static_cast<double>(l[count].first) - 1e-3); // truncated: complete only up to here
+            uint32_t dq = 0xffffu;
+            if (d < rb)
+                dq = static_cast<uint32_t>(std::min(65534.0, std::floor(d * 256.0)));
+            row.first[b] = static_cast<uint32_t>(row.items.size());
+            row.meta[b]  = static_cast<uint32_t>(count) | (dq << 16);
+            for (size_t i = 0; i < count; ++i)
+                row.items.push_back(l[i].second);
+            while (row.items.size() % 4)
+                row.items.push_back(0xffffu);
+        }
+    }
+};
+} // namespace
+
+bool build_beam_table(const Track &t, const BeamConfig &cfg, std::vector<uint8_t> &blob, std::string &err)
+{
+    if (!(cfg.cell >= 1.0f && cfg.cell <= 64.0f))
+    {
+        err = "beam cell must be in [1, 64] px";
+        return false;
+    }
+    if (cfg.bins < 8 || cfg.bins > 1024 || (cfg.bins & (cfg.bins - 1)))
+    {
+        err = "beam bins must be a power of two in [8, 1024]";
+        return false;
+    }
+    const int32_t n = t.n_points(), ns = t.n_segments();
+    if (n < 2 || ns < 1)
+    {
+        err = "empty track";
+        return false;
+    }
+    double lo_x = 1e300, lo_y = 1e300, hi_x = -1e300, hi_y = -1e300;
+    for (int32_t s = 0; s < ns; ++s)
+        for (int e = 0; e < 2; ++e)
+        {
+            lo_x = std::min<double>(lo_x, t.segments[4 * s + 2 * e]), hi_x = std::max<double>(hi_x, t.segments[4 * s + 2 * e]);
+            lo_y = std::min<double>(lo_y, t.segments[4 * s + 2 * e + 1]), hi_y = std::max<double>(hi_y, t.segments[4 * s + 2 * e + 1]);
+        }
+    Builder b{t, cfg};
+    b.h  = cfg.cell;
+    b.x0 = std::floor(lo_x - 1.0);
+    b.y0 = std::floor(lo_y - 1.0);
+    b.nx = std::max<int32_t>(1, static_cast<int32_t>(std::ceil((hi_x + 1.0 - b.x0) / b.h)));
+    b.ny = std::max<int32_t>(1, static_cast<int32_t>(std::ceil((hi_y + 1.0 - b.y0) / b.h)));
+    b.nb = cfg.bins;
+    b.rb = static_cast<double>(cfg.range) + 1.0;
+    b.dth = kBeamAngleMargin;
+    if (static_cast<int64_t>(b.nx) * b.ny > (1 << 24))
+    {
+        err = "beam grid has too many cells";
+        return false;
+    }
+    b.seg_mid.resize(ns), b.seg_half.resize(ns);
+    for (int32_t s = 0; s < ns; ++s)
+    {
+        const float *g = &t.segments[4 * static_cast<size_t>(s)];
+        b.seg_mid[s]   = {0.5 * (static_cast<double>(g[0]) + g[2]), 0.5 * (static_cast<double>(g[1]) + g[3])};
+        b.seg_half[s]  = 0.5 * std::hypot(static_cast<double>(g[2]) - g[0], static_cast<double>(g[3]) - g[1]);
+    }
+    const double dbin = 2.0 * M_PI / b.nb;
+    b.edge_lo.resize(b.nb), b.edge_hi.resize(b.nb), b.sample_dir.resize(2 * static_cast<size_t>(b.nb));
+    for (int32_t k = 0; k < b.nb; ++k)
+    {
+        b.edge_lo[k] = {std::cos(k * dbin - b.dth), std::sin(k * dbin - b.dth)};
+        b.edge_hi[k] = {std::cos((k + 1) * dbin + b.dth), std::sin((k + 1) * dbin + b.dth)};
+        b.sample_dir[2 * k]     = {std::cos(k * dbin), std::sin(k * dbin)};
+        b.sample_dir[2 * k + 1] = {std::cos((k + 0.5) * dbin), std::sin((k + 0.5) * dbin)};
+    }
+    // covered cells: everything within (lane half-width + 4 px) of a centre-line point
+    std::vector<uint32_t> rows(static_cast<size_t>(b.nx) * b.ny, 0xffffffffu);
+    std::vector<uint32_t> covered;
+    for (int32_t i = 0; i < n; ++i)
+    {
+        const double r   = std::max(t.w_left[i], t.w_right[i]) + 4.0;
+        const int32_t ix0 = std::max<int32_t>(0, static_cast<int32_t>(std::floor((t.x[i] - r - b.x0) / b.h)));
+        const int32_t ix1 = std::min<int32_t>(b.nx - 1, static_cast<int32_t>(std::floor((t.x[i] + r - b.x0) / b.h)));
+        const int32_t iy0 = std::max<int32_t>(0, static_cast<int32_t>(std::floor((t.y[i] - r - b.y0) / b.h)));
+        const int32_t iy1 = std::min<int32_t>(b.ny - 1, static_cast<int32_t>(std::floor((t.y[i] + r - b.y0) / b.h)));
+        for (int32_t iy = iy0; iy <= iy1; ++iy)
+            for (int32_t ix = ix0; ix <= ix1; ++ix)
+            { // cells that touch the disc
+                const double qx = std::min(std::max<double>(t.x[i], b.x0 + ix * b.h), b.x0 + (ix + 1) * b.h);
+                const double qy = std::min(std::max<double>(t.y[i], b.y0 + iy * b.h), b.y0 + (iy + 1) * b.h);
+                if ((qx - t.x[i]) * (qx - t.x[i]) + (qy - t.y[i]) * (qy - t.y[i]) <= r * r)
+                    rows[static_cast<size_t>(iy) * b.nx + ix] = 0;
+            }
+    }
+    for (size_t c = 0; c < rows.size(); ++c)
+        if (rows[c] == 0)
+        {
+            rows[c] = static_cast<uint32_t>(covered.size());
+            covered.push_back(static_cast<uint32_t>(c));
+        }
+    std::vector<Row>    built(covered.size());
+    std::atomic<size_t> next{0};
+    unsigned            nthreads = cfg.threads > 0 ? static_cast<unsigned>(cfg.threads) : std::thread::hardware_concurrency();
+    nthreads                     = std::max(1u, std::min(nthreads, 64u));
+    auto worker = [&]() {
+        Scratch sc;
+        for (;;)
+        {
+            const size_t i = next.fetch_add(1);
+            if (i >= covered.size())
+                break;
+            b.build_row(static_cast<int32_t>(covered[i] % b.nx), static_cast<int32_t>(covered[i] / b.nx), built[i], sc);
+        }
+    };
+    if (nthreads == 1)
+        worker();
+    else
+    {
+        std::vector<std::thread> pool;
+        for (unsigned k = 0; k < nthreads; ++k)
+            pool.emplace_back(worker);
+        for (auto &th : pool)
+            th.join();
+    }
+    size_t n_items = 0;
+    for (auto &r : built)
+        n_items += r.items.size();
+    if (n_items / 4 >= 0xffffffffull)
+    {
+        err = "beam table too large";
+        return false;
+    }
+    BeamHeader h{};
+    h.x0 = static_cast<float>(b.x0), h.y0 = static_cast<float>(b.y0);
+    h.h = cfg.cell, h.inv_h = 1.0f / cfg.cell;
+    h.nx = b.nx, h.ny = b.ny, h.nb = b.nb;
+    h.bin_scale = static_cast<float>(b.nb / (2.0 * M_PI));
+    h.rb        = static_cast<float>(b.rb);
+    h.n_rows    = static_cast<uint32_t>(covered.size());
+    h.n_chunks  = static_cast<uint32_t>(n_items / 4);
+    size_t off  = sizeof(BeamHeader);
+    h.off_rows  = static_cast<uint32_t>(off);
+    off += (rows.size() * 4 + 15) / 16 * 16;
+    h.off_entries = static_cast<uint32_t>(off);
+    off += (covered.size() * static_cast<size_t>(b.nb) * 8 + 15) / 16 * 16;
+    h.off_items = static_cast<uint32_t>(off);
+    off += (n_items * 2 + 15) / 16 * 16;
+    if (off >= 0xffffffffull)
+    {
+        err = "beam table too large";
+        return false;
+    }
+    h.bytes = static_cast<uint32_t>(off);
+    blob.assign(off, 0);
+    std::memcpy(blob.data(), &h, sizeof h);
+    std::memcpy(blob.data() + h.off_rows, rows.data(), rows.size() * 4);
+    uint32_t *entries = reinterpret_cast<uint32_t *>(blob.data() + h.off_entries);
+    uint16_t *items   = reinterpret_cast<uint16_t *>(blob.data() + h.off_items);
+    size_t    cursor  = 0;
+    for (size_t r = 0; r < built.size(); ++r)
+    {
+        for (int32_t k = 0; k < b.nb; ++k)
+        {
+            entries[2 * (r * b.nb + k)]     = static_cast<uint32_t>((cursor + built[r].first[k]) / 4);
+            entries[2 * (r * b.nb + k) + 1] = built[r].meta[k];
+        }
+        if (!built[r].items.empty())
+            std::memcpy(items + cursor, built[r].items.data(), built[r].items.size() * 2);
+        cursor += built[r].items.size();
+    }
+    return true;
+}
+
+bool beam_lookup(const std::vector<uint8_t> &blob, float x, float y, float angle, std::vector<uint16_t> &out, float &d_out)
+{
+    out.clear();
+    if (blob.size() < sizeof(BeamHeader))
+        return false;
+    BeamHeader h;
+    std::memcpy(&h, blob.data(), sizeof h);
+    // the device's arithmetic: binary32, same operation order (ok_kernels.cuh beam_row / beam_bin)
+    const float fx = (x - h.x0) * h.inv_h, fy = (y - h.y0) * h.inv_h;
+    if (!(fx >= 0.0f && fy >= 0.0f && fx < static_cast<float>(h.nx) && fy < static_cast<float>(h.ny)))
+        return false;
+    if (!(std::fabs(angle) < kBeamMaxAngle))
+        return false;
+    const int32_t ix = static_cast<int32_t>(fx), iy = static_cast<int32_t>(fy);
+    uint32_t      row;
+    std::memcpy(&row, blob.data() + h.off_rows + 4 * (static_cast<size_t>(iy) * h.nx + ix), 4);
+    if (row == 0xffffffffu)
+        return false;
+    const int32_t bin = static_cast<int32_t>(std::floor(angle * h.bin_scale)) & (h.nb - 1);
+    uint32_t      e[2];
+    std::memcpy(e, blob.data() + h.off_entries + 8 * (static_cast<size_t>(row) * h.nb + bin), 8);
+    const uint32_t count = e[1] & 0xffffu, dq = e[1] >> 16;
+    d_out                = dq == 0xffffu ? h.rb : static_cast<float>(dq) * (1.0f / 256.0f);
+    out.resize(count);
+    std::memcpy(out.data(), blob.data() + h.off_items + 2 * (4 * static_cast<size_t>(e[0])), 2 * static_cast<size_t>(count));
+    return true;
+}
+
+} // namespace ok

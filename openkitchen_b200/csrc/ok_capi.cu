@@ -3,6 +3,7 @@
 // fallback exists: without a CUDA device every compute entry point returns OK_ERR_NO_DEVICE.
 #include "../../include/openkitchen_b200.h"
 
+#include "ok_beam.hpp"
 #include "ok_kernels.cuh"
 #include "ok_track.hpp"
 
@@ -11,6 +12,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -103,6 +107,10 @@ struct OkEnv
     size_t        arena_bytes{0};
     size_t        max_blob_used{0};
     bool          arena_dirty{true};
+    // beam tables (OK_RAYCAST_BEAM): one blob per track in global memory
+    std::vector<std::shared_ptr<const std::vector<uint8_t>>> beams;
+    uint8_t      *d_beam_arena{nullptr};
+    bool          arena_has_beams{false};
     // agents
     int64_t              n_agents{0};
     int32_t              rays{0};
@@ -122,7 +130,7 @@ struct OkEnv
     // stats
     uint64_t launches{0};
     int32_t  grid{0};
-    size_t   smem{0};
+    size_t   smem{0}, smem_beam{0};
 };
 
 namespace
@@ -156,27 +164,99 @@ void free_agents(OkEnv *e)
     e->n_agents = 0, e->rays = 0, e->n_tiles = 0;
 }
 
+// Beam tables are pure functions of (segments, cell, bins, range) and take ~0.1-1 s of host time per track:
+// one process-wide cache so that envs over the same tracks share them.
+std::shared_ptr<const std::vector<uint8_t>> beam_table_for(const ok::Track &t, const ok::BeamConfig &cfg, std::string &err)
+{
+    static std::mutex                                                          mu;
+    static std::map<std::string, std::shared_ptr<const std::vector<uint8_t>>> cache;
+    uint64_t h = 1469598103934665603ull;
+    auto     mix = [&](const void *ptr, size_t n) {
+        const uint8_t *b = static_cast<const uint8_t *>(ptr);
+        for (size_t i = 0; i < n; ++i)
+            h = (h ^ b[i]) * 1099511628211ull;
+    };
+    mix(t.segments.data(), t.segments.size() * sizeof(float));
+    mix(t.x.data(), t.x.size() * sizeof(float));
+    mix(t.w_left.data(), t.w_left.size() * sizeof(float));
+    mix(t.w_right.data(), t.w_right.size() * sizeof(float));
+    char key[128];
+    std::snprintf(key, sizeof key, "%016llx:%zu:%g:%d:%g", static_cast<unsigned long long>(h), t.segments.size(),
+                  static_cast<double>(cfg.cell), cfg.bins, static_cast<double>(cfg.range));
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        auto                        it = cache.find(key);
+        if (it != cache.end())
+            return it->second;
+    }
+    auto blob = std::make_shared<std::vector<uint8_t>>();
+    if (!ok::build_beam_table(t, cfg, *blob, err))
+        return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() >= 64)
+        cache.clear();
+    cache[key] = blob;
+    return blob;
+}
+
+ok::BeamConfig beam_config(const OkEnv *e)
+{
+    ok::BeamConfig c;
+    c.cell  = e->cfg.beam_cell;
+    c.bins  = e->cfg.beam_bins;
+    c.range = 200.0f; // Agent::kSensorRange; a larger OkConfig::sensor_range stays exact through the grid walk
+    if (const char *env = std::getenv("OK_BEAM_THREADS"))
+        c.threads = std::atoi(env);
+    return c;
+}
+
 int ensure_arena(OkEnv *e)
 {
-    if (!e->arena_dirty)
+    const bool want_beams = e->cfg.raycast_mode == OK_RAYCAST_BEAM;
+    if (!e->arena_dirty && (!want_beams || e->arena_has_beams))
         return OK_SUCCESS;
     if (e->d_arena)
         cudaFree(e->d_arena);
     if (e->d_track_refs)
         cudaFree(e->d_track_refs);
-    e->d_arena = nullptr, e->d_track_refs = nullptr;
+    if (e->d_beam_arena)
+        cudaFree(e->d_beam_arena);
+    e->d_arena = nullptr, e->d_track_refs = nullptr, e->d_beam_arena = nullptr;
     std::vector<ok::TrackRef> refs;
-    size_t                    total = 0;
+    size_t                    total = 0, beam_total = 0;
     e->max_blob_used                = 0;
-    for (auto &t : e->tracks)
+    e->beams.resize(e->tracks.size());
+    for (size_t i = 0; i < e->tracks.size(); ++i)
     {
-        ok::TrackRef r{};
+        const ok::Track &t = e->tracks[i];
+        ok::TrackRef     r{};
         r.offset = total;
         r.bytes  = static_cast<uint32_t>(t.blob.size());
+        if (want_beams)
+        {
+            if (!e->beams[i])
+            {
+                std::string err;
+                e->beams[i] = beam_table_for(t, beam_config(e), err);
+                if (!e->beams[i])
+                    return fail(OK_ERR_INVALID_ARG, "beam table: " + err);
+            }
+            r.has_beam    = 1;
+            r.beam_offset = beam_total;
+            beam_total += (e->beams[i]->size() + 255) / 256 * 256;
+        }
         refs.push_back(r);
         total += (t.blob.size() + 127) / 128 * 128;
         e->max_blob_used = std::max(e->max_blob_used, t.blob.size());
     }
+    if (want_beams)
+    {
+        OK_CUDA(cudaMalloc(&e->d_beam_arena, std::max<size_t>(beam_total, 256)));
+        for (size_t i = 0; i < e->tracks.size(); ++i)
+            OK_CUDA(cudaMemcpy(e->d_beam_arena + refs[i].beam_offset, e->beams[i]->data(), e->beams[i]->size(),
+                               cudaMemcpyHostToDevice));
+    }
+    e->arena_has_beams = want_beams;
     std::vector<uint8_t> host(total, 0);
     for (size_t i = 0; i < e->tracks.size(); ++i)
         std::memcpy(host.data() + refs[i].offset, e->tracks[i].blob.data(), e->tracks[i].blob.size());
@@ -221,6 +301,7 @@ ok::StepParams base_params(OkEnv *e)
     p.start_y   = static_cast<float *>(e->d_buf[OK_BUF_START_Y]);
     p.ray_deg   = e->d_ray_deg;
     p.arena     = e->d_arena;
+    p.beam_arena = e->d_beam_arena;
     p.tracks    = e->d_track_refs;
     p.tiles     = e->d_tiles;
     p.n_tiles   = e->n_tiles;
@@ -260,9 +341,13 @@ int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
     int rc = ensure_arena(e);
     if (rc)
         return rc;
-    p.arena  = e->d_arena;
-    p.tracks = e->d_track_refs;
-    ok::step_kernel<kBlock><<<e->grid, kBlock, e->smem, s>>>(p);
+    p.arena      = e->d_arena;
+    p.beam_arena = e->d_beam_arena;
+    p.tracks     = e->d_track_refs;
+    if (e->cfg.raycast_mode == OK_RAYCAST_BEAM)
+        ok::step_kernel<kBlock, true><<<e->grid, kBlock, e->smem_beam, s>>>(p);
+    else
+        ok::step_kernel<kBlock, false><<<e->grid, kBlock, e->smem, s>>>(p);
     OK_CUDA(cudaGetLastError());
     e->launches++;
     return OK_SUCCESS;
@@ -306,7 +391,7 @@ void ok_config_default(OkConfig *c)
     c->device               = 0;
     c->movement_mode        = OK_MOVE_VELOCITY;
     c->reward_mode          = OK_REWARD_NONE;
-    c->raycast_mode         = OK_RAYCAST_GRID;
+    c->raycast_mode         = OK_RAYCAST_BEAM;
     c->auto_reset           = 0;
     c->auto_reset_stride    = 97;
     c->sensor_range         = 200.0f;
@@ -317,6 +402,8 @@ void ok_config_default(OkConfig *c)
     c->standstill_period    = 200u;
     c->standstill_threshold = 20.0f;
     c->grid_cell            = 8.0f;
+    c->beam_cell            = 8.0f;
+    c->beam_bins            = 64;
 }
 
 int ok_create(const OkConfig *cfg, OkEnv **out)
@@ -333,10 +420,17 @@ int ok_create(const OkConfig *cfg, OkEnv **out)
         return fail(OK_ERR_INVALID_ARG, "movement_mode must be VELOCITY or ACCELERATION");
     if (c.reward_mode < OK_REWARD_NONE || c.reward_mode > OK_REWARD_LANE_CENTER)
         return fail(OK_ERR_INVALID_ARG, "unknown reward_mode");
-    if (c.raycast_mode != OK_RAYCAST_GRID && c.raycast_mode != OK_RAYCAST_BRUTE)
+    if (c.raycast_mode < OK_RAYCAST_GRID || c.raycast_mode > OK_RAYCAST_BEAM)
         return fail(OK_ERR_INVALID_ARG, "unknown raycast_mode");
     if (!(c.grid_cell >= 1.0f && c.grid_cell <= 512.0f))
         return fail(OK_ERR_INVALID_ARG, "grid_cell must be in [1, 512] px");
+    if (c.beam_cell == 0.0f)
+        c.beam_cell = 8.0f;
+    if (c.beam_bins == 0)
+        c.beam_bins = 64;
+    if (!(c.beam_cell >= 1.0f && c.beam_cell <= 64.0f) || c.beam_bins < 8 || c.beam_bins > 1024 ||
+        (c.beam_bins & (c.beam_bins - 1)))
+        return fail(OK_ERR_INVALID_ARG, "beam_cell must be in [1, 64] px and beam_bins a power of two in [8, 1024]");
     auto e = new OkEnv();
     e->cfg = c;
     if (c.device >= 0)
@@ -375,11 +469,13 @@ int ok_update_config(OkEnv *e, const OkConfig *cfg)
         return fail(OK_ERR_INVALID_ARG, "movement_mode must be VELOCITY or ACCELERATION");
     if (cfg->reward_mode < OK_REWARD_NONE || cfg->reward_mode > OK_REWARD_LANE_CENTER)
         return fail(OK_ERR_INVALID_ARG, "unknown reward_mode");
-    if (cfg->raycast_mode != OK_RAYCAST_GRID && cfg->raycast_mode != OK_RAYCAST_BRUTE)
+    if (cfg->raycast_mode < OK_RAYCAST_GRID || cfg->raycast_mode > OK_RAYCAST_BEAM)
         return fail(OK_ERR_INVALID_ARG, "unknown raycast_mode");
     OkConfig c   = *cfg;
     c.device     = e->cfg.device;
     c.grid_cell  = e->cfg.grid_cell;
+    c.beam_cell  = e->cfg.beam_cell;
+    c.beam_bins  = e->cfg.beam_bins;
     e->cfg       = c;
     return OK_SUCCESS;
 }
@@ -404,6 +500,8 @@ void ok_destroy(OkEnv *e)
             cudaFree(e->d_arena);
         if (e->d_track_refs)
             cudaFree(e->d_track_refs);
+        if (e->d_beam_arena)
+            cudaFree(e->d_beam_arena);
         if (e->d_stage)
             cudaFree(e->d_stage);
     }
@@ -514,6 +612,8 @@ int ok_alloc_agents(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, c
         const size_t avail = static_cast<size_t>(e->smem_optin) > blob + 4096 ? e->smem_optin - blob - 4096 : 0;
         const size_t per   = ok::batch_smem_bytes(1, rays);
         int64_t      a     = static_cast<int64_t>(avail / per);
+        while (a > 1 && ok::beam_smem_bytes(static_cast<int>(a), rays, kBlock) > avail)
+            --a; // the beam layout (queue + per-thread scratch) must fit too
         int          cap   = kMaxBatchAgents;
         if (const char *env = std::getenv("OK_BATCH_AGENTS"))
             cap = std::max(1, std::atoi(env));
@@ -524,8 +624,11 @@ int ok_alloc_agents(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, c
             return fail(OK_ERR_CAPACITY, "shared memory cannot hold one agent's rays next to the largest track");
         e->batch_agents = static_cast<int32_t>(a);
         e->smem         = blob + ok::batch_smem_bytes(e->batch_agents, rays);
-        OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<kBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        e->smem_beam    = blob + ok::beam_smem_bytes(e->batch_agents, rays, kBlock);
+        OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<kBlock, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(e->smem)));
+        OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<kBlock, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     static_cast<int>(e->smem_beam)));
     }
 
     // one slab, 256-byte aligned sub-buffers
@@ -903,6 +1006,46 @@ int ok_eval_sincosf(OkEnv *e, const float *h_in, float *h_sin, float *h_cos, int
     if (err != cudaSuccess)
         return fail(OK_ERR_CUDA, cudaGetErrorString(err));
     return OK_SUCCESS;
+}
+
+static int host_beam(OkEnv *e, int32_t id)
+{
+    if (!e || id < 0 || id >= static_cast<int32_t>(e->tracks.size()))
+        return fail(OK_ERR_INVALID_ARG, "bad track id");
+    e->beams.resize(e->tracks.size());
+    if (!e->beams[id])
+    {
+        std::string err;
+        e->beams[id] = beam_table_for(e->tracks[id], beam_config(e), err);
+        if (!e->beams[id])
+            return fail(OK_ERR_INVALID_ARG, "beam table: " + err);
+    }
+    return OK_SUCCESS;
+}
+
+int32_t ok_beam_lookup(OkEnv *e, int32_t id, float x, float y, float angle, uint16_t *h_items, int32_t capacity,
+                       float *d_complete)
+{
+    int rc = host_beam(e, id);
+    if (rc)
+        return rc;
+    std::vector<uint16_t> items;
+    float                 d = 0.0f;
+    if (!ok::beam_lookup(*e->beams[id], x, y, angle, items, d))
+        return -1;
+    if (d_complete)
+        *d_complete = d;
+    if (h_items && capacity > 0)
+        std::memcpy(h_items, items.data(), 2 * std::min<size_t>(items.size(), static_cast<size_t>(capacity)));
+    return static_cast<int32_t>(items.size());
+}
+
+int64_t ok_beam_table_bytes(OkEnv *e, int32_t id)
+{
+    int rc = host_beam(e, id);
+    if (rc)
+        return rc;
+    return static_cast<int64_t>(e->beams[id]->size());
 }
 
 int ok_launch_stats(const OkEnv *e, OkLaunchStats *out)

@@ -22,6 +22,7 @@
 // The path is latency/issue bound, not HBM bound, and is not a contraction: no tensor cores.
 #pragma once
 
+#include "ok_beam.hpp"
 #include "ok_math.cuh"
 #include "ok_track.hpp"
 
@@ -39,9 +40,10 @@ struct Tile
 
 struct TrackRef
 {
-    uint64_t offset; // byte offset of the blob in the arena (128-byte aligned)
-    uint32_t bytes;  // blob_bytes
-    uint32_t pad;
+    uint64_t offset;      // byte offset of the blob in the arena (128-byte aligned)
+    uint32_t bytes;       // blob_bytes
+    uint32_t has_beam;    // the track has a beam table
+    uint64_t beam_offset; // byte offset of its beam blob in the beam arena (ok_beam.hpp)
 };
 
 struct StepParams
@@ -60,6 +62,7 @@ struct StepParams
     // static inputs
     const float   *ray_deg;
     const uint8_t *arena;
+    const uint8_t *beam_arena; // beam tables (global memory), OK_RAYCAST_BEAM
     const TrackRef *tracks;
     const Tile    *tiles;
     int32_t        n_tiles;
@@ -308,7 +311,7 @@ __device__ __forceinline__ uint32_t cell_items(const TrackView &tv, int c)
 
 // returns false when the ray cannot hit anything (result stays best = -1)
 __device__ __forceinline__ bool walk_begin(const TrackView &tv, RayWalk &w, float ox, float oy, float dx, float dy,
-                                           float range)
+                                           float range, float t_start = 0.0f)
 {
     w.ox = ox, w.oy = oy, w.dx = dx, w.dy = dy;
     w.min_t = range;
@@ -321,7 +324,7 @@ __device__ __forceinline__ bool walk_begin(const TrackView &tv, RayWalk &w, floa
     // clip box = the grid without its one-cell ring (every segment lies >= 1 px inside it)
     const float bx0 = tv.gx0 + tv.cell, by0 = tv.gy0 + tv.cell;
     const float bx1 = tv.gx0 + (tv.nx - 1) * tv.cell, by1 = tv.gy0 + (tv.ny - 1) * tv.cell;
-    float       t0 = 0.0f, t1 = range + OK_DDA_SLACK;
+    float       t0 = t_start, t1 = range + OK_DDA_SLACK; // t_start > 0: everything nearer is already decided
     float       inv_dx = 0.0f, inv_dy = 0.0f;
     if (dx != 0.0f)
     {
@@ -474,7 +477,7 @@ struct AgentRec
     float    rx, ry;         // where a reset put the agent (FLAG_RESET)
     int      min_d2_bits;    // running min of the squared hit norms (as int: all values are >= +0)
     uint32_t flags;
-    int32_t  pad;
+    int32_t  row;            // beam-table row of the lidar origin's cell, -1 = not covered (kBeam only)
 };
 static_assert(sizeof(AgentRec) == 48, "AgentRec layout");
 enum : uint32_t
@@ -484,9 +487,159 @@ enum : uint32_t
     kFlagReset = 4u
 };
 
+// ---------------------------------------------------------------------------------------------
+// Beam lists (ok_beam.hpp): the narrow phase reads, for the ray's start cell and direction bin, the
+// precomputed list of segments it can reach, nearest first, and tests them -- no traversal.  The
+// lists of a warp's 32 rays are cut into chunks of 4 candidates and dealt evenly to the 32 lanes
+// (a lane finds the owner of its chunk by a shuffle binary search over the chunk prefix sums), so
+// the heavy tail of the per-ray work does not idle lanes.  Results meet in a 64-bit key per ray in
+// shared memory, (exact t bits) << 32 | (0x7fffffff - segment): atomicMin implements the
+// reference's rule "smallest t, highest index among ties" (CollisionChecker.cu:49-66).
+// ---------------------------------------------------------------------------------------------
+struct BeamView
+{
+    const uint32_t *rows;
+    const uint2    *entries;
+    const uint2    *chunks; // 4 x uint16 segment indices per chunk
+    float           x0, y0, inv_h, bin_scale, rb;
+    int32_t         nx, ny, nb;
+    bool            valid;
+};
+
+__device__ __forceinline__ BeamView make_beam_view(const uint8_t *blob)
+{
+    BeamView          v;
+    const BeamHeader *h = reinterpret_cast<const BeamHeader *>(blob);
+    v.rows              = reinterpret_cast<const uint32_t *>(blob + h->off_rows);
+    v.entries           = reinterpret_cast<const uint2 *>(blob + h->off_entries);
+    v.chunks            = reinterpret_cast<const uint2 *>(blob + h->off_items);
+    v.x0 = h->x0, v.y0 = h->y0, v.inv_h = h->inv_h, v.bin_scale = h->bin_scale, v.rb = h->rb;
+    v.nx = h->nx, v.ny = h->ny, v.nb = h->nb;
+    v.valid = true;
+    return v;
+}
+
+// row of the beam cell that contains (ox, oy), -1 = not covered (same arithmetic as ok::beam_lookup)
+__device__ __forceinline__ int32_t beam_row(const BeamView &bv, float ox, float oy)
+{
+    if (!bv.valid)
+        return -1;
+    const float fx = fmul(fsub(ox, bv.x0), bv.inv_h), fy = fmul(fsub(oy, bv.y0), bv.inv_h);
+    if (!(fx >= 0.0f && fy >= 0.0f && fx < static_cast<float>(bv.nx) && fy < static_cast<float>(bv.ny)))
+        return -1;
+    return static_cast<int32_t>(__ldg(bv.rows + static_cast<int>(fy) * bv.nx + static_cast<int>(fx)));
+}
+
+__device__ __forceinline__ unsigned long long beam_key(float t, int idx)
+{ // t >= 0 (-0.0 orders as +0.0: the reference compares values)
+    const uint32_t tb = (t == 0.0f) ? 0u : __float_as_uint(t);
+    return (static_cast<unsigned long long>(tb) << 32) | static_cast<uint32_t>(0x7fffffff - idx);
+}
+
+// a candidate that survived the screens and sits comfortably inside the segment (s in [0,1] and t > 0 hold
+// without a division): only the order of its exact t matters
+__device__ __forceinline__ void beam_flush(const float4 *segs, int idx, float ox, float oy, float dx, float dy,
+                                           unsigned long long *key)
+{
+    atomicMin(key, beam_key(exact_t(segs[idx], ox, oy, dx, dy), idx));
+}
+
+// One candidate.  (tq_b, idx_b) is the lane's best candidate of the current chunk by approximate quotient;
+// every candidate is either strictly beaten by another candidate (error bounds as in test_segment) or
+// reaches the ray's key with its exact t.
+__device__ __forceinline__ void beam_test(const float4 *segs, const int idx, const float ox, const float oy, const float dx,
+                                          const float dy, const float m, float &tq_b, int &idx_b,
+                                          unsigned long long *key)
+{
+    const float4   sg    = segs[idx];
+    const float    ex    = fsub(sg.x, ox);
+    const float    ey    = fsub(sg.y, oy);
+    const float    denom = fsub(fmul(dx, sg.w), fmul(dy, sg.z));
+    const float    sn    = fsub(fmul(ex, dy), fmul(ey, dx));
+    const uint32_t db    = __float_as_uint(denom);
+    const uint32_t adb   = db & 0x7fffffffu;
+    const uint32_t sgn   = db & 0x80000000u;
+    const float    ad    = __uint_as_float(adb);
+    const float    b     = __uint_as_float(__float_as_uint(sn) ^ sgn);
+    if ((adb < 0x322BCC77u) | (b > ad) | (b < -0x1p-22f))
+        return;
+    const float tn = fsub(fmul(ex, sg.w), fmul(ey, sg.z));
+    const float a  = __uint_as_float(__float_as_uint(tn) ^ sgn);
+    if (a < -0x1p-22f)
+        return;
+    const float lim = fmul(ad, m);
+    if ((lim >= 0x1p-100f) & (a > fmul(lim, 1.000003814697265625f))) // RN(t) > m: cannot win
+        return;
+    if ((b >= 0.0f) & (adb < 0x5d800000u /* 2^60 */) & (a >= 0x1p-60f))
+    {
+        const float tq = __fdividef(a, ad);
+        if (tq > fmul(tq_b, 1.000003814697265625f))
+            return; // strictly beaten by the chunk's best
+        if (!(tq < fmul(tq_b, 0.999996185302734375f)) && idx_b >= 0)
+            beam_flush(segs, idx_b, ox, oy, dx, dy, key); // near tie: both go to the key with their exact t
+        tq_b  = tq;
+        idx_b = idx;
+        return;
+    }
+    // literal predicate of the reference (CollisionChecker.cu:25-33)
+    const float t    = __fdiv_rn(tn, denom);
+    bool        s_ok = (b >= 0.0f) & (adb < 0x7f800000u);
+    if (!s_ok)
+    {
+        const float s2 = __fdiv_rn(sn, denom);
+        s_ok           = (s2 >= 0.0f) && (s2 <= 1.0f);
+    }
+    if (s_ok && (t >= 0.0f))
+        atomicMin(key, beam_key(t, idx));
+}
+
+// hit point, unpack (CollisionChecker.cu:68-69,152-165) and the per-ray outputs of ray `gi`, whose nearest
+// segment is `seg` (-1 = none); returns the squared norm of the relative hit
+__device__ __forceinline__ float finish_ray(const StepParams &p, const TrackView &tv, const AgentRec &rec,
+                                            const int64_t gi, const float dx, const float dy, const int seg)
+{
+    float2 hit;
+    if (!(rec.flags & kFlagCrashed))
+    {
+        // min_t of CollisionChecker.cu:49-66: the winner's t by the reference's expression
+        const float t = seg >= 0 ? exact_t(tv.seg[seg], rec.ox, rec.oy, dx, dy) : p.sensor_range;
+        p.hit_seg[gi] = seg;
+        p.hit_t[gi]   = t;
+        hit.x         = fadd(rec.ox, fmul(t, dx));
+        hit.y         = fadd(rec.oy, fmul(t, dy));
+        reinterpret_cast<float2 *>(p.hit_abs)[gi] = hit;
+    }
+    else
+        hit = reinterpret_cast<const float2 *>(p.hit_abs)[gi]; // stale hit of a crashed agent
+    const float xt = fsub(hit.x, rec.ox), yt = fsub(hit.y, rec.oy);
+    float2      rel;
+    rel.x          = fsub(fmul(xt, rec.rc), fmul(yt, rec.rs));
+    rel.y          = fadd(fmul(xt, rec.rs), fmul(yt, rec.rc));
+    const float sq = fadd(fmul(rel.x, rel.x), fmul(rel.y, rel.y));
+    reinterpret_cast<float2 *>(p.hit_rel)[gi] = rel;
+    const float ob = __fdiv_rn(__fsqrt_rn(sq), p.sensor_range);
+    p.obs[gi]      = ob;
+    if (p.host_obs)
+        p.host_obs[gi] = ob;
+    return sq;
+}
+
 __host__ __device__ inline size_t batch_smem_bytes(int agents, int rays)
 { // AgentRec + per ray float2 direction
     return static_cast<size_t>(agents) * (sizeof(AgentRec) + 8u * static_cast<size_t>(rays));
+}
+// beam mode: AgentRec + the queue of rays left to the grid walk (uint16 per ray) + per-thread ray / key scratch
+__host__ __device__ inline size_t beam_queue_offset(int agents)
+{
+    return (static_cast<size_t>(agents) * sizeof(AgentRec) + 15u) / 16u * 16u;
+}
+__host__ __device__ inline size_t beam_scratch_offset(int agents, int rays)
+{
+    return beam_queue_offset(agents) + (static_cast<size_t>(agents) * static_cast<size_t>(rays) * 2u + 15u) / 16u * 16u;
+}
+__host__ __device__ inline size_t beam_smem_bytes(int agents, int rays, int block)
+{
+    return beam_scratch_offset(agents, rays) + static_cast<size_t>(block) * 24u;
 }
 
 #ifndef OK_UNITS
@@ -494,12 +647,12 @@ __host__ __device__ inline size_t batch_smem_bytes(int agents, int rays)
 #endif
 constexpr int kUnitsPerRefill = OK_UNITS; // units of work a lane does between two looks at the pool
 
-template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(const StepParams p)
+template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) step_kernel(const StepParams p)
 {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint16_t                      s_order[1024]; // pool order of the rays (p.ray_order)
     __shared__ __align__(8) uint64_t         bar;
-    __shared__ int                           s_tile, s_pool;
+    __shared__ int                           s_tile, s_pool, s_fb_n, s_fb_pool;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = kBlock / 32;
@@ -507,7 +660,13 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
 
     uint8_t  *blob    = smem;
     AgentRec *recs    = reinterpret_cast<AgentRec *>(smem + p.smem_blob_bytes);
-    float2   *dirs    = reinterpret_cast<float2 *>(recs + p.batch_agents);
+    float2   *dirs    = reinterpret_cast<float2 *>(recs + p.batch_agents); // !kBeam
+    // kBeam: rays left to the grid walk, then per-thread ray parameters and result keys
+    uint8_t  *bscr    = smem + p.smem_blob_bytes;
+    uint16_t *fb_q    = reinterpret_cast<uint16_t *>(bscr + beam_queue_offset(p.batch_agents));
+    float4   *w_ray   = reinterpret_cast<float4 *>(bscr + beam_scratch_offset(p.batch_agents, p.rays)) + (threadIdx.x & ~31);
+    unsigned long long *w_key =
+        reinterpret_cast<unsigned long long *>(bscr + beam_scratch_offset(p.batch_agents, p.rays) + 16u * kBlock) + (threadIdx.x & ~31);
 
     if (tid == 0)
         mbar_init(&bar, 1);
@@ -543,6 +702,14 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
             staged = tl.track;
         }
         const TrackView tv       = make_view(blob);
+        BeamView        bv;
+        bv.valid = false;
+        if (kBeam)
+        {
+            const TrackRef tr = p.tracks[tl.track];
+            if (tr.has_beam)
+                bv = make_beam_view(p.beam_arena + tr.beam_offset);
+        }
         const int       count    = tl.count;
         const int       n_rays   = count * R;
         const float     inv_cnt  = 1.0f / static_cast<float>(count);
@@ -661,12 +828,19 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
             rec.rc = rc, rec.rs = rs, rec.rot = rot, rec.x = x, rec.y = y, rec.rx = rx, rec.ry = ry;
             rec.min_d2_bits = __float_as_int(fmul(p.sensor_range, p.sensor_range));
             rec.flags       = flags | (crashed ? kFlagCrashed : 0u) | (timed_out ? kFlagTimedOut : 0u);
-            rec.pad         = 0;
+            rec.row         = kBeam ? beam_row(bv, rec.ox, rec.oy) : -1;
             recs[tid]       = rec;
         }
         if (tid == 0)
-            s_pool = 0;
+        {
+            s_pool    = 0;
+            s_fb_n    = 0;
+            s_fb_pool = 0;
+        }
         __syncthreads();
+        const int64_t ray_base = tl.begin * R; // global index of the batch's first ray
+        if (!kBeam)
+        {
 
         // =====================================================================================
         // phase 1b -- one thread per ray: direction (cosf/sinf of CollisionChecker.cu:47-48)
@@ -687,7 +861,6 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
         // the long rays of the heavy tail do not hold 31 lanes hostage.  The pool is ordered
         // ray-major with the fan's centre rays first (p.ray_order): those are the long ones.
         // =====================================================================================
-        const int64_t ray_base = tl.begin * R; // global index of the batch's first ray
         if (p.raycast_mode == 0)
         {
             // No warp-level primitive in this loop on purpose: every lane fetches and retires on its own
@@ -806,6 +979,229 @@ template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) step_kernel(c
             }
             else if (has && sq == sq)
                 atomicMin(&recs[al].min_d2_bits, __float_as_int(sq));
+        }
+        } // !kBeam
+        else
+        {
+            // =================================================================================
+            // beam phase A -- warps pull groups of 32 consecutive rays (lane = ray): direction, table lookup,
+            // balanced test of the listed candidates, outputs.  Rays the table cannot decide (cell not
+            // covered, hit beyond the list's completeness distance) are queued for phase B.
+            // =================================================================================
+            const int                n_groups = (n_rays + 31) >> 5;
+            const unsigned long long key_none =
+                (static_cast<unsigned long long>(__float_as_uint(p.sensor_range)) << 32) | 0x80000000ull;
+            const float inf = __int_as_float(0x7f800000);
+            // ray `lane` of group g: agent, angle and (prefetched one group ahead) its table entry
+            auto locate = [&](int g, int &q, int &al, float &ang, bool &active) {
+                q      = (g << 5) + lane;
+                active = false;
+                al     = 0;
+                ang    = 0.0f;
+                if (g < n_groups && q < n_rays)
+                {
+                    al                  = __float2int_rz((static_cast<float>(q) + 0.5f) * inv_R);
+                    const AgentRec &rec = recs[al];
+                    ang                 = fmul(OK_DEG2RAD, fadd(rec.rot, __ldg(p.ray_deg + (q - al * R))));
+                    active              = !(rec.flags & kFlagCrashed);
+                }
+            };
+            auto fetch = [&](int al, float ang, bool active, uint2 &ent) -> bool {
+                ent = make_uint2(0u, 0u);
+                if (!active)
+                    return false;
+                const int row = recs[al].row;
+                if (row < 0 || !(fabsf(ang) < kBeamMaxAngle))
+                    return false;
+                const int bin = __float2int_rd(fmul(ang, bv.bin_scale)) & (bv.nb - 1);
+                ent           = __ldg(bv.entries + static_cast<size_t>(row) * bv.nb + bin);
+                return true;
+            };
+            int g = 0;
+            if (lane == 0)
+                g = atomicAdd(&s_pool, 1);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            uint2 ent;
+            bool  cov;
+            {
+                int   q, al;
+                float ang;
+                bool  active;
+                locate(g, q, al, ang, active);
+                cov = fetch(al, ang, active, ent);
+            }
+            while (g < n_groups)
+            {
+                int g_next = 0;
+                if (lane == 0)
+                    g_next = atomicAdd(&s_pool, 1);
+                g_next = __shfl_sync(0xffffffffu, g_next, 0);
+                uint2 ent_next;
+                bool  cov_next;
+                {
+                    int   q, al;
+                    float ang;
+                    bool  active;
+                    locate(g_next, q, al, ang, active);
+                    cov_next = fetch(al, ang, active, ent_next);
+                }
+
+                int   q, al;
+                float ang;
+                bool  active;
+                locate(g, q, al, ang, active);
+                const bool has = q < n_rays;
+                float      dx = 0.0f, dy = 0.0f;
+                if (active)
+                    sincosf(ang, dy, dx); // cosf/sinf of CollisionChecker.cu:47-48
+                {
+                    const AgentRec &rec = recs[al];
+                    w_ray[lane]         = make_float4(rec.ox, rec.oy, dx, dy);
+                    w_key[lane]         = key_none;
+                }
+                const uint32_t cnt = cov ? (ent.y & 0xffffu) : 0u;
+                const uint32_t nch = (cnt + 3u) >> 2;
+                uint32_t       inc = nch;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o)
+                        inc += v;
+                }
+                const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+                __syncwarp();
+                for (uint32_t base = 0; base < total; base += 32)
+                {
+                    const uint32_t j     = base + lane;
+                    int            owner = 0;
+#pragma unroll
+                    for (int s2 = 16; s2 > 0; s2 >>= 1)
+                    {
+                        const uint32_t v = __shfl_sync(0xffffffffu, inc, owner + s2 - 1);
+                        if (v <= j)
+                            owner += s2;
+                    }
+                    const uint32_t o_first = __shfl_sync(0xffffffffu, inc - nch, owner);
+                    const uint32_t o_chunk = __shfl_sync(0xffffffffu, ent.x, owner);
+                    if (j < total)
+                    {
+                        const uint2  it  = __ldg(bv.chunks + o_chunk + (j - o_first));
+                        const float4 ray = w_ray[owner];
+                        const float  m   = __uint_as_float(reinterpret_cast<const uint32_t *>(w_key + owner)[1]);
+                        float        tq_b  = inf;
+                        int          idx_b = -1;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                        {
+                            const int idx = static_cast<int>(((u < 2 ? it.x : it.y) >> (16 * (u & 1))) & 0xffffu);
+                            if (idx != 0xffff)
+                                beam_test(tv.seg, idx, ray.x, ray.y, ray.z, ray.w, m, tq_b, idx_b, w_key + owner);
+                        }
+                        if (idx_b >= 0)
+                            beam_flush(tv.seg, idx_b, ray.x, ray.y, ray.z, ray.w, w_key + owner);
+                    }
+                }
+                __syncwarp();
+                float sq = inf;
+                if (has)
+                {
+                    const AgentRec          &rec  = recs[al];
+                    const int64_t            gi   = ray_base + q;
+                    const unsigned long long key  = w_key[lane];
+                    const int                best = static_cast<int>(0x7fffffffu - static_cast<uint32_t>(key));
+                    const float              min_t = __uint_as_float(static_cast<uint32_t>(key >> 32));
+                    const uint32_t           dq    = ent.y >> 16;
+                    const float              d_eff = dq == 0xffffu ? bv.rb : static_cast<float>(dq) * 0.00390625f;
+                    if (!active || (cov && min_t <= d_eff - kBeamSlack))
+                        sq = finish_ray(p, tv, rec, gi, dx, dy, best);
+                    else
+                    { // phase B continues from the list's completeness distance with the best listed hit
+                        p.hit_seg[gi]                   = best;
+                        p.hit_t[gi]                     = cov ? fmaxf(d_eff - 1.0f, 0.0f) : 0.0f;
+                        fb_q[atomicAdd(&s_fb_n, 1)] = static_cast<uint16_t>(q);
+                    }
+                }
+                // min_dist2 of CollisionChecker.cu:150,162-165: `if (sq < min) min = sq` skips NaN, and so
+                // does a signed-int min over the bit patterns of values >= +0 (a NaN made here is 0x7fffffff)
+                if ((R & 31) == 0)
+                {
+                    float m = (sq == sq) ? sq : inf;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+                        m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                    if (has && lane == 0)
+                        atomicMin(&recs[al].min_d2_bits, __float_as_int(m));
+                }
+                else if (has && sq == sq)
+                    atomicMin(&recs[al].min_d2_bits, __float_as_int(sq));
+                g   = g_next;
+                ent = ent_next;
+                cov = cov_next;
+            }
+            __syncthreads();
+            // =================================================================================
+            // beam phase B -- the queued rays: uniform-grid walk from where the list stopped, each lane
+            // pulling rays on its own (no warp-level primitive in this divergent loop)
+            // =================================================================================
+            {
+                const int n_fb = s_fb_n;
+                RayWalk   w;
+                int       mine = -1, mine_al = 0;
+                bool      more = n_fb > 0;
+                for (;;)
+                {
+                    if (mine < 0)
+                    {
+                        if (!more)
+                            break;
+                        const int qi = atomicAdd(&s_fb_pool, 1);
+                        if (qi >= n_fb)
+                            more = false;
+                        else
+                        {
+                            const int       q   = fb_q[qi];
+                            const int       al  = __float2int_rz((static_cast<float>(q) + 0.5f) * inv_R);
+                            const AgentRec &rec = recs[al];
+                            const int64_t   gi  = ray_base + q;
+                            float           s, c;
+                            sincosf(fmul(OK_DEG2RAD, fadd(rec.rot, __ldg(p.ray_deg + (q - al * R)))), s, c);
+                            const int   inc_best = p.hit_seg[gi];
+                            const float t_start  = p.hit_t[gi];
+                            if (walk_begin(tv, w, rec.ox, rec.oy, c, s, p.sensor_range, t_start))
+                            {
+                                if (inc_best >= 0)
+                                {
+                                    w.best  = inc_best;
+                                    w.min_t = exact_t(tv.seg[inc_best], rec.ox, rec.oy, c, s);
+                                }
+                                mine    = q;
+                                mine_al = al;
+                            }
+                            else
+                            {
+                                const float sq = finish_ray(p, tv, rec, gi, c, s, inc_best);
+                                if (sq == sq)
+                                    atomicMin(&recs[al].min_d2_bits, __float_as_int(sq));
+                            }
+                        }
+                    }
+#pragma unroll 1
+                    for (int u = 0; u < kUnitsPerRefill; ++u)
+                    {
+                        if (mine >= 0)
+                        {
+                            if (!walk_unit(tv, w))
+                            {
+                                const float sq = finish_ray(p, tv, recs[mine_al], ray_base + mine, w.dx, w.dy, w.best);
+                                if (sq == sq)
+                                    atomicMin(&recs[mine_al].min_d2_bits, __float_as_int(sq));
+                                mine = -1;
+                            }
+                        }
+                    }
+                }
+            }
         }
         __syncthreads();
 

@@ -92,7 +92,7 @@ class Env:
     def update_config(self, **cfg):
         """change per-tick constants of the live env (movement_mode, reward_mode, auto_reset, ...)"""
         for k, v in cfg.items():
-            if not hasattr(self.cfg, k) or k in ("device", "grid_cell"):
+            if not hasattr(self.cfg, k) or k in ("device", "grid_cell", "beam_cell", "beam_bins"):
                 raise AttributeError(f"cannot update {k}")
             setattr(self.cfg, k, v)
         check(self.lib.ok_update_config(self.h, C.byref(self.cfg)))
@@ -130,6 +130,21 @@ class Env:
         if name == "segments":
             return out.reshape(-1, 4)
         return out
+
+    def beam_lookup(self, t: int, x: float, y: float, angle_rad: float):
+        """OK_RAYCAST_BEAM's candidate list for a ray (host side): (segment indices nearest first, completeness
+        distance), or None when the start cell is not covered by the table."""
+        d = C.c_float(0.0)
+        n = self.lib.ok_beam_lookup(self.h, t, x, y, angle_rad, None, 0, C.byref(d))
+        if n == -1:
+            return None
+        check(n)
+        items = np.empty(max(n, 1), dtype=np.uint16)
+        check(self.lib.ok_beam_lookup(self.h, t, x, y, angle_rad, _vp(items), n, C.byref(d)))
+        return items[:n], float(d.value)
+
+    def beam_table_bytes(self, t: int) -> int:
+        return check(self.lib.ok_beam_table_bytes(self.h, t))
 
     # ---- agents -------------------------------------------------------------------------
     def alloc_agents(self, n: int, ray_deg, track_id=None):

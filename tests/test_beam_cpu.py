@@ -1,0 +1,79 @@
+"""CPU: the beam table of OK_RAYCAST_BEAM (openkitchen_b200/csrc/ok_beam.cpp) is a conservative candidate list.
+
+For random rays that start inside the lane, the segment the reference's loop selects (CollisionChecker.cu:49-66,
+restated here in numpy float64) must be in the ray's list whenever its hit parameter lies within the list's
+completeness distance -- that is the only property the kernel relies on; everything else goes to the grid walk."""
+import numpy as np
+import pytest
+
+import openkitchen_b200 as ok
+
+
+def _first_hits(seg, ox, oy, ang):
+    """vectorised over segments: (t, index) of CollisionChecker.cu:49-66 for one ray (float64)"""
+    dx, dy = np.cos(ang), np.sin(ang)
+    sx, sy = seg[:, 2] - seg[:, 0], seg[:, 3] - seg[:, 1]
+    den = dx * sy - dy * sx
+    ok_den = np.abs(den) >= 1e-8
+    den = np.where(ok_den, den, 1.0)
+    ex, ey = seg[:, 0] - ox, seg[:, 1] - oy
+    t = (ex * sy - ey * sx) / den
+    s = (ex * dy - ey * dx) / den
+    valid = ok_den & (t >= 0) & (t <= 200.0) & (s >= 0) & (s <= 1)
+    if not valid.any():
+        return 200.0, -1
+    tt = np.where(valid, t, np.inf)
+    tmin = tt.min()
+    return float(tmin), int(np.flatnonzero(tt == tmin).max())
+
+
+@pytest.mark.parametrize("name,cell,bins", [("Monza", 8.0, 64), ("Spa", 8.0, 64), ("Zandvoort", 6.0, 32)])
+def test_beam_lists_contain_the_reference_winner(name, cell, bins):
+    env = ok.Env(device=-1, beam_cell=cell, beam_bins=bins)
+    t = env.add_named_track(name)
+    seg = env.track_array(t, "segments").astype(np.float64)
+    x, y, head = env.track_array(t, "x"), env.track_array(t, "y"), env.track_array(t, "heading")
+    li, ri = env.track_array(t, "li"), env.track_array(t, "ri")
+    rng = np.random.default_rng(7)
+    n_rays, decided, covered = 1500, 0, 0
+    lengths = []
+    for _ in range(n_rays):
+        i = int(rng.integers(0, len(x)))
+        a = rng.uniform(0.05, 0.95)
+        ox = np.float32(a * li[i, 0] + (1 - a) * ri[i, 0])
+        oy = np.float32(a * li[i, 1] + (1 - a) * ri[i, 1])
+        ang = np.float32(np.deg2rad(head[i] + rng.uniform(-180, 180)))
+        got = env.beam_lookup(t, float(ox), float(oy), float(ang))
+        if got is None:
+            continue
+        covered += 1
+        items, d = got
+        lengths.append(len(items))
+        tmin, best = _first_hits(seg, float(ox), float(oy), float(ang))
+        if tmin <= d - 0.25:
+            decided += 1
+            if best >= 0:
+                assert best in items, f"{name}: winner {best} (t={tmin:.3f}) missing from the list (d={d:.3f})"
+        # the list is sorted by a lower bound of the distance and never names a segment twice
+        assert len(set(items.tolist())) == len(items)
+    assert covered > 0.99 * n_rays, "points inside the lane must be covered by the table"
+    assert decided > 0.97 * covered, "the lists should decide almost every ray"
+    assert np.mean(lengths) < 60
+    assert env.beam_table_bytes(t) > 0
+
+
+def test_beam_lookup_outside_the_lane_is_uncovered():
+    env = ok.Env(device=-1)
+    t = env.add_named_track("Monza")
+    assert env.beam_lookup(t, 5.0, 5.0, 0.3) is None          # far from the track
+    assert env.beam_lookup(t, float("nan"), 5.0, 0.3) is None
+    x, y = env.track_array(t, "x"), env.track_array(t, "y")
+    assert env.beam_lookup(t, float(x[10]), float(y[10]), 1000.0) is None  # |angle| beyond the table's range
+    assert env.beam_lookup(t, float(x[10]), float(y[10]), -3.0) is not None
+
+
+def test_beam_config_is_validated():
+    with pytest.raises(ok.OkError):
+        ok.Env(device=-1, beam_bins=48)
+    with pytest.raises(ok.OkError):
+        ok.Env(device=-1, beam_cell=0.5)

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "traces.npz"))
 
 
-@pytest.mark.parametrize("raycast", [ok.RAYCAST_GRID, ok.RAYCAST_BRUTE])
+@pytest.mark.parametrize("raycast", [ok.RAYCAST_BEAM, ok.RAYCAST_GRID, ok.RAYCAST_BRUTE])
 @pytest.mark.parametrize("name", list(mg.SCENARIOS))
 def test_cuda_path_matches_golden(name, raycast):
     tracks, n, rays, cfg, ticks, cps = mg.SCENARIOS[name]

@@ -1,5 +1,5 @@
 """GPU: size-independent properties at BASELINE's full size (65,536 agents x 32 rays x 23 tracks), where the
-CPU oracle is too slow to shadow every agent: grid == brute force on every ray, obs/hit consistency, a
+CPU oracle is too slow to shadow every agent: beam lists == grid == brute force on every ray, obs/hit consistency, a
 sampled slice against the oracle, determinism."""
 import numpy as np
 import pytest
@@ -23,12 +23,14 @@ def _run(raycast, ticks):
 
 def test_full_size_grid_equals_brute_force_and_is_deterministic():
     ticks = 25
-    a = _run(ok.RAYCAST_GRID, ticks)
+    a = _run(ok.RAYCAST_BEAM, ticks)
     b = _run(ok.RAYCAST_BRUTE, ticks)
-    c = _run(ok.RAYCAST_GRID, ticks)
+    c = _run(ok.RAYCAST_BEAM, ticks)
+    d = _run(ok.RAYCAST_GRID, ticks)
     for name in ok.BUFFERS:
-        x, y, z = a.read(name), b.read(name), c.read(name)
-        assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), f"grid vs brute force: {name}"
+        x, y, z, w = a.read(name), b.read(name), c.read(name), d.read(name)
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), f"beam lists vs brute force: {name}"
+        assert np.array_equal(w.view(np.uint8), y.view(np.uint8)), f"grid vs brute force: {name}"
         assert np.array_equal(x.view(np.uint8), z.view(np.uint8)), f"run-to-run: {name}"
     # invariants of the outputs
     obs, t, seg, rel = a.read("obs"), a.read("hit_t"), a.read("hit_seg"), a.read("hit_rel")
@@ -43,7 +45,7 @@ def test_full_size_grid_equals_brute_force_and_is_deterministic():
 def test_full_size_sampled_slice_matches_oracle():
     """agents are independent, so a slice of the big batch must evolve exactly like the same agents alone"""
     ticks = 40
-    env = _run(ok.RAYCAST_GRID, ticks)
+    env = _run(ok.RAYCAST_BEAM, ticks)
     names = ok.track_names()
     sel = np.arange(0, N, 997)[:64]
     tid_all = (np.arange(N, dtype=np.int64) * 23 // N).astype(np.int32)
