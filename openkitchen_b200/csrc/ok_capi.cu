@@ -451,11 +451,11 @@ int ok_create(const OkConfig *cfg, OkEnv **out)
         e->has_device = true;
         e->num_sms    = sms;
         e->smem_optin = optin;
-        e->max_blob   = optin > 2048 ? static_cast<size_t>(optin) - 1024 : 0;
+        e->max_blob   = optin > 65536 ? static_cast<size_t>(optin) - 40960 : 0; // room for the batch scratch
     }
     else
     {
-        e->max_blob = 227 * 1024 - 1024; // host-only env: tracks can be built and inspected, nothing else
+        e->max_blob = 227 * 1024 - 40960; // host-only env: tracks can be built and inspected, nothing else
     }
     *out = e;
     return OK_SUCCESS;
@@ -612,8 +612,8 @@ int ok_alloc_agents(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, c
         const size_t avail = static_cast<size_t>(e->smem_optin) > blob + 4096 ? e->smem_optin - blob - 4096 : 0;
         const size_t per   = ok::batch_smem_bytes(1, rays);
         int64_t      a     = static_cast<int64_t>(avail / per);
-        while (a > 1 && ok::beam_smem_bytes(static_cast<int>(a), rays, kBlock) > avail)
-            --a; // the beam layout (queue + per-thread scratch) must fit too
+        if (avail < 32768)
+            a = 0; // the beam kernel keeps 24 KB of per-thread scratch in static shared memory
         int          cap   = kMaxBatchAgents;
         if (const char *env = std::getenv("OK_BATCH_AGENTS"))
             cap = std::max(1, std::atoi(env));
@@ -624,7 +624,7 @@ int ok_alloc_agents(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, c
             return fail(OK_ERR_CAPACITY, "shared memory cannot hold one agent's rays next to the largest track");
         e->batch_agents = static_cast<int32_t>(a);
         e->smem         = blob + ok::batch_smem_bytes(e->batch_agents, rays);
-        e->smem_beam    = blob + ok::beam_smem_bytes(e->batch_agents, rays, kBlock);
+        e->smem_beam    = blob + ok::beam_smem_bytes(e->batch_agents);
         OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<kBlock, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(e->smem)));
         OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<kBlock, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -97,6 +97,7 @@ struct TrackView
     const float2   *pts;
     const float    *widths;
     const float    *headings;
+    const float    *safe; // windowed nearest-point search, ok_track.hpp kNearestWindow
     int32_t         n_pts, n_seg, nx, ny;
     float           gx0, gy0, cell, inv_cell;
 };
@@ -112,6 +113,7 @@ __device__ __forceinline__ TrackView make_view(const uint8_t *blob)
     v.pts      = reinterpret_cast<const float2 *>(blob + h->off_points);
     v.widths   = reinterpret_cast<const float *>(blob + h->off_widths);
     v.headings = reinterpret_cast<const float *>(blob + h->off_headings);
+    v.safe     = reinterpret_cast<const float *>(blob + h->off_safe);
     v.n_pts = h->n_points, v.n_seg = h->n_segments, v.nx = h->grid_nx, v.ny = h->grid_ny;
     v.gx0 = h->grid_x0, v.gy0 = h->grid_y0, v.cell = h->cell, v.inv_cell = h->inv_cell;
     return v;
@@ -466,6 +468,37 @@ __device__ __forceinline__ int nearest_index(const TrackView &tv, float qx, floa
     return bi;
 }
 
+// The same search for a full warp with a hint (the agent's previous nearest index): the 32 points around the
+// hint first, the rest only if the triangle inequality cannot rule them out (ok_track.hpp, kNearestWindow).
+// Every outside point is then STRICTLY farther than the window's best, so the window's lexicographic
+// (distance, index) minimum is the reference's result; otherwise the full search above runs.
+__device__ __forceinline__ int nearest_index_hint(const TrackView &tv, float qx, float qy, int hint, int lane, float &d2_out)
+{
+    const int n = tv.n_pts;
+    if (n > kNearestWindow)
+    {
+        const int h = min(max(hint, 0), n - 1);
+        int       i = h - kNearestWindow / 2 + lane;
+        i += (i < 0) ? n : 0;
+        i -= (i >= n) ? n : 0;
+        const float2 pt  = tv.pts[i];
+        const float  ddx = fsub(qx, pt.x), ddy = fsub(qy, pt.y);
+        const float  d   = fadd(fmul(ddx, ddx), fmul(ddy, ddy));
+        const bool   ok  = d < FLT_MAX; // `d < best` of the reference never takes NaN / inf
+        const uint32_t key  = ok ? __float_as_uint(d) : __float_as_uint(FLT_MAX);
+        const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
+        const int      imin = __reduce_min_sync(0xffffffffu, (key == kmin) ? (ok ? i : 0) : 0x7fffffff);
+        const float    dh   = __shfl_sync(0xffffffffu, d, kNearestWindow / 2); // the hint itself
+        const float    rb = __fsqrt_rn(__uint_as_float(kmin)), rh = __fsqrt_rn(dh);
+        if (fsub(fsub(tv.safe[h], rh), rb) > fadd(fmul(1e-3f, fadd(rh, rb)), 1e-3f))
+        {
+            d2_out = __uint_as_float(kmin);
+            return imin;
+        }
+    }
+    return nearest_index(tv, qx, qy, lane, 32, d2_out);
+}
+
 // ---------------------------------------------------------------------------------------------
 // the tick
 // ---------------------------------------------------------------------------------------------
@@ -544,53 +577,49 @@ __device__ __forceinline__ void beam_flush(const float4 *segs, int idx, float ox
     atomicMin(key, beam_key(exact_t(segs[idx], ox, oy, dx, dy), idx));
 }
 
-// One candidate.  (tq_b, idx_b) is the lane's best candidate of the current chunk by approximate quotient;
-// every candidate is either strictly beaten by another candidate (error bounds as in test_segment) or
-// reaches the ray's key with its exact t.
-__device__ __forceinline__ void beam_test(const float4 *segs, const int idx, const float ox, const float oy, const float dx,
-                                          const float dy, const float m, float &tq_b, int &idx_b,
-                                          unsigned long long *key)
+// One candidate, written without branches on the common paths (a warp's lanes hold unrelated rays, so every
+// branch here would be taken by a few lanes while the others wait).  (tq_b, idx_b) is the lane's best
+// candidate of the current chunk by approximate quotient; every candidate is either strictly beaten by
+// another candidate (error bounds as in test_segment) or reaches the ray's key with its exact t.
+__device__ __forceinline__ void beam_test(const float4 *segs, const int idx, const bool live, const float ox,
+                                          const float oy, const float dx, const float dy, const float m, float &tq_b,
+                                          int &idx_b, unsigned long long *key)
 {
     const float4   sg    = segs[idx];
     const float    ex    = fsub(sg.x, ox);
     const float    ey    = fsub(sg.y, oy);
     const float    denom = fsub(fmul(dx, sg.w), fmul(dy, sg.z));
     const float    sn    = fsub(fmul(ex, dy), fmul(ey, dx));
+    const float    tn    = fsub(fmul(ex, sg.w), fmul(ey, sg.z));
     const uint32_t db    = __float_as_uint(denom);
     const uint32_t adb   = db & 0x7fffffffu;
     const uint32_t sgn   = db & 0x80000000u;
     const float    ad    = __uint_as_float(adb);
     const float    b     = __uint_as_float(__float_as_uint(sn) ^ sgn);
-    if ((adb < 0x322BCC77u) | (b > ad) | (b < -0x1p-22f))
-        return;
-    const float tn = fsub(fmul(ex, sg.w), fmul(ey, sg.z));
-    const float a  = __uint_as_float(__float_as_uint(tn) ^ sgn);
-    if (a < -0x1p-22f)
-        return;
-    const float lim = fmul(ad, m);
-    if ((lim >= 0x1p-100f) & (a > fmul(lim, 1.000003814697265625f))) // RN(t) > m: cannot win
-        return;
-    if ((b >= 0.0f) & (adb < 0x5d800000u /* 2^60 */) & (a >= 0x1p-60f))
-    {
-        const float tq = __fdividef(a, ad);
-        if (tq > fmul(tq_b, 1.000003814697265625f))
-            return; // strictly beaten by the chunk's best
-        if (!(tq < fmul(tq_b, 0.999996185302734375f)) && idx_b >= 0)
-            beam_flush(segs, idx_b, ox, oy, dx, dy, key); // near tie: both go to the key with their exact t
-        tq_b  = tq;
-        idx_b = idx;
-        return;
+    const float    a     = __uint_as_float(__float_as_uint(tn) ^ sgn);
+    const float    lim   = fmul(ad, m);
+    // sufficient conditions for the reference's predicate to fail, or for RN(t) > m (see test_segment)
+    const bool rej = !live | (adb < 0x322BCC77u) | (b > ad) | (b < -0x1p-22f) | (a < -0x1p-22f) |
+                     ((lim >= 0x1p-100f) & (a > fmul(lim, 1.000003814697265625f)));
+    const bool comfy = (b >= 0.0f) & (adb < 0x5d800000u /* 2^60 */) & (a >= 0x1p-60f);
+    const float tq   = __fdividef(a, ad);
+    const bool  cand = !rej & comfy & !(tq > fmul(tq_b, 1.000003814697265625f));
+    if (cand & !(tq < fmul(tq_b, 0.999996185302734375f)) & (idx_b >= 0))
+        beam_flush(segs, idx_b, ox, oy, dx, dy, key); // near tie (rare): both reach the key with their exact t
+    tq_b  = cand ? tq : tq_b;
+    idx_b = cand ? idx : idx_b;
+    if (!rej & !comfy)
+    { // on an edge of the segment or at the origin (rare): literal predicate of the reference (CollisionChecker.cu:25-33)
+        const float t    = __fdiv_rn(tn, denom);
+        bool        s_ok = (b >= 0.0f) & (adb < 0x7f800000u);
+        if (!s_ok)
+        {
+            const float s2 = __fdiv_rn(sn, denom);
+            s_ok           = (s2 >= 0.0f) && (s2 <= 1.0f);
+        }
+        if (s_ok && (t >= 0.0f))
+            atomicMin(key, beam_key(t, idx));
     }
-    // literal predicate of the reference (CollisionChecker.cu:25-33)
-    const float t    = __fdiv_rn(tn, denom);
-    bool        s_ok = (b >= 0.0f) & (adb < 0x7f800000u);
-    if (!s_ok)
-    {
-        const float s2 = __fdiv_rn(sn, denom);
-        s_ok           = (s2 >= 0.0f) && (s2 <= 1.0f);
-    }
-    if (s_ok && (t >= 0.0f))
-        atomicMin(key, beam_key(t, idx));
 }
 
 // hit point, unpack (CollisionChecker.cu:68-69,152-165) and the per-ray outputs of ray `gi`, whose nearest
@@ -628,18 +657,10 @@ __host__ __device__ inline size_t batch_smem_bytes(int agents, int rays)
 { // AgentRec + per ray float2 direction
     return static_cast<size_t>(agents) * (sizeof(AgentRec) + 8u * static_cast<size_t>(rays));
 }
-// beam mode: AgentRec + the queue of rays left to the grid walk (uint16 per ray) + per-thread ray / key scratch
-__host__ __device__ inline size_t beam_queue_offset(int agents)
+// beam mode: AgentRec only (the per-thread scratch is static shared memory)
+__host__ __device__ inline size_t beam_smem_bytes(int agents)
 {
     return (static_cast<size_t>(agents) * sizeof(AgentRec) + 15u) / 16u * 16u;
-}
-__host__ __device__ inline size_t beam_scratch_offset(int agents, int rays)
-{
-    return beam_queue_offset(agents) + (static_cast<size_t>(agents) * static_cast<size_t>(rays) * 2u + 15u) / 16u * 16u;
-}
-__host__ __device__ inline size_t beam_smem_bytes(int agents, int rays, int block)
-{
-    return beam_scratch_offset(agents, rays) + static_cast<size_t>(block) * 24u;
 }
 
 #ifndef OK_UNITS
@@ -652,7 +673,7 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint16_t                      s_order[1024]; // pool order of the rays (p.ray_order)
     __shared__ __align__(8) uint64_t         bar;
-    __shared__ int                           s_tile, s_pool, s_fb_n, s_fb_pool;
+    __shared__ int                           s_tile, s_pool;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int kWarps = kBlock / 32;
@@ -661,12 +682,9 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
     uint8_t  *blob    = smem;
     AgentRec *recs    = reinterpret_cast<AgentRec *>(smem + p.smem_blob_bytes);
     float2   *dirs    = reinterpret_cast<float2 *>(recs + p.batch_agents); // !kBeam
-    // kBeam: rays left to the grid walk, then per-thread ray parameters and result keys
-    uint8_t  *bscr    = smem + p.smem_blob_bytes;
-    uint16_t *fb_q    = reinterpret_cast<uint16_t *>(bscr + beam_queue_offset(p.batch_agents));
-    float4   *w_ray   = reinterpret_cast<float4 *>(bscr + beam_scratch_offset(p.batch_agents, p.rays)) + (threadIdx.x & ~31);
-    unsigned long long *w_key =
-        reinterpret_cast<unsigned long long *>(bscr + beam_scratch_offset(p.batch_agents, p.rays) + 16u * kBlock) + (threadIdx.x & ~31);
+    // kBeam: per-thread ray parameters and result keys of the group a warp is working on
+    __shared__ __align__(16) float4             s_wray[kBeam ? kBlock : 1];
+    __shared__ __align__(8) unsigned long long s_wkey[kBeam ? kBlock : 1];
 
     if (tid == 0)
         mbar_init(&bar, 1);
@@ -832,11 +850,7 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
             recs[tid]       = rec;
         }
         if (tid == 0)
-        {
-            s_pool    = 0;
-            s_fb_n    = 0;
-            s_fb_pool = 0;
-        }
+            s_pool = 0;
         __syncthreads();
         const int64_t ray_base = tl.begin * R; // global index of the batch's first ray
         if (!kBeam)
@@ -984,72 +998,60 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
         else
         {
             // =================================================================================
-            // beam phase A -- warps pull groups of 32 consecutive rays (lane = ray): direction, table lookup,
-            // balanced test of the listed candidates, outputs.  Rays the table cannot decide (cell not
-            // covered, hit beyond the list's completeness distance) are queued for phase B.
+            // beam phase -- warps pull groups of 32 consecutive rays (lane = ray): direction, table lookup,
+            // balanced test of the listed candidates, outputs.  A ray the table cannot decide (cell not
+            // covered, hit beyond the list's completeness distance: ~0.1 %) continues with the grid walk
+            // from where its list stopped, in place.
             // =================================================================================
             const int                n_groups = (n_rays + 31) >> 5;
             const unsigned long long key_none =
                 (static_cast<unsigned long long>(__float_as_uint(p.sensor_range)) << 32) | 0x80000000ull;
             const float inf = __int_as_float(0x7f800000);
-            // ray `lane` of group g: agent, angle and (prefetched one group ahead) its table entry
-            auto locate = [&](int g, int &q, int &al, float &ang, bool &active) {
-                q      = (g << 5) + lane;
-                active = false;
-                al     = 0;
-                ang    = 0.0f;
+            float4             *w_ray = s_wray + (tid & ~31);
+            unsigned long long *w_key = s_wkey + (tid & ~31);
+            // ray `lane` of group g: agent, angle and its table entry (fetched one group ahead)
+            auto locate = [&](int g, int &al, float &ang, bool &active, bool &cov, uint2 &ent) {
+                const int q = (g << 5) + lane;
+                active = false, cov = false;
+                al  = 0;
+                ang = 0.0f;
+                ent = make_uint2(0u, 0u);
                 if (g < n_groups && q < n_rays)
                 {
                     al                  = __float2int_rz((static_cast<float>(q) + 0.5f) * inv_R);
                     const AgentRec &rec = recs[al];
                     ang                 = fmul(OK_DEG2RAD, fadd(rec.rot, __ldg(p.ray_deg + (q - al * R))));
                     active              = !(rec.flags & kFlagCrashed);
+                    if (active && rec.row >= 0 && fabsf(ang) < kBeamMaxAngle)
+                    {
+                        const int bin = __float2int_rd(fmul(ang, bv.bin_scale)) & (bv.nb - 1);
+                        ent           = __ldg(bv.entries + static_cast<size_t>(rec.row) * bv.nb + bin);
+                        cov           = true;
+                    }
                 }
-            };
-            auto fetch = [&](int al, float ang, bool active, uint2 &ent) -> bool {
-                ent = make_uint2(0u, 0u);
-                if (!active)
-                    return false;
-                const int row = recs[al].row;
-                if (row < 0 || !(fabsf(ang) < kBeamMaxAngle))
-                    return false;
-                const int bin = __float2int_rd(fmul(ang, bv.bin_scale)) & (bv.nb - 1);
-                ent           = __ldg(bv.entries + static_cast<size_t>(row) * bv.nb + bin);
-                return true;
             };
             int g = 0;
             if (lane == 0)
                 g = atomicAdd(&s_pool, 1);
             g = __shfl_sync(0xffffffffu, g, 0);
+            int   al;
+            float ang;
+            bool  active, cov;
             uint2 ent;
-            bool  cov;
-            {
-                int   q, al;
-                float ang;
-                bool  active;
-                locate(g, q, al, ang, active);
-                cov = fetch(al, ang, active, ent);
-            }
+            locate(g, al, ang, active, cov, ent);
             while (g < n_groups)
             {
                 int g_next = 0;
                 if (lane == 0)
                     g_next = atomicAdd(&s_pool, 1);
                 g_next = __shfl_sync(0xffffffffu, g_next, 0);
-                uint2 ent_next;
-                bool  cov_next;
-                {
-                    int   q, al;
-                    float ang;
-                    bool  active;
-                    locate(g_next, q, al, ang, active);
-                    cov_next = fetch(al, ang, active, ent_next);
-                }
+                int   al_n;
+                float ang_n;
+                bool  active_n, cov_n;
+                uint2 ent_n;
+                locate(g_next, al_n, ang_n, active_n, cov_n, ent_n);
 
-                int   q, al;
-                float ang;
-                bool  active;
-                locate(g, q, al, ang, active);
+                const int  q   = (g << 5) + lane;
                 const bool has = q < n_rays;
                 float      dx = 0.0f, dy = 0.0f;
                 if (active)
@@ -1059,8 +1061,7 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                     w_ray[lane]         = make_float4(rec.ox, rec.oy, dx, dy);
                     w_key[lane]         = key_none;
                 }
-                const uint32_t cnt = cov ? (ent.y & 0xffffu) : 0u;
-                const uint32_t nch = (cnt + 3u) >> 2;
+                const uint32_t nch = cov ? (((ent.y & 0xffffu) + 3u) >> 2) : 0u;
                 uint32_t       inc = nch;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1)
@@ -1070,6 +1071,7 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                         inc += v;
                 }
                 const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+                const uint32_t first = ent.x - (inc - nch); // chunk j of the group is chunk (first + j) of the table
                 __syncwarp();
                 for (uint32_t base = 0; base < total; base += 32)
                 {
@@ -1082,45 +1084,54 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                         if (v <= j)
                             owner += s2;
                     }
-                    const uint32_t o_first = __shfl_sync(0xffffffffu, inc - nch, owner);
-                    const uint32_t o_chunk = __shfl_sync(0xffffffffu, ent.x, owner);
+                    const uint32_t o_first = __shfl_sync(0xffffffffu, first, owner);
                     if (j < total)
                     {
-                        const uint2  it  = __ldg(bv.chunks + o_chunk + (j - o_first));
-                        const float4 ray = w_ray[owner];
-                        const float  m   = __uint_as_float(reinterpret_cast<const uint32_t *>(w_key + owner)[1]);
-                        float        tq_b  = inf;
-                        int          idx_b = -1;
+                        const uint2         it  = __ldg(bv.chunks + (o_first + j));
+                        const float4        ray = w_ray[owner];
+                        unsigned long long *key = w_key + owner;
+                        const float         m   = __uint_as_float(reinterpret_cast<const uint32_t *>(key)[1]);
+                        float               tq_b  = inf;
+                        int                 idx_b = -1;
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
                         {
-                            const int idx = static_cast<int>(((u < 2 ? it.x : it.y) >> (16 * (u & 1))) & 0xffffu);
-                            if (idx != 0xffff)
-                                beam_test(tv.seg, idx, ray.x, ray.y, ray.z, ray.w, m, tq_b, idx_b, w_key + owner);
+                            const uint32_t raw  = ((u < 2 ? it.x : it.y) >> (16 * (u & 1))) & 0xffffu;
+                            const bool     live = raw != 0xffffu; // chunks are padded with 0xffff
+                            beam_test(tv.seg, live ? static_cast<int>(raw) : 0, live, ray.x, ray.y, ray.z, ray.w, m, tq_b,
+                                      idx_b, key);
                         }
                         if (idx_b >= 0)
-                            beam_flush(tv.seg, idx_b, ray.x, ray.y, ray.z, ray.w, w_key + owner);
+                            beam_flush(tv.seg, idx_b, ray.x, ray.y, ray.z, ray.w, key);
                     }
                 }
                 __syncwarp();
                 float sq = inf;
                 if (has)
                 {
-                    const AgentRec          &rec  = recs[al];
-                    const int64_t            gi   = ray_base + q;
-                    const unsigned long long key  = w_key[lane];
-                    const int                best = static_cast<int>(0x7fffffffu - static_cast<uint32_t>(key));
+                    const AgentRec          &rec   = recs[al];
+                    const unsigned long long key   = w_key[lane];
+                    int                      best  = static_cast<int>(0x7fffffffu - static_cast<uint32_t>(key));
                     const float              min_t = __uint_as_float(static_cast<uint32_t>(key >> 32));
                     const uint32_t           dq    = ent.y >> 16;
                     const float              d_eff = dq == 0xffffu ? bv.rb : static_cast<float>(dq) * 0.00390625f;
-                    if (!active || (cov && min_t <= d_eff - kBeamSlack))
-                        sq = finish_ray(p, tv, rec, gi, dx, dy, best);
-                    else
-                    { // phase B continues from the list's completeness distance with the best listed hit
-                        p.hit_seg[gi]                   = best;
-                        p.hit_t[gi]                     = cov ? fmaxf(d_eff - 1.0f, 0.0f) : 0.0f;
-                        fb_q[atomicAdd(&s_fb_n, 1)] = static_cast<uint16_t>(q);
+                    if (active && !(cov && min_t <= d_eff - kBeamSlack))
+                    { // undecided: everything nearer than d_eff - 1 is settled, the grid walk covers the rest
+                        RayWalk w;
+                        if (walk_begin(tv, w, rec.ox, rec.oy, dx, dy, p.sensor_range, cov ? fmaxf(d_eff - 1.0f, 0.0f) : 0.0f))
+                        {
+                            if (best >= 0)
+                            {
+                                w.best  = best;
+                                w.min_t = min_t; // the exact t of `best`
+                            }
+                            while (walk_unit(tv, w))
+                            {
+                            }
+                            best = w.best;
+                        }
                     }
+                    sq = finish_ray(p, tv, rec, ray_base + q, dx, dy, best);
                 }
                 // min_dist2 of CollisionChecker.cu:150,162-165: `if (sq < min) min = sq` skips NaN, and so
                 // does a signed-int min over the bit patterns of values >= +0 (a NaN made here is 0x7fffffff)
@@ -1135,72 +1146,7 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                 }
                 else if (has && sq == sq)
                     atomicMin(&recs[al].min_d2_bits, __float_as_int(sq));
-                g   = g_next;
-                ent = ent_next;
-                cov = cov_next;
-            }
-            __syncthreads();
-            // =================================================================================
-            // beam phase B -- the queued rays: uniform-grid walk from where the list stopped, each lane
-            // pulling rays on its own (no warp-level primitive in this divergent loop)
-            // =================================================================================
-            {
-                const int n_fb = s_fb_n;
-                RayWalk   w;
-                int       mine = -1, mine_al = 0;
-                bool      more = n_fb > 0;
-                for (;;)
-                {
-                    if (mine < 0)
-                    {
-                        if (!more)
-                            break;
-                        const int qi = atomicAdd(&s_fb_pool, 1);
-                        if (qi >= n_fb)
-                            more = false;
-                        else
-                        {
-                            const int       q   = fb_q[qi];
-                            const int       al  = __float2int_rz((static_cast<float>(q) + 0.5f) * inv_R);
-                            const AgentRec &rec = recs[al];
-                            const int64_t   gi  = ray_base + q;
-                            float           s, c;
-                            sincosf(fmul(OK_DEG2RAD, fadd(rec.rot, __ldg(p.ray_deg + (q - al * R)))), s, c);
-                            const int   inc_best = p.hit_seg[gi];
-                            const float t_start  = p.hit_t[gi];
-                            if (walk_begin(tv, w, rec.ox, rec.oy, c, s, p.sensor_range, t_start))
-                            {
-                                if (inc_best >= 0)
-                                {
-                                    w.best  = inc_best;
-                                    w.min_t = exact_t(tv.seg[inc_best], rec.ox, rec.oy, c, s);
-                                }
-                                mine    = q;
-                                mine_al = al;
-                            }
-                            else
-                            {
-                                const float sq = finish_ray(p, tv, rec, gi, c, s, inc_best);
-                                if (sq == sq)
-                                    atomicMin(&recs[al].min_d2_bits, __float_as_int(sq));
-                            }
-                        }
-                    }
-#pragma unroll 1
-                    for (int u = 0; u < kUnitsPerRefill; ++u)
-                    {
-                        if (mine >= 0)
-                        {
-                            if (!walk_unit(tv, w))
-                            {
-                                const float sq = finish_ray(p, tv, recs[mine_al], ray_base + mine, w.dx, w.dy, w.best);
-                                if (sq == sq)
-                                    atomicMin(&recs[mine_al].min_d2_bits, __float_as_int(sq));
-                                mine = -1;
-                            }
-                        }
-                    }
-                }
+                g = g_next, al = al_n, ang = ang_n, active = active_n, cov = cov_n, ent = ent_n;
             }
         }
         __syncthreads();
@@ -1225,7 +1171,7 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                 if (rec.flags & kFlagReset)
                 { // prev_track_idx_ = nearest index of the post-reset pose (main_eigen.cpp:121-130)
                     float d2;
-                    prev = nearest_index(tv, rec.rx, rec.ry, lane, 32, d2);
+                    prev = nearest_index_hint(tv, rec.rx, rec.ry, p.reset_pt[a], lane, d2);
                     near = prev;
                 }
                 else if (p.do_move)
@@ -1234,7 +1180,7 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                     fitness = p.fitness[a];
                 }
                 if (need_idx)
-                    near = nearest_index(tv, rec.x, rec.y, lane, 32, near_d2);
+                    near = nearest_index_hint(tv, rec.x, rec.y, (rec.flags & kFlagReset) ? prev : p.nearest[a], lane, near_d2);
                 if (lane == 0)
                 {
                     if (p.do_move)

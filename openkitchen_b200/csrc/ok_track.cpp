@@ -234,7 +234,23 @@ void pack_blob(Track &t)
     h.off_points   = static_cast<uint32_t>(append_section(t.blob, pts.data(), pts.size()));
     h.off_widths   = static_cast<uint32_t>(append_section(t.blob, widths.data(), widths.size()));
     h.off_headings = static_cast<uint32_t>(append_section(t.blob, t.heading.data(), t.heading.size()));
-    h.blob_bytes   = static_cast<uint32_t>(t.blob.size());
+    // safe radius of the windowed nearest-point search (ok_track.hpp, kNearestWindow)
+    t.safe_radius.assign(n, std::numeric_limits<float>::infinity());
+    if (n > kNearestWindow)
+        for (int32_t i = 0; i < n; ++i)
+        {
+            double best = 1e300;
+            for (int32_t j = 0; j < n; ++j)
+            {
+                const int32_t fwd = ((j - i) % n + n) % n; // cyclic offset of j from i
+                if (fwd < kNearestWindow / 2 || fwd >= n - kNearestWindow / 2)
+                    continue; // inside the window [i - 16, i + 16)
+                best = std::min(best, std::hypot(static_cast<double>(t.x[j]) - t.x[i], static_cast<double>(t.y[j]) - t.y[i]));
+            }
+            t.safe_radius[i] = static_cast<float>(best * (1.0 - 1e-6));
+        }
+    h.off_safe   = static_cast<uint32_t>(append_section(t.blob, t.safe_radius.data(), t.safe_radius.size()));
+    h.blob_bytes = static_cast<uint32_t>(t.blob.size());
     std::memcpy(t.blob.data(), &h, sizeof h);
 }
 } // namespace

@@ -35,8 +35,17 @@ struct TrackHeader
     uint32_t off_widths;   // float  w_left + w_right [n_points]
     uint32_t off_headings; // float  heading degrees [n_points]
     uint32_t blob_bytes;   // multiple of 16
+    uint32_t off_safe;     // float  [n_points]: see kNearestWindow
+    uint32_t pad[3];
 };
-static_assert(sizeof(TrackHeader) == 64, "TrackHeader must be 64 bytes");
+static_assert(sizeof(TrackHeader) == 80, "TrackHeader must be 80 bytes");
+
+// Nearest-centre-line-point search (RaceTrack.cpp:16-31) with a hint h: the kernel looks at the cyclic window
+// [h - kNearestWindow/2, h + kNearestWindow/2) first.  safe[h] = min distance from point h to any point OUTSIDE
+// that window (rounded down): if safe[h] - |q - p_h| exceeds the best distance found in the window (plus
+// slack), no outside point can be nearer -- |q - p_j| >= |p_j - p_h| - |q - p_h| -- and the windowed argmin
+// is the global one; otherwise the kernel falls back to the full search.
+constexpr int kNearestWindow = 32;
 
 struct Track
 {
@@ -50,6 +59,7 @@ struct Track
     std::vector<uint32_t> cell_words; // pairs {occupancy bits, occupied-cell rank} per 32 cells
     std::vector<uint32_t> cell_starts; // per occupied cell: first item | (one past the last) << 16
     std::vector<uint16_t> items;
+    std::vector<float>    safe_radius; // per centre-line point, see kNearestWindow
     // staged form
     std::vector<uint8_t> blob;
 
