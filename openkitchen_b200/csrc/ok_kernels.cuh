@@ -511,8 +511,12 @@ struct AgentRec
     int      min_d2_bits;    // running min of the squared hit norms (as int: all values are >= +0)
     uint32_t flags;
     int32_t  row;            // beam-table row of the lidar origin's cell, -1 = not covered (kBeam only)
+    int32_t  prev;           // prev_track_idx_ / accumulated fitness before this tick (phase 4 works from shared memory)
+    float    fitness;
+    int32_t  hint;           // where the nearest-centre-line search starts: last tick's index, or the reset point
+    int32_t  pad;
 };
-static_assert(sizeof(AgentRec) == 48, "AgentRec layout");
+static_assert(sizeof(AgentRec) == 64, "AgentRec layout");
 enum : uint32_t
 {
     kFlagCrashed = 1u,
@@ -577,13 +581,16 @@ __device__ __forceinline__ void beam_flush(const float4 *segs, int idx, float ox
     atomicMin(key, beam_key(exact_t(segs[idx], ox, oy, dx, dy), idx));
 }
 
-// One candidate, written without branches on the common paths (a warp's lanes hold unrelated rays, so every
-// branch here would be taken by a few lanes while the others wait).  (tq_b, idx_b) is the lane's best
-// candidate of the current chunk by approximate quotient; every candidate is either strictly beaten by
-// another candidate (error bounds as in test_segment) or reaches the ray's key with its exact t.
-__device__ __forceinline__ void beam_test(const float4 *segs, const int idx, const bool live, const float ox,
-                                          const float oy, const float dx, const float dy, const float m, float &tq_b,
-                                          int &idx_b, unsigned long long *key)
+// One candidate, written without branches (a warp's lanes hold unrelated rays, so every branch here would be
+// taken by a few lanes while the others wait) and free of dependences on the other candidates of the chunk, so
+// the four evaluations of a chunk interleave.  Returns the approximate quotient tq = a * rcp(ad)
+// (|tq - RN(t)| <= 2^-21 RN(t)) and two flags:
+//   el  -- a real crossing comfortably inside the segment: s in [0,1] and t > 0 hold without a division, only
+//          the order of its exact t matters;
+//   lit -- on an edge of the segment or at the origin (rare): needs the reference's literal predicate.
+// Everything else fails the reference's predicate (sufficient conditions, see test_segment).
+__device__ __forceinline__ float beam_eval(const float4 *segs, const int idx, const bool live, const float ox,
+                                           const float oy, const float dx, const float dy, bool &el, bool &lit)
 {
     const float4   sg    = segs[idx];
     const float    ex    = fsub(sg.x, ox);
@@ -597,29 +604,29 @@ __device__ __forceinline__ void beam_test(const float4 *segs, const int idx, con
     const float    ad    = __uint_as_float(adb);
     const float    b     = __uint_as_float(__float_as_uint(sn) ^ sgn);
     const float    a     = __uint_as_float(__float_as_uint(tn) ^ sgn);
-    const float    lim   = fmul(ad, m);
-    // sufficient conditions for the reference's predicate to fail, or for RN(t) > m (see test_segment)
-    const bool rej = !live | (adb < 0x322BCC77u) | (b > ad) | (b < -0x1p-22f) | (a < -0x1p-22f) |
-                     ((lim >= 0x1p-100f) & (a > fmul(lim, 1.000003814697265625f)));
-    const bool comfy = (b >= 0.0f) & (adb < 0x5d800000u /* 2^60 */) & (a >= 0x1p-60f);
-    const float tq   = __fdividef(a, ad);
-    const bool  cand = !rej & comfy & !(tq > fmul(tq_b, 1.000003814697265625f));
-    if (cand & !(tq < fmul(tq_b, 0.999996185302734375f)) & (idx_b >= 0))
-        beam_flush(segs, idx_b, ox, oy, dx, dy, key); // near tie (rare): both reach the key with their exact t
-    tq_b  = cand ? tq : tq_b;
-    idx_b = cand ? idx : idx_b;
-    if (!rej & !comfy)
-    { // on an edge of the segment or at the origin (rare): literal predicate of the reference (CollisionChecker.cu:25-33)
-        const float t    = __fdiv_rn(tn, denom);
-        bool        s_ok = (b >= 0.0f) & (adb < 0x7f800000u);
-        if (!s_ok)
-        {
-            const float s2 = __fdiv_rn(sn, denom);
-            s_ok           = (s2 >= 0.0f) && (s2 <= 1.0f);
-        }
-        if (s_ok && (t >= 0.0f))
-            atomicMin(key, beam_key(t, idx));
-    }
+    const bool     rej   = !live | (adb < 0x322BCC77u) | (b > ad) | (b < -0x1p-22f) | (a < -0x1p-22f);
+    const bool     comfy = (b >= 0.0f) & (adb < 0x5d800000u /* 2^60 */) & (a >= 0x1p-60f);
+    el                   = !rej & comfy;
+    lit                  = !rej & !comfy;
+    return __fdividef(a, ad);
+}
+
+// literal predicate of the reference (CollisionChecker.cu:25-33) for a candidate flagged `lit`
+__device__ __noinline__ void beam_literal(const float4 *segs, int idx, float ox, float oy, float dx, float dy,
+                                          unsigned long long *key)
+{
+    const float4 sg    = segs[idx];
+    const float  ex    = fsub(sg.x, ox);
+    const float  ey    = fsub(sg.y, oy);
+    const float  denom = fsub(fmul(dx, sg.w), fmul(dy, sg.z));
+    const float  sn    = fsub(fmul(ex, dy), fmul(ey, dx));
+    const float  tn    = fsub(fmul(ex, sg.w), fmul(ey, sg.z));
+    if (fabsf(denom) < 1e-8f)
+        return;
+    const float t = __fdiv_rn(tn, denom);
+    const float s2 = __fdiv_rn(sn, denom);
+    if ((s2 >= 0.0f) && (s2 <= 1.0f) && (t >= 0.0f))
+        atomicMin(key, beam_key(t, idx));
 }
 
 // hit point, unpack (CollisionChecker.cu:68-69,152-165) and the per-ray outputs of ray `gi`, whose nearest
@@ -742,8 +749,14 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
             bool     crashed = p.crashed[a] != 0, timed_out = p.timed_out[a] != 0;
             uint32_t flags = 0;
             float    rx = 0.0f, ry = 0.0f;
+            float    hs = 0.0f, hc = 0.0f; // sin / cos of the heading, when the move already computed them
+            bool     have_sc = false;
+            int32_t  hint = p.nearest[a], prev_idx = 0;
+            float    fitness = 0.0f;
             if (p.do_move)
             {
+                prev_idx = p.prev[a];
+                fitness  = p.fitness[a];
                 float thr, steer;
                 if (p.action_source == 1)
                 { // synthetic stream: Philox4x32-10, counter (agent, step), key (seed, 0)
@@ -786,6 +799,9 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                     thr = 0.0f, steer = 0.0f; // Agent::reset zeroes current_action_
                     rx = x, ry = y;
                     flags |= kFlagReset;
+                    hint     = pt;
+                    prev_idx = 0;
+                    fitness  = 0.0f;
                     p.reset_pt[a] = pt;
                     p.start_x[a]  = x;
                     p.start_y[a]  = y;
@@ -808,6 +824,7 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                     }
                     float ms, mc;
                     sincosf(fmul(OK_DEG2RAD, rot), ms, mc);
+                    hs = ms, hc = mc, have_sc = true; // the lidar origin below uses the same heading
                     x = fadd(x, fmul(fmul(mc, speed), p.dt));
                     y = fadd(y, fmul(fmul(ms, speed), p.dt));
                     // checkAndUpdateStandstill, Environment.cpp:16-39
@@ -838,8 +855,9 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                 p.timed_out[a] = timed_out;
             }
             // lidar origin, CollisionChecker.cu:121-124
-            float rs, rc;
-            sincosf(fmul(OK_DEG2RAD, rot), rs, rc);
+            float rs = hs, rc = hc;
+            if (!have_sc)
+                sincosf(fmul(OK_DEG2RAD, rot), rs, rc);
             AgentRec rec;
             rec.ox = fadd(x, fmul(p.sensor_offset, rc));
             rec.oy = fadd(y, fmul(p.sensor_offset, rs));
@@ -847,6 +865,7 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
             rec.min_d2_bits = __float_as_int(fmul(p.sensor_range, p.sensor_range));
             rec.flags       = flags | (crashed ? kFlagCrashed : 0u) | (timed_out ? kFlagTimedOut : 0u);
             rec.row         = kBeam ? beam_row(bv, rec.ox, rec.oy) : -1;
+            rec.prev = prev_idx, rec.fitness = fitness, rec.hint = hint, rec.pad = 0;
             recs[tid]       = rec;
         }
         if (tid == 0)
@@ -1073,10 +1092,9 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                 const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
                 const uint32_t first = ent.x - (inc - nch); // chunk j of the group is chunk (first + j) of the table
                 __syncwarp();
-                for (uint32_t base = 0; base < total; base += 32)
-                {
-                    const uint32_t j     = base + lane;
-                    int            owner = 0;
+                // chunk j of the group belongs to the lane `owner` whose prefix range contains j
+                auto find_chunk = [&](uint32_t j, int &owner) -> uint32_t {
+                    owner = 0;
 #pragma unroll
                     for (int s2 = 16; s2 > 0; s2 >>= 1)
                     {
@@ -1084,26 +1102,70 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                         if (v <= j)
                             owner += s2;
                     }
-                    const uint32_t o_first = __shfl_sync(0xffffffffu, first, owner);
-                    if (j < total)
+                    return __shfl_sync(0xffffffffu, first, owner) + j;
+                };
+                int   owner = 0;
+                uint2 it    = make_uint2(0xffffffffu, 0xffffffffu);
+                if (total > 0)
+                {
+                    const uint32_t ch = find_chunk(lane, owner);
+                    if (static_cast<uint32_t>(lane) < total)
+                        it = __ldg(bv.chunks + ch);
+                }
+                for (uint32_t base = 0; base < total; base += 32)
+                {
+                    // the next round's candidates are requested before this round's are tested
+                    int   owner_n = 0;
+                    uint2 it_n    = make_uint2(0xffffffffu, 0xffffffffu);
+                    if (base + 32 < total)
                     {
-                        const uint2         it  = __ldg(bv.chunks + (o_first + j));
+                        const uint32_t jn = base + 32 + lane;
+                        const uint32_t ch = find_chunk(jn, owner_n);
+                        if (jn < total)
+                            it_n = __ldg(bv.chunks + ch);
+                    }
+                    if (base + lane < total)
+                    {
                         const float4        ray = w_ray[owner];
                         unsigned long long *key = w_key + owner;
                         const float         m   = __uint_as_float(reinterpret_cast<const uint32_t *>(key)[1]);
-                        float               tq_b  = inf;
-                        int                 idx_b = -1;
+                        int                 idx[4];
+                        float               tq[4];
+                        bool                el[4], lit[4];
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
                         {
                             const uint32_t raw  = ((u < 2 ? it.x : it.y) >> (16 * (u & 1))) & 0xffffu;
                             const bool     live = raw != 0xffffu; // chunks are padded with 0xffff
-                            beam_test(tv.seg, live ? static_cast<int>(raw) : 0, live, ray.x, ray.y, ray.z, ray.w, m, tq_b,
-                                      idx_b, key);
+                            idx[u]              = live ? static_cast<int>(raw) : 0;
+                            tq[u] = beam_eval(tv.seg, idx[u], live, ray.x, ray.y, ray.z, ray.w, el[u], lit[u]);
+                        }
+                        // the chunk's best by approximate quotient, starting from the ray's incumbent (exact t = m,
+                        // already in the key).  Every candidate is either strictly beaten by another one (the two
+                        // quotients differ by more than both error bounds) or reaches the key with its exact t.
+                        float tq_b  = m;
+                        int   idx_b = -1;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                        {
+                            const bool cand = el[u] & !(tq[u] > fmul(tq_b, 1.000003814697265625f));
+                            if (cand & !(tq[u] < fmul(tq_b, 0.999996185302734375f)) & (idx_b >= 0))
+                                beam_flush(tv.seg, idx_b, ray.x, ray.y, ray.z, ray.w, key); // near tie (rare)
+                            tq_b  = cand ? tq[u] : tq_b;
+                            idx_b = cand ? idx[u] : idx_b;
                         }
                         if (idx_b >= 0)
                             beam_flush(tv.seg, idx_b, ray.x, ray.y, ray.z, ray.w, key);
+                        if (lit[0] | lit[1] | lit[2] | lit[3])
+                        {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (lit[u])
+                                    beam_literal(tv.seg, idx[u], ray.x, ray.y, ray.z, ray.w, key);
+                        }
                     }
+                    owner = owner_n;
+                    it    = it_n;
                 }
                 __syncwarp();
                 float sq = inf;
@@ -1166,21 +1228,16 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                 const bool     timed_out = (rec.flags & kFlagTimedOut) != 0;
                 if (min_d2 < p.collision_dist2) // CollisionChecker.cu:167-171
                     crashed = true;
-                int32_t prev = 0, near = 0;
-                float   fitness = 0.0f, near_d2 = 0.0f;
+                int32_t prev = rec.prev, near = 0;
+                float   fitness = rec.fitness, near_d2 = 0.0f;
                 if (rec.flags & kFlagReset)
                 { // prev_track_idx_ = nearest index of the post-reset pose (main_eigen.cpp:121-130)
                     float d2;
-                    prev = nearest_index_hint(tv, rec.rx, rec.ry, p.reset_pt[a], lane, d2);
+                    prev = nearest_index_hint(tv, rec.rx, rec.ry, rec.hint, lane, d2);
                     near = prev;
                 }
-                else if (p.do_move)
-                {
-                    prev    = p.prev[a];
-                    fitness = p.fitness[a];
-                }
                 if (need_idx)
-                    near = nearest_index_hint(tv, rec.x, rec.y, (rec.flags & kFlagReset) ? prev : p.nearest[a], lane, near_d2);
+                    near = nearest_index_hint(tv, rec.x, rec.y, (rec.flags & kFlagReset) ? prev : rec.hint, lane, near_d2);
                 if (lane == 0)
                 {
                     if (p.do_move)
