@@ -499,6 +499,42 @@ __device__ __forceinline__ int nearest_index_hint(const TrackView &tv, float qx,
     return nearest_index(tv, qx, qy, lane, 32, d2_out);
 }
 
+// The windowed search by ONE thread (phase 4 runs a thread per agent): same window, same exactness test.
+// ok = false means "not proven": the caller runs the full search.  Ties: lowest index, like the reference
+// (the window wraps around the end of the centre line, so index order is not visiting order).
+__device__ __forceinline__ int nearest_index_window(const TrackView &tv, float qx, float qy, int hint, float &d2_out, bool &ok)
+{
+    const int n = tv.n_pts;
+    ok          = false;
+    d2_out      = FLT_MAX;
+    if (n <= kNearestWindow)
+        return 0;
+    const int h    = min(max(hint, 0), n - 1);
+    float     best = FLT_MAX, dh = FLT_MAX;
+    int       bi   = 0;
+    int       i    = h - kNearestWindow / 2;
+    i += (i < 0) ? n : 0;
+#pragma unroll 4
+    for (int k = 0; k < kNearestWindow; ++k)
+    {
+        const float2 pt  = tv.pts[i];
+        const float  ddx = fsub(qx, pt.x), ddy = fsub(qy, pt.y);
+        const float  d   = fadd(fmul(ddx, ddx), fmul(ddy, ddy));
+        dh               = (k == kNearestWindow / 2) ? d : dh;
+        if (d < best || (d == best && d < FLT_MAX && i < bi))
+        {
+            best = d;
+            bi   = i;
+        }
+        ++i;
+        i = (i >= n) ? 0 : i;
+    }
+    const float rb = __fsqrt_rn(best), rh = __fsqrt_rn(dh);
+    ok             = fsub(fsub(tv.safe[h], rh), rb) > fadd(fmul(1e-3f, fadd(rh, rb)), 1e-3f);
+    d2_out         = best;
+    return bi;
+}
+
 // ---------------------------------------------------------------------------------------------
 // the tick
 // ---------------------------------------------------------------------------------------------
@@ -1214,98 +1250,125 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
         __syncthreads();
 
         // =====================================================================================
-        // phase 4 -- one warp per agent: crash flag, centre-line search, progress / reward / done
+        // phase 4 -- one thread per agent: crash flag, centre-line search, progress / reward / done
         // =====================================================================================
+        if ((warp << 5) < count)
         {
             const int  mode     = p.reward_mode;
             const bool need_idx = p.do_move && (mode == 1 || mode == 2 || mode == 6 || mode == 7);
-            for (int al = warp; al < count; al += kWarps)
+            const bool valid    = tid < count;
+            const int  al       = valid ? tid : 0;
+            const AgentRec rec  = recs[al];
+            const int64_t  a    = tl.begin + al;
+            const float    min_d2 = __int_as_float(rec.min_d2_bits);
+            bool           crashed = (rec.flags & kFlagCrashed) != 0;
+            const bool     timed_out = (rec.flags & kFlagTimedOut) != 0;
+            if (min_d2 < p.collision_dist2) // CollisionChecker.cu:167-171
+                crashed = true;
+            int32_t prev = rec.prev, near = 0;
+            float   fitness = rec.fitness, near_d2 = 0.0f;
+            // RaceTrack::findNearestTrackIndexBruteForce: the window around last tick's index first; the rare
+            // agents it cannot prove (teleported by a buffer write, track folding back on itself) get the
+            // full search, their warp's 32 lanes sharing it
+            const bool want_reset = valid && (rec.flags & kFlagReset) != 0;
+            bool       ok_reset   = true;
+            if (want_reset)
+            { // prev_track_idx_ = nearest index of the post-reset pose (main_eigen.cpp:121-130)
+                float d2;
+                prev = nearest_index_window(tv, rec.rx, rec.ry, rec.hint, d2, ok_reset);
+            }
+            for (unsigned need = __ballot_sync(0xffffffffu, !ok_reset); need; need &= need - 1)
             {
-                const AgentRec rec = recs[al];
-                const int64_t  a   = tl.begin + al;
-                const float    min_d2 = __int_as_float(rec.min_d2_bits);
-                bool           crashed = (rec.flags & kFlagCrashed) != 0;
-                const bool     timed_out = (rec.flags & kFlagTimedOut) != 0;
-                if (min_d2 < p.collision_dist2) // CollisionChecker.cu:167-171
-                    crashed = true;
-                int32_t prev = rec.prev, near = 0;
-                float   fitness = rec.fitness, near_d2 = 0.0f;
-                if (rec.flags & kFlagReset)
-                { // prev_track_idx_ = nearest index of the post-reset pose (main_eigen.cpp:121-130)
-                    float d2;
-                    prev = nearest_index_hint(tv, rec.rx, rec.ry, rec.hint, lane, d2);
-                    near = prev;
-                }
-                if (need_idx)
-                    near = nearest_index_hint(tv, rec.x, rec.y, (rec.flags & kFlagReset) ? prev : rec.hint, lane, near_d2);
-                if (lane == 0)
+                const int   src = __ffs(need) - 1;
+                float       d2;
+                const int   r = nearest_index(tv, __shfl_sync(0xffffffffu, rec.rx, src), __shfl_sync(0xffffffffu, rec.ry, src), lane, 32, d2);
+                if (lane == src)
+                    prev = r;
+            }
+            if (want_reset)
+                near = prev;
+            const bool want_near = valid && need_idx;
+            bool       ok_near   = true;
+            if (want_near)
+                near = nearest_index_window(tv, rec.x, rec.y, want_reset ? prev : rec.hint, near_d2, ok_near);
+            for (unsigned need = __ballot_sync(0xffffffffu, !ok_near); need; need &= need - 1)
+            {
+                const int   src = __ffs(need) - 1;
+                float       d2;
+                const int   r = nearest_index(tv, __shfl_sync(0xffffffffu, rec.x, src), __shfl_sync(0xffffffffu, rec.y, src), lane, 32, d2);
+                if (lane == src)
                 {
-                    if (p.do_move)
-                    {
-                        float reward = 0.0f;
-                        switch (mode)
-                        {
-                        case 1: // QAgent.hpp:150-168
-                            if (crashed)
-                                reward = -200.0f;
-                            else
-                            {
-                                const int32_t prog = near - prev;
-                                prev               = near;
-                                const int32_t ab = prog < 0 ? -prog : prog, len = tv.n_pts;
-                                reward = static_cast<float>(ab > (len / 2) ? len - ab : ab);
-                            }
-                            break;
-                        case 2: // main_eigen.cpp:147-163
-                            if (!crashed)
-                            {
-                                const int32_t prog = near - prev;
-                                prev               = near;
-                                reward             = static_cast<float>(prog < 0 ? -prog : prog);
-                                fitness            = fadd(fitness, reward);
-                            }
-                            else if (timed_out)
-                                fitness = 0.0f;
-                            break;
-                        case 3: reward = 1.0f; break; // ppo_sim.cpp:76
-                        case 4:                       // ReinforceContinuous/reinforce_sim.cpp:59-73
-                        {
-                            const float ddx = fsub(rec.x, p.start_x[a]), ddy = fsub(rec.y, p.start_y[a]);
-                            reward = crashed ? -5.0f : __fsqrt_rn(fadd(fmul(ddx, ddx), fmul(ddy, ddy)));
-                            break;
-                        }
-                        case 5: // DQAgent.hpp:161-180: min over rays of norm() == sqrt of the min squared norm
-                        {
-                            const float m = __fsqrt_rn(min_d2);
-                            reward        = crashed ? -200.0f : (p.sensor_range > m ? m : p.sensor_range);
-                            break;
-                        }
-                        case 6: reward = static_cast<float>(near); break; // MiscUtils.hpp:64-71
-                        case 7:                                           // WorldModelVaeRnn/main.cpp:336-342
-                            if (!crashed)
-                            {
-                                reward  = fsub(1.0f, __fdiv_rn(__fsqrt_rn(near_d2), tv.widths[near])); // RaceTrack.cpp:53-72
-                                fitness = fadd(fitness, reward);
-                            }
-                            else if (timed_out)
-                                fitness = 0.0f;
-                            break;
-                        default: break;
-                        }
-                        p.reward[a]  = reward;
-                        if (p.host_reward)
-                            p.host_reward[a] = reward;
-                        p.fitness[a] = fitness;
-                        p.prev[a]    = prev;
-                        if (need_idx || (rec.flags & kFlagReset))
-                            p.nearest[a] = near;
-                    }
-                    p.crashed[a]   = crashed;
-                    p.done[a]      = crashed; // Agent::isDone, Agent.cpp:138-144 (completed_ is never set)
-                    if (p.host_done)
-                        p.host_done[a] = crashed;
-                    p.min_dist2[a] = min_d2;
+                    near    = r;
+                    near_d2 = d2;
                 }
+            }
+            if (valid)
+            {
+                if (p.do_move)
+                {
+                    float reward = 0.0f;
+                    switch (mode)
+                    {
+                    case 1: // QAgent.hpp:150-168
+                        if (crashed)
+                            reward = -200.0f;
+                        else
+                        {
+                            const int32_t prog = near - prev;
+                            prev               = near;
+                            const int32_t ab = prog < 0 ? -prog : prog, len = tv.n_pts;
+                            reward = static_cast<float>(ab > (len / 2) ? len - ab : ab);
+                        }
+                        break;
+                    case 2: // main_eigen.cpp:147-163
+                        if (!crashed)
+                        {
+                            const int32_t prog = near - prev;
+                            prev               = near;
+                            reward             = static_cast<float>(prog < 0 ? -prog : prog);
+                            fitness            = fadd(fitness, reward);
+                        }
+                        else if (timed_out)
+                            fitness = 0.0f;
+                        break;
+                    case 3: reward = 1.0f; break; // ppo_sim.cpp:76
+                    case 4:                       // ReinforceContinuous/reinforce_sim.cpp:59-73
+                    {
+                        const float ddx = fsub(rec.x, p.start_x[a]), ddy = fsub(rec.y, p.start_y[a]);
+                        reward = crashed ? -5.0f : __fsqrt_rn(fadd(fmul(ddx, ddx), fmul(ddy, ddy)));
+                        break;
+                    }
+                    case 5: // DQAgent.hpp:161-180: min over rays of norm() == sqrt of the min squared norm
+                    {
+                        const float m = __fsqrt_rn(min_d2);
+                        reward        = crashed ? -200.0f : (p.sensor_range > m ? m : p.sensor_range);
+                        break;
+                    }
+                    case 6: reward = static_cast<float>(near); break; // MiscUtils.hpp:64-71
+                    case 7:                                           // WorldModelVaeRnn/main.cpp:336-342
+                        if (!crashed)
+                        {
+                            reward  = fsub(1.0f, __fdiv_rn(__fsqrt_rn(near_d2), tv.widths[near])); // RaceTrack.cpp:53-72
+                            fitness = fadd(fitness, reward);
+                        }
+                        else if (timed_out)
+                            fitness = 0.0f;
+                        break;
+                    default: break;
+                    }
+                    p.reward[a]  = reward;
+                    if (p.host_reward)
+                        p.host_reward[a] = reward;
+                    p.fitness[a] = fitness;
+                    p.prev[a]    = prev;
+                    if (need_idx || (rec.flags & kFlagReset))
+                        p.nearest[a] = near;
+                }
+                p.crashed[a]   = crashed;
+                p.done[a]      = crashed; // Agent::isDone, Agent.cpp:138-144 (completed_ is never set)
+                if (p.host_done)
+                    p.host_done[a] = crashed;
+                p.min_dist2[a] = min_d2;
             }
         }
     }
