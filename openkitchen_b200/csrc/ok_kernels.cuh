@@ -46,6 +46,7 @@ struct TrackRef
     uint64_t beam_offset; // byte offset of its beam blob in the beam arena (ok_beam.hpp)
 };
 
+struct AgentRec;
 struct StepParams
 {
     // agent state, structure of arrays
@@ -71,6 +72,11 @@ struct StepParams
     uint32_t       smem_blob_bytes; // offset of the batch scratch behind the staged track
     const uint16_t *ray_order;      // ray indices sorted by |angle|: pool order, long (central) rays first
     int32_t       *sched;           // {next tile, CTAs finished}: dynamic tile scheduler
+    // split pipeline (pre / cast / post kernels): per-agent records in global memory and small tiles
+    struct AgentRec *recs_g;
+    uint4         *ray_recs;        // per ray: {first chunk, count | dq << 16, dx, dy} (ray_prep_kernel)
+    const Tile    *cast_tiles;
+    int32_t        n_cast_tiles;
     // this launch
     const float *ext_thr, *ext_steer; // nullable: actions supplied by the caller
     int32_t      action_source;       // 0 stored/ext, 1 philox
@@ -542,12 +548,13 @@ __device__ __forceinline__ int nearest_index_window(const TrackView &tv, float q
 struct AgentRec
 {
     float    ox, oy, rc, rs; // lidar origin, cos/sin of the heading
-    float    rot, x, y;      // pose after the move
-    float    rx, ry;         // where a reset put the agent (FLAG_RESET)
-    int      min_d2_bits;    // running min of the squared hit norms (as int: all values are >= +0)
+    float    rot;            // heading after the move (degrees)
     uint32_t flags;
-    int32_t  row;            // beam-table row of the lidar origin's cell, -1 = not covered (kBeam only)
-    int32_t  prev;           // prev_track_idx_ / accumulated fitness before this tick (phase 4 works from shared memory)
+    int32_t  row;            // beam-table row of the lidar origin's cell, -1 = not covered (beam modes only)
+    int      min_d2_bits;    // running min of the squared hit norms (as int: all values are >= +0)
+    float    x, y;           // pose after the move
+    float    rx, ry;         // where a reset put the agent (FLAG_RESET)
+    int32_t  prev;           // prev_track_idx_ / accumulated fitness before this tick (phase 4 works from this record)
     float    fitness;
     int32_t  hint;           // where the nearest-centre-line search starts: last tick's index, or the reset point
     int32_t  pad;
@@ -665,16 +672,38 @@ __device__ __noinline__ void beam_literal(const float4 *segs, int idx, float ox,
         atomicMin(key, beam_key(t, idx));
 }
 
+// The rare ray a beam list cannot decide: uniform-grid walk from t_start with the best listed hit (best, min_t)
+// as the incumbent.  Out of line on purpose: the walk's state would otherwise count against the registers of
+// the hot loop around the call.
+__device__ __noinline__ int beam_walk_fallback(const uint8_t *blob, float ox, float oy, float dx, float dy, float range,
+                                               float t_start, int best, float min_t)
+{
+    const TrackView tv = make_view(blob);
+    RayWalk         w;
+    if (!walk_begin(tv, w, ox, oy, dx, dy, range, t_start))
+        return best;
+    if (best >= 0)
+    {
+        w.best  = best;
+        w.min_t = min_t; // the exact t of `best`
+    }
+    while (walk_unit(tv, w))
+    {
+    }
+    return w.best;
+}
+
 // hit point, unpack (CollisionChecker.cu:68-69,152-165) and the per-ray outputs of ray `gi`, whose nearest
 // segment is `seg` (-1 = none); returns the squared norm of the relative hit
-__device__ __forceinline__ float finish_ray(const StepParams &p, const TrackView &tv, const AgentRec &rec,
-                                            const int64_t gi, const float dx, const float dy, const int seg)
+template <typename Rec>
+__device__ __forceinline__ float finish_ray(const StepParams &p, const float4 *segs, const Rec &rec, const int64_t gi,
+                                            const float dx, const float dy, const int seg)
 {
     float2 hit;
     if (!(rec.flags & kFlagCrashed))
     {
         // min_t of CollisionChecker.cu:49-66: the winner's t by the reference's expression
-        const float t = seg >= 0 ? exact_t(tv.seg[seg], rec.ox, rec.oy, dx, dy) : p.sensor_range;
+        const float t = seg >= 0 ? exact_t(segs[seg], rec.ox, rec.oy, dx, dy) : p.sensor_range;
         p.hit_seg[gi] = seg;
         p.hit_t[gi]   = t;
         hit.x         = fadd(rec.ox, fmul(t, dx));
@@ -704,6 +733,254 @@ __host__ __device__ inline size_t batch_smem_bytes(int agents, int rays)
 __host__ __device__ inline size_t beam_smem_bytes(int agents)
 {
     return (static_cast<size_t>(agents) * sizeof(AgentRec) + 15u) / 16u * 16u;
+}
+
+// Phase 1 for agent `a` (one thread): optional auto-reset, kinematics from the action, standstill timeout
+// (Environment.cpp:128-143), lidar origin (CollisionChecker.cu:121-124).  Writes the agent's state buffers and
+// returns the record the ray and reward phases work from.
+__device__ __forceinline__ AgentRec agent_pre(const StepParams &p, const TrackView &tv, const BeamView &bv, const int64_t a)
+{
+    float    x = p.x[a], y = p.y[a], rot = p.rot[a], speed = p.speed[a], accel = p.accel[a];
+    bool     crashed = p.crashed[a] != 0, timed_out = p.timed_out[a] != 0;
+    uint32_t flags = 0;
+    float    rx = 0.0f, ry = 0.0f;
+    float    hs = 0.0f, hc = 0.0f; // sin / cos of the heading, when the move already computed them
+    bool     have_sc = false;
+    int32_t  hint = p.nearest[a], prev_idx = 0;
+    float    fitness = 0.0f;
+    if (p.do_move)
+    {
+        prev_idx = p.prev[a];
+        fitness  = p.fitness[a];
+        float thr, steer;
+        if (p.action_source == 1)
+        { // synthetic stream: Philox4x32-10, counter (agent, step), key (seed, 0)
+            uint32_t o[4];
+            philox4x32_10(static_cast<uint32_t>(a), static_cast<uint32_t>(static_cast<uint64_t>(a) >> 32),
+                          static_cast<uint32_t>(p.step), static_cast<uint32_t>(p.step >> 32), p.seed, 0u, o);
+            if (p.movement_mode == 1)
+            { // GeneticAgent.hpp:22-24 action set
+                const uint32_t ti = o[0] % 3u, si = o[1] % 5u;
+                thr   = ti == 0 ? -0.3f : (ti == 1 ? 0.0f : 0.3f);
+                steer = si == 0 ? -4.0f : (si == 1 ? -1.0f : (si == 2 ? 0.0f : (si == 3 ? 1.0f : 4.0f)));
+            }
+            else
+            { // ReinforceAgent.hpp:92-93 ranges
+                thr   = fmul(100.0f, fmul(static_cast<float>(o[0] >> 8), 0x1p-24f));
+                steer = fsub(fmul(10.0f, fmul(static_cast<float>(o[1] >> 8), 0x1p-24f)), 5.0f);
+            }
+        }
+        else if (p.ext_thr)
+        {
+            thr   = p.ext_thr[a];
+            steer = p.ext_steer[a];
+        }
+        else
+        {
+            thr   = p.act_thr[a];
+            steer = p.act_steer[a];
+        }
+        // app-side reset of a crashed agent before the tick (GuidedCostLearning/test.cpp:102-111):
+        // Environment::resetAgent + Agent::reset, Environment.cpp:103-121 / Agent.cpp:123-135.
+        // prev / nearest / fitness are finalised in phase 4 (they need a centre-line search).
+        if (p.auto_reset && crashed)
+        {
+            const int32_t pt =
+                static_cast<int32_t>((static_cast<int64_t>(p.reset_pt[a]) + p.auto_reset_stride) % tv.n_pts);
+            const float2 c = tv.pts[pt];
+            x = c.x, y = c.y, rot = tv.headings[pt];
+            accel = 0.0f, speed = 0.0f;
+            crashed = false, timed_out = false;
+            thr = 0.0f, steer = 0.0f; // Agent::reset zeroes current_action_
+            rx = x, ry = y;
+            flags |= kFlagReset;
+            hint     = pt;
+            prev_idx = 0;
+            fitness  = 0.0f;
+            p.reset_pt[a] = pt;
+            p.start_x[a]  = x;
+            p.start_y[a]  = y;
+        }
+        p.act_thr[a]   = thr;
+        p.act_steer[a] = steer;
+        if (!crashed)
+        {
+            rot = fadd(rot, steer);
+            if (p.movement_mode == 1)
+            { // moveViaAcceleration, Agent.cpp:82-98
+                accel = fadd(accel, thr);
+                speed = fadd(speed, fmul(accel, p.dt));
+                speed = (speed < 0.0f) ? 0.0f : speed;
+                speed = (speed > p.speed_limit) ? p.speed_limit : speed;
+            }
+            else
+            { // moveViaVelocity, Agent.cpp:108-119
+                speed = thr;
+            }
+            float ms, mc;
+            sincosf(fmul(OK_DEG2RAD, rot), ms, mc);
+            hs = ms, hc = mc, have_sc = true; // the lidar origin below uses the same heading
+            x = fadd(x, fmul(fmul(mc, speed), p.dt));
+            y = fadd(y, fmul(fmul(ms, speed), p.dt));
+            // checkAndUpdateStandstill, Environment.cpp:16-39
+            uint32_t ctr = p.ss_ctr[a];
+            bool     out = false;
+            if (ctr == 0)
+            {
+                p.ss_x[a] = x;
+                p.ss_y[a] = y;
+                ctr       = 1;
+            }
+            else if (ctr >= p.standstill_period)
+            {
+                const float mx = fsub(x, p.ss_x[a]), my = fsub(y, p.ss_y[a]);
+                out = fadd(fmul(mx, mx), fmul(my, my)) < p.standstill_thr2;
+                ctr = 0;
+            }
+            else
+                ++ctr;
+            p.ss_ctr[a] = ctr;
+            if (out)
+            {
+                crashed   = true;
+                timed_out = true;
+            }
+        }
+        p.x[a] = x, p.y[a] = y, p.rot[a] = rot, p.speed[a] = speed, p.accel[a] = accel;
+        p.timed_out[a] = timed_out;
+    }
+    // lidar origin, CollisionChecker.cu:121-124
+    float rs = hs, rc = hc;
+    if (!have_sc)
+        sincosf(fmul(OK_DEG2RAD, rot), rs, rc);
+    AgentRec rec;
+    rec.ox = fadd(x, fmul(p.sensor_offset, rc));
+    rec.oy = fadd(y, fmul(p.sensor_offset, rs));
+    rec.rc = rc, rec.rs = rs, rec.rot = rot, rec.x = x, rec.y = y, rec.rx = rx, rec.ry = ry;
+    rec.min_d2_bits = __float_as_int(fmul(p.sensor_range, p.sensor_range));
+    rec.flags       = flags | (crashed ? kFlagCrashed : 0u) | (timed_out ? kFlagTimedOut : 0u);
+    rec.row         = beam_row(bv, rec.ox, rec.oy); // -1 when bv is not valid
+    rec.prev = prev_idx, rec.fitness = fitness, rec.hint = hint, rec.pad = 0;
+    return rec;
+}
+
+// Phase 4 for agent `a` (one thread; the WHOLE warp must call this, lanes without an agent with valid = false):
+// crash flag (CollisionChecker.cu:167-171), nearest centre-line index, progress / reward / done.
+__device__ __forceinline__ void agent_post(const StepParams &p, const TrackView &tv, const AgentRec &rec, const int64_t a,
+                                           const bool valid, const int lane)
+{
+    const int  mode     = p.reward_mode;
+    const bool need_idx = p.do_move && (mode == 1 || mode == 2 || mode == 6 || mode == 7);
+            const float    min_d2 = __int_as_float(rec.min_d2_bits);
+    bool           crashed = (rec.flags & kFlagCrashed) != 0;
+    const bool     timed_out = (rec.flags & kFlagTimedOut) != 0;
+    if (min_d2 < p.collision_dist2) // CollisionChecker.cu:167-171
+        crashed = true;
+    int32_t prev = rec.prev, near = 0;
+    float   fitness = rec.fitness, near_d2 = 0.0f;
+    // RaceTrack::findNearestTrackIndexBruteForce: the window around last tick's index first; the rare
+    // agents it cannot prove (teleported by a buffer write, track folding back on itself) get the
+    // full search, their warp's 32 lanes sharing it
+    const bool want_reset = valid && (rec.flags & kFlagReset) != 0;
+    bool       ok_reset   = true;
+    if (want_reset)
+    { // prev_track_idx_ = nearest index of the post-reset pose (main_eigen.cpp:121-130)
+        float d2;
+        prev = nearest_index_window(tv, rec.rx, rec.ry, rec.hint, d2, ok_reset);
+    }
+    for (unsigned need = __ballot_sync(0xffffffffu, !ok_reset); need; need &= need - 1)
+    {
+        const int   src = __ffs(need) - 1;
+        float       d2;
+        const int   r = nearest_index(tv, __shfl_sync(0xffffffffu, rec.rx, src), __shfl_sync(0xffffffffu, rec.ry, src), lane, 32, d2);
+        if (lane == src)
+            prev = r;
+    }
+    if (want_reset)
+        near = prev;
+    const bool want_near = valid && need_idx;
+    bool       ok_near   = true;
+    if (want_near)
+        near = nearest_index_window(tv, rec.x, rec.y, want_reset ? prev : rec.hint, near_d2, ok_near);
+    for (unsigned need = __ballot_sync(0xffffffffu, !ok_near); need; need &= need - 1)
+    {
+        const int   src = __ffs(need) - 1;
+        float       d2;
+        const int   r = nearest_index(tv, __shfl_sync(0xffffffffu, rec.x, src), __shfl_sync(0xffffffffu, rec.y, src), lane, 32, d2);
+        if (lane == src)
+        {
+            near    = r;
+            near_d2 = d2;
+        }
+    }
+    if (valid)
+    {
+        if (p.do_move)
+        {
+            float reward = 0.0f;
+            switch (mode)
+            {
+            case 1: // QAgent.hpp:150-168
+                if (crashed)
+                    reward = -200.0f;
+                else
+                {
+                    const int32_t prog = near - prev;
+                    prev               = near;
+                    const int32_t ab = prog < 0 ? -prog : prog, len = tv.n_pts;
+                    reward = static_cast<float>(ab > (len / 2) ? len - ab : ab);
+                }
+                break;
+            case 2: // main_eigen.cpp:147-163
+                if (!crashed)
+                {
+                    const int32_t prog = near - prev;
+                    prev               = near;
+                    reward             = static_cast<float>(prog < 0 ? -prog : prog);
+                    fitness            = fadd(fitness, reward);
+                }
+                else if (timed_out)
+                    fitness = 0.0f;
+                break;
+            case 3: reward = 1.0f; break; // ppo_sim.cpp:76
+            case 4:                       // ReinforceContinuous/reinforce_sim.cpp:59-73
+            {
+                const float ddx = fsub(rec.x, p.start_x[a]), ddy = fsub(rec.y, p.start_y[a]);
+                reward = crashed ? -5.0f : __fsqrt_rn(fadd(fmul(ddx, ddx), fmul(ddy, ddy)));
+                break;
+            }
+            case 5: // DQAgent.hpp:161-180: min over rays of norm() == sqrt of the min squared norm
+            {
+                const float m = __fsqrt_rn(min_d2);
+                reward        = crashed ? -200.0f : (p.sensor_range > m ? m : p.sensor_range);
+                break;
+            }
+            case 6: reward = static_cast<float>(near); break; // MiscUtils.hpp:64-71
+            case 7:                                           // WorldModelVaeRnn/main.cpp:336-342
+                if (!crashed)
+                {
+                    reward  = fsub(1.0f, __fdiv_rn(__fsqrt_rn(near_d2), tv.widths[near])); // RaceTrack.cpp:53-72
+                    fitness = fadd(fitness, reward);
+                }
+                else if (timed_out)
+                    fitness = 0.0f;
+                break;
+            default: break;
+            }
+            p.reward[a]  = reward;
+            if (p.host_reward)
+                p.host_reward[a] = reward;
+            p.fitness[a] = fitness;
+            p.prev[a]    = prev;
+            if (need_idx || (rec.flags & kFlagReset))
+                p.nearest[a] = near;
+        }
+        p.crashed[a]   = crashed;
+        p.done[a]      = crashed; // Agent::isDone, Agent.cpp:138-144 (completed_ is never set)
+        if (p.host_done)
+            p.host_done[a] = crashed;
+        p.min_dist2[a] = min_d2;
+    }
 }
 
 #ifndef OK_UNITS
@@ -779,131 +1056,7 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
         // phase 1 -- one thread per agent: optional reset, kinematics, standstill (Environment.cpp:128-143)
         // =====================================================================================
         if (tid < count)
-        {
-            const int64_t a = tl.begin + tid;
-            float    x = p.x[a], y = p.y[a], rot = p.rot[a], speed = p.speed[a], accel = p.accel[a];
-            bool     crashed = p.crashed[a] != 0, timed_out = p.timed_out[a] != 0;
-            uint32_t flags = 0;
-            float    rx = 0.0f, ry = 0.0f;
-            float    hs = 0.0f, hc = 0.0f; // sin / cos of the heading, when the move already computed them
-            bool     have_sc = false;
-            int32_t  hint = p.nearest[a], prev_idx = 0;
-            float    fitness = 0.0f;
-            if (p.do_move)
-            {
-                prev_idx = p.prev[a];
-                fitness  = p.fitness[a];
-                float thr, steer;
-                if (p.action_source == 1)
-                { // synthetic stream: Philox4x32-10, counter (agent, step), key (seed, 0)
-                    uint32_t o[4];
-                    philox4x32_10(static_cast<uint32_t>(a), static_cast<uint32_t>(static_cast<uint64_t>(a) >> 32),
-                                  static_cast<uint32_t>(p.step), static_cast<uint32_t>(p.step >> 32), p.seed, 0u, o);
-                    if (p.movement_mode == 1)
-                    { // GeneticAgent.hpp:22-24 action set
-                        const uint32_t ti = o[0] % 3u, si = o[1] % 5u;
-                        thr   = ti == 0 ? -0.3f : (ti == 1 ? 0.0f : 0.3f);
-                        steer = si == 0 ? -4.0f : (si == 1 ? -1.0f : (si == 2 ? 0.0f : (si == 3 ? 1.0f : 4.0f)));
-                    }
-                    else
-                    { // ReinforceAgent.hpp:92-93 ranges
-                        thr   = fmul(100.0f, fmul(static_cast<float>(o[0] >> 8), 0x1p-24f));
-                        steer = fsub(fmul(10.0f, fmul(static_cast<float>(o[1] >> 8), 0x1p-24f)), 5.0f);
-                    }
-                }
-                else if (p.ext_thr)
-                {
-                    thr   = p.ext_thr[a];
-                    steer = p.ext_steer[a];
-                }
-                else
-                {
-                    thr   = p.act_thr[a];
-                    steer = p.act_steer[a];
-                }
-                // app-side reset of a crashed agent before the tick (GuidedCostLearning/test.cpp:102-111):
-                // Environment::resetAgent + Agent::reset, Environment.cpp:103-121 / Agent.cpp:123-135.
-                // prev / nearest / fitness are finalised in phase 4 (they need a centre-line search).
-                if (p.auto_reset && crashed)
-                {
-                    const int32_t pt =
-                        static_cast<int32_t>((static_cast<int64_t>(p.reset_pt[a]) + p.auto_reset_stride) % tv.n_pts);
-                    const float2 c = tv.pts[pt];
-                    x = c.x, y = c.y, rot = tv.headings[pt];
-                    accel = 0.0f, speed = 0.0f;
-                    crashed = false, timed_out = false;
-                    thr = 0.0f, steer = 0.0f; // Agent::reset zeroes current_action_
-                    rx = x, ry = y;
-                    flags |= kFlagReset;
-                    hint     = pt;
-                    prev_idx = 0;
-                    fitness  = 0.0f;
-                    p.reset_pt[a] = pt;
-                    p.start_x[a]  = x;
-                    p.start_y[a]  = y;
-                }
-                p.act_thr[a]   = thr;
-                p.act_steer[a] = steer;
-                if (!crashed)
-                {
-                    rot = fadd(rot, steer);
-                    if (p.movement_mode == 1)
-                    { // moveViaAcceleration, Agent.cpp:82-98
-                        accel = fadd(accel, thr);
-                        speed = fadd(speed, fmul(accel, p.dt));
-                        speed = (speed < 0.0f) ? 0.0f : speed;
-                        speed = (speed > p.speed_limit) ? p.speed_limit : speed;
-                    }
-                    else
-                    { // moveViaVelocity, Agent.cpp:108-119
-                        speed = thr;
-                    }
-                    float ms, mc;
-                    sincosf(fmul(OK_DEG2RAD, rot), ms, mc);
-                    hs = ms, hc = mc, have_sc = true; // the lidar origin below uses the same heading
-                    x = fadd(x, fmul(fmul(mc, speed), p.dt));
-                    y = fadd(y, fmul(fmul(ms, speed), p.dt));
-                    // checkAndUpdateStandstill, Environment.cpp:16-39
-                    uint32_t ctr = p.ss_ctr[a];
-                    bool     out = false;
-                    if (ctr == 0)
-                    {
-                        p.ss_x[a] = x;
-                        p.ss_y[a] = y;
-                        ctr       = 1;
-                    }
-                    else if (ctr >= p.standstill_period)
-                    {
-                        const float mx = fsub(x, p.ss_x[a]), my = fsub(y, p.ss_y[a]);
-                        out = fadd(fmul(mx, mx), fmul(my, my)) < p.standstill_thr2;
-                        ctr = 0;
-                    }
-                    else
-                        ++ctr;
-                    p.ss_ctr[a] = ctr;
-                    if (out)
-                    {
-                        crashed   = true;
-                        timed_out = true;
-                    }
-                }
-                p.x[a] = x, p.y[a] = y, p.rot[a] = rot, p.speed[a] = speed, p.accel[a] = accel;
-                p.timed_out[a] = timed_out;
-            }
-            // lidar origin, CollisionChecker.cu:121-124
-            float rs = hs, rc = hc;
-            if (!have_sc)
-                sincosf(fmul(OK_DEG2RAD, rot), rs, rc);
-            AgentRec rec;
-            rec.ox = fadd(x, fmul(p.sensor_offset, rc));
-            rec.oy = fadd(y, fmul(p.sensor_offset, rs));
-            rec.rc = rc, rec.rs = rs, rec.rot = rot, rec.x = x, rec.y = y, rec.rx = rx, rec.ry = ry;
-            rec.min_d2_bits = __float_as_int(fmul(p.sensor_range, p.sensor_range));
-            rec.flags       = flags | (crashed ? kFlagCrashed : 0u) | (timed_out ? kFlagTimedOut : 0u);
-            rec.row         = kBeam ? beam_row(bv, rec.ox, rec.oy) : -1;
-            rec.prev = prev_idx, rec.fitness = fitness, rec.hint = hint, rec.pad = 0;
-            recs[tid]       = rec;
-        }
+            recs[tid] = agent_pre(p, tv, bv, tl.begin + tid);
         if (tid == 0)
             s_pool = 0;
         __syncthreads();
@@ -1215,21 +1368,10 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                     const float              d_eff = dq == 0xffffu ? bv.rb : static_cast<float>(dq) * 0.00390625f;
                     if (active && !(cov && min_t <= d_eff - kBeamSlack))
                     { // undecided: everything nearer than d_eff - 1 is settled, the grid walk covers the rest
-                        RayWalk w;
-                        if (walk_begin(tv, w, rec.ox, rec.oy, dx, dy, p.sensor_range, cov ? fmaxf(d_eff - 1.0f, 0.0f) : 0.0f))
-                        {
-                            if (best >= 0)
-                            {
-                                w.best  = best;
-                                w.min_t = min_t; // the exact t of `best`
-                            }
-                            while (walk_unit(tv, w))
-                            {
-                            }
-                            best = w.best;
-                        }
+                        best = beam_walk_fallback(blob, rec.ox, rec.oy, dx, dy, p.sensor_range,
+                                                  cov ? fmaxf(d_eff - 1.0f, 0.0f) : 0.0f, best, min_t);
                     }
-                    sq = finish_ray(p, tv, rec, ray_base + q, dx, dy, best);
+                    sq = finish_ray(p, tv.seg, rec, ray_base + q, dx, dy, best);
                 }
                 // min_dist2 of CollisionChecker.cu:150,162-165: `if (sq < min) min = sq` skips NaN, and so
                 // does a signed-int min over the bit patterns of values >= +0 (a NaN made here is 0x7fffffff)
@@ -1254,122 +1396,435 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
         // =====================================================================================
         if ((warp << 5) < count)
         {
-            const int  mode     = p.reward_mode;
-            const bool need_idx = p.do_move && (mode == 1 || mode == 2 || mode == 6 || mode == 7);
-            const bool valid    = tid < count;
-            const int  al       = valid ? tid : 0;
-            const AgentRec rec  = recs[al];
-            const int64_t  a    = tl.begin + al;
-            const float    min_d2 = __int_as_float(rec.min_d2_bits);
-            bool           crashed = (rec.flags & kFlagCrashed) != 0;
-            const bool     timed_out = (rec.flags & kFlagTimedOut) != 0;
-            if (min_d2 < p.collision_dist2) // CollisionChecker.cu:167-171
-                crashed = true;
-            int32_t prev = rec.prev, near = 0;
-            float   fitness = rec.fitness, near_d2 = 0.0f;
-            // RaceTrack::findNearestTrackIndexBruteForce: the window around last tick's index first; the rare
-            // agents it cannot prove (teleported by a buffer write, track folding back on itself) get the
-            // full search, their warp's 32 lanes sharing it
-            const bool want_reset = valid && (rec.flags & kFlagReset) != 0;
-            bool       ok_reset   = true;
-            if (want_reset)
-            { // prev_track_idx_ = nearest index of the post-reset pose (main_eigen.cpp:121-130)
-                float d2;
-                prev = nearest_index_window(tv, rec.rx, rec.ry, rec.hint, d2, ok_reset);
-            }
-            for (unsigned need = __ballot_sync(0xffffffffu, !ok_reset); need; need &= need - 1)
-            {
-                const int   src = __ffs(need) - 1;
-                float       d2;
-                const int   r = nearest_index(tv, __shfl_sync(0xffffffffu, rec.rx, src), __shfl_sync(0xffffffffu, rec.ry, src), lane, 32, d2);
-                if (lane == src)
-                    prev = r;
-            }
-            if (want_reset)
-                near = prev;
-            const bool want_near = valid && need_idx;
-            bool       ok_near   = true;
-            if (want_near)
-                near = nearest_index_window(tv, rec.x, rec.y, want_reset ? prev : rec.hint, near_d2, ok_near);
-            for (unsigned need = __ballot_sync(0xffffffffu, !ok_near); need; need &= need - 1)
-            {
-                const int   src = __ffs(need) - 1;
-                float       d2;
-                const int   r = nearest_index(tv, __shfl_sync(0xffffffffu, rec.x, src), __shfl_sync(0xffffffffu, rec.y, src), lane, 32, d2);
-                if (lane == src)
+            const bool valid = tid < count;
+            agent_post(p, tv, recs[valid ? tid : 0], tl.begin + (valid ? tid : 0), valid, lane);
+        }
+    }
+
+    // last CTA out re-arms the tile scheduler for the next launch on this stream
+    if (tid == 0)
+    {
+        __threadfence();
+        if (atomicAdd(p.sched + 1, 1) == static_cast<int>(gridDim.x) - 1)
+        {
+            p.sched[0] = 0;
+            p.sched[1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Split pipeline for large populations (beam mode): the same three phases as three launches.
+//   agent_pre_kernel   one thread per agent (phase 1), records to global memory
+//   beam_cast_kernel   persistent CTAs, warps pull groups of 32 rays; NO CTA barrier except when a CTA moves to
+//                      another track (the fused kernel idles 24 of 32 warps during phases 1 and 4 of every batch
+//                      and drains at each batch end: ~20 % of its time at 65,536 agents)
+//   agent_post_kernel  one thread per agent (phase 4)
+// Track data for the per-agent kernels comes from the global arena (L2); only the cast kernel stages blobs.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) agent_pre_kernel(const StepParams p, const int64_t n)
+{
+    const int64_t a = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (a >= n)
+        return;
+    const TrackRef  tr = p.tracks[p.track_id[a]];
+    const TrackView tv = make_view(p.arena + tr.offset);
+    BeamView        bv;
+    bv.valid = false;
+    if (tr.has_beam)
+        bv = make_beam_view(p.beam_arena + tr.beam_offset);
+    p.recs_g[a] = agent_pre(p, tv, bv, a);
+}
+
+__global__ void __launch_bounds__(256) agent_post_kernel(const StepParams p, const int64_t n)
+{
+    const int64_t a0    = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const bool    valid = a0 < n;
+    const int64_t a     = valid ? a0 : n - 1; // whole warps run agent_post (its fallback search is warp-wide)
+    const TrackView tv  = make_view(p.arena + p.tracks[p.track_id[a]].offset);
+    const AgentRec  rec = p.recs_g[a];
+    agent_post(p, tv, rec, a, valid, threadIdx.x & 31);
+}
+
+// Per-ray preparation for the cast kernel, one thread per ray: direction (cosf/sinf of CollisionChecker.cu:47-48)
+// and the ray's beam-table entry, written as one 16-byte record so that the cast kernel's only per-ray input is
+// a coalesced load whose address depends on nothing but the ray index.
+constexpr uint32_t kRayInactive  = 0xffffffffu; // the agent is crashed: its rays are not cast (CollisionChecker.cu:44)
+constexpr uint32_t kRayUncovered = 0xfffffffeu; // no table entry: the grid walk decides the ray
+
+__global__ void __launch_bounds__(256) ray_prep_kernel(const StepParams p, const int64_t n_rays_total)
+{
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n_rays_total)
+        return;
+    int64_t a;
+    if (n_rays_total <= 0x7fffffff) // 32-bit division is several times cheaper than the 64-bit sequence
+        a = static_cast<int64_t>(static_cast<uint32_t>(i) / static_cast<uint32_t>(p.rays));
+    else
+        a = i / p.rays;
+    const int    r  = static_cast<int>(i - a * p.rays);
+    const float4 w1 = *(reinterpret_cast<const float4 *>(p.recs_g + a) + 1); // rot, flags, row, min_d2
+    uint4         rec = make_uint4(kRayInactive, 0u, 0u, 0u);
+    if (!(__float_as_uint(w1.y) & kFlagCrashed))
+    {
+        const float ang = fmul(OK_DEG2RAD, fadd(w1.x, __ldg(p.ray_deg + r)));
+        float       sn, cs;
+        sincosf(ang, sn, cs);
+        rec.x = kRayUncovered;
+        rec.z = __float_as_uint(cs);
+        rec.w = __float_as_uint(sn);
+        const int row = __float_as_int(w1.z);
+        if (row >= 0 && fabsf(ang) < kBeamMaxAngle)
+        {
+            const TrackRef    tr = p.tracks[p.track_id[a]];
+            const BeamHeader *h  = reinterpret_cast<const BeamHeader *>(p.beam_arena + tr.beam_offset);
+            const int         nb = h->nb;
+            const int         bin = __float2int_rd(fmul(ang, h->bin_scale)) & (nb - 1);
+            const uint2       ent = __ldg(reinterpret_cast<const uint2 *>(p.beam_arena + tr.beam_offset + h->off_entries) +
+                                          static_cast<size_t>(row) * nb + bin);
+            rec.x = ent.x;
+            rec.y = ent.y;
+        }
+    }
+    p.ray_recs[i] = rec;
+}
+
+struct RayOrigin
+{
+    float    ox, oy, rc, rs;
+    uint32_t flags;
+};
+
+struct CastTile
+{ // an epoch of the cast kernel's CTA-local scheduler (shared memory ring)
+    int64_t begin;    // first agent of the tile
+    int32_t n_rays;   // count * R
+    int32_t n_groups; // groups of 32 rays in the tile
+    int32_t track;
+    int32_t flags;    // 1: the track differs from the previous tile's (stage it first), 2: no more tiles
+    int32_t epoch;    // which epoch this slot currently describes
+    int32_t pad;
+};
+constexpr int kCastRing = 64;
+
+#define OK_SPIN_LIMIT (1 << 22)
+
+template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) beam_cast_kernel(const StepParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(16) float4             s_wray[kBlock];
+    __shared__ __align__(8) unsigned long long s_wkey[kBlock];
+    __shared__ __align__(8) uint64_t           bar;
+    __shared__ unsigned long long              s_pool;  // (epoch << 32) | next group of the epoch's tile
+    __shared__ int                             s_claim; // number of epochs whose successor has been opened
+    __shared__ int                             s_ready; // highest epoch whose descriptor is in the ring
+    __shared__ __align__(16) CastTile          s_tile[kCastRing];
+    __shared__ BeamView                        s_bv; // the staged track's table (every warp passes a staging epoch together)
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int R   = p.rays;
+    uint8_t  *blob = smem;
+    float4             *w_ray = s_wray + (tid & ~31);
+    unsigned long long *w_key = s_wkey + (tid & ~31);
+
+    // descriptors are fetched one epoch ahead of their use, so that opening an epoch never waits on global memory
+    auto load_tile = [&](int epoch, int prev_track) { // one thread
+        const int t = atomicAdd(p.sched, 1);
+        CastTile  ct{};
+        ct.epoch = epoch;
+        if (t >= p.n_cast_tiles)
+            ct.flags = 2;
+        else
+        {
+            const Tile tl = p.cast_tiles[t];
+            ct.begin      = tl.begin;
+            ct.track      = tl.track;
+            ct.n_rays     = tl.count * R;
+            ct.n_groups   = (ct.n_rays + 31) >> 5;
+            ct.flags      = tl.track != prev_track ? 1 : 0;
+        }
+        s_tile[epoch & (kCastRing - 1)] = ct;
+    };
+    if (tid == 0)
+    {
+        mbar_init(&bar, 1);
+        load_tile(0, -1);
+        if (!(s_tile[0].flags & 2))
+            load_tile(1, s_tile[0].track);
+        else
+            s_tile[1] = s_tile[0], s_tile[1].epoch = 1;
+        s_ready = 1;
+        s_pool  = 0ull;
+        s_claim = 0;
+    }
+    __syncthreads();
+
+    const float inv_R = 1.0f / static_cast<float>(R);
+    const float inf   = __int_as_float(0x7f800000);
+    const unsigned long long key_none =
+        (static_cast<unsigned long long>(__float_as_uint(p.sensor_range)) << 32) | 0x80000000ull;
+    uint32_t phase  = 0;
+    int      staged = -1; // last STAGING epoch this warp has passed
+    // segments are the blob's first section (pack_blob): a constant offset, no register
+    const float4 *segs = reinterpret_cast<const float4 *>(blob + sizeof(TrackHeader));
+    const BeamView &bv = s_bv;
+
+    // one group = (epoch, index).  grab() only takes a number (and the epoch's descriptor, valid at that moment:
+    // an epoch shows in the pool after its descriptor is written, and the ring is kCastRing deep); resolve()
+    // turns it into work, blocking where needed.
+    auto grab = [&](int &e, int &gi, CastTile &ct) {
+        unsigned long long v = 0;
+        if (lane == 0)
+            v = atomicAdd(&s_pool, 1ull);
+        v  = __shfl_sync(0xffffffffu, v, 0);
+        e  = static_cast<int>(v >> 32);
+        gi = static_cast<int>(static_cast<uint32_t>(v));
+        ct = s_tile[e & (kCastRing - 1)];
+        if (ct.epoch != e)
+            __trap(); // the ring was lapped (a warp fell kCastRing tiles behind): never continue on a stale descriptor
+    };
+    // returns false when there is no more work; otherwise (e, gi) is a valid group of a staged tile
+    auto resolve = [&](int &e, int &gi, CastTile &ct) -> bool {
+        for (int spin = 0;; ++spin)
+        {
+            if (ct.flags & 2)
+                return false;
+            if ((ct.flags & 1) && staged < e)
+            { // every warp of the CTA passes here exactly once per staging epoch, with no group in flight
+                __syncthreads();
+                if (tid == 0)
                 {
-                    near    = r;
-                    near_d2 = d2;
+                    const TrackRef tr = p.tracks[ct.track];
+                    BeamView       v;
+                    v.valid = false;
+                    if (tr.has_beam)
+                        v = make_beam_view(p.beam_arena + tr.beam_offset);
+                    s_bv = v; // released by the mbarrier arrive below, acquired by every waiter
+                    fence_proxy_async();
+                    mbar_expect_tx(&bar, tr.bytes);
+                    tma_bulk_g2s(blob, p.arena + tr.offset, tr.bytes, &bar);
+                }
+                mbar_wait(&bar, phase);
+                phase ^= 1u;
+                staged = e;
+            }
+            if (gi < ct.n_groups)
+                return true;
+            // the epoch's tile is used up: one warp opens the next epoch (its descriptor is already in the ring)
+            // and then fetches the descriptor after that
+            if (lane == 0)
+            {
+                if (atomicCAS(&s_claim, e, e + 1) == e)
+                {
+                    for (int w = 0; *reinterpret_cast<volatile int *>(&s_ready) < e + 1; ++w)
+                    {
+                        __nanosleep(32);
+                        if (w > OK_SPIN_LIMIT)
+                            __trap();
+                    }
+                    __threadfence_block();
+                    const CastTile nx = s_tile[(e + 1) & (kCastRing - 1)];
+                    atomicExch(&s_pool, static_cast<unsigned long long>(e + 1) << 32);
+                    if (!(nx.flags & 2))
+                    {
+                        load_tile(e + 2, nx.track);
+                        __threadfence_block();
+                        *reinterpret_cast<volatile int *>(&s_ready) = e + 2;
+                    }
+                }
+                else
+                    __nanosleep(32);
+            }
+            __syncwarp();
+            if (spin > OK_SPIN_LIMIT)
+                __trap(); // a lost wake-up must not hang the device
+            int      e2, g2;
+            CastTile c2;
+            grab(e2, g2, c2);
+            if (e2 == e)
+                continue; // still the exhausted epoch
+            e  = e2;
+            gi = g2;
+            ct = c2;
+        }
+    };
+    // this lane's ray of a group: the prepared record (ray_prep_kernel) and where it belongs
+    struct Group
+    {
+        int64_t a;  // global agent
+        int     q;  // ray within the tile, -1 = none
+        uint4   rr; // {first chunk, count | dq << 16, dx, dy}
+    };
+    auto locate = [&](const CastTile &ct, int g, Group &G) {
+        const int q = (g << 5) + lane;
+        G.q         = q < ct.n_rays ? q : -1;
+        G.rr        = make_uint4(kRayInactive, 0u, 0u, 0u);
+        const int al = G.q >= 0 ? __float2int_rz((static_cast<float>(q) + 0.5f) * inv_R) : 0;
+        G.a          = ct.begin + al;
+        if (G.q >= 0)
+            G.rr = __ldg(p.ray_recs + (ct.begin * R + q));
+    };
+
+    int      e, gi;
+    CastTile ct;
+    grab(e, gi, ct);
+    bool  more = resolve(e, gi, ct);
+    Group G{};
+    if (more)
+        locate(ct, gi, G);
+    while (more)
+    {
+        // next group: its table entry is requested now unless its tile still needs work from resolve()
+        // (staging of another track, exhausted, or no more tiles).  A later epoch seen here can only be
+        // separated from the current one by same-track tiles: staging epochs are never skipped.
+        int   e_n, gi_n;
+        bool  ahead;
+        Group G_n{};
+        {
+            CastTile ct_n;
+            grab(e_n, gi_n, ct_n);
+            ahead = gi_n < ct_n.n_groups && !(ct_n.flags & 2) && (!(ct_n.flags & 1) || staged >= e_n);
+            if (ahead)
+                locate(ct_n, gi_n, G_n);
+        }
+
+        const bool has    = G.q >= 0;
+        const bool active = has && G.rr.x != kRayInactive;
+        const bool cov    = active && G.rr.x != kRayUncovered;
+        RayOrigin  rec;
+        {
+            const float4 w0 = __ldg(reinterpret_cast<const float4 *>(p.recs_g + G.a)); // ox, oy, rc, rs
+            rec.ox = w0.x, rec.oy = w0.y, rec.rc = w0.z, rec.rs = w0.w;
+            rec.flags = active ? 0u : kFlagCrashed;
+        }
+        const float dx = __uint_as_float(G.rr.z), dy = __uint_as_float(G.rr.w);
+        w_ray[lane] = make_float4(rec.ox, rec.oy, dx, dy);
+        w_key[lane] = key_none;
+        const uint32_t nch = cov ? (((G.rr.y & 0xffffu) + 3u) >> 2) : 0u;
+        uint32_t       inc = nch;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o)
+                inc += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+        const uint32_t first = G.rr.x - (inc - nch);
+        __syncwarp();
+        auto find_chunk = [&](uint32_t j, int &owner) -> uint32_t {
+            owner = 0;
+#pragma unroll
+            for (int s2 = 16; s2 > 0; s2 >>= 1)
+            {
+                const uint32_t v = __shfl_sync(0xffffffffu, inc, owner + s2 - 1);
+                if (v <= j)
+                    owner += s2;
+            }
+            return __shfl_sync(0xffffffffu, first, owner) + j;
+        };
+        int   owner = 0;
+        uint2 it    = make_uint2(0xffffffffu, 0xffffffffu);
+        if (total > 0)
+        {
+            const uint32_t ch = find_chunk(lane, owner);
+            if (static_cast<uint32_t>(lane) < total)
+                it = __ldg(bv.chunks + ch);
+        }
+        for (uint32_t base = 0; base < total; base += 32)
+        {
+            int   owner_n = 0;
+            uint2 it_n    = make_uint2(0xffffffffu, 0xffffffffu);
+            if (base + 32 < total)
+            {
+                const uint32_t jn = base + 32 + lane;
+                const uint32_t ch = find_chunk(jn, owner_n);
+                if (jn < total)
+                    it_n = __ldg(bv.chunks + ch);
+            }
+            if (base + lane < total)
+            {
+                const float4        ray = w_ray[owner];
+                unsigned long long *key = w_key + owner;
+                const float         m   = __uint_as_float(reinterpret_cast<const uint32_t *>(key)[1]);
+                int                 idx[4];
+                float               tq[4];
+                bool                el[4], lit[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                {
+                    const uint32_t raw  = ((u < 2 ? it.x : it.y) >> (16 * (u & 1))) & 0xffffu;
+                    const bool     live = raw != 0xffffu;
+                    idx[u]              = live ? static_cast<int>(raw) : 0;
+                    tq[u] = beam_eval(segs, idx[u], live, ray.x, ray.y, ray.z, ray.w, el[u], lit[u]);
+                }
+                float tq_b  = m;
+                int   idx_b = -1;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                {
+                    const bool cand = el[u] & !(tq[u] > fmul(tq_b, 1.000003814697265625f));
+                    if (cand & !(tq[u] < fmul(tq_b, 0.999996185302734375f)) & (idx_b >= 0))
+                        beam_flush(segs, idx_b, ray.x, ray.y, ray.z, ray.w, key);
+                    tq_b  = cand ? tq[u] : tq_b;
+                    idx_b = cand ? idx[u] : idx_b;
+                }
+                if (idx_b >= 0)
+                    beam_flush(segs, idx_b, ray.x, ray.y, ray.z, ray.w, key);
+                if (lit[0] | lit[1] | lit[2] | lit[3])
+                {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (lit[u])
+                            beam_literal(segs, idx[u], ray.x, ray.y, ray.z, ray.w, key);
                 }
             }
-            if (valid)
-            {
-                if (p.do_move)
-                {
-                    float reward = 0.0f;
-                    switch (mode)
-                    {
-                    case 1: // QAgent.hpp:150-168
-                        if (crashed)
-                            reward = -200.0f;
-                        else
-                        {
-                            const int32_t prog = near - prev;
-                            prev               = near;
-                            const int32_t ab = prog < 0 ? -prog : prog, len = tv.n_pts;
-                            reward = static_cast<float>(ab > (len / 2) ? len - ab : ab);
-                        }
-                        break;
-                    case 2: // main_eigen.cpp:147-163
-                        if (!crashed)
-                        {
-                            const int32_t prog = near - prev;
-                            prev               = near;
-                            reward             = static_cast<float>(prog < 0 ? -prog : prog);
-                            fitness            = fadd(fitness, reward);
-                        }
-                        else if (timed_out)
-                            fitness = 0.0f;
-                        break;
-                    case 3: reward = 1.0f; break; // ppo_sim.cpp:76
-                    case 4:                       // ReinforceContinuous/reinforce_sim.cpp:59-73
-                    {
-                        const float ddx = fsub(rec.x, p.start_x[a]), ddy = fsub(rec.y, p.start_y[a]);
-                        reward = crashed ? -5.0f : __fsqrt_rn(fadd(fmul(ddx, ddx), fmul(ddy, ddy)));
-                        break;
-                    }
-                    case 5: // DQAgent.hpp:161-180: min over rays of norm() == sqrt of the min squared norm
-                    {
-                        const float m = __fsqrt_rn(min_d2);
-                        reward        = crashed ? -200.0f : (p.sensor_range > m ? m : p.sensor_range);
-                        break;
-                    }
-                    case 6: reward = static_cast<float>(near); break; // MiscUtils.hpp:64-71
-                    case 7:                                           // WorldModelVaeRnn/main.cpp:336-342
-                        if (!crashed)
-                        {
-                            reward  = fsub(1.0f, __fdiv_rn(__fsqrt_rn(near_d2), tv.widths[near])); // RaceTrack.cpp:53-72
-                            fitness = fadd(fitness, reward);
-                        }
-                        else if (timed_out)
-                            fitness = 0.0f;
-                        break;
-                    default: break;
-                    }
-                    p.reward[a]  = reward;
-                    if (p.host_reward)
-                        p.host_reward[a] = reward;
-                    p.fitness[a] = fitness;
-                    p.prev[a]    = prev;
-                    if (need_idx || (rec.flags & kFlagReset))
-                        p.nearest[a] = near;
-                }
-                p.crashed[a]   = crashed;
-                p.done[a]      = crashed; // Agent::isDone, Agent.cpp:138-144 (completed_ is never set)
-                if (p.host_done)
-                    p.host_done[a] = crashed;
-                p.min_dist2[a] = min_d2;
+            owner = owner_n;
+            it    = it_n;
+        }
+        __syncwarp();
+        float sq = inf;
+        if (has)
+        {
+            const unsigned long long key   = w_key[lane];
+            int                      best  = static_cast<int>(0x7fffffffu - static_cast<uint32_t>(key));
+            const float              min_t = __uint_as_float(static_cast<uint32_t>(key >> 32));
+            const uint32_t           dq    = G.rr.y >> 16;
+            const float              d_eff = dq == 0xffffu ? bv.rb : static_cast<float>(dq) * 0.00390625f;
+            if (active && !(cov && min_t <= d_eff - kBeamSlack))
+            { // undecided: everything nearer than d_eff - 1 is settled, the grid walk covers the rest
+                best = beam_walk_fallback(blob, rec.ox, rec.oy, dx, dy, p.sensor_range,
+                                          cov ? fmaxf(d_eff - 1.0f, 0.0f) : 0.0f, best, min_t);
             }
+            const int al = __float2int_rz((static_cast<float>(G.q) + 0.5f) * inv_R);
+            sq           = finish_ray(p, segs, rec, (G.a - al) * R + G.q, dx, dy, best);
+        }
+        // min_dist2 of CollisionChecker.cu:150,162-165 (NaN never lowers it)
+        if ((R & 31) == 0)
+        {
+            float m = (sq == sq) ? sq : inf;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (has && lane == 0)
+                atomicMin(&p.recs_g[G.a].min_d2_bits, __float_as_int(m));
+        }
+        else if (has && sq == sq)
+            atomicMin(&p.recs_g[G.a].min_d2_bits, __float_as_int(sq));
+
+        e = e_n, gi = gi_n;
+        if (ahead)
+            G = G_n;
+        else
+        { // the descriptor is read again rather than carried across the group (registers); a lapped ring traps
+            ct = s_tile[e & (kCastRing - 1)];
+            if (ct.epoch != e)
+                __trap();
+            more = resolve(e, gi, ct);
+            if (more)
+                locate(ct, gi, G);
         }
     }
 

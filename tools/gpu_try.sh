@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 tag=${1:-try}; shift
 ( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/pytest_gpu_$tag.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu_$tag.log
-tail -4 gpurun_out/pytest_gpu_$tag.log | head -2
+grep -E "passed|failed|error" gpurun_out/pytest_gpu_$tag.log | tail -3
 if [ $# -eq 0 ]; then set -- "beam 8 64" "beam 4 128"; fi
 for cfg in "$@"; do
   set -- $cfg
