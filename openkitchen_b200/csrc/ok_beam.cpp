@@ -267,7 +267,7 @@ struct Builder
             for (size_t i = 0; i < count; ++i)
                 row.items.push_back(l[i].second);
             while (row.items.size() % 4)
-                row.items.push_back(0xffffu);
+                row.items.push_back(static_cast<uint16_t>(t.n_segments())); // the blob's null segment
         }
     }
 };

@@ -40,7 +40,7 @@ struct BeamHeader
     float    rb;         // completeness distance of entries flagged complete (dq = 0xffff)
     uint32_t off_rows;   // uint32[nx * ny]: row of the cell in `entries`, 0xffffffff = not covered
     uint32_t off_entries; // uint2[n_rows * nb]: {first chunk, count | dq << 16}; dq = floor(d * 256), 0xffff = rb
-    uint32_t off_items;  // uint16[]: segment indices in chunks of 4, padded with 0xffff
+    uint32_t off_items;  // uint16[]: segment indices in chunks of 4, padded with n_segments (the blob's null segment)
     uint32_t n_rows;
     uint32_t n_chunks;
     uint32_t bytes;

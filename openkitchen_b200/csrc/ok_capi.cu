@@ -122,13 +122,6 @@ struct OkEnv
     int32_t              batch_agents{0};
     uint16_t            *d_ray_order{nullptr};
     int32_t             *d_sched{nullptr};
-    // split pipeline (pre / cast / post kernels) for large populations in beam mode
-    ok::AgentRec        *d_recs{nullptr};
-    uint4               *d_ray_recs{nullptr};
-    ok::Tile            *d_cast_tiles{nullptr};
-    int32_t              n_cast_tiles{0};
-    int32_t              cast_grid{0};
-    bool                 use_split{false};
     int                  smem_optin{0};
     std::vector<int32_t> h_track_id;
     // staging for the *_host entry points
@@ -165,13 +158,6 @@ void free_agents(OkEnv *e)
         cudaFree(e->d_ray_order);
     if (e->d_sched)
         cudaFree(e->d_sched);
-    if (e->d_recs)
-        cudaFree(e->d_recs);
-    if (e->d_cast_tiles)
-        cudaFree(e->d_cast_tiles);
-    if (e->d_ray_recs)
-        cudaFree(e->d_ray_recs);
-    e->d_recs = nullptr, e->d_cast_tiles = nullptr, e->n_cast_tiles = 0, e->d_ray_recs = nullptr;
     e->d_slab = nullptr, e->d_ray_deg = nullptr, e->d_tiles = nullptr, e->d_ray_order = nullptr, e->d_sched = nullptr;
     for (auto &b : e->d_buf)
         b = nullptr;
@@ -324,10 +310,6 @@ ok::StepParams base_params(OkEnv *e)
     p.smem_blob_bytes   = static_cast<uint32_t>((e->max_blob_used + 127) / 128 * 128);
     p.ray_order         = e->d_ray_order;
     p.sched             = e->d_sched;
-    p.recs_g            = e->d_recs;
-    p.ray_recs          = e->d_ray_recs;
-    p.cast_tiles        = e->d_cast_tiles;
-    p.n_cast_tiles      = e->n_cast_tiles;
     p.movement_mode     = e->cfg.movement_mode;
     p.reward_mode       = e->cfg.reward_mode;
     p.raycast_mode      = e->cfg.raycast_mode;
@@ -362,20 +344,6 @@ int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
     p.arena      = e->d_arena;
     p.beam_arena = e->d_beam_arena;
     p.tracks     = e->d_track_refs;
-    if (e->cfg.raycast_mode == OK_RAYCAST_BEAM && e->use_split)
-    { // large populations: phase 1 / rays / phase 4 as three launches (ok_kernels.cuh, "split pipeline")
-        const int      threads = 256;
-        const unsigned blocks  = static_cast<unsigned>((e->n_agents + threads - 1) / threads);
-        p.sched                = e->d_sched + 16;
-        ok::agent_pre_kernel<<<blocks, threads, 0, s>>>(p, e->n_agents);
-        const int64_t  total_rays = e->n_agents * e->rays;
-        ok::ray_prep_kernel<<<static_cast<unsigned>((total_rays + threads - 1) / threads), threads, 0, s>>>(p, total_rays);
-        ok::beam_cast_kernel<kBlock><<<e->cast_grid, kBlock, (e->max_blob_used + 127) / 128 * 128, s>>>(p);
-        ok::agent_post_kernel<<<blocks, threads, 0, s>>>(p, e->n_agents);
-        OK_CUDA(cudaGetLastError());
-        e->launches += 4;
-        return OK_SUCCESS;
-    }
     if (e->cfg.raycast_mode == OK_RAYCAST_BEAM)
         ok::step_kernel<kBlock, true><<<e->grid, kBlock, e->smem_beam, s>>>(p);
     else
@@ -728,40 +696,6 @@ int ok_alloc_agents(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, c
     OK_CUDA(cudaMalloc(&e->d_tiles, sizeof(ok::Tile) * tiles.size()));
     OK_CUDA(cudaMemcpy(e->d_tiles, tiles.data(), sizeof(ok::Tile) * tiles.size(), cudaMemcpyHostToDevice));
     e->grid = std::max(1, std::min(e->num_sms, e->n_tiles));
-
-    // split pipeline: per-agent records in global memory, small same-track tiles (about 64 groups of 32 rays each)
-    {
-        e->use_split = n >= 8192;
-        if (const char *env = std::getenv("OK_SPLIT"))
-            e->use_split = std::atoi(env) != 0;
-        OK_CUDA(cudaMalloc(&e->d_recs, sizeof(ok::AgentRec) * static_cast<size_t>(n)));
-        OK_CUDA(cudaMemset(e->d_recs, 0, sizeof(ok::AgentRec) * static_cast<size_t>(n)));
-        if (e->use_split)
-            OK_CUDA(cudaMalloc(&e->d_ray_recs, sizeof(uint4) * static_cast<size_t>(n) * static_cast<size_t>(rays)));
-        const int64_t         per = std::max<int64_t>(1, (2048 + rays - 1) / rays);
-        std::vector<ok::Tile> ct;
-        for (int64_t i = 0; i < n;)
-        {
-            int64_t j = i;
-            while (j < n && e->h_track_id[j] == e->h_track_id[i])
-                ++j;
-            for (int64_t b = i; b < j; b += per)
-            {
-                ok::Tile t{};
-                t.track = e->h_track_id[i];
-                t.begin = b;
-                t.count = static_cast<int32_t>(std::min<int64_t>(per, j - b));
-                ct.push_back(t);
-            }
-            i = j;
-        }
-        e->n_cast_tiles = static_cast<int32_t>(ct.size());
-        OK_CUDA(cudaMalloc(&e->d_cast_tiles, sizeof(ok::Tile) * ct.size()));
-        OK_CUDA(cudaMemcpy(e->d_cast_tiles, ct.data(), sizeof(ok::Tile) * ct.size(), cudaMemcpyHostToDevice));
-        e->cast_grid = std::max(1, std::min(e->num_sms, e->n_cast_tiles));
-        OK_CUDA(cudaFuncSetAttribute(ok::beam_cast_kernel<kBlock>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>((e->max_blob_used + 127) / 128 * 128)));
-    }
 
     // every agent starts where `Environment::resetAgent(agent, false)` puts it: RaceTrack::kStartingIdx
     std::vector<int32_t> pt(static_cast<size_t>(n));

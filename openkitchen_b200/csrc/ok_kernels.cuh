@@ -46,7 +46,6 @@ struct TrackRef
     uint64_t beam_offset; // byte offset of its beam blob in the beam arena (ok_beam.hpp)
 };
 
-struct AgentRec;
 struct StepParams
 {
     // agent state, structure of arrays
@@ -72,11 +71,6 @@ struct StepParams
     uint32_t       smem_blob_bytes; // offset of the batch scratch behind the staged track
     const uint16_t *ray_order;      // ray indices sorted by |angle|: pool order, long (central) rays first
     int32_t       *sched;           // {next tile, CTAs finished}: dynamic tile scheduler
-    // split pipeline (pre / cast / post kernels): per-agent records in global memory and small tiles
-    struct AgentRec *recs_g;
-    uint4         *ray_recs;        // per ray: {first chunk, count | dq << 16, dx, dy} (ray_prep_kernel)
-    const Tile    *cast_tiles;
-    int32_t        n_cast_tiles;
     // this launch
     const float *ext_thr, *ext_steer; // nullable: actions supplied by the caller
     int32_t      action_source;       // 0 stored/ext, 1 philox
@@ -632,8 +626,8 @@ __device__ __forceinline__ void beam_flush(const float4 *segs, int idx, float ox
 //          the order of its exact t matters;
 //   lit -- on an edge of the segment or at the origin (rare): needs the reference's literal predicate.
 // Everything else fails the reference's predicate (sufficient conditions, see test_segment).
-__device__ __forceinline__ float beam_eval(const float4 *segs, const int idx, const bool live, const float ox,
-                                           const float oy, const float dx, const float dy, bool &el, bool &lit)
+__device__ __forceinline__ float beam_eval(const float4 *segs, const int idx, const float ox, const float oy,
+                                           const float dx, const float dy, bool &el, bool &lit)
 {
     const float4   sg    = segs[idx];
     const float    ex    = fsub(sg.x, ox);
@@ -647,11 +641,15 @@ __device__ __forceinline__ float beam_eval(const float4 *segs, const int idx, co
     const float    ad    = __uint_as_float(adb);
     const float    b     = __uint_as_float(__float_as_uint(sn) ^ sgn);
     const float    a     = __uint_as_float(__float_as_uint(tn) ^ sgn);
-    const bool     rej   = !live | (adb < 0x322BCC77u) | (b > ad) | (b < -0x1p-22f) | (a < -0x1p-22f);
+    const bool     rej   = (adb < 0x322BCC77u) | (b > ad) | (b < -0x1p-22f) | (a < -0x1p-22f);
     const bool     comfy = (b >= 0.0f) & (adb < 0x5d800000u /* 2^60 */) & (a >= 0x1p-60f);
     el                   = !rej & comfy;
     lit                  = !rej & !comfy;
-    return __fdividef(a, ad);
+    // a * rcp(ad): rcp.approx is within 1 ulp and the product adds half an ulp, inside the 2^-21 bound; where
+    // `el` holds, ad < 2^60 and a >= 2^-60, so nothing is flushed or overflows
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(ad));
+    return fmul(a, r);
 }
 
 // literal predicate of the reference (CollisionChecker.cu:25-33) for a candidate flagged `lit`
@@ -1015,16 +1013,19 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
     int      staged = -1;
     uint32_t phase  = 0;
     const float inv_R = 1.0f / static_cast<float>(R);
+    if (tid == 0)
+        s_tile = atomicAdd(p.sched, 1);
 
     for (;;)
     {
-        // ---- dynamic tile scheduler: tiles are batches of same-track agents, in agent order ----
-        if (tid == 0)
-            s_tile = atomicAdd(p.sched, 1);
-        __syncthreads(); // also: everyone is done with the previous batch and its track
+        // ---- dynamic tile scheduler: tiles are batches of same-track agents, in agent order.  The next tile is
+        // claimed as LATE as possible (after the rays of this batch): claiming it at the start of the batch hides
+        // the atomic's latency but turns the schedule static -- measured 0.190 ms vs 0.150 ms per tick ----
+        __syncthreads(); // everyone is done with the previous batch and its track; s_tile is published
         const int tile = s_tile;
         if (tile >= p.n_tiles)
             break;
+
         const Tile tl = p.tiles[tile];
         if (tl.track != staged)
         {
@@ -1294,7 +1295,7 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                     return __shfl_sync(0xffffffffu, first, owner) + j;
                 };
                 int   owner = 0;
-                uint2 it    = make_uint2(0xffffffffu, 0xffffffffu);
+                uint2 it    = make_uint2(0u, 0u);
                 if (total > 0)
                 {
                     const uint32_t ch = find_chunk(lane, owner);
@@ -1305,7 +1306,7 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                 {
                     // the next round's candidates are requested before this round's are tested
                     int   owner_n = 0;
-                    uint2 it_n    = make_uint2(0xffffffffu, 0xffffffffu);
+                    uint2 it_n    = make_uint2(0u, 0u);
                     if (base + 32 < total)
                     {
                         const uint32_t jn = base + 32 + lane;
@@ -1324,10 +1325,10 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
 #pragma unroll
                         for (int u = 0; u < 4; ++u)
                         {
-                            const uint32_t raw  = ((u < 2 ? it.x : it.y) >> (16 * (u & 1))) & 0xffffu;
-                            const bool     live = raw != 0xffffu; // chunks are padded with 0xffff
-                            idx[u]              = live ? static_cast<int>(raw) : 0;
-                            tq[u] = beam_eval(tv.seg, idx[u], live, ray.x, ray.y, ray.z, ray.w, el[u], lit[u]);
+                            // chunks are padded with the index of the track's null segment (zero length: denom = 0
+                            // fails the reference's parallel test), so padding needs no special case
+                            idx[u] = static_cast<int>(((u < 2 ? it.x : it.y) >> (16 * (u & 1))) & 0xffffu);
+                            tq[u]  = beam_eval(tv.seg, idx[u], ray.x, ray.y, ray.z, ray.w, el[u], lit[u]);
                         }
                         // the chunk's best by approximate quotient, starting from the ray's incumbent (exact t = m,
                         // already in the key).  Every candidate is either strictly beaten by another one (the two
@@ -1390,6 +1391,8 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
             }
         }
         __syncthreads();
+        if (tid == 0)
+            s_tile = atomicAdd(p.sched, 1); // every thread read the old value long ago; visible after the loop-top barrier
 
         // =====================================================================================
         // phase 4 -- one thread per agent: crash flag, centre-line search, progress / reward / done
@@ -1414,432 +1417,6 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
     }
 }
 
-
-// ---------------------------------------------------------------------------------------------
-// Split pipeline for large populations (beam mode): the same three phases as three launches.
-//   agent_pre_kernel   one thread per agent (phase 1), records to global memory
-//   beam_cast_kernel   persistent CTAs, warps pull groups of 32 rays; NO CTA barrier except when a CTA moves to
-//                      another track (the fused kernel idles 24 of 32 warps during phases 1 and 4 of every batch
-//                      and drains at each batch end: ~20 % of its time at 65,536 agents)
-//   agent_post_kernel  one thread per agent (phase 4)
-// Track data for the per-agent kernels comes from the global arena (L2); only the cast kernel stages blobs.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) agent_pre_kernel(const StepParams p, const int64_t n)
-{
-    const int64_t a = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (a >= n)
-        return;
-    const TrackRef  tr = p.tracks[p.track_id[a]];
-    const TrackView tv = make_view(p.arena + tr.offset);
-    BeamView        bv;
-    bv.valid = false;
-    if (tr.has_beam)
-        bv = make_beam_view(p.beam_arena + tr.beam_offset);
-    p.recs_g[a] = agent_pre(p, tv, bv, a);
-}
-
-__global__ void __launch_bounds__(256) agent_post_kernel(const StepParams p, const int64_t n)
-{
-    const int64_t a0    = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    const bool    valid = a0 < n;
-    const int64_t a     = valid ? a0 : n - 1; // whole warps run agent_post (its fallback search is warp-wide)
-    const TrackView tv  = make_view(p.arena + p.tracks[p.track_id[a]].offset);
-    const AgentRec  rec = p.recs_g[a];
-    agent_post(p, tv, rec, a, valid, threadIdx.x & 31);
-}
-
-// Per-ray preparation for the cast kernel, one thread per ray: direction (cosf/sinf of CollisionChecker.cu:47-48)
-// and the ray's beam-table entry, written as one 16-byte record so that the cast kernel's only per-ray input is
-// a coalesced load whose address depends on nothing but the ray index.
-constexpr uint32_t kRayInactive  = 0xffffffffu; // the agent is crashed: its rays are not cast (CollisionChecker.cu:44)
-constexpr uint32_t kRayUncovered = 0xfffffffeu; // no table entry: the grid walk decides the ray
-
-__global__ void __launch_bounds__(256) ray_prep_kernel(const StepParams p, const int64_t n_rays_total)
-{
-    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= n_rays_total)
-        return;
-    int64_t a;
-    if (n_rays_total <= 0x7fffffff) // 32-bit division is several times cheaper than the 64-bit sequence
-        a = static_cast<int64_t>(static_cast<uint32_t>(i) / static_cast<uint32_t>(p.rays));
-    else
-        a = i / p.rays;
-    const int    r  = static_cast<int>(i - a * p.rays);
-    const float4 w1 = *(reinterpret_cast<const float4 *>(p.recs_g + a) + 1); // rot, flags, row, min_d2
-    uint4         rec = make_uint4(kRayInactive, 0u, 0u, 0u);
-    if (!(__float_as_uint(w1.y) & kFlagCrashed))
-    {
-        const float ang = fmul(OK_DEG2RAD, fadd(w1.x, __ldg(p.ray_deg + r)));
-        float       sn, cs;
-        sincosf(ang, sn, cs);
-        rec.x = kRayUncovered;
-        rec.z = __float_as_uint(cs);
-        rec.w = __float_as_uint(sn);
-        const int row = __float_as_int(w1.z);
-        if (row >= 0 && fabsf(ang) < kBeamMaxAngle)
-        {
-            const TrackRef    tr = p.tracks[p.track_id[a]];
-            const BeamHeader *h  = reinterpret_cast<const BeamHeader *>(p.beam_arena + tr.beam_offset);
-            const int         nb = h->nb;
-            const int         bin = __float2int_rd(fmul(ang, h->bin_scale)) & (nb - 1);
-            const uint2       ent = __ldg(reinterpret_cast<const uint2 *>(p.beam_arena + tr.beam_offset + h->off_entries) +
-                                          static_cast<size_t>(row) * nb + bin);
-            rec.x = ent.x;
-            rec.y = ent.y;
-        }
-    }
-    p.ray_recs[i] = rec;
-}
-
-struct RayOrigin
-{
-    float    ox, oy, rc, rs;
-    uint32_t flags;
-};
-
-struct CastTile
-{ // an epoch of the cast kernel's CTA-local scheduler (shared memory ring)
-    int64_t begin;    // first agent of the tile
-    int32_t n_rays;   // count * R
-    int32_t n_groups; // groups of 32 rays in the tile
-    int32_t track;
-    int32_t flags;    // 1: the track differs from the previous tile's (stage it first), 2: no more tiles
-    int32_t epoch;    // which epoch this slot currently describes
-    int32_t pad;
-};
-constexpr int kCastRing = 64;
-
-#define OK_SPIN_LIMIT (1 << 22)
-
-template <int kBlock> __global__ void __launch_bounds__(kBlock, 1) beam_cast_kernel(const StepParams p)
-{
-    extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(16) float4             s_wray[kBlock];
-    __shared__ __align__(8) unsigned long long s_wkey[kBlock];
-    __shared__ __align__(8) uint64_t           bar;
-    __shared__ unsigned long long              s_pool;  // (epoch << 32) | next group of the epoch's tile
-    __shared__ int                             s_claim; // number of epochs whose successor has been opened
-    __shared__ int                             s_ready; // highest epoch whose descriptor is in the ring
-    __shared__ __align__(16) CastTile          s_tile[kCastRing];
-    __shared__ BeamView                        s_bv; // the staged track's table (every warp passes a staging epoch together)
-
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int R   = p.rays;
-    uint8_t  *blob = smem;
-    float4             *w_ray = s_wray + (tid & ~31);
-    unsigned long long *w_key = s_wkey + (tid & ~31);
-
-    // descriptors are fetched one epoch ahead of their use, so that opening an epoch never waits on global memory
-    auto load_tile = [&](int epoch, int prev_track) { // one thread
-        const int t = atomicAdd(p.sched, 1);
-        CastTile  ct{};
-        ct.epoch = epoch;
-        if (t >= p.n_cast_tiles)
-            ct.flags = 2;
-        else
-        {
-            const Tile tl = p.cast_tiles[t];
-            ct.begin      = tl.begin;
-            ct.track      = tl.track;
-            ct.n_rays     = tl.count * R;
-            ct.n_groups   = (ct.n_rays + 31) >> 5;
-            ct.flags      = tl.track != prev_track ? 1 : 0;
-        }
-        s_tile[epoch & (kCastRing - 1)] = ct;
-    };
-    if (tid == 0)
-    {
-        mbar_init(&bar, 1);
-        load_tile(0, -1);
-        if (!(s_tile[0].flags & 2))
-            load_tile(1, s_tile[0].track);
-        else
-            s_tile[1] = s_tile[0], s_tile[1].epoch = 1;
-        s_ready = 1;
-        s_pool  = 0ull;
-        s_claim = 0;
-    }
-    __syncthreads();
-
-    const float inv_R = 1.0f / static_cast<float>(R);
-    const float inf   = __int_as_float(0x7f800000);
-    const unsigned long long key_none =
-        (static_cast<unsigned long long>(__float_as_uint(p.sensor_range)) << 32) | 0x80000000ull;
-    uint32_t phase  = 0;
-    int      staged = -1; // last STAGING epoch this warp has passed
-    // segments are the blob's first section (pack_blob): a constant offset, no register
-    const float4 *segs = reinterpret_cast<const float4 *>(blob + sizeof(TrackHeader));
-    const BeamView &bv = s_bv;
-
-    // one group = (epoch, index).  grab() only takes a number (and the epoch's descriptor, valid at that moment:
-    // an epoch shows in the pool after its descriptor is written, and the ring is kCastRing deep); resolve()
-    // turns it into work, blocking where needed.
-    auto grab = [&](int &e, int &gi, CastTile &ct) {
-        unsigned long long v = 0;
-        if (lane == 0)
-            v = atomicAdd(&s_pool, 1ull);
-        v  = __shfl_sync(0xffffffffu, v, 0);
-        e  = static_cast<int>(v >> 32);
-        gi = static_cast<int>(static_cast<uint32_t>(v));
-        ct = s_tile[e & (kCastRing - 1)];
-        if (ct.epoch != e)
-            __trap(); // the ring was lapped (a warp fell kCastRing tiles behind): never continue on a stale descriptor
-    };
-    // returns false when there is no more work; otherwise (e, gi) is a valid group of a staged tile
-    auto resolve = [&](int &e, int &gi, CastTile &ct) -> bool {
-        for (int spin = 0;; ++spin)
-        {
-            if (ct.flags & 2)
-                return false;
-            if ((ct.flags & 1) && staged < e)
-            { // every warp of the CTA passes here exactly once per staging epoch, with no group in flight
-                __syncthreads();
-                if (tid == 0)
-                {
-                    const TrackRef tr = p.tracks[ct.track];
-                    BeamView       v;
-                    v.valid = false;
-                    if (tr.has_beam)
-                        v = make_beam_view(p.beam_arena + tr.beam_offset);
-                    s_bv = v; // released by the mbarrier arrive below, acquired by every waiter
-                    fence_proxy_async();
-                    mbar_expect_tx(&bar, tr.bytes);
-                    tma_bulk_g2s(blob, p.arena + tr.offset, tr.bytes, &bar);
-                }
-                mbar_wait(&bar, phase);
-                phase ^= 1u;
-                staged = e;
-            }
-            if (gi < ct.n_groups)
-                return true;
-            // the epoch's tile is used up: one warp opens the next epoch (its descriptor is already in the ring)
-            // and then fetches the descriptor after that
-            if (lane == 0)
-            {
-                if (atomicCAS(&s_claim, e, e + 1) == e)
-                {
-                    for (int w = 0; *reinterpret_cast<volatile int *>(&s_ready) < e + 1; ++w)
-                    {
-                        __nanosleep(32);
-                        if (w > OK_SPIN_LIMIT)
-                            __trap();
-                    }
-                    __threadfence_block();
-                    const CastTile nx = s_tile[(e + 1) & (kCastRing - 1)];
-                    atomicExch(&s_pool, static_cast<unsigned long long>(e + 1) << 32);
-                    if (!(nx.flags & 2))
-                    {
-                        load_tile(e + 2, nx.track);
-                        __threadfence_block();
-                        *reinterpret_cast<volatile int *>(&s_ready) = e + 2;
-                    }
-                }
-                else
-                    __nanosleep(32);
-            }
-            __syncwarp();
-            if (spin > OK_SPIN_LIMIT)
-                __trap(); // a lost wake-up must not hang the device
-            int      e2, g2;
-            CastTile c2;
-            grab(e2, g2, c2);
-            if (e2 == e)
-                continue; // still the exhausted epoch
-            e  = e2;
-            gi = g2;
-            ct = c2;
-        }
-    };
-    // this lane's ray of a group: the prepared record (ray_prep_kernel) and where it belongs
-    struct Group
-    {
-        int64_t a;  // global agent
-        int     q;  // ray within the tile, -1 = none
-        uint4   rr; // {first chunk, count | dq << 16, dx, dy}
-    };
-    auto locate = [&](const CastTile &ct, int g, Group &G) {
-        const int q = (g << 5) + lane;
-        G.q         = q < ct.n_rays ? q : -1;
-        G.rr        = make_uint4(kRayInactive, 0u, 0u, 0u);
-        const int al = G.q >= 0 ? __float2int_rz((static_cast<float>(q) + 0.5f) * inv_R) : 0;
-        G.a          = ct.begin + al;
-        if (G.q >= 0)
-            G.rr = __ldg(p.ray_recs + (ct.begin * R + q));
-    };
-
-    int      e, gi;
-    CastTile ct;
-    grab(e, gi, ct);
-    bool  more = resolve(e, gi, ct);
-    Group G{};
-    if (more)
-        locate(ct, gi, G);
-    while (more)
-    {
-        // next group: its table entry is requested now unless its tile still needs work from resolve()
-        // (staging of another track, exhausted, or no more tiles).  A later epoch seen here can only be
-        // separated from the current one by same-track tiles: staging epochs are never skipped.
-        int   e_n, gi_n;
-        bool  ahead;
-        Group G_n{};
-        {
-            CastTile ct_n;
-            grab(e_n, gi_n, ct_n);
-            ahead = gi_n < ct_n.n_groups && !(ct_n.flags & 2) && (!(ct_n.flags & 1) || staged >= e_n);
-            if (ahead)
-                locate(ct_n, gi_n, G_n);
-        }
-
-        const bool has    = G.q >= 0;
-        const bool active = has && G.rr.x != kRayInactive;
-        const bool cov    = active && G.rr.x != kRayUncovered;
-        RayOrigin  rec;
-        {
-            const float4 w0 = __ldg(reinterpret_cast<const float4 *>(p.recs_g + G.a)); // ox, oy, rc, rs
-            rec.ox = w0.x, rec.oy = w0.y, rec.rc = w0.z, rec.rs = w0.w;
-            rec.flags = active ? 0u : kFlagCrashed;
-        }
-        const float dx = __uint_as_float(G.rr.z), dy = __uint_as_float(G.rr.w);
-        w_ray[lane] = make_float4(rec.ox, rec.oy, dx, dy);
-        w_key[lane] = key_none;
-        const uint32_t nch = cov ? (((G.rr.y & 0xffffu) + 3u) >> 2) : 0u;
-        uint32_t       inc = nch;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
-        {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o)
-                inc += v;
-        }
-        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-        const uint32_t first = G.rr.x - (inc - nch);
-        __syncwarp();
-        auto find_chunk = [&](uint32_t j, int &owner) -> uint32_t {
-            owner = 0;
-#pragma unroll
-            for (int s2 = 16; s2 > 0; s2 >>= 1)
-            {
-                const uint32_t v = __shfl_sync(0xffffffffu, inc, owner + s2 - 1);
-                if (v <= j)
-                    owner += s2;
-            }
-            return __shfl_sync(0xffffffffu, first, owner) + j;
-        };
-        int   owner = 0;
-        uint2 it    = make_uint2(0xffffffffu, 0xffffffffu);
-        if (total > 0)
-        {
-            const uint32_t ch = find_chunk(lane, owner);
-            if (static_cast<uint32_t>(lane) < total)
-                it = __ldg(bv.chunks + ch);
-        }
-        for (uint32_t base = 0; base < total; base += 32)
-        {
-            int   owner_n = 0;
-            uint2 it_n    = make_uint2(0xffffffffu, 0xffffffffu);
-            if (base + 32 < total)
-            {
-                const uint32_t jn = base + 32 + lane;
-                const uint32_t ch = find_chunk(jn, owner_n);
-                if (jn < total)
-                    it_n = __ldg(bv.chunks + ch);
-            }
-            if (base + lane < total)
-            {
-                const float4        ray = w_ray[owner];
-                unsigned long long *key = w_key + owner;
-                const float         m   = __uint_as_float(reinterpret_cast<const uint32_t *>(key)[1]);
-                int                 idx[4];
-                float               tq[4];
-                bool                el[4], lit[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                {
-                    const uint32_t raw  = ((u < 2 ? it.x : it.y) >> (16 * (u & 1))) & 0xffffu;
-                    const bool     live = raw != 0xffffu;
-                    idx[u]              = live ? static_cast<int>(raw) : 0;
-                    tq[u] = beam_eval(segs, idx[u], live, ray.x, ray.y, ray.z, ray.w, el[u], lit[u]);
-                }
-                float tq_b  = m;
-                int   idx_b = -1;
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                {
-                    const bool cand = el[u] & !(tq[u] > fmul(tq_b, 1.000003814697265625f));
-                    if (cand & !(tq[u] < fmul(tq_b, 0.999996185302734375f)) & (idx_b >= 0))
-                        beam_flush(segs, idx_b, ray.x, ray.y, ray.z, ray.w, key);
-                    tq_b  = cand ? tq[u] : tq_b;
-                    idx_b = cand ? idx[u] : idx_b;
-                }
-                if (idx_b >= 0)
-                    beam_flush(segs, idx_b, ray.x, ray.y, ray.z, ray.w, key);
-                if (lit[0] | lit[1] | lit[2] | lit[3])
-                {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (lit[u])
-                            beam_literal(segs, idx[u], ray.x, ray.y, ray.z, ray.w, key);
-                }
-            }
-            owner = owner_n;
-            it    = it_n;
-        }
-        __syncwarp();
-        float sq = inf;
-        if (has)
-        {
-            const unsigned long long key   = w_key[lane];
-            int                      best  = static_cast<int>(0x7fffffffu - static_cast<uint32_t>(key));
-            const float              min_t = __uint_as_float(static_cast<uint32_t>(key >> 32));
-            const uint32_t           dq    = G.rr.y >> 16;
-            const float              d_eff = dq == 0xffffu ? bv.rb : static_cast<float>(dq) * 0.00390625f;
-            if (active && !(cov && min_t <= d_eff - kBeamSlack))
-            { // undecided: everything nearer than d_eff - 1 is settled, the grid walk covers the rest
-                best = beam_walk_fallback(blob, rec.ox, rec.oy, dx, dy, p.sensor_range,
-                                          cov ? fmaxf(d_eff - 1.0f, 0.0f) : 0.0f, best, min_t);
-            }
-            const int al = __float2int_rz((static_cast<float>(G.q) + 0.5f) * inv_R);
-            sq           = finish_ray(p, segs, rec, (G.a - al) * R + G.q, dx, dy, best);
-        }
-        // min_dist2 of CollisionChecker.cu:150,162-165 (NaN never lowers it)
-        if ((R & 31) == 0)
-        {
-            float m = (sq == sq) ? sq : inf;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-                m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if (has && lane == 0)
-                atomicMin(&p.recs_g[G.a].min_d2_bits, __float_as_int(m));
-        }
-        else if (has && sq == sq)
-            atomicMin(&p.recs_g[G.a].min_d2_bits, __float_as_int(sq));
-
-        e = e_n, gi = gi_n;
-        if (ahead)
-            G = G_n;
-        else
-        { // the descriptor is read again rather than carried across the group (registers); a lapped ring traps
-            ct = s_tile[e & (kCastRing - 1)];
-            if (ct.epoch != e)
-                __trap();
-            more = resolve(e, gi, ct);
-            if (more)
-                locate(ct, gi, G);
-        }
-    }
-
-    // last CTA out re-arms the tile scheduler for the next launch on this stream
-    if (tid == 0)
-    {
-        __threadfence();
-        if (atomicAdd(p.sched + 1, 1) == static_cast<int>(gridDim.x) - 1)
-        {
-            p.sched[0] = 0;
-            p.sched[1] = 0;
-            __threadfence();
-        }
-    }
-}
 
 // Environment::resetAgent (Environment.cpp:79-122) + Agent::reset (Agent.cpp:123-135), one thread
 // per request, reading the track blobs from global memory.

@@ -208,7 +208,9 @@ bool build_grid(Track &t, float cell, std::string &err)
 void pack_blob(Track &t)
 {
     const int32_t      n = t.n_points(), ns = t.n_segments();
-    std::vector<float> seg4(static_cast<size_t>(ns) * 4), pts(static_cast<size_t>(n) * 2), widths(n);
+    // one extra, all-zero "null segment" at index ns: zero length makes denom = 0, which fails the parallel test
+    // of CollisionChecker.cu:23 for every ray -- the beam lists pad their chunks with it
+    std::vector<float> seg4(static_cast<size_t>(ns + 1) * 4, 0.0f), pts(static_cast<size_t>(n) * 2), widths(n);
     for (int32_t s = 0; s < ns; ++s)
     {
         const float *g  = &t.segments[4 * s];
