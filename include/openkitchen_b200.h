@@ -128,8 +128,8 @@ typedef struct OkConfig {
     uint32_t standstill_period;    /* DisplacementStats::kPeriod 200 Environment.h:19 */
     float    standstill_threshold; /* kDisplamentThreshold 20        Environment.h:20 */
     float    grid_cell;            /* broadphase cell size in px (8) */
-    float    beam_cell;            /* OK_RAYCAST_BEAM: start-cell size in px (8); 0 = default */
-    int32_t  beam_bins;            /* OK_RAYCAST_BEAM: direction bins, a power of two (64); 0 = default */
+    float    beam_cell;            /* OK_RAYCAST_BEAM: start-cell size in px (4); 0 = default */
+    int32_t  beam_bins;            /* OK_RAYCAST_BEAM: direction bins, a power of two (128); 0 = default */
     int32_t  reserved[2];
 } OkConfig;
 

@@ -402,8 +402,8 @@ void ok_config_default(OkConfig *c)
     c->standstill_period    = 200u;
     c->standstill_threshold = 20.0f;
     c->grid_cell            = 8.0f;
-    c->beam_cell            = 8.0f;
-    c->beam_bins            = 64;
+    c->beam_cell            = 4.0f;
+    c->beam_bins            = 128;
 }
 
 int ok_create(const OkConfig *cfg, OkEnv **out)
@@ -425,9 +425,9 @@ int ok_create(const OkConfig *cfg, OkEnv **out)
     if (!(c.grid_cell >= 1.0f && c.grid_cell <= 512.0f))
         return fail(OK_ERR_INVALID_ARG, "grid_cell must be in [1, 512] px");
     if (c.beam_cell == 0.0f)
-        c.beam_cell = 8.0f;
+        c.beam_cell = 4.0f;
     if (c.beam_bins == 0)
-        c.beam_bins = 64;
+        c.beam_bins = 128;
     if (!(c.beam_cell >= 1.0f && c.beam_cell <= 64.0f) || c.beam_bins < 8 || c.beam_bins > 1024 ||
         (c.beam_bins & (c.beam_bins - 1)))
         return fail(OK_ERR_INVALID_ARG, "beam_cell must be in [1, 64] px and beam_bins a power of two in [8, 1024]");
