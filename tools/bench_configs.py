@@ -147,6 +147,30 @@ def c4():
     report("C4 PPO rollout 4096 envs x 256 steps, torch actor 5-128-3 on DLPack views", n, rays, 1e3 * dt / steps,
            {"env_steps": n * steps, "env_steps_per_sec": n * steps / dt, "wall_s": dt})
 
+    # the same collection as ONE CUDA graph (openkitchen_b200.rollout.GraphedRollout): in-kernel auto-reset instead of
+    # the host-synchronising reset of done agents, no host work between the ticks
+    from openkitchen_b200.rollout import GraphedRollout, discounted_returns
+
+    env2 = ok.BatchEnv(["Monza"], n, rays=[-70, -30, 0, 30, 70], reward_mode=ok.REWARD_CONSTANT, auto_reset=1)
+    table = torch.stack([amap_thr, amap_st], dim=1)
+    clamped = torch.nn.Sequential(actor, torch.nn.Hardtanh(1e-6, 1 - 1e-6))
+    ro = GraphedRollout(env2, clamped, table, steps, sample=True)
+    env2.reset_random()
+    env2.cast_rays()
+    ro.capture()
+    ro.run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        ro.run()
+        ret = discounted_returns(ro.rewards, 0.99, ro.dones)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    report("C4 PPO rollout 4096 envs x 256 steps as one CUDA graph (GraphedRollout) + device return scan", n, rays,
+           1e3 * dt / steps, {"env_steps": n * steps, "env_steps_per_sec": n * steps / dt, "wall_s": dt,
+                              "crashed_fraction": float(ro.dones.float().mean())})
+
 
 def c5s():
     n, rays = 1_048_576, 32
