@@ -994,7 +994,6 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
     __shared__ int                           s_tile, s_pool;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int kWarps = kBlock / 32;
     const int     R      = p.rays;
 
     uint8_t  *blob    = smem;
