@@ -468,40 +468,12 @@ __device__ __forceinline__ int nearest_index(const TrackView &tv, float qx, floa
     return bi;
 }
 
-// The same search for a full warp with a hint (the agent's previous nearest index): the 32 points around the
-// hint first, the rest only if the triangle inequality cannot rule them out (ok_track.hpp, kNearestWindow).
-// Every outside point is then STRICTLY farther than the window's best, so the window's lexicographic
-// (distance, index) minimum is the reference's result; otherwise the full search above runs.
-__device__ __forceinline__ int nearest_index_hint(const TrackView &tv, float qx, float qy, int hint, int lane, float &d2_out)
-{
-    const int n = tv.n_pts;
-    if (n > kNearestWindow)
-    {
-        const int h = min(max(hint, 0), n - 1);
-        int       i = h - kNearestWindow / 2 + lane;
-        i += (i < 0) ? n : 0;
-        i -= (i >= n) ? n : 0;
-        const float2 pt  = tv.pts[i];
-        const float  ddx = fsub(qx, pt.x), ddy = fsub(qy, pt.y);
-        const float  d   = fadd(fmul(ddx, ddx), fmul(ddy, ddy));
-        const bool   ok  = d < FLT_MAX; // `d < best` of the reference never takes NaN / inf
-        const uint32_t key  = ok ? __float_as_uint(d) : __float_as_uint(FLT_MAX);
-        const uint32_t kmin = __reduce_min_sync(0xffffffffu, key);
-        const int      imin = __reduce_min_sync(0xffffffffu, (key == kmin) ? (ok ? i : 0) : 0x7fffffff);
-        const float    dh   = __shfl_sync(0xffffffffu, d, kNearestWindow / 2); // the hint itself
-        const float    rb = __fsqrt_rn(__uint_as_float(kmin)), rh = __fsqrt_rn(dh);
-        if (fsub(fsub(tv.safe[h], rh), rb) > fadd(fmul(1e-3f, fadd(rh, rb)), 1e-3f))
-        {
-            d2_out = __uint_as_float(kmin);
-            return imin;
-        }
-    }
-    return nearest_index(tv, qx, qy, lane, 32, d2_out);
-}
-
-// The windowed search by ONE thread (phase 4 runs a thread per agent): same window, same exactness test.
-// ok = false means "not proven": the caller runs the full search.  Ties: lowest index, like the reference
-// (the window wraps around the end of the centre line, so index order is not visiting order).
+// The same search by ONE thread with a hint (the agent's previous nearest index; phase 4 runs a thread per agent):
+// the 32 points around the hint first; the rest only if the triangle inequality cannot rule them out
+// (ok_track.hpp, kNearestWindow).  ok = true: every outside point is STRICTLY farther than the window's best, so the
+// window's lexicographic (distance, index) minimum is the reference's result.  ok = false means "not proven": the
+// caller runs the full search above.  Ties: lowest index, like the reference (the window wraps around the end of the
+// centre line, so index order is not visiting order).
 __device__ __forceinline__ int nearest_index_window(const TrackView &tv, float qx, float qy, int hint, float &d2_out, bool &ok)
 {
     const int n = tv.n_pts;
@@ -1438,7 +1410,6 @@ __global__ void reset_kernel(const StepParams p, const ResetParams r)
         return;
     const uint8_t    *blob = p.arena + p.tracks[p.track_id[a]].offset;
     const TrackView   tv   = make_view(blob);
-    const TrackHeader *h   = reinterpret_cast<const TrackHeader *>(blob);
     int32_t           pt   = r.pt_idx[k];
     pt                     = min(max(pt, 0), tv.n_pts - 1);
     float sx, sy;
@@ -1466,7 +1437,6 @@ __global__ void reset_kernel(const StepParams p, const ResetParams r)
         const float2 c = tv.pts[pt];
         sx = c.x, sy = c.y;
     }
-    (void)h;
     const float off = r.heading_off ? r.heading_off[k] : 0.0f;
     p.x[a] = sx, p.y[a] = sy;
     p.rot[a]       = fadd(tv.headings[pt], off);

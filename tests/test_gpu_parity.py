@@ -175,3 +175,21 @@ def test_many_tracks_per_cta_beam(rays):
         ora.step()
         if step % 10 == 0 or step == 59:
             assert_same(env, ora, ctx=f"many tracks, step {step}")
+
+
+def test_switching_raycast_mode_at_runtime():
+    """ok_update_config may change the narrow phase of a live env: the beam tables are built on the first beam launch"""
+    env, ora, tid = make_pair(["Monza", "Silverstone"], 96, 32, raycast_mode=ok.RAYCAST_GRID,
+                              reward_mode=ok.REWARD_Q_PROGRESS, auto_reset=1)
+    pts = spread_points(ora, tid)
+    env.reset(None, pts)
+    ora.reset(None, pts)
+    modes = [ok.RAYCAST_GRID, ok.RAYCAST_BEAM, ok.RAYCAST_BRUTE, ok.RAYCAST_BEAM, ok.RAYCAST_GRID]
+    for step in range(50):
+        if step % 10 == 0:
+            env.update_config(raycast_mode=modes[step // 10])
+        env.launch_steps_random(step, 1)
+        ora.fill_random_actions(step)
+        ora.step()
+        if step % 10 == 9:
+            assert_same(env, ora, ctx=f"mode {modes[step // 10]}, step {step}")
