@@ -56,6 +56,8 @@ struct BeamConfig
     int32_t threads{0};   // 0 = std::thread::hardware_concurrency()
 };
 
+// bump when build_beam_table changes what it produces (the on-disk cache is keyed on it)
+constexpr int    kBeamBuildVersion = 1;
 constexpr double kBeamCellMargin  = 0.0625; // px: the cell is grown by this much on every side
 constexpr double kBeamAngleMargin = 1e-4;   // rad: the bin's cone is widened by this much on both sides
 constexpr float  kBeamSlack       = 0.25f;  // px: a list result is trusted up to d - slack

@@ -12,7 +12,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <fcntl.h>
 #include <map>
+#include <sys/stat.h>
+#include <thread>
+#include <unistd.h>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -164,39 +169,163 @@ void free_agents(OkEnv *e)
     e->n_agents = 0, e->rays = 0, e->n_tiles = 0;
 }
 
-// Beam tables are pure functions of (segments, cell, bins, range) and take ~0.1-1 s of host time per track:
-// one process-wide cache so that envs over the same tracks share them.
-std::shared_ptr<const std::vector<uint8_t>> beam_table_for(const ok::Track &t, const ok::BeamConfig &cfg, std::string &err)
+// Beam tables are pure functions of (segments, cell, bins, range) and take ~0.1-1 s of host time per track.
+// Two caches: one per process (envs over the same tracks share a table), and one on disk
+// ($OK_BEAM_CACHE_DIR, default $TMPDIR/openkitchen_b200-cache-<uid>; OK_BEAM_CACHE=0 disables it) so that the ranks
+// of one box -- which all need every table -- build each table once between them instead of once each.
+uint64_t fnv1a(const void *ptr, size_t n, uint64_t h = 1469598103934665603ull)
 {
-    static std::mutex                                                          mu;
-    static std::map<std::string, std::shared_ptr<const std::vector<uint8_t>>> cache;
-    uint64_t h = 1469598103934665603ull;
-    auto     mix = [&](const void *ptr, size_t n) {
-        const uint8_t *b = static_cast<const uint8_t *>(ptr);
-        for (size_t i = 0; i < n; ++i)
-            h = (h ^ b[i]) * 1099511628211ull;
-    };
-    mix(t.segments.data(), t.segments.size() * sizeof(float));
-    mix(t.x.data(), t.x.size() * sizeof(float));
-    mix(t.w_left.data(), t.w_left.size() * sizeof(float));
-    mix(t.w_right.data(), t.w_right.size() * sizeof(float));
-    char key[128];
-    std::snprintf(key, sizeof key, "%016llx:%zu:%g:%d:%g", static_cast<unsigned long long>(h), t.segments.size(),
-                  static_cast<double>(cfg.cell), cfg.bins, static_cast<double>(cfg.range));
+    const uint8_t *b = static_cast<const uint8_t *>(ptr);
+    for (size_t i = 0; i < n; ++i)
+        h = (h ^ b[i]) * 1099511628211ull;
+    return h;
+}
+
+std::string beam_cache_dir()
+{
+    if (const char *off = std::getenv("OK_BEAM_CACHE"))
+        if (std::atoi(off) == 0)
+            return "";
+    std::string dir;
+    if (const char *d = std::getenv("OK_BEAM_CACHE_DIR"))
+        dir = d;
+    else
     {
-        std::lock_guard<std::mutex> lock(mu);
-        auto                        it = cache.find(key);
-        if (it != cache.end())
-            return it->second;
+        const char *tmp = std::getenv("TMPDIR");
+        dir             = std::string(tmp && *tmp ? tmp : "/tmp") + "/openkitchen_b200-cache-" + std::to_string(getuid());
     }
-    auto blob = std::make_shared<std::vector<uint8_t>>();
-    if (!ok::build_beam_table(t, cfg, *blob, err))
-        return nullptr;
-    std::lock_guard<std::mutex> lock(mu);
-    if (cache.size() >= 64)
-        cache.clear();
-    cache[key] = blob;
+    ::mkdir(dir.c_str(), 0700);
+    return dir;
+}
+
+struct BeamFileHeader
+{
+    char     magic[8]; // "OKBEAM01"
+    uint64_t bytes, checksum;
+};
+
+bool beam_file_load(const std::string &path, std::vector<uint8_t> &blob)
+{
+    FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f)
+        return false;
+    BeamFileHeader h{};
+    bool           ok = std::fread(&h, sizeof h, 1, f) == 1 && std::memcmp(h.magic, "OKBEAM01", 8) == 0 && h.bytes >= sizeof(ok::BeamHeader) &&
+              h.bytes < (1ull << 32);
+    if (ok)
+    {
+        blob.resize(h.bytes);
+        ok = std::fread(blob.data(), 1, h.bytes, f) == h.bytes && fnv1a(blob.data(), blob.size()) == h.checksum;
+    }
+    std::fclose(f);
+    if (!ok)
+        blob.clear();
+    return ok;
+}
+
+void beam_file_save(const std::string &path, const std::vector<uint8_t> &blob)
+{
+    const std::string tmp = path + ".tmp." + std::to_string(getpid());
+    FILE             *f   = std::fopen(tmp.c_str(), "wb");
+    if (!f)
+        return;
+    BeamFileHeader h{};
+    std::memcpy(h.magic, "OKBEAM01", 8);
+    h.bytes    = blob.size();
+    h.checksum = fnv1a(blob.data(), blob.size());
+    const bool ok = std::fwrite(&h, sizeof h, 1, f) == 1 && std::fwrite(blob.data(), 1, blob.size(), f) == blob.size();
+    std::fclose(f);
+    if (ok && std::rename(tmp.c_str(), path.c_str()) == 0)
+        return;
+    std::remove(tmp.c_str());
+}
+
+std::string beam_key(const ok::Track &t, const ok::BeamConfig &cfg)
+{
+    uint64_t h = fnv1a(t.segments.data(), t.segments.size() * sizeof(float));
+    h          = fnv1a(t.x.data(), t.x.size() * sizeof(float), h);
+    h          = fnv1a(t.y.data(), t.y.size() * sizeof(float), h);
+    h          = fnv1a(t.w_left.data(), t.w_left.size() * sizeof(float), h);
+    h          = fnv1a(t.w_right.data(), t.w_right.size() * sizeof(float), h);
+    char key[128];
+    std::snprintf(key, sizeof key, "v%d-%016llx-%zu-%g-%d-%g", ok::kBeamBuildVersion, static_cast<unsigned long long>(h),
+                  t.segments.size(), static_cast<double>(cfg.cell), cfg.bins, static_cast<double>(cfg.range));
+    return key;
+}
+
+std::mutex                                                          g_beam_mu;
+std::map<std::string, std::shared_ptr<const std::vector<uint8_t>>> g_beam_cache;
+
+std::shared_ptr<const std::vector<uint8_t>> beam_cached(const std::string &key)
+{
+    std::lock_guard<std::mutex> lock(g_beam_mu);
+    auto                        it = g_beam_cache.find(key);
+    return it == g_beam_cache.end() ? nullptr : it->second;
+}
+
+std::shared_ptr<const std::vector<uint8_t>> beam_remember(const std::string &key, std::shared_ptr<std::vector<uint8_t>> blob)
+{
+    std::lock_guard<std::mutex> lock(g_beam_mu);
+    if (g_beam_cache.size() >= 64)
+        g_beam_cache.clear();
+    g_beam_cache[key] = blob;
     return blob;
+}
+
+// `wait` = false: return nullptr (no error) when another process holds the track's build lock, so that the caller
+// can build other tracks in the meantime; `wait` = true: wait for that process's file, or build after a timeout.
+std::shared_ptr<const std::vector<uint8_t>> beam_table_for(const ok::Track &t, const ok::BeamConfig &cfg, bool wait, std::string &err)
+{
+    const std::string key = beam_key(t, cfg);
+    if (auto hit = beam_cached(key))
+        return hit;
+    auto              blob = std::make_shared<std::vector<uint8_t>>();
+    const std::string dir  = beam_cache_dir();
+    const std::string path = dir.empty() ? "" : dir + "/beam-" + key + ".bin", lock = path + ".lock";
+    bool              locked = false;
+    if (!path.empty())
+    {
+        if (beam_file_load(path, *blob))
+            return beam_remember(key, blob);
+        const int fd = ::open(lock.c_str(), O_CREAT | O_EXCL | O_WRONLY, 0600);
+        if (fd >= 0)
+        {
+            ::close(fd);
+            locked = true;
+        }
+        else
+        {
+            struct stat st
+            {
+            };
+            const bool stale = ::stat(lock.c_str(), &st) == 0 && std::time(nullptr) - st.st_mtime > 300;
+            if (stale)
+                std::remove(lock.c_str());
+            else if (!wait)
+                return nullptr; // someone else is building it
+            else
+                for (int i = 0; i < 2400 && ::stat(lock.c_str(), &st) == 0; ++i) // up to two minutes
+                {
+                    std::this_thread::sleep_for(std::chrono::milliseconds(50));
+                    if (beam_file_load(path, *blob))
+                        return beam_remember(key, blob);
+                }
+            if (beam_file_load(path, *blob))
+                return beam_remember(key, blob);
+        }
+    }
+    const bool built = ok::build_beam_table(t, cfg, *blob, err);
+    if (built && !path.empty())
+        beam_file_save(path, *blob);
+    if (locked)
+        std::remove(lock.c_str());
+    if (!built)
+    {
+        if (err.empty())
+            err = "beam table build failed";
+        return nullptr;
+    }
+    return beam_remember(key, blob);
 }
 
 ok::BeamConfig beam_config(const OkEnv *e)
@@ -207,6 +336,8 @@ ok::BeamConfig beam_config(const OkEnv *e)
     c.range = 200.0f; // Agent::kSensorRange; a larger OkConfig::sensor_range stays exact through the grid walk
     if (const char *env = std::getenv("OK_BEAM_THREADS"))
         c.threads = std::atoi(env);
+    else if (const char *lws = std::getenv("LOCAL_WORLD_SIZE")) // torchrun: the ranks of a box share its cores
+        c.threads = std::max(1, static_cast<int>(std::thread::hardware_concurrency()) / std::max(1, std::atoi(lws)));
     return c;
 }
 
@@ -226,6 +357,18 @@ int ensure_arena(OkEnv *e)
     size_t                    total = 0, beam_total = 0;
     e->max_blob_used                = 0;
     e->beams.resize(e->tracks.size());
+    if (want_beams)
+    { // first every table nobody else is building, then the ones other ranks of this box were busy with
+        for (int pass = 0; pass < 2; ++pass)
+            for (size_t i = 0; i < e->tracks.size(); ++i)
+                if (!e->beams[i])
+                {
+                    std::string err;
+                    e->beams[i] = beam_table_for(e->tracks[i], beam_config(e), pass == 1, err);
+                    if (!e->beams[i] && (pass == 1 || !err.empty()))
+                        return fail(OK_ERR_INVALID_ARG, "beam table: " + err);
+                }
+    }
     for (size_t i = 0; i < e->tracks.size(); ++i)
     {
         const ok::Track &t = e->tracks[i];
@@ -234,13 +377,6 @@ int ensure_arena(OkEnv *e)
         r.bytes  = static_cast<uint32_t>(t.blob.size());
         if (want_beams)
         {
-            if (!e->beams[i])
-            {
-                std::string err;
-                e->beams[i] = beam_table_for(t, beam_config(e), err);
-                if (!e->beams[i])
-                    return fail(OK_ERR_INVALID_ARG, "beam table: " + err);
-            }
             r.has_beam    = 1;
             r.beam_offset = beam_total;
             beam_total += (e->beams[i]->size() + 255) / 256 * 256;
@@ -1016,7 +1152,7 @@ static int host_beam(OkEnv *e, int32_t id)
     if (!e->beams[id])
     {
         std::string err;
-        e->beams[id] = beam_table_for(e->tracks[id], beam_config(e), err);
+        e->beams[id] = beam_table_for(e->tracks[id], beam_config(e), true, err);
         if (!e->beams[id])
             return fail(OK_ERR_INVALID_ARG, "beam table: " + err);
     }

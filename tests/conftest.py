@@ -9,6 +9,10 @@ if ROOT not in sys.path:
 
 
 def pytest_configure(config):
+    # a fresh on-disk beam-table cache per test session: the tables under test are the ones this build produces
+    import tempfile
+
+    os.environ["OK_BEAM_CACHE_DIR"] = tempfile.mkdtemp(prefix="ok_beam_cache_")
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
     config.addinivalue_line("markers", "slow: long-running CPU check")
 

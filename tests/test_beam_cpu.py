@@ -77,3 +77,34 @@ def test_beam_config_is_validated():
         ok.Env(device=-1, beam_bins=48)
     with pytest.raises(ok.OkError):
         ok.Env(device=-1, beam_cell=0.5)
+
+
+def test_disk_cache_is_shared_between_processes(tmp_path):
+    """the ranks of one box build each table once between them: two processes, one cache directory"""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import openkitchen_b200 as ok\n"
+        "env = ok.Env(device=-1, beam_cell=8.0, beam_bins=32)\n"
+        "out = []\n"
+        "for nm in ['Monza', 'Spielberg', 'Zandvoort']:\n"
+        "    t = env.add_named_track(nm)\n"
+        "    items, d = env.beam_lookup(t, float(env.track_array(t, 'x')[5]), float(env.track_array(t, 'y')[5]), 0.5)\n"
+        "    out.append((env.beam_table_bytes(t), items.tolist(), d))\n"
+        "print(out)\n"
+    )
+    envv = dict(os.environ, OK_BEAM_CACHE_DIR=str(tmp_path), OK_BEAM_THREADS="2")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    procs = [subprocess.Popen([sys.executable, "-c", code], cwd=root, env=envv, stdout=subprocess.PIPE, text=True) for _ in range(2)]
+    outs = [p.communicate(timeout=300)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs)
+    assert outs[0] == outs[1] and "[" in outs[0]
+    files = sorted(f for f in os.listdir(tmp_path) if f.endswith(".bin"))
+    assert len(files) == 3 and not [f for f in os.listdir(tmp_path) if f.endswith(".lock")]
+    # a third process only reads; a cache written with OK_BEAM_CACHE=0 semantics must give the same answer
+    again = subprocess.run([sys.executable, "-c", code], cwd=root, env=envv, capture_output=True, text=True, timeout=300)
+    fresh = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(envv, OK_BEAM_CACHE="0"), capture_output=True,
+                           text=True, timeout=300)
+    assert again.returncode == 0 and fresh.returncode == 0 and again.stdout == outs[0] == fresh.stdout
