@@ -345,6 +345,18 @@ def main():
         value = total_agents / (ms_per_step * 1e-3)
         peak, peak_src = peak_hbm()
         achieved = n * BYTES_PER_AGENT_STEP / (ms_per_step * 1e-3) / 1e9  # per GPU, GB/s
+        ev = ncu_evidence() or {}
+        issue = None
+        if ev.get("warp_instructions_per_launch") and clocks and clocks.get("sm_mhz") and n == N_AGENTS and args.raycast == "beam":
+            # the bound that actually binds: warp instructions issued per second against 4 schedulers x SMs x clock.
+            # The instruction count is the committed ncu capture's (same command, same workload); the time is this run's.
+            sms = torch.cuda.get_device_properties(local).multi_processor_count
+            peak_issue = 4.0 * sms * clocks["sm_mhz"] * 1e6
+            ach_issue = ev["warp_instructions_per_launch"] / (ms_per_step * 1e-3)
+            issue = {"achieved": ach_issue, "peak": peak_issue, "unit": "warp-instructions/s", "frac": ach_issue / peak_issue,
+                     "warp_instructions_per_launch": ev["warp_instructions_per_launch"],
+                     "active_threads_per_instruction": ev.get("active_threads_per_instruction"),
+                     "source": ev.get("source")}
         line = {
             "metric": "agent_steps_per_sec", "value": value, "unit": "agent-steps/s",
             "ray_casts_per_sec": value * N_RAYS,
@@ -358,7 +370,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (ncu_evidence() or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
                          "traffic_source": (ncu_evidence() or {}).get("source"),
-                         "algorithmic_bytes_per_launch": n * BYTES_PER_AGENT_STEP,
+                         "algorithmic_bytes_per_launch": n * BYTES_PER_AGENT_STEP, "issue": issue,
                          "note": "not HBM bound: warp-issue bound (ncu: 63% issue slots, 26 active threads/instr, ALU pipe 45%, "
                                  "FMA pipe 18%, L1/shared 41%); measured DRAM traffic exceeds the algorithmic bytes because the beam-table "
                                  "lookups (8 B entry + ~2.6 candidate chunks per ray from a 640 MB table) trade memory traffic for "

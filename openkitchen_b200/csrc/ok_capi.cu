@@ -125,6 +125,11 @@ struct OkEnv
     ok::Tile            *d_tiles{nullptr};
     int32_t              n_tiles{0};
     int32_t              batch_agents{0};
+    // the beam kernel's batches are not limited by per-ray scratch: its own batch size, tile table and grid
+    ok::Tile            *d_tiles_beam{nullptr};
+    int32_t              n_tiles_beam{0};
+    int32_t              batch_agents_beam{0};
+    int32_t              grid_beam{0};
     uint16_t            *d_ray_order{nullptr};
     int32_t             *d_sched{nullptr};
     int                  smem_optin{0};
@@ -159,6 +164,9 @@ void free_agents(OkEnv *e)
         cudaFree(e->d_ray_deg);
     if (e->d_tiles)
         cudaFree(e->d_tiles);
+    if (e->d_tiles_beam)
+        cudaFree(e->d_tiles_beam);
+    e->d_tiles_beam = nullptr, e->n_tiles_beam = 0;
     if (e->d_ray_order)
         cudaFree(e->d_ray_order);
     if (e->d_sched)
@@ -481,7 +489,12 @@ int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
     p.beam_arena = e->d_beam_arena;
     p.tracks     = e->d_track_refs;
     if (e->cfg.raycast_mode == OK_RAYCAST_BEAM)
-        ok::step_kernel<kBlock, true><<<e->grid, kBlock, e->smem_beam, s>>>(p);
+    {
+        p.tiles        = e->d_tiles_beam;
+        p.n_tiles      = e->n_tiles_beam;
+        p.batch_agents = e->batch_agents_beam;
+        ok::step_kernel<kBlock, true><<<e->grid_beam, kBlock, e->smem_beam, s>>>(p);
+    }
     else
         ok::step_kernel<kBlock, false><<<e->grid, kBlock, e->smem, s>>>(p);
     OK_CUDA(cudaGetLastError());
@@ -760,7 +773,21 @@ int ok_alloc_agents(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, c
             return fail(OK_ERR_CAPACITY, "shared memory cannot hold one agent's rays next to the largest track");
         e->batch_agents = static_cast<int32_t>(a);
         e->smem         = blob + ok::batch_smem_bytes(e->batch_agents, rays);
-        e->smem_beam    = blob + ok::beam_smem_bytes(e->batch_agents);
+        // beam kernel: one 64-byte record per agent; phases 1 / 4 run a thread per agent, so at most kBlock agents.
+        // Bigger batches mean fewer barriers but coarser scheduling: 256 unless every SM gets several larger ones.
+        int64_t ab = static_cast<int64_t>((avail - 28672) / sizeof(ok::AgentRec));
+        // measured at 1,048,576 agents: 1.736 ms/tick with 256-agent batches, 1.643 with 512, 1.606 with 1,024
+        int capb = kMaxBatchAgents;
+        if (2 * n >= static_cast<int64_t>(e->num_sms) * 1024 * 3)
+            capb = 1024;
+        else if (2 * n >= static_cast<int64_t>(e->num_sms) * 512 * 3)
+            capb = 512;
+        if (const char *env = std::getenv("OK_BEAM_BATCH_AGENTS"))
+            capb = std::max(1, std::atoi(env));
+        ab = std::min<int64_t>({ab, capb, kBlock});
+        ab = std::min<int64_t>(ab, std::max<int64_t>(1, (n + e->num_sms - 1) / std::max(1, e->num_sms)));
+        e->batch_agents_beam = static_cast<int32_t>(std::max<int64_t>(1, ab));
+        e->smem_beam         = blob + ok::beam_smem_bytes(e->batch_agents_beam);
         OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<kBlock, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      static_cast<int>(e->smem)));
         OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<kBlock, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -802,36 +829,43 @@ int ok_alloc_agents(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, c
     // tiles: maximal runs of one track, cut into batches.  Guided self-scheduling: CTAs pull tiles in
     // list order, so full-size batches come first and a tail of quarter-size ones (about half a big
     // batch per SM) evens out the finish.
-    const int     big   = e->batch_agents;
-    const int     small = std::max(1, big / 4);
-    const int64_t tail_agents = std::min<int64_t>(n / 2, static_cast<int64_t>(e->num_sms) * big / 2);
-    std::vector<ok::Tile> tiles, tail;
-    for (int64_t i = 0; i < n;)
-    {
-        int64_t j = i;
-        while (j < n && e->h_track_id[j] == e->h_track_id[i])
-            ++j;
-        // this run's share of the small-tile tail
-        const int64_t run_tail = (j - i) * tail_agents / n;
-        const int64_t split    = j - run_tail;
-        for (int64_t b = i; b < j;)
+    auto build_tiles = [&](int big, ok::Tile **d_out, int32_t *n_out) -> int {
+        const int     small = std::max(1, big / 4);
+        const int64_t tail_agents = std::min<int64_t>(n / 2, static_cast<int64_t>(e->num_sms) * big / 2);
+        std::vector<ok::Tile> tiles, tail;
+        for (int64_t i = 0; i < n;)
         {
-            const bool    in_tail = b >= split;
-            const int64_t lim     = in_tail ? j : split;
-            ok::Tile      t{};
-            t.track = e->h_track_id[i];
-            t.begin = b;
-            t.count = static_cast<int32_t>(std::min<int64_t>(in_tail ? small : big, lim - b));
-            (in_tail ? tail : tiles).push_back(t);
-            b += t.count;
+            int64_t j = i;
+            while (j < n && e->h_track_id[j] == e->h_track_id[i])
+                ++j;
+            // this run's share of the small-tile tail
+            const int64_t run_tail = (j - i) * tail_agents / n;
+            const int64_t split    = j - run_tail;
+            for (int64_t b = i; b < j;)
+            {
+                const bool    in_tail = b >= split;
+                const int64_t lim     = in_tail ? j : split;
+                ok::Tile      t{};
+                t.track = e->h_track_id[i];
+                t.begin = b;
+                t.count = static_cast<int32_t>(std::min<int64_t>(in_tail ? small : big, lim - b));
+                (in_tail ? tail : tiles).push_back(t);
+                b += t.count;
+            }
+            i = j;
         }
-        i = j;
-    }
-    tiles.insert(tiles.end(), tail.begin(), tail.end());
-    e->n_tiles = static_cast<int32_t>(tiles.size());
-    OK_CUDA(cudaMalloc(&e->d_tiles, sizeof(ok::Tile) * tiles.size()));
-    OK_CUDA(cudaMemcpy(e->d_tiles, tiles.data(), sizeof(ok::Tile) * tiles.size(), cudaMemcpyHostToDevice));
-    e->grid = std::max(1, std::min(e->num_sms, e->n_tiles));
+        tiles.insert(tiles.end(), tail.begin(), tail.end());
+        *n_out = static_cast<int32_t>(tiles.size());
+        OK_CUDA(cudaMalloc(d_out, sizeof(ok::Tile) * tiles.size()));
+        OK_CUDA(cudaMemcpy(*d_out, tiles.data(), sizeof(ok::Tile) * tiles.size(), cudaMemcpyHostToDevice));
+        return OK_SUCCESS;
+    };
+    if (int rc = build_tiles(e->batch_agents, &e->d_tiles, &e->n_tiles))
+        return rc;
+    if (int rc = build_tiles(e->batch_agents_beam, &e->d_tiles_beam, &e->n_tiles_beam))
+        return rc;
+    e->grid      = std::max(1, std::min(e->num_sms, e->n_tiles));
+    e->grid_beam = std::max(1, std::min(e->num_sms, e->n_tiles_beam));
 
     // every agent starts where `Environment::resetAgent(agent, false)` puts it: RaceTrack::kStartingIdx
     std::vector<int32_t> pt(static_cast<size_t>(n));
@@ -1189,10 +1223,10 @@ int ok_launch_stats(const OkEnv *e, OkLaunchStats *out)
     if (!e || !out)
         return fail(OK_ERR_INVALID_ARG, "NULL argument");
     out->kernel_launches = e->launches;
-    out->grid_blocks     = e->grid;
+    out->grid_blocks     = e->cfg.raycast_mode == OK_RAYCAST_BEAM ? e->grid_beam : e->grid;
     out->block_threads   = kBlock;
-    out->smem_bytes      = static_cast<int32_t>(e->smem);
-    out->tiles           = e->n_tiles;
+    out->smem_bytes      = static_cast<int32_t>(e->cfg.raycast_mode == OK_RAYCAST_BEAM ? e->smem_beam : e->smem);
+    out->tiles           = e->cfg.raycast_mode == OK_RAYCAST_BEAM ? e->n_tiles_beam : e->n_tiles;
     return OK_SUCCESS;
 }
 }

@@ -7,6 +7,7 @@ its env -- and therefore the memory -- alive.  Layout follows dlpack.h v0.8 (the
 """
 from __future__ import annotations
 
+import atexit
 import ctypes as C
 
 import numpy as np
@@ -54,6 +55,17 @@ C.pythonapi.PyCapsule_New.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
 @_DELETER
 def _release(managed_ptr):
     _live.pop(C.addressof(managed_ptr.contents), None)
+
+
+@atexit.register
+def _detach_at_exit():
+    """Tensors that are still alive when the interpreter shuts down are released by their consumer AFTER Python is
+    gone: calling back into ``_release`` then is a crash.  Clear their deleter (DLPack allows a NULL deleter) and leak
+    the few bytes of descriptor they point to."""
+    for m, shp, _owner in list(_live.values()):
+        C.cast(C.byref(m, DLManagedTensor.deleter.offset), C.POINTER(C.c_void_p))[0] = None
+        C.pythonapi.Py_IncRef(C.py_object(m))
+        C.pythonapi.Py_IncRef(C.py_object(shp))
 
 
 def to_capsule(ptr: int, shape, dtype, device_id: int, owner):

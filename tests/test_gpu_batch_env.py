@@ -54,3 +54,20 @@ def test_reset_mask_and_random_resets():
     torch.cuda.synchronize()
     assert env.pos_x.unique().numel() > 100 and not env.crashed.any()
     env.close()
+
+
+def test_views_alive_at_interpreter_exit_do_not_crash():
+    """a BatchEnv left in a module global is torn down after Python: the DLPack deleters must not call back"""
+    import os
+    import subprocess
+    import sys
+
+    code = ("import torch, openkitchen_b200 as ok\n"
+            "env = ok.BatchEnv(['Monza'], 64, rays=5)\n"
+            "env.step_random(2)\n"
+            "keep = [env.obs, env.reward, env['pos_x']]\n"
+            "torch.cuda.synchronize()\n"
+            "print('done', flush=True)\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
+    assert "done" in r.stdout and r.returncode == 0, (r.returncode, r.stderr[-500:])
