@@ -128,8 +128,8 @@ typedef struct OkConfig {
     uint32_t standstill_period;    /* DisplacementStats::kPeriod 200 Environment.h:19 */
     float    standstill_threshold; /* kDisplamentThreshold 20        Environment.h:20 */
     float    grid_cell;            /* broadphase cell size in px (8) */
-    float    beam_cell;            /* OK_RAYCAST_BEAM: start-cell size in px (4); 0 = default */
-    int32_t  beam_bins;            /* OK_RAYCAST_BEAM: direction bins, a power of two (128); 0 = default */
+    float    beam_cell;            /* OK_RAYCAST_BEAM: start-cell size in px (2); 0 = default */
+    int32_t  beam_bins;            /* OK_RAYCAST_BEAM: direction bins, a power of two (256); 0 = default */
     int32_t  reserved[2];
 } OkConfig;
 
@@ -239,8 +239,9 @@ int ok_eval_sincosf(OkEnv *env, const float *h_in, float *h_sin, float *h_cos, i
 
 /* OK_RAYCAST_BEAM's candidate table, host side (no device needed; built on first use, ok_beam.hpp): the
  * segments a ray starting at (x, y) with direction `angle_rad` can reach within *d_complete px, nearest first.
- * Copies min(count, capacity) indices to h_items and returns count; -1 = the start cell is not covered (the
- * kernel then uses the grid walk); other negative values are OkStatus errors.  Test / inspection hook. */
+ * Copies min(count, capacity) indices to h_items and returns count; OK_BEAM_NOT_COVERED = the start cell is not
+ * covered (the kernel then uses the grid walk); other negative values are OkStatus errors.  Test / inspection hook. */
+#define OK_BEAM_NOT_COVERED (-100)
 int32_t ok_beam_lookup(OkEnv *env, int32_t track_id, float x, float y, float angle_rad, uint16_t *h_items,
                        int32_t capacity, float *d_complete);
 /* size of the track's beam table in bytes (builds it if needed) */

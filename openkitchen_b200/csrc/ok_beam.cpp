@@ -1,5 +1,6 @@
 // ok_beam.cpp -- see ok_beam.hpp.  Host code, binary64 geometry.
 #include "ok_beam.hpp"
+#include "ok_beam_geom.hpp"
 
 #include <algorithm>
 #include <atomic>
@@ -11,86 +12,7 @@ namespace ok
 {
 namespace
 {
-struct V2
-{
-    double x, y;
-};
-inline double cross(const V2 &a, const V2 &b)
-{
-    return a.x * b.y - a.y * b.x;
-}
-
-// convex hull (counter-clockwise, no collinear points) of at most 8 points; returns the vertex count
-int convex_hull8(V2 *pts, int n, V2 *out)
-{
-    std::sort(pts, pts + n, [](const V2 &a, const V2 &b) { return a.x < b.x || (a.x == b.x && a.y < b.y); });
-    int k = 0;
-    for (int i = 0; i < n; ++i)
-    {
-        while (k >= 2 && cross({out[k - 1].x - out[k - 2].x, out[k - 1].y - out[k - 2].y},
-                               {pts[i].x - out[k - 2].x, pts[i].y - out[k - 2].y}) <= 0)
-            --k;
-        out[k++] = pts[i];
-    }
-    for (int i = n - 2, lo = k + 1; i >= 0; --i)
-    {
-        while (k >= lo && cross({out[k - 1].x - out[k - 2].x, out[k - 1].y - out[k - 2].y},
-                                {pts[i].x - out[k - 2].x, pts[i].y - out[k - 2].y}) <= 0)
-            --k;
-        out[k++] = pts[i];
-    }
-    return k > 1 ? k - 1 : k;
-}
-
-// keeps the part of the convex polygon with cross(n, v) >= 0
-int clip_half_plane(const V2 *poly, int m, const V2 &n, V2 *out)
-{
-    int k = 0;
-    for (int i = 0; i < m; ++i)
-    {
-        const V2     a = poly[i], b = poly[(i + 1) % m];
-        const double fa = cross(n, a), fb = cross(n, b);
-        if (fa >= 0)
-            out[k++] = a;
-        if ((fa >= 0) != (fb >= 0))
-        {
-            const double t = fa / (fa - fb);
-            out[k++]       = {a.x + t * (b.x - a.x), a.y + t * (b.y - a.y)};
-        }
-    }
-    return k;
-}
-
-// distance from the origin to a convex polygon (counter-clockwise), 0 when the origin is inside
-double origin_distance(const V2 *poly, int m)
-{
-    if (m == 0)
-        return 1e300;
-    if (m == 1)
-        return std::hypot(poly[0].x, poly[0].y);
-    bool   inside = m >= 3;
-    double best   = 1e300;
-    for (int i = 0; i < m; ++i)
-    {
-        const V2 a = poly[i], b = poly[(i + 1) % m];
-        const V2 e = {b.x - a.x, b.y - a.y};
-        if (cross(e, {-a.x, -a.y}) < 0)
-            inside = false;
-        const double l2 = e.x * e.x + e.y * e.y;
-        double       t  = l2 > 0 ? (-(a.x * e.x) - a.y * e.y) / l2 : 0.0;
-        t               = std::min(1.0, std::max(0.0, t));
-        best            = std::min(best, std::hypot(a.x + t * e.x, a.y + t * e.y));
-    }
-    return inside ? 0.0 : best;
-}
-
-double point_segment_distance(double px, double py, double ax, double ay, double bx, double by)
-{
-    const double ex = bx - ax, ey = by - ay, l2 = ex * ex + ey * ey;
-    double       t  = l2 > 0 ? ((px - ax) * ex + (py - ay) * ey) / l2 : 0.0;
-    t               = std::min(1.0, std::max(0.0, t));
-    return std::hypot(ax + t * ex - px, ay + t * ey - py);
-}
+using namespace beamgeom;
 
 struct Cand
 {
@@ -211,7 +133,7 @@ struct Builder
         {
             const double far =
                 std::max(sc.sample_hit[2 * b], std::max(sc.sample_hit[2 * b + 1], sc.sample_hit[(2 * b + 2) % (2 * nb)]));
-            double d = far + 1.0;
+            double d = far + cfg.pad;
             if (far >= cfg.range || d >= rb)
                 d = rb;
             sc.dcomp[b] = d;
@@ -273,7 +195,7 @@ struct Builder
 };
 } // namespace
 
-bool build_beam_table(const Track &t, const BeamConfig &cfg, std::vector<uint8_t> &blob, std::string &err)
+bool beam_plan(const Track &t, const BeamConfig &cfg, BeamPlan &pl, std::string &err)
 {
     if (!(cfg.cell >= 1.0f && cfg.cell <= 64.0f))
     {
@@ -298,20 +220,94 @@ bool build_beam_table(const Track &t, const BeamConfig &cfg, std::vector<uint8_t
             lo_x = std::min<double>(lo_x, t.segments[4 * s + 2 * e]), hi_x = std::max<double>(hi_x, t.segments[4 * s + 2 * e]);
             lo_y = std::min<double>(lo_y, t.segments[4 * s + 2 * e + 1]), hi_y = std::max<double>(hi_y, t.segments[4 * s + 2 * e + 1]);
         }
-    Builder b{t, cfg};
-    b.h  = cfg.cell;
-    b.x0 = std::floor(lo_x - 1.0);
-    b.y0 = std::floor(lo_y - 1.0);
-    b.nx = std::max<int32_t>(1, static_cast<int32_t>(std::ceil((hi_x + 1.0 - b.x0) / b.h)));
-    b.ny = std::max<int32_t>(1, static_cast<int32_t>(std::ceil((hi_y + 1.0 - b.y0) / b.h)));
-    b.nb = cfg.bins;
-    b.rb = static_cast<double>(cfg.range) + 1.0;
-    b.dth = kBeamAngleMargin;
-    if (static_cast<int64_t>(b.nx) * b.ny > (1 << 24))
+    pl.h  = cfg.cell;
+    pl.x0 = std::floor(lo_x - 1.0);
+    pl.y0 = std::floor(lo_y - 1.0);
+    pl.nx = std::max<int32_t>(1, static_cast<int32_t>(std::ceil((hi_x + 1.0 - pl.x0) / pl.h)));
+    pl.ny = std::max<int32_t>(1, static_cast<int32_t>(std::ceil((hi_y + 1.0 - pl.y0) / pl.h)));
+    pl.nb = cfg.bins;
+    pl.rb = static_cast<double>(cfg.range) + 1.0;
+    if (static_cast<int64_t>(pl.nx) * pl.ny > (1 << 24))
     {
         err = "beam grid has too many cells";
         return false;
     }
+    // covered cells: everything within (lane half-width + 4 px) of a centre-line point
+    pl.rows.assign(static_cast<size_t>(pl.nx) * pl.ny, 0xffffffffu);
+    pl.covered.clear();
+    for (int32_t i = 0; i < n; ++i)
+    {
+        const double r   = std::max(t.w_left[i], t.w_right[i]) + 4.0;
+        const int32_t ix0 = std::max<int32_t>(0, static_cast<int32_t>(std::floor((t.x[i] - r - pl.x0) / pl.h)));
+        const int32_t ix1 = std::min<int32_t>(pl.nx - 1, static_cast<int32_t>(std::floor((t.x[i] + r - pl.x0) / pl.h)));
+        const int32_t iy0 = std::max<int32_t>(0, static_cast<int32_t>(std::floor((t.y[i] - r - pl.y0) / pl.h)));
+        const int32_t iy1 = std::min<int32_t>(pl.ny - 1, static_cast<int32_t>(std::floor((t.y[i] + r - pl.y0) / pl.h)));
+        for (int32_t iy = iy0; iy <= iy1; ++iy)
+            for (int32_t ix = ix0; ix <= ix1; ++ix)
+            { // cells that touch the disc
+                const double qx = std::min(std::max<double>(t.x[i], pl.x0 + ix * pl.h), pl.x0 + (ix + 1) * pl.h);
+                const double qy = std::min(std::max<double>(t.y[i], pl.y0 + iy * pl.h), pl.y0 + (iy + 1) * pl.h);
+                if ((qx - t.x[i]) * (qx - t.x[i]) + (qy - t.y[i]) * (qy - t.y[i]) <= r * r)
+                    pl.rows[static_cast<size_t>(iy) * pl.nx + ix] = 0;
+            }
+    }
+    for (size_t c = 0; c < pl.rows.size(); ++c)
+        if (pl.rows[c] == 0)
+        {
+            pl.rows[c] = static_cast<uint32_t>(pl.covered.size());
+            pl.covered.push_back(static_cast<uint32_t>(c));
+        }
+    return true;
+}
+
+bool beam_assemble(const BeamPlan &pl, const BeamConfig &cfg, const uint32_t *entries, const uint16_t *items, size_t n_items,
+                   std::vector<uint8_t> &blob, std::string &err)
+{
+    if (n_items / 4 >= 0xffffffffull)
+    {
+        err = "beam table too large";
+        return false;
+    }
+    BeamHeader h{};
+    h.x0 = static_cast<float>(pl.x0), h.y0 = static_cast<float>(pl.y0);
+    h.h = cfg.cell, h.inv_h = 1.0f / cfg.cell;
+    h.nx = pl.nx, h.ny = pl.ny, h.nb = pl.nb;
+    h.bin_scale = static_cast<float>(pl.nb / (2.0 * M_PI));
+    h.rb        = static_cast<float>(pl.rb);
+    h.n_rows    = static_cast<uint32_t>(pl.covered.size());
+    h.n_chunks  = static_cast<uint32_t>(n_items / 4);
+    size_t off  = sizeof(BeamHeader);
+    h.off_rows  = static_cast<uint32_t>(off);
+    off += (pl.rows.size() * 4 + 15) / 16 * 16;
+    h.off_entries = static_cast<uint32_t>(off);
+    const size_t entry_bytes = pl.covered.size() * static_cast<size_t>(pl.nb) * 8;
+    off += (entry_bytes + 15) / 16 * 16;
+    h.off_items = static_cast<uint32_t>(off);
+    off += (n_items * 2 + 15) / 16 * 16;
+    if (off >= 0xffffffffull)
+    {
+        err = "beam table too large";
+        return false;
+    }
+    h.bytes = static_cast<uint32_t>(off);
+    blob.assign(off, 0);
+    std::memcpy(blob.data(), &h, sizeof h);
+    std::memcpy(blob.data() + h.off_rows, pl.rows.data(), pl.rows.size() * 4);
+    std::memcpy(blob.data() + h.off_entries, entries, entry_bytes);
+    if (n_items)
+        std::memcpy(blob.data() + h.off_items, items, n_items * 2);
+    return true;
+}
+
+bool build_beam_table(const Track &t, const BeamConfig &cfg, std::vector<uint8_t> &blob, std::string &err)
+{
+    BeamPlan pl;
+    if (!beam_plan(t, cfg, pl, err))
+        return false;
+    const int32_t ns = t.n_segments();
+    Builder b{t, cfg};
+    b.h = pl.h, b.x0 = pl.x0, b.y0 = pl.y0, b.nx = pl.nx, b.ny = pl.ny, b.nb = pl.nb, b.rb = pl.rb;
+    b.dth = kBeamAngleMargin;
     b.seg_mid.resize(ns), b.seg_half.resize(ns);
     for (int32_t s = 0; s < ns; ++s)
     {
@@ -328,31 +324,7 @@ bool build_beam_table(const Track &t, const BeamConfig &cfg, std::vector<uint8_t
         b.sample_dir[2 * k]     = {std::cos(k * dbin), std::sin(k * dbin)};
         b.sample_dir[2 * k + 1] = {std::cos((k + 0.5) * dbin), std::sin((k + 0.5) * dbin)};
     }
-    // covered cells: everything within (lane half-width + 4 px) of a centre-line point
-    std::vector<uint32_t> rows(static_cast<size_t>(b.nx) * b.ny, 0xffffffffu);
-    std::vector<uint32_t> covered;
-    for (int32_t i = 0; i < n; ++i)
-    {
-        const double r   = std::max(t.w_left[i], t.w_right[i]) + 4.0;
-        const int32_t ix0 = std::max<int32_t>(0, static_cast<int32_t>(std::floor((t.x[i] - r - b.x0) / b.h)));
-        const int32_t ix1 = std::min<int32_t>(b.nx - 1, static_cast<int32_t>(std::floor((t.x[i] + r - b.x0) / b.h)));
-        const int32_t iy0 = std::max<int32_t>(0, static_cast<int32_t>(std::floor((t.y[i] - r - b.y0) / b.h)));
-        const int32_t iy1 = std::min<int32_t>(b.ny - 1, static_cast<int32_t>(std::floor((t.y[i] + r - b.y0) / b.h)));
-        for (int32_t iy = iy0; iy <= iy1; ++iy)
-            for (int32_t ix = ix0; ix <= ix1; ++ix)
-            { // cells that touch the disc
-                const double qx = std::min(std::max<double>(t.x[i], b.x0 + ix * b.h), b.x0 + (ix + 1) * b.h);
-                const double qy = std::min(std::max<double>(t.y[i], b.y0 + iy * b.h), b.y0 + (iy + 1) * b.h);
-                if ((qx - t.x[i]) * (qx - t.x[i]) + (qy - t.y[i]) * (qy - t.y[i]) <= r * r)
-                    rows[static_cast<size_t>(iy) * b.nx + ix] = 0;
-            }
-    }
-    for (size_t c = 0; c < rows.size(); ++c)
-        if (rows[c] == 0)
-        {
-            rows[c] = static_cast<uint32_t>(covered.size());
-            covered.push_back(static_cast<uint32_t>(c));
-        }
+    const auto         &covered = pl.covered;
     std::vector<Row>    built(covered.size());
     std::atomic<size_t> next{0};
     unsigned            nthreads = cfg.threads > 0 ? static_cast<unsigned>(cfg.threads) : std::thread::hardware_concurrency();
@@ -380,38 +352,9 @@ bool build_beam_table(const Track &t, const BeamConfig &cfg, std::vector<uint8_t
     size_t n_items = 0;
     for (auto &r : built)
         n_items += r.items.size();
-    if (n_items / 4 >= 0xffffffffull)
-    {
-        err = "beam table too large";
-        return false;
-    }
-    BeamHeader h{};
-    h.x0 = static_cast<float>(b.x0), h.y0 = static_cast<float>(b.y0);
-    h.h = cfg.cell, h.inv_h = 1.0f / cfg.cell;
-    h.nx = b.nx, h.ny = b.ny, h.nb = b.nb;
-    h.bin_scale = static_cast<float>(b.nb / (2.0 * M_PI));
-    h.rb        = static_cast<float>(b.rb);
-    h.n_rows    = static_cast<uint32_t>(covered.size());
-    h.n_chunks  = static_cast<uint32_t>(n_items / 4);
-    size_t off  = sizeof(BeamHeader);
-    h.off_rows  = static_cast<uint32_t>(off);
-    off += (rows.size() * 4 + 15) / 16 * 16;
-    h.off_entries = static_cast<uint32_t>(off);
-    off += (covered.size() * static_cast<size_t>(b.nb) * 8 + 15) / 16 * 16;
-    h.off_items = static_cast<uint32_t>(off);
-    off += (n_items * 2 + 15) / 16 * 16;
-    if (off >= 0xffffffffull)
-    {
-        err = "beam table too large";
-        return false;
-    }
-    h.bytes = static_cast<uint32_t>(off);
-    blob.assign(off, 0);
-    std::memcpy(blob.data(), &h, sizeof h);
-    std::memcpy(blob.data() + h.off_rows, rows.data(), rows.size() * 4);
-    uint32_t *entries = reinterpret_cast<uint32_t *>(blob.data() + h.off_entries);
-    uint16_t *items   = reinterpret_cast<uint16_t *>(blob.data() + h.off_items);
-    size_t    cursor  = 0;
+    std::vector<uint32_t> entries(covered.size() * static_cast<size_t>(b.nb) * 2);
+    std::vector<uint16_t> items(n_items);
+    size_t                cursor = 0;
     for (size_t r = 0; r < built.size(); ++r)
     {
         for (int32_t k = 0; k < b.nb; ++k)
@@ -420,10 +363,10 @@ bool build_beam_table(const Track &t, const BeamConfig &cfg, std::vector<uint8_t
             entries[2 * (r * b.nb + k) + 1] = built[r].meta[k];
         }
         if (!built[r].items.empty())
-            std::memcpy(items + cursor, built[r].items.data(), built[r].items.size() * 2);
+            std::memcpy(items.data() + cursor, built[r].items.data(), built[r].items.size() * 2);
         cursor += built[r].items.size();
     }
-    return true;
+    return beam_assemble(pl, cfg, entries.data(), items.data(), n_items, blob, err);
 }
 
 bool beam_lookup(const std::vector<uint8_t> &blob, float x, float y, float angle, std::vector<uint16_t> &out, float &d_out)

@@ -53,6 +53,7 @@ struct BeamConfig
     float   cell{8.f};
     int32_t bins{64};
     float   range{200.f}; // Agent::kSensorRange; lists flagged complete cover range + 1
+    float   pad{1.0f};    // px added to the farthest sampled first hit to get the completeness distance
     int32_t threads{0};   // 0 = std::thread::hardware_concurrency()
 };
 
@@ -63,8 +64,25 @@ constexpr double kBeamAngleMargin = 1e-4;   // rad: the bin's cone is widened by
 constexpr float  kBeamSlack       = 0.25f;  // px: a list result is trusted up to d - slack
 constexpr float  kBeamMaxAngle    = 100.0f; // rad: rays with a larger |angle| skip the table (bin rounding)
 
-// Builds the blob.  False (with err) if the configuration is unusable; never throws.
+// The grid over the lane and the covered cells (shared by the host and the device builder).
+struct BeamPlan
+{
+    double                x0{0}, y0{0}, h{0}, rb{0};
+    int32_t               nx{0}, ny{0}, nb{0};
+    std::vector<uint32_t> rows;    // per cell: row, 0xffffffff = not covered
+    std::vector<uint32_t> covered; // per row: cell
+};
+bool beam_plan(const Track &t, const BeamConfig &cfg, BeamPlan &plan, std::string &err);
+// entries: 2 x uint32 per (row, bin) = {first chunk, count | dq << 16}; items: uint16 chunks of 4
+bool beam_assemble(const BeamPlan &plan, const BeamConfig &cfg, const uint32_t *entries, const uint16_t *items, size_t n_items,
+                   std::vector<uint8_t> &blob, std::string &err);
+
+// Builds the blob on the host.  False (with err) if the configuration is unusable; never throws.
 bool build_beam_table(const Track &t, const BeamConfig &cfg, std::vector<uint8_t> &blob, std::string &err);
+
+// The same table built by a kernel on CUDA device `device` (ok_beam_gpu.cu): one CTA per covered cell.  Same
+// construction, binary64 on the device; libm differences may move a list boundary by an ulp, never its validity.
+bool build_beam_table_gpu(const Track &t, const BeamConfig &cfg, int device, std::vector<uint8_t> &blob, std::string &err);
 
 // Host-side lookup used by the CPU tests: the list of (x, y, angle[rad]); returns false when the cell is not
 // covered or the angle is out of range.  d_out = completeness distance.

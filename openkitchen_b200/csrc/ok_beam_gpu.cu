@@ -1,0 +1,389 @@
+// ok_beam_gpu.cu -- the beam-table builder of ok_beam.hpp as a kernel: one CTA per covered cell (row).
+//
+// Same construction as the host builder (ok_beam.cpp, build_row), restated for a CTA:
+//   1. candidates  = segments within reach of the cell, with a lower bound `lb` of their distance and a conservative
+//                    range of direction bins (threads stride over the segments, list in global scratch);
+//   2. completeness distance per bin from 15 sample rays (threads stride over the candidates, each trying the sample
+//                    rays of the bins it can be seen in; first hits meet in shared-memory minima);
+//   3. membership  = exact distance from the origin to (S (+) -C) clipped to the bin's cone, binary64, for every
+//                    (candidate, bin) the lower bound cannot rule out (threads stride over candidates);
+//   4. per bin: sort by (distance, segment), pad to chunks of four, append to the item array (one global atomic per
+//      list), write the entry.
+// A list that does not fit the per-bin scratch is written as "decides nothing" (count 0, d = 0): the kernel then
+// walks the grid for those rays -- slower, never wrong.
+#include "ok_beam.hpp"
+#include "ok_beam_geom.hpp"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace ok
+{
+namespace
+{
+using namespace beamgeom;
+
+constexpr int kThreads = 256;
+constexpr int kListCap = 256; // candidates a (cell, bin) list can hold while it is being built
+
+struct GpuBuild
+{
+    const float4 *seg; // x1, y1, x2, y2
+    int32_t       ns;
+    double        x0, y0, h, rb, range, pad, dth;
+    int32_t       nx, nb;
+    const uint32_t *covered;
+    int32_t         n_rows;
+    // scratch, per CTA
+    float    *cand_lb;
+    uint16_t *cand_seg, *cand_b0, *cand_bn;
+    float    *list_d;
+    uint16_t *list_s;
+    // output
+    uint2              *entries;
+    uint16_t           *items;
+    unsigned long long *item_cursor;
+    unsigned long long  item_capacity;
+    int32_t            *row_cursor;
+    int32_t            *overflow; // [0]: lists that did not fit the scratch, [1]: item array full
+};
+
+__global__ void __launch_bounds__(kThreads) beam_build_kernel(const GpuBuild g)
+{
+    extern __shared__ unsigned char smem_raw[];
+    double       *dir_xy   = reinterpret_cast<double *>(smem_raw);               // [2 * nb][2] sample directions
+    unsigned int *hit_bits = reinterpret_cast<unsigned int *>(dir_xy + 4 * g.nb); // [2 * nb][5] first hit per sample ray
+    float        *dcomp    = reinterpret_cast<float *>(hit_bits + 10 * g.nb); // [nb]
+    int          *bin_cnt  = reinterpret_cast<int *>(dcomp + g.nb);           // [nb]
+    __shared__ int s_row, s_ncand;
+
+    const int    tid   = threadIdx.x;
+    const size_t slot  = blockIdx.x;
+    float       *c_lb  = g.cand_lb + slot * g.ns;
+    uint16_t    *c_seg = g.cand_seg + slot * g.ns, *c_b0 = g.cand_b0 + slot * g.ns, *c_bn = g.cand_bn + slot * g.ns;
+    float       *l_d   = g.list_d + slot * static_cast<size_t>(g.nb) * kListCap;
+    uint16_t    *l_s   = g.list_s + slot * static_cast<size_t>(g.nb) * kListCap;
+    const double two_pi = 2.0 * M_PI, dbin = two_pi / g.nb;
+    for (int j = tid; j < 2 * g.nb; j += kThreads)
+    { // bin edges (even j) and bin centres (odd j)
+        dir_xy[2 * j]     = cos(0.5 * j * dbin);
+        dir_xy[2 * j + 1] = sin(0.5 * j * dbin);
+    }
+    const float miss = static_cast<float>(2.0 * g.rb);
+
+    for (;;)
+    {
+        __syncthreads();
+        if (tid == 0)
+        {
+            s_row   = atomicAdd(g.row_cursor, 1);
+            s_ncand = 0;
+        }
+        __syncthreads();
+        const int row = s_row;
+        if (row >= g.n_rows)
+            break;
+        const uint32_t cell = g.covered[row];
+        const int      cx = static_cast<int>(cell % g.nx), cy = static_cast<int>(cell / g.nx);
+        const double   m   = kBeamCellMargin;
+        const double   bx0 = g.x0 + cx * g.h - m, bx1 = g.x0 + (cx + 1) * g.h + m;
+        const double   by0 = g.y0 + cy * g.h - m, by1 = g.y0 + (cy + 1) * g.h + m;
+        const double   ccx = 0.5 * (bx0 + bx1), ccy = 0.5 * (by0 + by1);
+        const double   half_diag = 0.5 * hypot(bx1 - bx0, by1 - by0);
+        for (int i = tid; i < 10 * g.nb; i += kThreads)
+            hit_bits[i] = __float_as_uint(miss);
+        for (int i = tid; i < g.nb; i += kThreads)
+            bin_cnt[i] = 0;
+
+        // ---- 1. candidates ----
+        for (int s = tid; s < g.ns; s += kThreads)
+        {
+            const float4 sg = g.seg[s];
+            const double mx = 0.5 * (static_cast<double>(sg.x) + sg.z), my = 0.5 * (static_cast<double>(sg.y) + sg.w);
+            const double hl = 0.5 * hypot(static_cast<double>(sg.z) - sg.x, static_cast<double>(sg.w) - sg.y);
+            const double vx = mx - ccx, vy = my - ccy;
+            const double dist = hypot(vx, vy), rho = half_diag + hl;
+            if (dist - rho > g.rb)
+                continue;
+            const double d = point_segment_distance(ccx, ccy, sg.x, sg.y, sg.z, sg.w) - half_diag;
+            if (d > g.rb)
+                continue;
+            int b0 = 0, bn = g.nb;
+            if (dist > rho * 1.0000001)
+            { // q - p lies in the disc of radius rho around (midpoint - cell centre)
+                const double phi = atan2(vy, vx), alpha = asin(fmin(1.0, rho / dist)) + 2.0 * g.dth;
+                const double f_lo = floor((phi - alpha) / dbin), f_hi = floor((phi + alpha) / dbin);
+                bn = static_cast<int>(fmin(static_cast<double>(g.nb), f_hi - f_lo + 1.0));
+                b0 = static_cast<int>(fmod(fmod(f_lo, static_cast<double>(g.nb)) + g.nb, static_cast<double>(g.nb)));
+            }
+            const int k = atomicAdd(&s_ncand, 1);
+            c_lb[k]     = static_cast<float>(fmax(0.0, d) * (1.0 - 1e-6)); // rounded down: stays a lower bound in binary32
+            c_seg[k]    = static_cast<uint16_t>(s);
+            c_b0[k]     = static_cast<uint16_t>(b0);
+            c_bn[k]     = static_cast<uint16_t>(bn);
+        }
+        __syncthreads();
+        const int ncand = s_ncand;
+
+        // ---- 2. completeness distance: rays from the four corners and the centre, bin edges and centres.  A thread
+        // takes a candidate and tries the sample rays of the bins it can be seen in; the first hit of a ray is a
+        // shared-memory minimum (bit patterns of non-negative floats order like the floats) ----
+        for (int c = tid; c < ncand; c += kThreads)
+        {
+            const float4 sg = g.seg[c_seg[c]];
+            const double sx = static_cast<double>(sg.z) - sg.x, sy = static_cast<double>(sg.w) - sg.y;
+            const int    b0 = c_b0[c], bn = c_bn[c];
+            for (int k = 0; k < 2 * bn; ++k)
+            {
+                const int    j  = (2 * b0 + k) & (2 * g.nb - 1);
+                const double dx = dir_xy[2 * j], dy = dir_xy[2 * j + 1];
+                const double den = dx * sy - dy * sx;
+                if (fabs(den) < 1e-12)
+                    continue;
+                for (int o = 0; o < 5; ++o)
+                {
+                    const double ox = o == 4 ? ccx : ((o & 1) ? bx1 : bx0), oy = o == 4 ? ccy : ((o & 2) ? by1 : by0);
+                    const double ex = sg.x - ox, ey = sg.y - oy;
+                    const double tt = (ex * sy - ey * sx) / den, ss = (ex * dy - ey * dx) / den;
+                    if (tt >= 0 && ss >= 0 && ss <= 1 && tt < miss)
+                    { // rounded UP to binary32: the sampled distance is never understated
+                        float bf = static_cast<float>(tt);
+                        if (static_cast<double>(bf) < tt)
+                            bf = nextafterf(bf, 3.0e38f);
+                        atomicMin(&hit_bits[5 * j + o], __float_as_uint(bf));
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        for (int b = tid; b < g.nb; b += kThreads)
+        {
+            float far = 0.0f;
+            for (int e = 0; e < 3; ++e)
+            {
+                const int j = (2 * b + e) & (2 * g.nb - 1);
+                for (int o = 0; o < 5; ++o)
+                    far = fmaxf(far, __uint_as_float(hit_bits[5 * j + o]));
+            }
+            double d = static_cast<double>(far) + g.pad;
+            if (far >= g.range || d >= g.rb)
+                d = g.rb;
+            dcomp[b] = static_cast<float>(d);
+        }
+        __syncthreads();
+
+        // ---- 3. membership ----
+        for (int c = tid; c < ncand; c += kThreads)
+        {
+            const float lb = c_lb[c];
+            const int   b0 = c_b0[c], bn = c_bn[c];
+            bool        any = false;
+            for (int k = 0; k < bn && !any; ++k)
+                any = lb <= dcomp[(b0 + k) & (g.nb - 1)];
+            if (!any)
+                continue;
+            const float4 sg = g.seg[c_seg[c]];
+            V2           pts[8], hull[9];
+            int          np = 0;
+            for (int e = 0; e < 2; ++e)
+                for (int k = 0; k < 4; ++k)
+                    pts[np++] = {(e ? sg.z : sg.x) - ((k & 1) ? bx1 : bx0), (e ? sg.w : sg.y) - ((k & 2) ? by1 : by0)};
+            const int nh = convex_hull8(pts, np, hull);
+            for (int k = 0; k < bn; ++k)
+            {
+                const int b = (b0 + k) & (g.nb - 1);
+                if (lb > dcomp[b])
+                    continue;
+                const V2 lo  = {cos(b * dbin - g.dth), sin(b * dbin - g.dth)};
+                const V2 hi  = {-cos((b + 1) * dbin + g.dth), -sin((b + 1) * dbin + g.dth)};
+                V2       c1[12], c2[14];
+                const int    n1 = clip_half_plane(hull, nh, lo, c1);
+                const int    n2 = clip_half_plane(c1, n1, hi, c2);
+                const double d  = origin_distance(c2, n2);
+                if (d <= dcomp[b])
+                {
+                    const int slot_k = atomicAdd(&bin_cnt[b], 1);
+                    if (slot_k < kListCap)
+                    {
+                        l_d[static_cast<size_t>(b) * kListCap + slot_k] = static_cast<float>(d);
+                        l_s[static_cast<size_t>(b) * kListCap + slot_k] = c_seg[c];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- 4. sort, pad, append, entry ----
+        for (int b = tid; b < g.nb; b += kThreads)
+        {
+            int       cnt = bin_cnt[b];
+            float    *dd  = l_d + static_cast<size_t>(b) * kListCap;
+            uint16_t *ss  = l_s + static_cast<size_t>(b) * kListCap;
+            double    d   = dcomp[b];
+            if (cnt > kListCap)
+            { // the scratch holds an arbitrary subset: this list decides nothing
+                atomicAdd(&g.overflow[0], 1);
+                cnt = 0;
+                d   = 0.0;
+            }
+            for (int i = 1; i < cnt; ++i)
+            { // insertion sort by (distance, segment)
+                const float    vd = dd[i];
+                const uint16_t vs = ss[i];
+                int            j  = i - 1;
+                while (j >= 0 && (dd[j] > vd || (dd[j] == vd && ss[j] > vs)))
+                {
+                    dd[j + 1] = dd[j];
+                    ss[j + 1] = ss[j];
+                    --j;
+                }
+                dd[j + 1] = vd;
+                ss[j + 1] = vs;
+            }
+            const unsigned long long padded = static_cast<unsigned long long>((cnt + 3) & ~3);
+            unsigned long long       off    = padded ? atomicAdd(g.item_cursor, padded) : 0ull;
+            if (off + padded > g.item_capacity)
+            {
+                atomicAdd(&g.overflow[1], 1);
+                cnt = 0;
+                d   = 0.0;
+                off = 0;
+            }
+            else
+            {
+                for (int i = 0; i < static_cast<int>(padded); ++i)
+                    g.items[off + i] = i < cnt ? ss[i] : static_cast<uint16_t>(g.ns); // the blob's null segment
+            }
+            uint32_t dq = 0xffffu;
+            if (d < g.rb)
+                dq = static_cast<uint32_t>(fmin(65534.0, floor(d * 256.0)));
+            g.entries[static_cast<size_t>(row) * g.nb + b] = make_uint2(static_cast<uint32_t>(off / 4), static_cast<uint32_t>(cnt) | (dq << 16));
+        }
+    }
+}
+
+#define BEAM_CUDA(expr)                                                                                                \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t e__ = (expr);                                                                                      \
+        if (e__ != cudaSuccess)                                                                                        \
+        {                                                                                                              \
+            err = std::string(#expr) + ": " + cudaGetErrorString(e__);                                                 \
+            goto done;                                                                                                 \
+        }                                                                                                              \
+    } while (0)
+} // namespace
+
+static bool build_once(const Track &t, const BeamConfig &cfg, int device, int items_per_entry, std::vector<uint8_t> &blob,
+                       std::string &err, bool &full)
+{
+    full = false;
+    BeamPlan pl;
+    if (!beam_plan(t, cfg, pl, err))
+        return false;
+    const int32_t ns = t.n_segments(), nb = pl.nb;
+    const size_t  n_rows = pl.covered.size();
+    int           prev = -1, sms = 0;
+    bool          ok = false;
+    void         *d_seg = nullptr, *d_cov = nullptr, *d_scratch = nullptr, *d_entries = nullptr, *d_items = nullptr, *d_ctr = nullptr;
+    std::vector<uint32_t> h_entries;
+    std::vector<uint16_t> h_items;
+    unsigned long long    used = 0, capacity = 0;
+    int32_t               counters[4] = {0, 0, 0, 0};
+    if (cudaGetDevice(&prev) != cudaSuccess)
+    {
+        cudaGetLastError();
+        err = "no CUDA device";
+        return false;
+    }
+    {
+        BEAM_CUDA(cudaSetDevice(device));
+        BEAM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+        const int    grid = static_cast<int>(std::min<size_t>(n_rows, static_cast<size_t>(sms) * 4));
+        const size_t per_cta = static_cast<size_t>(ns) * (4 + 2 + 2 + 2) + static_cast<size_t>(nb) * kListCap * (4 + 2);
+        // 24 candidates per (cell, bin) on average; the caller retries with more when the kernel reports the array full
+        capacity = static_cast<unsigned long long>(n_rows) * nb * static_cast<unsigned long long>(items_per_entry) + 1024ull;
+        GpuBuild g{};
+        BEAM_CUDA(cudaMalloc(&d_seg, sizeof(float4) * ns));
+        BEAM_CUDA(cudaMemcpy(d_seg, t.segments.data(), sizeof(float4) * ns, cudaMemcpyHostToDevice));
+        BEAM_CUDA(cudaMalloc(&d_cov, 4 * std::max<size_t>(n_rows, 1)));
+        BEAM_CUDA(cudaMemcpy(d_cov, pl.covered.data(), 4 * n_rows, cudaMemcpyHostToDevice));
+        BEAM_CUDA(cudaMalloc(&d_scratch, per_cta * grid + 256));
+        BEAM_CUDA(cudaMalloc(&d_entries, 8 * std::max<size_t>(n_rows * nb, 1)));
+        BEAM_CUDA(cudaMalloc(&d_items, 2 * capacity));
+        BEAM_CUDA(cudaMalloc(&d_ctr, 64));
+        BEAM_CUDA(cudaMemset(d_ctr, 0, 64));
+        g.seg = static_cast<const float4 *>(d_seg);
+        g.ns  = ns;
+        g.x0 = pl.x0, g.y0 = pl.y0, g.h = pl.h, g.rb = pl.rb, g.range = cfg.range, g.pad = cfg.pad, g.dth = kBeamAngleMargin;
+        g.nx = pl.nx, g.nb = nb;
+        g.covered = static_cast<const uint32_t *>(d_cov);
+        g.n_rows  = static_cast<int32_t>(n_rows);
+        {
+            uint8_t *p = static_cast<uint8_t *>(d_scratch);
+            g.cand_lb  = reinterpret_cast<float *>(p);
+            p += static_cast<size_t>(grid) * ns * 4;
+            g.list_d = reinterpret_cast<float *>(p);
+            p += static_cast<size_t>(grid) * nb * kListCap * 4;
+            g.cand_seg = reinterpret_cast<uint16_t *>(p);
+            p += static_cast<size_t>(grid) * ns * 2;
+            g.cand_b0 = reinterpret_cast<uint16_t *>(p);
+            p += static_cast<size_t>(grid) * ns * 2;
+            g.cand_bn = reinterpret_cast<uint16_t *>(p);
+            p += static_cast<size_t>(grid) * ns * 2;
+            g.list_s = reinterpret_cast<uint16_t *>(p);
+        }
+        g.entries       = static_cast<uint2 *>(d_entries);
+        g.items         = static_cast<uint16_t *>(d_items);
+        g.item_cursor   = static_cast<unsigned long long *>(d_ctr);
+        g.item_capacity = capacity;
+        g.row_cursor    = reinterpret_cast<int32_t *>(static_cast<uint8_t *>(d_ctr) + 8);
+        g.overflow      = reinterpret_cast<int32_t *>(static_cast<uint8_t *>(d_ctr) + 16);
+        if (n_rows)
+        {
+            const size_t smem = static_cast<size_t>(nb) * (32 + 40 + 8);
+            BEAM_CUDA(cudaFuncSetAttribute(beam_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            beam_build_kernel<<<grid, kThreads, smem>>>(g);
+            BEAM_CUDA(cudaGetLastError());
+            BEAM_CUDA(cudaDeviceSynchronize());
+        }
+        BEAM_CUDA(cudaMemcpy(&used, d_ctr, 8, cudaMemcpyDeviceToHost));
+        BEAM_CUDA(cudaMemcpy(counters, static_cast<uint8_t *>(d_ctr) + 16, 8, cudaMemcpyDeviceToHost));
+        if (counters[1] != 0 || used > capacity)
+        {
+            err  = "beam table: item array full";
+            full = true;
+            goto done;
+        }
+        h_entries.resize(n_rows * static_cast<size_t>(nb) * 2);
+        h_items.resize(used);
+        if (n_rows)
+            BEAM_CUDA(cudaMemcpy(h_entries.data(), d_entries, 8 * n_rows * nb, cudaMemcpyDeviceToHost));
+        if (used)
+            BEAM_CUDA(cudaMemcpy(h_items.data(), d_items, 2 * used, cudaMemcpyDeviceToHost));
+        ok = beam_assemble(pl, cfg, h_entries.data(), h_items.data(), used, blob, err);
+    }
+done:
+    cudaFree(d_seg), cudaFree(d_cov), cudaFree(d_scratch), cudaFree(d_entries), cudaFree(d_items), cudaFree(d_ctr);
+    if (prev >= 0)
+        cudaSetDevice(prev);
+    return ok;
+}
+
+bool build_beam_table_gpu(const Track &t, const BeamConfig &cfg, int device, std::vector<uint8_t> &blob, std::string &err)
+{
+    for (int per = 24; per <= 384; per *= 4)
+    {
+        bool full = false;
+        if (build_once(t, cfg, device, per, blob, err, full))
+            return true;
+        if (!full)
+            return false;
+    }
+    return false;
+}
+
+} // namespace ok

@@ -274,7 +274,10 @@ std::shared_ptr<const std::vector<uint8_t>> beam_cached(const std::string &key)
 std::shared_ptr<const std::vector<uint8_t>> beam_remember(const std::string &key, std::shared_ptr<std::vector<uint8_t>> blob)
 {
     std::lock_guard<std::mutex> lock(g_beam_mu);
-    if (g_beam_cache.size() >= 64)
+    size_t                      held = blob->size();
+    for (auto &kv : g_beam_cache)
+        held += kv.second->size();
+    if (held > (size_t{12} << 30)) // envs keep their own references; this only bounds what the cache itself pins
         g_beam_cache.clear();
     g_beam_cache[key] = blob;
     return blob;
@@ -282,12 +285,29 @@ std::shared_ptr<const std::vector<uint8_t>> beam_remember(const std::string &key
 
 // `wait` = false: return nullptr (no error) when another process holds the track's build lock, so that the caller
 // can build other tracks in the meantime; `wait` = true: wait for that process's file, or build after a timeout.
-std::shared_ptr<const std::vector<uint8_t>> beam_table_for(const ok::Track &t, const ok::BeamConfig &cfg, bool wait, std::string &err)
+std::shared_ptr<const std::vector<uint8_t>> beam_table_for(const ok::Track &t, const ok::BeamConfig &cfg, int device, bool wait,
+                                                           std::string &err)
 {
     const std::string key = beam_key(t, cfg);
     if (auto hit = beam_cached(key))
         return hit;
-    auto              blob = std::make_shared<std::vector<uint8_t>>();
+    auto blob = std::make_shared<std::vector<uint8_t>>();
+    {
+        // the device builder takes tens of milliseconds per track: faster than reading a table from disk
+        const char *force = std::getenv("OK_BEAM_BUILDER");
+        if (device >= 0 && !(force && std::strcmp(force, "cpu") == 0))
+        {
+            std::string gerr;
+            if (ok::build_beam_table_gpu(t, cfg, device, *blob, gerr))
+                return beam_remember(key, blob);
+            if (force && std::strcmp(force, "gpu") == 0)
+            {
+                err = "device builder: " + gerr;
+                return nullptr;
+            }
+            blob->clear();
+        }
+    }
     const std::string dir  = beam_cache_dir();
     const std::string path = dir.empty() ? "" : dir + "/beam-" + key + ".bin", lock = path + ".lock";
     bool              locked = false;
@@ -372,7 +392,7 @@ int ensure_arena(OkEnv *e)
                 if (!e->beams[i])
                 {
                     std::string err;
-                    e->beams[i] = beam_table_for(e->tracks[i], beam_config(e), pass == 1, err);
+                    e->beams[i] = beam_table_for(e->tracks[i], beam_config(e), e->has_device ? e->cfg.device : -1, pass == 1, err);
                     if (!e->beams[i] && (pass == 1 || !err.empty()))
                         return fail(OK_ERR_INVALID_ARG, "beam table: " + err);
                 }
@@ -551,8 +571,8 @@ void ok_config_default(OkConfig *c)
     c->standstill_period    = 200u;
     c->standstill_threshold = 20.0f;
     c->grid_cell            = 8.0f;
-    c->beam_cell            = 4.0f;
-    c->beam_bins            = 128;
+    c->beam_cell            = 2.0f;
+    c->beam_bins            = 256;
 }
 
 int ok_create(const OkConfig *cfg, OkEnv **out)
@@ -574,9 +594,9 @@ int ok_create(const OkConfig *cfg, OkEnv **out)
     if (!(c.grid_cell >= 1.0f && c.grid_cell <= 512.0f))
         return fail(OK_ERR_INVALID_ARG, "grid_cell must be in [1, 512] px");
     if (c.beam_cell == 0.0f)
-        c.beam_cell = 4.0f;
+        c.beam_cell = 2.0f;
     if (c.beam_bins == 0)
-        c.beam_bins = 128;
+        c.beam_bins = 256;
     if (!(c.beam_cell >= 1.0f && c.beam_cell <= 64.0f) || c.beam_bins < 8 || c.beam_bins > 1024 ||
         (c.beam_bins & (c.beam_bins - 1)))
         return fail(OK_ERR_INVALID_ARG, "beam_cell must be in [1, 64] px and beam_bins a power of two in [8, 1024]");
@@ -1186,7 +1206,7 @@ static int host_beam(OkEnv *e, int32_t id)
     if (!e->beams[id])
     {
         std::string err;
-        e->beams[id] = beam_table_for(e->tracks[id], beam_config(e), true, err);
+        e->beams[id] = beam_table_for(e->tracks[id], beam_config(e), e->has_device ? e->cfg.device : -1, true, err);
         if (!e->beams[id])
             return fail(OK_ERR_INVALID_ARG, "beam table: " + err);
     }
@@ -1202,7 +1222,7 @@ int32_t ok_beam_lookup(OkEnv *e, int32_t id, float x, float y, float angle, uint
     std::vector<uint16_t> items;
     float                 d = 0.0f;
     if (!ok::beam_lookup(*e->beams[id], x, y, angle, items, d))
-        return -1;
+        return OK_BEAM_NOT_COVERED;
     if (d_complete)
         *d_complete = d;
     if (h_items && capacity > 0)

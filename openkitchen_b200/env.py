@@ -136,7 +136,7 @@ class Env:
         distance), or None when the start cell is not covered by the table."""
         d = C.c_float(0.0)
         n = self.lib.ok_beam_lookup(self.h, t, x, y, angle_rad, None, 0, C.byref(d))
-        if n == -1:
+        if n == -100:  # OK_BEAM_NOT_COVERED
             return None
         check(n)
         items = np.empty(max(n, 1), dtype=np.uint16)

@@ -29,7 +29,11 @@ def _first_hits(seg, ox, oy, ang):
 
 @pytest.mark.parametrize("name,cell,bins", [("Monza", 8.0, 64), ("Spa", 8.0, 64), ("Zandvoort", 6.0, 32)])
 def test_beam_lists_contain_the_reference_winner(name, cell, bins):
-    env = ok.Env(device=-1, beam_cell=cell, beam_bins=bins)
+    check_beam_lists(ok.Env(device=-1, beam_cell=cell, beam_bins=bins), name)
+
+
+def check_beam_lists(env, name):
+    """shared with tests/test_gpu_beam_builder.py (the same property for tables built by the device builder)"""
     t = env.add_named_track(name)
     seg = env.track_array(t, "segments").astype(np.float64)
     x, y, head = env.track_array(t, "x"), env.track_array(t, "y"), env.track_array(t, "heading")

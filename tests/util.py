@@ -22,7 +22,7 @@ def make_pair(track_names, n, rays_or_fan, kind="port", grouped=True, **cfg):
     nt = len(track_names)
     tid = (np.arange(n) * nt // n).astype(np.int32) if grouped else (np.arange(n) % nt).astype(np.int32)
     env = ok.Env(device=0, **cfg)
-    ocfg = {k: v for k, v in cfg.items() if k not in ("raycast_mode", "grid_cell")}
+    ocfg = {k: v for k, v in cfg.items() if k not in ("raycast_mode", "grid_cell", "beam_cell", "beam_bins")}
     ora = Oracle(kind, **ocfg)
     for nm in track_names:
         env.add_named_track(nm)
