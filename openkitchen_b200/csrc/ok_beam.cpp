@@ -260,15 +260,14 @@ bool beam_plan(const Track &t, const BeamConfig &cfg, BeamPlan &pl, std::string 
     return true;
 }
 
-bool beam_assemble(const BeamPlan &pl, const BeamConfig &cfg, const uint32_t *entries, const uint16_t *items, size_t n_items,
-                   std::vector<uint8_t> &blob, std::string &err)
+bool beam_layout(const BeamPlan &pl, const BeamConfig &cfg, size_t n_items, BeamHeader &h, std::string &err)
 {
     if (n_items / 4 >= 0xffffffffull)
     {
         err = "beam table too large";
         return false;
     }
-    BeamHeader h{};
+    h    = BeamHeader{};
     h.x0 = static_cast<float>(pl.x0), h.y0 = static_cast<float>(pl.y0);
     h.h = cfg.cell, h.inv_h = 1.0f / cfg.cell;
     h.nx = pl.nx, h.ny = pl.ny, h.nb = pl.nb;
@@ -280,8 +279,7 @@ bool beam_assemble(const BeamPlan &pl, const BeamConfig &cfg, const uint32_t *en
     h.off_rows  = static_cast<uint32_t>(off);
     off += (pl.rows.size() * 4 + 15) / 16 * 16;
     h.off_entries = static_cast<uint32_t>(off);
-    const size_t entry_bytes = pl.covered.size() * static_cast<size_t>(pl.nb) * 8;
-    off += (entry_bytes + 15) / 16 * 16;
+    off += (pl.covered.size() * static_cast<size_t>(pl.nb) * 8 + 15) / 16 * 16;
     h.off_items = static_cast<uint32_t>(off);
     off += (n_items * 2 + 15) / 16 * 16;
     if (off >= 0xffffffffull)
@@ -290,10 +288,19 @@ bool beam_assemble(const BeamPlan &pl, const BeamConfig &cfg, const uint32_t *en
         return false;
     }
     h.bytes = static_cast<uint32_t>(off);
-    blob.assign(off, 0);
+    return true;
+}
+
+bool beam_assemble(const BeamPlan &pl, const BeamConfig &cfg, const uint32_t *entries, const uint16_t *items, size_t n_items,
+                   std::vector<uint8_t> &blob, std::string &err)
+{
+    BeamHeader h;
+    if (!beam_layout(pl, cfg, n_items, h, err))
+        return false;
+    blob.assign(h.bytes, 0);
     std::memcpy(blob.data(), &h, sizeof h);
     std::memcpy(blob.data() + h.off_rows, pl.rows.data(), pl.rows.size() * 4);
-    std::memcpy(blob.data() + h.off_entries, entries, entry_bytes);
+    std::memcpy(blob.data() + h.off_entries, entries, pl.covered.size() * static_cast<size_t>(pl.nb) * 8);
     if (n_items)
         std::memcpy(blob.data() + h.off_items, items, n_items * 2);
     return true;

@@ -73,6 +73,8 @@ struct BeamPlan
     std::vector<uint32_t> covered; // per row: cell
 };
 bool beam_plan(const Track &t, const BeamConfig &cfg, BeamPlan &plan, std::string &err);
+// section offsets of a table with n_items uint16 items
+bool beam_layout(const BeamPlan &plan, const BeamConfig &cfg, size_t n_items, BeamHeader &h, std::string &err);
 // entries: 2 x uint32 per (row, bin) = {first chunk, count | dq << 16}; items: uint16 chunks of 4
 bool beam_assemble(const BeamPlan &plan, const BeamConfig &cfg, const uint32_t *entries, const uint16_t *items, size_t n_items,
                    std::vector<uint8_t> &blob, std::string &err);
@@ -82,7 +84,8 @@ bool build_beam_table(const Track &t, const BeamConfig &cfg, std::vector<uint8_t
 
 // The same table built by a kernel on CUDA device `device` (ok_beam_gpu.cu): one CTA per covered cell.  Same
 // construction, binary64 on the device; libm differences may move a list boundary by an ulp, never its validity.
-bool build_beam_table_gpu(const Track &t, const BeamConfig &cfg, int device, std::vector<uint8_t> &blob, std::string &err);
+// The blob is left in device memory (*d_blob, cudaMalloc'ed on `device`, owned by the caller).
+bool build_beam_table_device(const Track &t, const BeamConfig &cfg, int device, uint8_t **d_blob, size_t *bytes, std::string &err);
 
 // Host-side lookup used by the CPU tests: the list of (x, y, angle[rad]); returns false when the cell is not
 // covered or the angle is out of range.  d_out = completeness distance.

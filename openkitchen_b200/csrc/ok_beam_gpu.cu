@@ -17,7 +17,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace ok
@@ -277,11 +280,12 @@ __global__ void __launch_bounds__(kThreads) beam_build_kernel(const GpuBuild g)
     } while (0)
 } // namespace
 
-static bool build_once(const Track &t, const BeamConfig &cfg, int device, int items_per_entry, std::vector<uint8_t> &blob,
-                       std::string &err, bool &full)
+static bool build_once(const Track &t, const BeamConfig &cfg, int device, int items_per_entry, uint8_t **d_blob_out,
+                       size_t *bytes_out, std::string &err, bool &full)
 {
     full = false;
-    BeamPlan pl;
+    const auto t_begin = std::chrono::steady_clock::now();
+    BeamPlan   pl;
     if (!beam_plan(t, cfg, pl, err))
         return false;
     const int32_t ns = t.n_segments(), nb = pl.nb;
@@ -289,8 +293,8 @@ static bool build_once(const Track &t, const BeamConfig &cfg, int device, int it
     int           prev = -1, sms = 0;
     bool          ok = false;
     void         *d_seg = nullptr, *d_cov = nullptr, *d_scratch = nullptr, *d_entries = nullptr, *d_items = nullptr, *d_ctr = nullptr;
-    std::vector<uint32_t> h_entries;
-    std::vector<uint16_t> h_items;
+    uint8_t      *d_blob = nullptr;
+    BeamHeader    hdr{};
     unsigned long long    used = 0, capacity = 0;
     int32_t               counters[4] = {0, 0, 0, 0};
     if (cudaGetDevice(&prev) != cudaSuccess)
@@ -342,6 +346,7 @@ static bool build_once(const Track &t, const BeamConfig &cfg, int device, int it
         g.item_capacity = capacity;
         g.row_cursor    = reinterpret_cast<int32_t *>(static_cast<uint8_t *>(d_ctr) + 8);
         g.overflow      = reinterpret_cast<int32_t *>(static_cast<uint8_t *>(d_ctr) + 16);
+        const auto t_k0 = std::chrono::steady_clock::now();
         if (n_rows)
         {
             const size_t smem = static_cast<size_t>(nb) * (32 + 40 + 8);
@@ -350,6 +355,7 @@ static bool build_once(const Track &t, const BeamConfig &cfg, int device, int it
             BEAM_CUDA(cudaGetLastError());
             BEAM_CUDA(cudaDeviceSynchronize());
         }
+        const auto t_k1 = std::chrono::steady_clock::now();
         BEAM_CUDA(cudaMemcpy(&used, d_ctr, 8, cudaMemcpyDeviceToHost));
         BEAM_CUDA(cudaMemcpy(counters, static_cast<uint8_t *>(d_ctr) + 16, 8, cudaMemcpyDeviceToHost));
         if (counters[1] != 0 || used > capacity)
@@ -358,27 +364,47 @@ static bool build_once(const Track &t, const BeamConfig &cfg, int device, int it
             full = true;
             goto done;
         }
-        h_entries.resize(n_rows * static_cast<size_t>(nb) * 2);
-        h_items.resize(used);
+        // the table in its final layout, assembled on the device: header | rows | entries | items
+        if (!beam_layout(pl, cfg, used, hdr, err))
+            goto done;
+        BEAM_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_blob), hdr.bytes));
+        BEAM_CUDA(cudaMemset(d_blob, 0, hdr.bytes));
+        BEAM_CUDA(cudaMemcpy(d_blob, &hdr, sizeof hdr, cudaMemcpyHostToDevice));
+        BEAM_CUDA(cudaMemcpy(d_blob + hdr.off_rows, pl.rows.data(), pl.rows.size() * 4, cudaMemcpyHostToDevice));
         if (n_rows)
-            BEAM_CUDA(cudaMemcpy(h_entries.data(), d_entries, 8 * n_rows * nb, cudaMemcpyDeviceToHost));
+            BEAM_CUDA(cudaMemcpy(d_blob + hdr.off_entries, d_entries, 8 * n_rows * nb, cudaMemcpyDeviceToDevice));
         if (used)
-            BEAM_CUDA(cudaMemcpy(h_items.data(), d_items, 2 * used, cudaMemcpyDeviceToHost));
-        ok = beam_assemble(pl, cfg, h_entries.data(), h_items.data(), used, blob, err);
+            BEAM_CUDA(cudaMemcpy(d_blob + hdr.off_items, d_items, 2 * used, cudaMemcpyDeviceToDevice));
+        BEAM_CUDA(cudaDeviceSynchronize());
+        ok = true;
+        if (std::getenv("OK_BEAM_VERBOSE"))
+        {
+            const auto t_a1 = std::chrono::steady_clock::now();
+            auto       ms   = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+            std::fprintf(stderr, "[ok_beam_gpu] rows %zu bins %d: setup %.1f ms, kernel %.1f ms, assemble %.1f ms, %.1f MB, %d lists overflowed\n",
+                         n_rows, nb, ms(t_begin, t_k0), ms(t_k0, t_k1), ms(t_k1, t_a1), hdr.bytes / 1e6, counters[0]);
+        }
     }
 done:
     cudaFree(d_seg), cudaFree(d_cov), cudaFree(d_scratch), cudaFree(d_entries), cudaFree(d_items), cudaFree(d_ctr);
+    if (ok)
+    {
+        *d_blob_out = d_blob;
+        *bytes_out  = hdr.bytes;
+    }
+    else if (d_blob)
+        cudaFree(d_blob);
     if (prev >= 0)
         cudaSetDevice(prev);
     return ok;
 }
 
-bool build_beam_table_gpu(const Track &t, const BeamConfig &cfg, int device, std::vector<uint8_t> &blob, std::string &err)
+bool build_beam_table_device(const Track &t, const BeamConfig &cfg, int device, uint8_t **d_blob, size_t *bytes, std::string &err)
 {
     for (int per = 24; per <= 384; per *= 4)
     {
         bool full = false;
-        if (build_once(t, cfg, device, per, blob, err, full))
+        if (build_once(t, cfg, device, per, d_blob, bytes, err, full))
             return true;
         if (!full)
             return false;

@@ -99,6 +99,27 @@ size_t dtype_size(int32_t dt)
 }
 } // namespace
 
+// a beam table in device memory, shared by every env of the process on that device
+struct DeviceBlob
+{
+    uint8_t *ptr{nullptr};
+    size_t   bytes{0};
+    int      device{0};
+    DeviceBlob(uint8_t *p, size_t b, int d) : ptr(p), bytes(b), device(d)
+    {
+    }
+    DeviceBlob(const DeviceBlob &) = delete;
+    DeviceBlob &operator=(const DeviceBlob &) = delete;
+    ~DeviceBlob()
+    {
+        if (ptr)
+        {
+            DeviceGuard g(device);
+            cudaFree(ptr); // an error after the runtime has shut down is harmless
+        }
+    }
+};
+
 struct OkEnv
 {
     OkConfig               cfg{};
@@ -113,8 +134,8 @@ struct OkEnv
     size_t        max_blob_used{0};
     bool          arena_dirty{true};
     // beam tables (OK_RAYCAST_BEAM): one blob per track in global memory
-    std::vector<std::shared_ptr<const std::vector<uint8_t>>> beams;
-    uint8_t      *d_beam_arena{nullptr};
+    std::vector<std::shared_ptr<const std::vector<uint8_t>>> beams;     // host copies (host-only envs, ok_beam_lookup)
+    std::vector<std::shared_ptr<const struct DeviceBlob>>    beams_dev; // what the kernels read; shared between envs
     bool          arena_has_beams{false};
     // agents
     int64_t              n_agents{0};
@@ -285,29 +306,12 @@ std::shared_ptr<const std::vector<uint8_t>> beam_remember(const std::string &key
 
 // `wait` = false: return nullptr (no error) when another process holds the track's build lock, so that the caller
 // can build other tracks in the meantime; `wait` = true: wait for that process's file, or build after a timeout.
-std::shared_ptr<const std::vector<uint8_t>> beam_table_for(const ok::Track &t, const ok::BeamConfig &cfg, int device, bool wait,
-                                                           std::string &err)
+std::shared_ptr<const std::vector<uint8_t>> beam_table_for(const ok::Track &t, const ok::BeamConfig &cfg, bool wait, std::string &err)
 {
     const std::string key = beam_key(t, cfg);
     if (auto hit = beam_cached(key))
         return hit;
-    auto blob = std::make_shared<std::vector<uint8_t>>();
-    {
-        // the device builder takes tens of milliseconds per track: faster than reading a table from disk
-        const char *force = std::getenv("OK_BEAM_BUILDER");
-        if (device >= 0 && !(force && std::strcmp(force, "cpu") == 0))
-        {
-            std::string gerr;
-            if (ok::build_beam_table_gpu(t, cfg, device, *blob, gerr))
-                return beam_remember(key, blob);
-            if (force && std::strcmp(force, "gpu") == 0)
-            {
-                err = "device builder: " + gerr;
-                return nullptr;
-            }
-            blob->clear();
-        }
-    }
+    auto              blob = std::make_shared<std::vector<uint8_t>>();
     const std::string dir  = beam_cache_dir();
     const std::string path = dir.empty() ? "" : dir + "/beam-" + key + ".bin", lock = path + ".lock";
     bool              locked = false;
@@ -356,6 +360,63 @@ std::shared_ptr<const std::vector<uint8_t>> beam_table_for(const ok::Track &t, c
     return beam_remember(key, blob);
 }
 
+// never destroyed: at process exit the CUDA runtime may already be gone when static destructors run
+std::map<std::string, std::shared_ptr<const DeviceBlob>> &g_beam_dev_cache = *new std::map<std::string, std::shared_ptr<const DeviceBlob>>();
+
+// The track's table in the memory of `device`: built there by the kernel builder (ok_beam_gpu.cu); OK_BEAM_BUILDER=cpu
+// (or a failure of the device builder) builds it on the host instead and uploads it.  `wait` as in beam_table_for.
+std::shared_ptr<const DeviceBlob> beam_device_table_for(const ok::Track &t, const ok::BeamConfig &cfg, int device, bool wait,
+                                                        std::string &err)
+{
+    const std::string key = beam_key(t, cfg) + "@" + std::to_string(device);
+    {
+        std::lock_guard<std::mutex> lock(g_beam_mu);
+        auto                        it = g_beam_dev_cache.find(key);
+        if (it != g_beam_dev_cache.end())
+            return it->second;
+    }
+    std::shared_ptr<const DeviceBlob> out;
+    const char                       *force = std::getenv("OK_BEAM_BUILDER");
+    if (!(force && std::strcmp(force, "cpu") == 0))
+    {
+        uint8_t    *d = nullptr;
+        size_t      bytes = 0;
+        std::string gerr;
+        if (ok::build_beam_table_device(t, cfg, device, &d, &bytes, gerr))
+            out = std::make_shared<DeviceBlob>(d, bytes, device);
+        else if (force && std::strcmp(force, "gpu") == 0)
+        {
+            err = "device builder: " + gerr;
+            return nullptr;
+        }
+    }
+    if (!out)
+    {
+        auto host = beam_table_for(t, cfg, wait, err);
+        if (!host)
+            return nullptr;
+        DeviceGuard g(device);
+        uint8_t    *d = nullptr;
+        if (cudaMalloc(reinterpret_cast<void **>(&d), host->size()) != cudaSuccess ||
+            cudaMemcpy(d, host->data(), host->size(), cudaMemcpyHostToDevice) != cudaSuccess)
+        {
+            err = std::string("beam table upload: ") + cudaGetErrorString(cudaGetLastError());
+            if (d)
+                cudaFree(d);
+            return nullptr;
+        }
+        out = std::make_shared<DeviceBlob>(d, host->size(), device);
+    }
+    std::lock_guard<std::mutex> lock(g_beam_mu);
+    size_t                      held = out->bytes;
+    for (auto &kv : g_beam_dev_cache)
+        held += kv.second->bytes;
+    if (held > (size_t{24} << 30)) // envs keep their own references; this only bounds what the cache itself pins
+        g_beam_dev_cache.clear();
+    g_beam_dev_cache[key] = out;
+    return out;
+}
+
 ok::BeamConfig beam_config(const OkEnv *e)
 {
     ok::BeamConfig c;
@@ -378,22 +439,20 @@ int ensure_arena(OkEnv *e)
         cudaFree(e->d_arena);
     if (e->d_track_refs)
         cudaFree(e->d_track_refs);
-    if (e->d_beam_arena)
-        cudaFree(e->d_beam_arena);
-    e->d_arena = nullptr, e->d_track_refs = nullptr, e->d_beam_arena = nullptr;
+    e->d_arena = nullptr, e->d_track_refs = nullptr;
     std::vector<ok::TrackRef> refs;
-    size_t                    total = 0, beam_total = 0;
+    size_t                    total = 0;
     e->max_blob_used                = 0;
-    e->beams.resize(e->tracks.size());
+    e->beams_dev.resize(e->tracks.size());
     if (want_beams)
-    { // first every table nobody else is building, then the ones other ranks of this box were busy with
+    { // (host-built tables only) first every table nobody else is building, then the ones other ranks were busy with
         for (int pass = 0; pass < 2; ++pass)
             for (size_t i = 0; i < e->tracks.size(); ++i)
-                if (!e->beams[i])
+                if (!e->beams_dev[i])
                 {
                     std::string err;
-                    e->beams[i] = beam_table_for(e->tracks[i], beam_config(e), e->has_device ? e->cfg.device : -1, pass == 1, err);
-                    if (!e->beams[i] && (pass == 1 || !err.empty()))
+                    e->beams_dev[i] = beam_device_table_for(e->tracks[i], beam_config(e), e->cfg.device, pass == 1, err);
+                    if (!e->beams_dev[i] && (pass == 1 || !err.empty()))
                         return fail(OK_ERR_INVALID_ARG, "beam table: " + err);
                 }
     }
@@ -406,19 +465,11 @@ int ensure_arena(OkEnv *e)
         if (want_beams)
         {
             r.has_beam    = 1;
-            r.beam_offset = beam_total;
-            beam_total += (e->beams[i]->size() + 255) / 256 * 256;
+            r.beam_offset = reinterpret_cast<uint64_t>(e->beams_dev[i]->ptr); // absolute: the table is its own allocation
         }
         refs.push_back(r);
         total += (t.blob.size() + 127) / 128 * 128;
         e->max_blob_used = std::max(e->max_blob_used, t.blob.size());
-    }
-    if (want_beams)
-    {
-        OK_CUDA(cudaMalloc(&e->d_beam_arena, std::max<size_t>(beam_total, 256)));
-        for (size_t i = 0; i < e->tracks.size(); ++i)
-            OK_CUDA(cudaMemcpy(e->d_beam_arena + refs[i].beam_offset, e->beams[i]->data(), e->beams[i]->size(),
-                               cudaMemcpyHostToDevice));
     }
     e->arena_has_beams = want_beams;
     std::vector<uint8_t> host(total, 0);
@@ -465,7 +516,7 @@ ok::StepParams base_params(OkEnv *e)
     p.start_y   = static_cast<float *>(e->d_buf[OK_BUF_START_Y]);
     p.ray_deg   = e->d_ray_deg;
     p.arena     = e->d_arena;
-    p.beam_arena = e->d_beam_arena;
+    p.beam_arena = nullptr; // TrackRef::beam_offset holds absolute addresses
     p.tracks    = e->d_track_refs;
     p.tiles     = e->d_tiles;
     p.n_tiles   = e->n_tiles;
@@ -506,7 +557,7 @@ int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
     if (rc)
         return rc;
     p.arena      = e->d_arena;
-    p.beam_arena = e->d_beam_arena;
+    p.beam_arena = nullptr; // TrackRef::beam_offset holds absolute addresses
     p.tracks     = e->d_track_refs;
     if (e->cfg.raycast_mode == OK_RAYCAST_BEAM)
     {
@@ -669,8 +720,6 @@ void ok_destroy(OkEnv *e)
             cudaFree(e->d_arena);
         if (e->d_track_refs)
             cudaFree(e->d_track_refs);
-        if (e->d_beam_arena)
-            cudaFree(e->d_beam_arena);
         if (e->d_stage)
             cudaFree(e->d_stage);
     }
@@ -1203,13 +1252,23 @@ static int host_beam(OkEnv *e, int32_t id)
     if (!e || id < 0 || id >= static_cast<int32_t>(e->tracks.size()))
         return fail(OK_ERR_INVALID_ARG, "bad track id");
     e->beams.resize(e->tracks.size());
-    if (!e->beams[id])
-    {
-        std::string err;
-        e->beams[id] = beam_table_for(e->tracks[id], beam_config(e), e->has_device ? e->cfg.device : -1, true, err);
-        if (!e->beams[id])
+    if (e->beams[id])
+        return OK_SUCCESS;
+    std::string err;
+    if (e->has_device)
+    { // the table the kernels use, copied back
+        auto dev = beam_device_table_for(e->tracks[id], beam_config(e), e->cfg.device, true, err);
+        if (!dev)
             return fail(OK_ERR_INVALID_ARG, "beam table: " + err);
+        auto        host = std::make_shared<std::vector<uint8_t>>(dev->bytes);
+        DeviceGuard g(e->cfg.device);
+        OK_CUDA(cudaMemcpy(host->data(), dev->ptr, dev->bytes, cudaMemcpyDeviceToHost));
+        e->beams[id] = host;
+        return OK_SUCCESS;
     }
+    e->beams[id] = beam_table_for(e->tracks[id], beam_config(e), true, err);
+    if (!e->beams[id])
+        return fail(OK_ERR_INVALID_ARG, "beam table: " + err);
     return OK_SUCCESS;
 }
 

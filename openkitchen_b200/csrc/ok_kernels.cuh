@@ -43,7 +43,7 @@ struct TrackRef
     uint64_t offset;      // byte offset of the blob in the arena (128-byte aligned)
     uint32_t bytes;       // blob_bytes
     uint32_t has_beam;    // the track has a beam table
-    uint64_t beam_offset; // byte offset of its beam blob in the beam arena (ok_beam.hpp)
+    uint64_t beam_offset; // device address of its beam table (ok_beam.hpp), its own allocation
 };
 
 struct StepParams
@@ -62,7 +62,7 @@ struct StepParams
     // static inputs
     const float   *ray_deg;
     const uint8_t *arena;
-    const uint8_t *beam_arena; // beam tables (global memory), OK_RAYCAST_BEAM
+    const uint8_t *beam_arena; // unused: TrackRef::beam_offset is an absolute address
     const TrackRef *tracks;
     const Tile    *tiles;
     int32_t        n_tiles;
@@ -1018,7 +1018,7 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
         {
             const TrackRef tr = p.tracks[tl.track];
             if (tr.has_beam)
-                bv = make_beam_view(p.beam_arena + tr.beam_offset);
+                bv = make_beam_view(reinterpret_cast<const uint8_t *>(tr.beam_offset));
         }
         const int       count    = tl.count;
         const int       n_rays   = count * R;
