@@ -516,7 +516,6 @@ ok::StepParams base_params(OkEnv *e)
     p.start_y   = static_cast<float *>(e->d_buf[OK_BUF_START_Y]);
     p.ray_deg   = e->d_ray_deg;
     p.arena     = e->d_arena;
-    p.beam_arena = nullptr; // TrackRef::beam_offset holds absolute addresses
     p.tracks    = e->d_track_refs;
     p.tiles     = e->d_tiles;
     p.n_tiles   = e->n_tiles;
@@ -557,7 +556,6 @@ int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
     if (rc)
         return rc;
     p.arena      = e->d_arena;
-    p.beam_arena = nullptr; // TrackRef::beam_offset holds absolute addresses
     p.tracks     = e->d_track_refs;
     if (e->cfg.raycast_mode == OK_RAYCAST_BEAM)
     {

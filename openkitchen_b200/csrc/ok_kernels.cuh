@@ -62,7 +62,6 @@ struct StepParams
     // static inputs
     const float   *ray_deg;
     const uint8_t *arena;
-    const uint8_t *beam_arena; // unused: TrackRef::beam_offset is an absolute address
     const TrackRef *tracks;
     const Tile    *tiles;
     int32_t        n_tiles;
