@@ -1359,9 +1359,13 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                     atomicMin(&recs[al].min_d2_bits, __float_as_int(sq));
                 g = g_next, al = al_n, ang = ang_n, active = active_n, cov = cov_n, ent = ent_n;
             }
+            // claim the next batch now: late enough to keep the schedule dynamic (see the loop top), early enough
+            // for the atomic's latency to hide behind the other warps' last groups and phase 4
+            if (tid == 0)
+                s_tile = atomicAdd(p.sched, 1); // every thread read the old value before phase 1
         }
         __syncthreads();
-        if (tid == 0)
+        if (!kBeam && tid == 0)
             s_tile = atomicAdd(p.sched, 1); // every thread read the old value long ago; visible after the loop-top barrier
 
         // =====================================================================================

@@ -193,3 +193,20 @@ def test_switching_raycast_mode_at_runtime():
         ora.step()
         if step % 10 == 9:
             assert_same(env, ora, ctx=f"mode {modes[step // 10]}, step {step}")
+
+
+@pytest.mark.parametrize("sensor_range", [120.0, 300.0])
+def test_beam_mode_with_another_sensor_range(sensor_range):
+    """the beam tables are built for the reference's 200 px range: a shorter range just ignores the far candidates, a
+    longer one leaves the tail of every ray to the grid walk -- the results must not change"""
+    env, ora, tid = make_pair(["Monza", "Catalunya"], 80, 32, raycast_mode=ok.RAYCAST_BEAM, sensor_range=sensor_range,
+                              reward_mode=ok.REWARD_MIN_RAY, auto_reset=1)
+    pts = spread_points(ora, tid)
+    env.reset(None, pts)
+    ora.reset(None, pts)
+    for step in range(40):
+        env.launch_steps_random(step, 1)
+        ora.fill_random_actions(step)
+        ora.step()
+    assert_same(env, ora, ctx=f"sensor range {sensor_range}")
+    assert float(ora.buffer("hit_t").max()) <= sensor_range
