@@ -1232,15 +1232,53 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
 
                 const int  q   = (g << 5) + lane;
                 const bool has = q < n_rays;
-                float      dx = 0.0f, dy = 0.0f;
+                // every ray's FIRST chunk (the nearest candidates: the winner is among them for ~9 rays in 10) is
+                // tested by the ray's own lane -- no owner search, ray parameters in registers; only the chunks
+                // beyond the first are dealt across the warp
+                const uint32_t cnt  = cov ? (ent.y & 0xffffu) : 0u;
+                uint2          it_0 = make_uint2(0u, 0u);
+                if (cnt)
+                    it_0 = __ldg(bv.chunks + ent.x);
+                float dx = 0.0f, dy = 0.0f;
                 if (active)
                     sincosf(ang, dy, dx); // cosf/sinf of CollisionChecker.cu:47-48
+                const float rox = recs[al].ox, roy = recs[al].oy;
+                w_ray[lane]     = make_float4(rox, roy, dx, dy);
+                w_key[lane]     = key_none;
+                if (cnt)
                 {
-                    const AgentRec &rec = recs[al];
-                    w_ray[lane]         = make_float4(rec.ox, rec.oy, dx, dy);
-                    w_key[lane]         = key_none;
+                    unsigned long long *key = w_key + lane;
+                    int                 idx[4];
+                    float               tq[4];
+                    bool                el[4], lit[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                    {
+                        idx[u] = static_cast<int>(((u < 2 ? it_0.x : it_0.y) >> (16 * (u & 1))) & 0xffffu);
+                        tq[u]  = beam_eval(tv.seg, idx[u], rox, roy, dx, dy, el[u], lit[u]);
+                    }
+                    float tq_b  = p.sensor_range;
+                    int   idx_b = -1;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                    {
+                        const bool cand = el[u] & !(tq[u] > fmul(tq_b, 1.000003814697265625f));
+                        if (cand & !(tq[u] < fmul(tq_b, 0.999996185302734375f)) & (idx_b >= 0))
+                            beam_flush(tv.seg, idx_b, rox, roy, dx, dy, key); // near tie (rare)
+                        tq_b  = cand ? tq[u] : tq_b;
+                        idx_b = cand ? idx[u] : idx_b;
+                    }
+                    if (idx_b >= 0)
+                        beam_flush(tv.seg, idx_b, rox, roy, dx, dy, key);
+                    if (lit[0] | lit[1] | lit[2] | lit[3])
+                    {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (lit[u])
+                                beam_literal(tv.seg, idx[u], rox, roy, dx, dy, key);
+                    }
                 }
-                const uint32_t nch = cov ? (((ent.y & 0xffffu) + 3u) >> 2) : 0u;
+                const uint32_t nch = cnt ? ((cnt + 3u) >> 2) - 1u : 0u; // chunks beyond the first
                 uint32_t       inc = nch;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1)
@@ -1250,7 +1288,7 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                         inc += v;
                 }
                 const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-                const uint32_t first = ent.x - (inc - nch); // chunk j of the group is chunk (first + j) of the table
+                const uint32_t first = ent.x + 1u - (inc - nch); // chunk j of the rest is chunk (first + j) of the table
                 __syncwarp();
                 // chunk j of the group belongs to the lane `owner` whose prefix range contains j
                 auto find_chunk = [&](uint32_t j, int &owner) -> uint32_t {
