@@ -664,15 +664,17 @@ __device__ __noinline__ int beam_walk_fallback(const uint8_t *blob, float ox, fl
 
 // hit point, unpack (CollisionChecker.cu:68-69,152-165) and the per-ray outputs of ray `gi`, whose nearest
 // segment is `seg` (-1 = none); returns the squared norm of the relative hit
+// t_known != 0: the winner's exact t is already at hand (the beam key holds it; a zero is recomputed because the
+// key does not keep its sign)
 template <typename Rec>
 __device__ __forceinline__ float finish_ray(const StepParams &p, const float4 *segs, const Rec &rec, const int64_t gi,
-                                            const float dx, const float dy, const int seg)
+                                            const float dx, const float dy, const int seg, const float t_known = 0.0f)
 {
     float2 hit;
     if (!(rec.flags & kFlagCrashed))
     {
         // min_t of CollisionChecker.cu:49-66: the winner's t by the reference's expression
-        const float t = seg >= 0 ? exact_t(segs[seg], rec.ox, rec.oy, dx, dy) : p.sensor_range;
+        const float t = seg >= 0 ? (t_known != 0.0f ? t_known : exact_t(segs[seg], rec.ox, rec.oy, dx, dy)) : p.sensor_range;
         p.hit_seg[gi] = seg;
         p.hit_t[gi]   = t;
         hit.x         = fadd(rec.ox, fmul(t, dx));
@@ -1375,12 +1377,14 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                     const float              min_t = __uint_as_float(static_cast<uint32_t>(key >> 32));
                     const uint32_t           dq    = ent.y >> 16;
                     const float              d_eff = dq == 0xffffu ? bv.rb : static_cast<float>(dq) * 0.00390625f;
+                    float t_known = min_t; // the key holds the exact t of `best`
                     if (active && !(cov && min_t <= d_eff - kBeamSlack))
                     { // undecided: everything nearer than d_eff - 1 is settled, the grid walk covers the rest
                         best = beam_walk_fallback(blob, rec.ox, rec.oy, dx, dy, p.sensor_range,
                                                   cov ? fmaxf(d_eff - 1.0f, 0.0f) : 0.0f, best, min_t);
+                        t_known = 0.0f;
                     }
-                    sq = finish_ray(p, tv.seg, rec, ray_base + q, dx, dy, best);
+                    sq = finish_ray(p, tv.seg, rec, ray_base + q, dx, dy, best, t_known);
                 }
                 // min_dist2 of CollisionChecker.cu:150,162-165: `if (sq < min) min = sq` skips NaN, and so
                 // does a signed-int min over the bit patterns of values >= +0 (a NaN made here is 0x7fffffff)
