@@ -709,7 +709,9 @@ __host__ __device__ inline size_t beam_smem_bytes(int agents)
 // Phase 1 for agent `a` (one thread): optional auto-reset, kinematics from the action, standstill timeout
 // (Environment.cpp:128-143), lidar origin (CollisionChecker.cu:121-124).  Writes the agent's state buffers and
 // returns the record the ray and reward phases work from.
-__device__ __forceinline__ AgentRec agent_pre(const StepParams &p, const TrackView &tv, const BeamView &bv, const int64_t a)
+// `gblob` is the track's blob in the GLOBAL arena: only a crashed agent's auto-reset reads it (centre line, headings),
+// so phase 1 does not have to wait for the blob to be staged in shared memory.
+__device__ __forceinline__ AgentRec agent_pre(const StepParams &p, const uint8_t *gblob, const BeamView &bv, const int64_t a)
 {
     float    x = p.x[a], y = p.y[a], rot = p.rot[a], speed = p.speed[a], accel = p.accel[a];
     bool     crashed = p.crashed[a] != 0, timed_out = p.timed_out[a] != 0;
@@ -756,7 +758,8 @@ __device__ __forceinline__ AgentRec agent_pre(const StepParams &p, const TrackVi
         // prev / nearest / fitness are finalised in phase 4 (they need a centre-line search).
         if (p.auto_reset && crashed)
         {
-            const int32_t pt =
+            const TrackView tv = make_view(gblob);
+            const int32_t   pt =
                 static_cast<int32_t>((static_cast<int64_t>(p.reset_pt[a]) + p.auto_reset_stride) % tv.n_pts);
             const float2 c = tv.pts[pt];
             x = c.x, y = c.y, rot = tv.headings[pt];
@@ -998,29 +1001,20 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
         if (tile >= p.n_tiles)
             break;
 
-        const Tile tl = p.tiles[tile];
-        if (tl.track != staged)
+        const Tile     tl = p.tiles[tile];
+        const TrackRef tr = p.tracks[tl.track];
+        // the bulk copy of the track runs under phase 1, which reads no staged data; it is awaited before the rays
+        const bool restage = tl.track != staged;
+        if (restage && tid == 0)
         {
-            if (tid == 0)
-            {
-                const TrackRef tr = p.tracks[tl.track];
-                fence_proxy_async();
-                mbar_expect_tx(&bar, tr.bytes);
-                tma_bulk_g2s(blob, p.arena + tr.offset, tr.bytes, &bar);
-            }
-            mbar_wait(&bar, phase);
-            phase ^= 1u;
-            staged = tl.track;
+            fence_proxy_async();
+            mbar_expect_tx(&bar, tr.bytes);
+            tma_bulk_g2s(blob, p.arena + tr.offset, tr.bytes, &bar);
         }
-        const TrackView tv       = make_view(blob);
-        BeamView        bv;
+        BeamView bv;
         bv.valid = false;
-        if (kBeam)
-        {
-            const TrackRef tr = p.tracks[tl.track];
-            if (tr.has_beam)
-                bv = make_beam_view(reinterpret_cast<const uint8_t *>(tr.beam_offset));
-        }
+        if (kBeam && tr.has_beam)
+            bv = make_beam_view(reinterpret_cast<const uint8_t *>(tr.beam_offset));
         const int       count    = tl.count;
         const int       n_rays   = count * R;
         const float     inv_cnt  = 1.0f / static_cast<float>(count);
@@ -1029,10 +1023,17 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
         // phase 1 -- one thread per agent: optional reset, kinematics, standstill (Environment.cpp:128-143)
         // =====================================================================================
         if (tid < count)
-            recs[tid] = agent_pre(p, tv, bv, tl.begin + tid);
+            recs[tid] = agent_pre(p, p.arena + tr.offset, bv, tl.begin + tid);
         if (tid == 0)
             s_pool = 0;
+        if (restage)
+        {
+            mbar_wait(&bar, phase);
+            phase ^= 1u;
+            staged = tl.track;
+        }
         __syncthreads();
+        const TrackView tv = make_view(blob);
         const int64_t ray_base = tl.begin * R; // global index of the batch's first ray
         if (!kBeam)
         {
