@@ -473,9 +473,15 @@ __device__ __forceinline__ int nearest_index(const TrackView &tv, float qx, floa
 // window's lexicographic (distance, index) minimum is the reference's result.  ok = false means "not proven": the
 // caller runs the full search above.  Ties: lowest index, like the reference (the window wraps around the end of the
 // centre line, so index order is not visiting order).
-__device__ __forceinline__ int nearest_index_window(const TrackView &tv, float qx, float qy, int hint, float &d2_out, bool &ok)
-{
-    const int n = tv.n_pts;
+// kPostLanes = lanes that share one agent in phase 4 (4 for batches of up to 256 agents: every warp of the CTA gets
+// work and the window scan is 4x shorter; 1 for the larger batches of large populations)
+template <int kPostLanes>
+__device__ __forceinline__ int nearest_index_window(const TrackView &tv, float qx, float qy, int hint, int lane, float &d2_out,
+                                                    bool &ok)
+{ // called by whole warps; kPostLanes consecutive lanes hold the same query and split the window between them
+    const int n   = tv.n_pts;
+    const int sub = lane & (kPostLanes - 1);
+    constexpr int per = kNearestWindow / kPostLanes;
     ok          = false;
     d2_out      = FLT_MAX;
     if (n <= kNearestWindow)
@@ -483,15 +489,16 @@ __device__ __forceinline__ int nearest_index_window(const TrackView &tv, float q
     const int h    = min(max(hint, 0), n - 1);
     float     best = FLT_MAX, dh = FLT_MAX;
     int       bi   = 0;
-    int       i    = h - kNearestWindow / 2;
+    int       i    = h - kNearestWindow / 2 + sub * per;
     i += (i < 0) ? n : 0;
-#pragma unroll 4
-    for (int k = 0; k < kNearestWindow; ++k)
+    i -= (i >= n) ? n : 0;
+#pragma unroll
+    for (int k = 0; k < per; ++k)
     {
         const float2 pt  = tv.pts[i];
         const float  ddx = fsub(qx, pt.x), ddy = fsub(qy, pt.y);
         const float  d   = fadd(fmul(ddx, ddx), fmul(ddy, ddy));
-        dh               = (k == kNearestWindow / 2) ? d : dh;
+        dh               = (k == (kNearestWindow / 2) % per) ? d : dh; // the hint itself, in lane (window / 2) / per
         if (d < best || (d == best && d < FLT_MAX && i < bi))
         {
             best = d;
@@ -500,6 +507,18 @@ __device__ __forceinline__ int nearest_index_window(const TrackView &tv, float q
         ++i;
         i = (i >= n) ? 0 : i;
     }
+#pragma unroll
+    for (int o = 1; o < kPostLanes; o <<= 1)
+    {
+        const float od = __shfl_xor_sync(0xffffffffu, best, o);
+        const int   oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (od < best || (od == best && od < FLT_MAX && oi < bi))
+        {
+            best = od;
+            bi   = oi;
+        }
+    }
+    dh             = __shfl_sync(0xffffffffu, dh, (lane & ~(kPostLanes - 1)) + (kNearestWindow / 2) / per);
     const float rb = __fsqrt_rn(best), rh = __fsqrt_rn(dh);
     ok             = fsub(fsub(tv.safe[h], rh), rb) > fadd(fmul(1e-3f, fadd(rh, rb)), 1e-3f);
     d2_out         = best;
@@ -838,8 +857,10 @@ __device__ __forceinline__ AgentRec agent_pre(const StepParams &p, const uint8_t
     return rec;
 }
 
-// Phase 4 for agent `a` (one thread; the WHOLE warp must call this, lanes without an agent with valid = false):
+// Phase 4 for agent `a` (kPostLanes consecutive lanes per agent, they split the centre-line window; the WHOLE warp must
+// call this, lanes without an agent with valid = false):
 // crash flag (CollisionChecker.cu:167-171), nearest centre-line index, progress / reward / done.
+template <int kPostLanes>
 __device__ __forceinline__ void agent_post(const StepParams &p, const TrackView &tv, const AgentRec &rec, const int64_t a,
                                            const bool valid, const int lane)
 {
@@ -855,39 +876,56 @@ __device__ __forceinline__ void agent_post(const StepParams &p, const TrackView 
     // RaceTrack::findNearestTrackIndexBruteForce: the window around last tick's index first; the rare
     // agents it cannot prove (teleported by a buffer write, track folding back on itself) get the
     // full search, their warp's 32 lanes sharing it
+    const bool leader     = (lane & (kPostLanes - 1)) == 0; // the lane that writes the agent's results
     const bool want_reset = valid && (rec.flags & kFlagReset) != 0;
     bool       ok_reset   = true;
-    if (want_reset)
+    if (__any_sync(0xffffffffu, want_reset))
     { // prev_track_idx_ = nearest index of the post-reset pose (main_eigen.cpp:121-130)
-        float d2;
-        prev = nearest_index_window(tv, rec.rx, rec.ry, rec.hint, d2, ok_reset);
+        float     d2;
+        bool      okw;
+        const int r = nearest_index_window<kPostLanes>(tv, rec.rx, rec.ry, rec.hint, lane, d2, okw);
+        if (want_reset)
+        {
+            prev     = r;
+            ok_reset = okw;
+        }
     }
-    for (unsigned need = __ballot_sync(0xffffffffu, !ok_reset); need; need &= need - 1)
+    for (unsigned need = __ballot_sync(0xffffffffu, !ok_reset && leader); need; need &= need - 1)
     {
-        const int   src = __ffs(need) - 1;
-        float       d2;
-        const int   r = nearest_index(tv, __shfl_sync(0xffffffffu, rec.rx, src), __shfl_sync(0xffffffffu, rec.ry, src), lane, 32, d2);
-        if (lane == src)
+        const int src = __ffs(need) - 1;
+        float     d2;
+        const int r = nearest_index(tv, __shfl_sync(0xffffffffu, rec.rx, src), __shfl_sync(0xffffffffu, rec.ry, src), lane, 32, d2);
+        if ((lane & ~(kPostLanes - 1)) == src)
             prev = r;
     }
     if (want_reset)
         near = prev;
     const bool want_near = valid && need_idx;
     bool       ok_near   = true;
-    if (want_near)
-        near = nearest_index_window(tv, rec.x, rec.y, want_reset ? prev : rec.hint, near_d2, ok_near);
-    for (unsigned need = __ballot_sync(0xffffffffu, !ok_near); need; need &= need - 1)
+    if (__any_sync(0xffffffffu, want_near))
     {
-        const int   src = __ffs(need) - 1;
-        float       d2;
-        const int   r = nearest_index(tv, __shfl_sync(0xffffffffu, rec.x, src), __shfl_sync(0xffffffffu, rec.y, src), lane, 32, d2);
-        if (lane == src)
+        float     d2;
+        bool      okw;
+        const int r = nearest_index_window<kPostLanes>(tv, rec.x, rec.y, want_reset ? prev : rec.hint, lane, d2, okw);
+        if (want_near)
+        {
+            near    = r;
+            near_d2 = d2;
+            ok_near = okw;
+        }
+    }
+    for (unsigned need = __ballot_sync(0xffffffffu, !ok_near && leader); need; need &= need - 1)
+    {
+        const int src = __ffs(need) - 1;
+        float     d2;
+        const int r = nearest_index(tv, __shfl_sync(0xffffffffu, rec.x, src), __shfl_sync(0xffffffffu, rec.y, src), lane, 32, d2);
+        if ((lane & ~(kPostLanes - 1)) == src)
         {
             near    = r;
             near_d2 = d2;
         }
     }
-    if (valid)
+    if (valid && leader)
     {
         if (p.do_move)
         {
@@ -1412,12 +1450,19 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
             s_tile = atomicAdd(p.sched, 1); // every thread read the old value long ago; visible after the loop-top barrier
 
         // =====================================================================================
-        // phase 4 -- one thread per agent: crash flag, centre-line search, progress / reward / done
+        // phase 4 -- four lanes (small batches) or one thread per agent: crash flag, centre-line search, reward, done
         // =====================================================================================
-        if ((warp << 5) < count)
+        if (count <= kBlock / 4)
+        {
+            const int  al    = tid >> 2;
+            const bool valid = al < count;
+            if ((warp << 3) < count) // warp-uniform: this warp has at least one agent
+                agent_post<4>(p, tv, recs[valid ? al : 0], tl.begin + (valid ? al : 0), valid, lane);
+        }
+        else if ((warp << 5) < count)
         {
             const bool valid = tid < count;
-            agent_post(p, tv, recs[valid ? tid : 0], tl.begin + (valid ? tid : 0), valid, lane);
+            agent_post<1>(p, tv, recs[valid ? tid : 0], tl.begin + (valid ? tid : 0), valid, lane);
         }
     }
 

@@ -72,3 +72,15 @@ def test_full_size_sampled_slice_matches_oracle():
         got, want = env2.read(name)[sel], ora.buffer(name)
         assert np.array_equal(got.view(np.uint8), want.view(np.uint8)), name
         assert np.array_equal(env.read(name)[sel].view(np.uint8), want.view(np.uint8)), name + " (fused random actions)"
+
+
+def test_large_batches_give_the_same_bits(monkeypatch):
+    """large populations use batches of up to 1,024 agents (phase 4 then runs one thread per agent instead of four
+    lanes): force that layout at 65,536 agents and compare with the default 256-agent batches"""
+    ticks = 20
+    a = _run(ok.RAYCAST_BEAM, ticks)
+    monkeypatch.setenv("OK_BEAM_BATCH_AGENTS", "1024")
+    b = _run(ok.RAYCAST_BEAM, ticks)
+    assert b.launch_stats().tiles < a.launch_stats().tiles
+    for name in ok.BUFFERS:
+        assert np.array_equal(a.read(name).view(np.uint8), b.read(name).view(np.uint8)), f"1,024-agent batches: {name}"
