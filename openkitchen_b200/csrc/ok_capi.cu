@@ -1127,7 +1127,12 @@ int ok_step_host(OkEnv *e, const float *h_thr, const float *h_steer, float *h_ob
     }
     // only the lidar goes through the mapping (full 128-byte warp stores); reward / done are one element per warp,
     // which would be 2 tiny PCIe writes per agent -- a 0.3 MB copy after the kernel is cheaper
-    p.host_obs    = pinned_alias(h_obs);
+    // OK_HOST_OBS=copy: a DMA copy after the kernel instead of stores through the host mapping
+    static const bool obs_by_copy = [] {
+        const char *v = std::getenv("OK_HOST_OBS");
+        return v && std::strcmp(v, "copy") == 0;
+    }();
+    p.host_obs    = obs_by_copy ? nullptr : pinned_alias(h_obs);
     p.host_reward = nullptr;
     p.host_done   = nullptr;
     rc            = launch_step(e, p, s);
