@@ -734,6 +734,10 @@ __device__ __forceinline__ AgentRec agent_pre(const StepParams &p, const uint8_t
 {
     float    x = p.x[a], y = p.y[a], rot = p.rot[a], speed = p.speed[a], accel = p.accel[a];
     bool     crashed = p.crashed[a] != 0, timed_out = p.timed_out[a] != 0;
+    // the standstill record is read up front with the rest of the state: a load issued only after the kinematics
+    // would add a second trip to memory to the latency of this (latency-bound) phase
+    const uint32_t ss_ctr0 = p.ss_ctr[a];
+    const float    ss_x0 = p.ss_x[a], ss_y0 = p.ss_y[a];
     uint32_t flags = 0;
     float    rx = 0.0f, ry = 0.0f;
     float    hs = 0.0f, hc = 0.0f; // sin / cos of the heading, when the move already computed them
@@ -816,7 +820,7 @@ __device__ __forceinline__ AgentRec agent_pre(const StepParams &p, const uint8_t
             x = fadd(x, fmul(fmul(mc, speed), p.dt));
             y = fadd(y, fmul(fmul(ms, speed), p.dt));
             // checkAndUpdateStandstill, Environment.cpp:16-39
-            uint32_t ctr = p.ss_ctr[a];
+            uint32_t ctr = ss_ctr0;
             bool     out = false;
             if (ctr == 0)
             {
@@ -826,7 +830,7 @@ __device__ __forceinline__ AgentRec agent_pre(const StepParams &p, const uint8_t
             }
             else if (ctr >= p.standstill_period)
             {
-                const float mx = fsub(x, p.ss_x[a]), my = fsub(y, p.ss_y[a]);
+                const float mx = fsub(x, ss_x0), my = fsub(y, ss_y0);
                 out = fadd(fmul(mx, mx), fmul(my, my)) < p.standstill_thr2;
                 ctr = 0;
             }
