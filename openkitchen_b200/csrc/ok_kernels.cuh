@@ -9,17 +9,19 @@
 // with no host round trip.
 //
 // Mapping to the machine
-//   * persistent CTAs, one per SM (the staged track fills most of the 227 KB of shared memory);
-//     the agent range is cut into tiles of same-track agents, each CTA walks a contiguous run of
-//     tiles and re-stages a track only when the tile's track changes;
-//   * a track is staged with ONE TMA bulk copy (cp.async.bulk ... mbarrier::complete_tx) of its
-//     blob: segments as float4, the uniform-grid cell table, the centre line;
-//   * LPA = min(32, pow2ceil(R)) lanes serve one agent, one ray per lane (32/LPA agents per warp);
-//     the per-agent work (kinematics, standstill) is computed redundantly by those lanes -- a warp
-//     instruction costs the same for 1 or 32 active lanes -- and the per-agent reductions
-//     (min hit distance, nearest centre-line index) are warp shuffles;
+//   * persistent CTAs, one per SM (the staged track fills most of the 227 KB of shared memory) x 1024 threads; the
+//     agent range is cut into tiles (batches) of same-track agents that the CTAs pull from a global cursor;
+//   * a track is staged with ONE TMA bulk copy (cp.async.bulk ... mbarrier::complete_tx) of its blob: segments as
+//     float4, the uniform-grid cell table, the centre line; the copy runs under phase 1;
+//   * phase 1 (kinematics, standstill; agent_pre) is one thread per agent; phase 4 (crash flag, nearest centre-line
+//     index, reward; agent_post) four lanes or one thread per agent; both leave / read a 64-byte record per agent in
+//     shared memory;
+//   * the rays: kBeam = true reads precomputed candidate lists (ok_beam.hpp) -- warps pull groups of 32 rays, a ray's
+//     first chunk of candidates is tested by its own lane, the rest is dealt evenly over the warp, results meet in a
+//     64-bit atomicMin key per ray; kBeam = false walks a uniform grid ray by ray from a CTA-wide pool (or tests every
+//     segment: the reference's loop);
 //   * state is structure-of-arrays; per-ray outputs are written coalesced (lane = ray).
-// The path is latency/issue bound, not HBM bound, and is not a contraction: no tensor cores.
+// The path is warp-issue bound, not HBM bound, and is not a contraction: no tensor cores.
 #pragma once
 
 #include "ok_beam.hpp"
