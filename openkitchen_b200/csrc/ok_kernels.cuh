@@ -1096,10 +1096,9 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
         __syncthreads();
 
         // =====================================================================================
-        // phase 2 -- the casts.  Rays are pulled from a CTA-wide pool: a warp refills its idle lanes
-        // (warp-aggregated atomic on the pool cursor) whenever kRefillThreshold of them are idle, so
-        // the long rays of the heavy tail do not hold 31 lanes hostage.  The pool is ordered
-        // ray-major with the fan's centre rays first (p.ray_order): those are the long ones.
+        // phase 2 -- the casts (grid / brute modes).  Rays are pulled from a CTA-wide pool, every lane on its own
+        // (one shared-memory atomic per ray), so the long rays of the heavy tail do not hold 31 lanes hostage.
+        // The pool is ordered ray-major with the fan's centre rays first (p.ray_order): those are the long ones.
         // =====================================================================================
         if (p.raycast_mode == 0)
         {
