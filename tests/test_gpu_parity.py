@@ -210,3 +210,26 @@ def test_beam_mode_with_another_sensor_range(sensor_range):
         ora.step()
     assert_same(env, ora, ctx=f"sensor range {sensor_range}")
     assert float(ora.buffer("hit_t").max()) <= sensor_range
+
+
+
+def test_host_step_with_pinned_buffers():
+    """ok_step_host with pinned host buffers (used in place: actions read and observations written through the host
+    mapping) on several tracks"""
+    n = 4 * 61
+    env, ora, tid = make_pair(["Monza", "Spa", "Sochi", "IMS"], n, 32, raycast_mode=ok.RAYCAST_BEAM,
+                              reward_mode=ok.REWARD_CMAES_PROGRESS, auto_reset=1)
+    pts = spread_points(ora, tid)
+    env.reset(None, pts)
+    ora.reset(None, pts)
+    thr, steer = ok.pinned_array((n,), np.float32), ok.pinned_array((n,), np.float32)
+    obs, rew, done = ok.pinned_array((n, 32), np.float32), ok.pinned_array((n,), np.float32), ok.pinned_array((n,), np.uint8)
+    rng = np.random.default_rng(1)
+    for step in range(40):
+        thr[:] = rng.random(n, dtype=np.float32) * 100.0
+        steer[:] = rng.random(n, dtype=np.float32) * 10.0 - 5.0
+        env.step_host(thr, steer, obs, rew, done)
+        ora.step(thr.copy(), steer.copy())
+        assert np.array_equal(obs.view(np.uint32), ora.buffer("obs").view(np.uint32)), f"obs, step {step}"
+        assert np.array_equal(rew, ora.buffer("reward")) and np.array_equal(done, ora.buffer("done")), f"step {step}"
+    assert_same(env, ora, ctx="host step, pinned buffers")
