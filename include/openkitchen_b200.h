@@ -246,6 +246,10 @@ int32_t ok_beam_lookup(OkEnv *env, int32_t track_id, float x, float y, float ang
                        int32_t capacity, float *d_complete);
 /* size of the track's beam table in bytes (builds it if needed) */
 int64_t ok_beam_table_bytes(OkEnv *env, int32_t track_id);
+/* Beam tables are shared between the envs of a process through a cache (host copies and, per device, the tables the
+ * kernels read: ~250 MB per track at the default resolution).  This drops the cache's own references; a table is freed
+ * when the last env that uses it is destroyed. */
+void ok_release_caches(void);
 
 #ifdef __cplusplus
 }

@@ -116,6 +116,7 @@ SIGNATURES = {
     "ok_eval_sincosf": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
     "ok_beam_lookup": (C.c_int32, [_P, C.c_int32, C.c_float, C.c_float, C.c_float, _P, C.c_int32, C.POINTER(C.c_float)]),
     "ok_beam_table_bytes": (C.c_int64, [_P, C.c_int32]),
+    "ok_release_caches": (None, []),
 }
 
 _lib = None

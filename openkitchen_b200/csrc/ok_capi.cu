@@ -1292,6 +1292,13 @@ int32_t ok_beam_lookup(OkEnv *e, int32_t id, float x, float y, float angle, uint
     return static_cast<int32_t>(items.size());
 }
 
+void ok_release_caches(void)
+{
+    std::lock_guard<std::mutex> lock(g_beam_mu);
+    g_beam_cache.clear();
+    g_beam_dev_cache.clear(); // tables still referenced by live envs stay alive until those envs are destroyed
+}
+
 int64_t ok_beam_table_bytes(OkEnv *e, int32_t id)
 {
     int rc = host_beam(e, id);

@@ -44,6 +44,11 @@ def write_track_csv(name: str, path: str):
             f.write("%.9g,%.9g,%.9g,%.9g\n" % (x[i], y[i], wr[i], wl[i]))
 
 
+def release_caches() -> None:
+    """drop the process-wide beam-table caches (tables in use by live envs stay alive until those envs are closed)"""
+    _capi.load().ok_release_caches()
+
+
 def ray_fan(n_rays: int) -> np.ndarray:
     """Evenly spaced fan -70..70 deg in binary32: the generator of main_torch.cpp:26-34."""
     if n_rays == 1:
