@@ -233,3 +233,44 @@ def test_host_step_with_pinned_buffers():
         assert np.array_equal(obs.view(np.uint32), ora.buffer("obs").view(np.uint32)), f"obs, step {step}"
         assert np.array_equal(rew, ora.buffer("reward")) and np.array_equal(done, ora.buffer("done")), f"step {step}"
     assert_same(env, ora, ctx="host step, pinned buffers")
+
+
+@pytest.mark.parametrize("n_points", [12, 33, 40, 100])
+def test_small_synthetic_tracks(n_points):
+    """ovals with very few centre-line points: at most 32 points means the windowed nearest-index search never applies
+    (every agent takes the full search), 33-40 points make its window wrap around most of the track"""
+    from oracle.api import Oracle
+
+    th = np.linspace(0.0, 2.0 * np.pi, n_points, endpoint=False)
+    cols = (300.0 * np.cos(th), 200.0 * np.sin(th), np.full(n_points, 5.0), np.full(n_points, 5.0))
+    cols = tuple(np.asarray(c, dtype=np.float32) for c in cols)
+    n, rays = 48, 32
+    env = ok.Env(device=0, raycast_mode=ok.RAYCAST_BEAM, reward_mode=ok.REWARD_Q_PROGRESS, auto_reset=1)
+    ora = Oracle("port", reward_mode=ok.REWARD_Q_PROGRESS, auto_reset=1)
+    env.add_track(cols)
+    ora.add_track(cols)
+    fan = ok.ray_fan(rays)
+    env.alloc_agents(n, fan, None)
+    ora.alloc_agents(n, fan, None)
+    pts = (np.arange(n) * 5 % n_points).astype(np.int32)
+    env.reset(None, pts)
+    ora.reset(None, pts)
+    for step in range(60):
+        env.launch_steps_random(step, 1)
+        ora.fill_random_actions(step)
+        ora.step()
+        if step % 15 == 14:
+            assert_same(env, ora, ctx=f"{n_points}-point oval, step {step}")
+
+
+def test_maximum_ray_count():
+    """1,024 rays per agent, the most ok_alloc_agents accepts: 32 groups of rays per agent"""
+    env, ora, tid = make_pair(["Zandvoort"], 6, 1024, raycast_mode=ok.RAYCAST_BEAM, reward_mode=ok.REWARD_MIN_RAY, auto_reset=1)
+    pts = spread_points(ora, tid)
+    env.reset(None, pts)
+    ora.reset(None, pts)
+    for step in range(8):
+        env.launch_steps_random(step, 1)
+        ora.fill_random_actions(step)
+        ora.step()
+    assert_same(env, ora, ctx="1024 rays")
