@@ -39,7 +39,7 @@ WORKLOAD = "C3: 65536 agents over 23 tracks x 32 rays, random actions, auto-rese
 
 def ncu_evidence():
     """DRAM traffic per launch of the step kernel from the committed `ncu --set full` capture (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "r1h_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r1i_traffic.json")
     try:
         return json.load(open(p))
     except Exception:
@@ -374,7 +374,7 @@ def main():
                          "note": "not HBM bound: warp-issue bound (ncu: 62% issue slots, 25.5 active threads/instr, ALU pipe 45%, "
                                  "FMA pipe 17%, L1/shared 40%); measured DRAM traffic exceeds the algorithmic bytes because the beam-table "
                                  "lookups (8 B entry + ~1.4 candidate chunks per ray from a 5.7 GB table) trade memory traffic for "
-                                 "instructions -- profiles/r1h_step_kernel_summary.txt, profiles/r1h_step_kernel_phases.txt"},
+                                 "instructions -- profiles/r1i_step_kernel_summary.txt, profiles/r1i_step_kernel_phases.txt"},
             "e2e": {"value": total_agents / (e2e_ms * 1e-3), "unit": "agent-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps},
             "gpu_launches": int(launches), "clocks": clocks,
