@@ -1,16 +1,34 @@
-#!/usr/bin/env python
-"""Soak test: many ticks of the bench workload at several population sizes, under a watchdog.
-usage: timeout 300 python tools/soak.py [steps]"""
-import sys, time
-sys.path.insert(0, '.')
-import bench, openkitchen_b200 as ok
-steps = int(sys.argv[1]) if len(sys.argv) > 1 else 300
-for n in (2300, 23000, 65536):
-    env = ok.Env(device=0, movement_mode=0, reward_mode=2, auto_reset=1)
-    bench.build_workload(ok, env, n)
-    t0 = time.time()
-    for s in range(0, steps, 20):
-        env.launch_steps_random(s, 20)
-        env.sync()
-    print(f"n={n} {steps} ticks ok in {time.time()-t0:.2f}s", flush=True)
-    env.close()
+"""long full-size comparison of the three narrow phases: beam lists vs brute force (and grid) on every buffer
+usage: python tools/soak.py [ticks] [check_every]"""
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, ".")
+import bench  # noqa: E402
+import openkitchen_b200 as ok  # noqa: E402
+
+ticks = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+every = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+envs = {}
+for name, mode in (("beam", ok.RAYCAST_BEAM), ("brute", ok.RAYCAST_BRUTE), ("grid", ok.RAYCAST_GRID)):
+    e = ok.Env(device=0, movement_mode=ok.MOVE_VELOCITY, reward_mode=ok.REWARD_CMAES_PROGRESS, auto_reset=1, raycast_mode=mode)
+    bench.build_workload(ok, e, 65536)
+    envs[name] = e
+t0 = time.time()
+bad = 0
+for start in range(0, ticks, every):
+    for e in envs.values():
+        e.launch_steps_random(start, every)
+    for e in envs.values():
+        e.sync()
+    ref = envs["brute"]
+    for name in ("beam", "grid"):
+        for buf in ok.BUFFERS:
+            a, b = envs[name].read(buf), ref.read(buf)
+            if not np.array_equal(a.view(np.uint8), b.view(np.uint8)):
+                bad += 1
+                print(f"MISMATCH after {start + every} ticks: {name} vs brute, buffer {buf}, {(a != b).sum()} elements", flush=True)
+    print(f"{start + every} ticks ok so far: {bad == 0}  ({time.time() - t0:.0f} s), crashed {envs['beam'].read('crashed').mean():.4f}", flush=True)
+print("SOAK", "PASSED" if bad == 0 else "FAILED", ticks, "ticks x 2,097,152 rays")
