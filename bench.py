@@ -104,8 +104,10 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def build_workload(ok, env_or_oracle, n_agents, is_oracle=False):
-    """tracks + agents + deterministic reset of SURVEY 8(d); identical for the product and the oracle"""
+def build_workload(ok, env_or_oracle, n_agents, is_oracle=False, id_base=0, n_total=None):
+    """tracks + agents + deterministic reset of SURVEY 8(d); identical for the product and the oracle.
+    `id_base` / `n_total`: this env holds agents [id_base, id_base + n_agents) of a population of n_total agents
+    (a rank's shard): track assignment and reset point are functions of the GLOBAL agent id."""
     names = ok.track_names()
     pts_per_track = []
     for nm in names:
@@ -116,9 +118,11 @@ def build_workload(ok, env_or_oracle, n_agents, is_oracle=False):
             env_or_oracle.add_track(cols)
         pts_per_track.append(len(cols[0]))
     nt = len(names)
-    tid = (np.arange(n_agents, dtype=np.int64) * nt // n_agents).astype(np.int32)  # contiguous per track
+    n_total = n_agents if n_total is None else n_total
+    gid = np.arange(id_base, id_base + n_agents, dtype=np.int64)
+    tid = (gid * nt // n_total).astype(np.int32)  # contiguous per track
     env_or_oracle.alloc_agents(n_agents, ok.ray_fan(N_RAYS), tid)
-    ids = np.arange(n_agents, dtype=np.uint64)
+    ids = gid.astype(np.uint64)
     pts = ((ids * np.uint64(2654435761)) % np.uint64(2**32) % np.asarray(pts_per_track, dtype=np.uint64)[tid]).astype(np.int32)
     env_or_oracle.reset(None, pts)
     return tid

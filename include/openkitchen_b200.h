@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define OK_ABI_VERSION 1
+#define OK_ABI_VERSION 2
 
 typedef enum OkStatus {
     OK_SUCCESS            = 0,
@@ -130,7 +130,9 @@ typedef struct OkConfig {
     float    grid_cell;            /* broadphase cell size in px (8) */
     float    beam_cell;            /* OK_RAYCAST_BEAM: start-cell size in px (2); 0 = default */
     int32_t  beam_bins;            /* OK_RAYCAST_BEAM: direction bins, a power of two (256); 0 = default */
-    int32_t  reserved[2];
+    uint64_t agent_id_base;        /* global id of this env's agent 0 (multi-GPU: the first agent of the rank's slice).
+                                      The synthetic Philox action stream is keyed by (agent_id_base + a, step), so a
+                                      shard reproduces, bit for bit, its slice of the unsharded population */
 } OkConfig;
 
 typedef struct OkTrackInfo {
@@ -202,6 +204,16 @@ int ok_launch_steps_random(OkEnv *env, uint64_t first_step, int32_t k, uint32_t 
 /* write the Philox actions for `step` into the ACT_* buffers without stepping */
 int ok_fill_random_actions(OkEnv *env, uint64_t step, uint32_t seed, void *stream);
 
+/* Track queries for arbitrary points (the app-side reward code of WorldModelVaeRnn/main.cpp:336-337 and every
+ * progress reward): RaceTrack::findNearestTrackIndexBruteForce (RaceTrack.cpp:16-31), getDistanceToLaneCenter
+ * (RaceTrack.cpp:53-72) and getNearestDistanceToTrackBoundary (RaceTrack.cpp:33-51) for n points.  d_x, d_y f32[n];
+ * d_track_id i32[n] or NULL (track 0); each output is nullable.  One warp per query; asynchronous on `stream`. */
+int ok_track_query(OkEnv *env, const float *d_x, const float *d_y, const int32_t *d_track_id, int64_t n,
+                   int32_t *d_nearest_idx, float *d_dist_lane_center, float *d_dist_boundary, void *stream);
+/* same with HOST arrays (staged; synchronises `stream`) */
+int ok_track_query_host(OkEnv *env, const float *h_x, const float *h_y, const int32_t *h_track_id, int64_t n,
+                        int32_t *h_nearest_idx, float *h_dist_lane_center, float *h_dist_boundary, void *stream);
+
 /* The EvolutionaryRacer policy for the whole population: GeneticAgent::updateAction +
  * Network::infer (EvolutionaryRacer/GeneticAgent.hpp:37-50, Network.hpp:119-155).  Agent i has its own weights
  * d_w1[i] (f32 [R+2][hidden], inputs speed/100, normalizeAngleDeg(rot)/360, hits/200) and d_w2[i] (f32 [hidden][6]);
@@ -236,6 +248,12 @@ int ok_launch_stats(const OkEnv *env, OkLaunchStats *out);
 /* evaluates the kernels' sincosf (the glibc-2.39 restatement, ok_math.cuh) on `n` host floats: lets a test
  * compare the DEVICE function with libm / the oracle directly (tests/test_gpu_math.py) */
 int ok_eval_sincosf(OkEnv *env, const float *h_in, float *h_sin, float *h_cos, int64_t n);
+
+/* Host-link probe (measurement only, no env needed): moves `bytes` between a pinned host buffer and device memory
+ * `iters` times on one stream and returns the achieved GB/s in *gbps_out.  mode 0: device->host DMA copies; 1: a kernel
+ * storing through the host mapping (what ok_step_host does with the lidar observations); 2: host->device DMA copies.
+ * bench.py and tools/pcie_ceiling.py run it on all ranks at once to measure the box's ceiling for the end-to-end path. */
+int ok_pcie_probe(int32_t device, size_t bytes, int32_t iters, int32_t mode, double *gbps_out);
 
 /* OK_RAYCAST_BEAM's candidate table, host side (no device needed; built on first use, ok_beam.hpp): the
  * segments a ray starting at (x, y) with direction `angle_rad` can reach within *d_complete px, nearest first.

@@ -52,7 +52,7 @@ class OkConfig(C.Structure):
         ("grid_cell", C.c_float),
         ("beam_cell", C.c_float),
         ("beam_bins", C.c_int32),
-        ("reserved", C.c_int32 * 2),
+        ("agent_id_base", C.c_uint64),
     ]
 
 
@@ -117,6 +117,9 @@ SIGNATURES = {
     "ok_beam_lookup": (C.c_int32, [_P, C.c_int32, C.c_float, C.c_float, C.c_float, _P, C.c_int32, C.POINTER(C.c_float)]),
     "ok_beam_table_bytes": (C.c_int64, [_P, C.c_int32]),
     "ok_release_caches": (None, []),
+    "ok_track_query": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P, _P, _P]),
+    "ok_track_query_host": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P, _P, _P]),
+    "ok_pcie_probe": (C.c_int, [C.c_int32, C.c_size_t, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),
 }
 
 _lib = None

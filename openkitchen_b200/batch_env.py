@@ -146,5 +146,10 @@ class BatchEnv:
         self.reset(idx, pt, la, ho)
 
     def close(self):
+        """Drops this object's views and closes the env.  Tensors the caller still holds keep the device memory alive:
+        the OkEnv is destroyed when the last of them is released (openkitchen_b200.dlpack)."""
         self._views.clear()
+        for name in ("obs", "hits", "hit_points", "hit_seg", "hit_t", "reward", "fitness", "done", "crashed", "timed_out",
+                     "nearest_idx", "pos_x", "pos_y", "rot", "speed", "act_throttle", "act_steer"):
+            setattr(self, name, None)
         self.env.close()

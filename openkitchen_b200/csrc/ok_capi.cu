@@ -224,6 +224,13 @@ std::string beam_cache_dir()
         dir             = std::string(tmp && *tmp ? tmp : "/tmp") + "/openkitchen_b200-cache-" + std::to_string(getuid());
     }
     ::mkdir(dir.c_str(), 0700);
+    // the tables loaded from here steer device reads: only a real directory that belongs to this user and that nobody
+    // else can write is trusted; anything else (a planted directory or symlink in a shared /tmp) disables the cache
+    struct stat st
+    {
+    };
+    if (::lstat(dir.c_str(), &st) != 0 || !S_ISDIR(st.st_mode) || st.st_uid != getuid() || (st.st_mode & (S_IWGRP | S_IWOTH)))
+        return "";
     return dir;
 }
 
@@ -536,6 +543,7 @@ ok::StepParams base_params(OkEnv *e)
     p.sensor_offset     = e->cfg.sensor_offset;
     p.standstill_thr2   = e->cfg.standstill_threshold * e->cfg.standstill_threshold; // Environment.cpp:26
     p.standstill_period = e->cfg.standstill_period;
+    p.id_base           = e->cfg.agent_id_base;
     return p;
 }
 
@@ -547,6 +555,19 @@ int check_ready(OkEnv *e)
         return fail(OK_ERR_NO_DEVICE, "this env was created without a CUDA device (device = -1): no compute entry point is available");
     if (e->n_agents <= 0)
         return fail(OK_ERR_STATE, "ok_alloc_agents has not been called");
+    return OK_SUCCESS;
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize of both step kernels = everything the device allows.  Idempotent.
+int arm_shared_memory_limit(OkEnv *e)
+{
+    cudaFuncAttributes fa{};
+    OK_CUDA(cudaFuncGetAttributes(&fa, ok::step_kernel<kBlock, false>));
+    OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<kBlock, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 e->smem_optin - static_cast<int>(fa.sharedSizeBytes)));
+    OK_CUDA(cudaFuncGetAttributes(&fa, ok::step_kernel<kBlock, true>));
+    OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<kBlock, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 e->smem_optin - static_cast<int>(fa.sharedSizeBytes)));
     return OK_SUCCESS;
 }
 
@@ -574,6 +595,7 @@ int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
 
 namespace
 {
+int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, const int32_t *h_track_id);
 // device-visible alias of a pinned (cudaMallocHost / cudaHostRegister) host pointer, or nullptr if pageable
 template <typename T> T *pinned_alias(T *h)
 {
@@ -816,12 +838,29 @@ int ok_alloc_agents(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, c
         if (h_track_id[i] < 0 || h_track_id[i] >= static_cast<int32_t>(e->tracks.size()))
             return fail(OK_ERR_INVALID_ARG, "track id out of range for agent " + std::to_string(i));
     DeviceGuard g(e->cfg.device);
-    free_agents(e);
-    e->n_agents = n;
-    e->rays     = rays;
+    // everything that can fail without touching the current agents comes first
     int rc0 = ensure_arena(e);
     if (rc0)
         return rc0;
+    free_agents(e);
+    const int rc1 = alloc_agents_impl(e, n, rays, h_ray_deg, h_track_id);
+    if (rc1)
+    { // never leave a half-built set behind: n_agents = 0 makes every entry point report OK_ERR_STATE
+        const std::string msg = g_last_error;
+        free_agents(e);
+        cudaGetLastError();
+        g_last_error = msg;
+    }
+    return rc1;
+}
+} // extern "C"
+
+namespace
+{
+int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, const int32_t *h_track_id)
+{
+    e->n_agents = n;
+    e->rays     = rays;
     // batch = the agents a CTA keeps in flight: as many as fit behind the largest staged track
     {
         const size_t blob  = (e->max_blob_used + 127) / 128 * 128;
@@ -855,10 +894,10 @@ int ok_alloc_agents(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, c
         ab = std::min<int64_t>(ab, std::max<int64_t>(1, (n + e->num_sms - 1) / std::max(1, e->num_sms)));
         e->batch_agents_beam = static_cast<int32_t>(std::max<int64_t>(1, ab));
         e->smem_beam         = blob + ok::beam_smem_bytes(e->batch_agents_beam);
-        OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<kBlock, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(e->smem)));
-        OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<kBlock, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     static_cast<int>(e->smem_beam)));
+        // The limit is an attribute of the FUNCTION on this device, not of the env: it is raised to the opt-in maximum
+        // (minus the kernel's static shared memory), so that envs of different sizes can interleave their launches.
+        if (int rc = arm_shared_memory_limit(e))
+            return rc;
     }
 
     // one slab, 256-byte aligned sub-buffers
@@ -940,7 +979,10 @@ int ok_alloc_agents(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, c
         pt[i] = e->tracks[e->h_track_id[i]].n_points() > 3 ? 3 : 0;
     return ok_reset_agents_host(e, nullptr, pt.data(), nullptr, nullptr, n, nullptr);
 }
+} // namespace
 
+extern "C"
+{
 int64_t ok_num_agents(const OkEnv *e)
 {
     return e ? e->n_agents : 0;
@@ -1093,6 +1135,81 @@ int ok_genetic_policy(OkEnv *e, const float *d_w1, const float *d_w2, int32_t hi
         p, d_w1, d_w2, hidden, e->n_agents);
     OK_CUDA(cudaGetLastError());
     e->launches++;
+    return OK_SUCCESS;
+}
+
+int ok_track_query(OkEnv *e, const float *d_x, const float *d_y, const int32_t *d_track, int64_t n, int32_t *d_idx,
+                   float *d_lane, float *d_bound, void *stream)
+{
+    if (!e)
+        return fail(OK_ERR_INVALID_ARG, "env is NULL");
+    if (!e->has_device)
+        return fail(OK_ERR_NO_DEVICE, "this env was created without a CUDA device (device = -1)");
+    if (e->tracks.empty())
+        return fail(OK_ERR_STATE, "no track has been added");
+    if (n <= 0)
+        return OK_SUCCESS;
+    if (!d_x || !d_y)
+        return fail(OK_ERR_INVALID_ARG, "query coordinates are NULL");
+    if (n > (int64_t{1} << 31) / 32 * 255)
+        return fail(OK_ERR_INVALID_ARG, "too many queries for one launch");
+    DeviceGuard g(e->cfg.device);
+    int         rc = ensure_arena(e);
+    if (rc)
+        return rc;
+    ok::StepParams  p{};
+    p.arena  = e->d_arena;
+    p.tracks = e->d_track_refs;
+    ok::QueryParams q{d_x, d_y, d_track, n, static_cast<int32_t>(e->tracks.size()), d_idx, d_lane, d_bound};
+    const int       threads = 256;
+    const int64_t   blocks  = (n * 32 + threads - 1) / threads;
+    ok::track_query_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(p, q);
+    OK_CUDA(cudaGetLastError());
+    e->launches++;
+    return OK_SUCCESS;
+}
+
+int ok_track_query_host(OkEnv *e, const float *h_x, const float *h_y, const int32_t *h_track, int64_t n, int32_t *h_idx,
+                        float *h_lane, float *h_bound, void *stream)
+{
+    if (!e)
+        return fail(OK_ERR_INVALID_ARG, "env is NULL");
+    if (!e->has_device)
+        return fail(OK_ERR_NO_DEVICE, "this env was created without a CUDA device (device = -1)");
+    if (n <= 0)
+        return OK_SUCCESS;
+    if (!h_x || !h_y)
+        return fail(OK_ERR_INVALID_ARG, "query coordinates are NULL");
+    DeviceGuard  g(e->cfg.device);
+    cudaStream_t s     = static_cast<cudaStream_t>(stream);
+    const size_t bytes = 4 * static_cast<size_t>(n);
+    uint8_t     *d     = nullptr;
+    OK_CUDA(cudaMalloc(&d, 6 * bytes));
+    float   *d_x = reinterpret_cast<float *>(d), *d_y = reinterpret_cast<float *>(d + bytes);
+    int32_t *d_t = reinterpret_cast<int32_t *>(d + 2 * bytes), *d_i = reinterpret_cast<int32_t *>(d + 3 * bytes);
+    float   *d_l = reinterpret_cast<float *>(d + 4 * bytes), *d_b = reinterpret_cast<float *>(d + 5 * bytes);
+    cudaError_t err = cudaMemcpyAsync(d_x, h_x, bytes, cudaMemcpyHostToDevice, s);
+    if (err == cudaSuccess)
+        err = cudaMemcpyAsync(d_y, h_y, bytes, cudaMemcpyHostToDevice, s);
+    if (err == cudaSuccess && h_track)
+        err = cudaMemcpyAsync(d_t, h_track, bytes, cudaMemcpyHostToDevice, s);
+    int rc = OK_SUCCESS;
+    if (err == cudaSuccess)
+        rc = ok_track_query(e, d_x, d_y, h_track ? d_t : nullptr, n, h_idx ? d_i : nullptr, h_lane ? d_l : nullptr,
+                            h_bound ? d_b : nullptr, stream);
+    if (err == cudaSuccess && rc == OK_SUCCESS && h_idx)
+        err = cudaMemcpyAsync(h_idx, d_i, bytes, cudaMemcpyDeviceToHost, s);
+    if (err == cudaSuccess && rc == OK_SUCCESS && h_lane)
+        err = cudaMemcpyAsync(h_lane, d_l, bytes, cudaMemcpyDeviceToHost, s);
+    if (err == cudaSuccess && rc == OK_SUCCESS && h_bound)
+        err = cudaMemcpyAsync(h_bound, d_b, bytes, cudaMemcpyDeviceToHost, s);
+    if (err == cudaSuccess)
+        err = cudaStreamSynchronize(s);
+    cudaFree(d);
+    if (rc)
+        return rc;
+    if (err != cudaSuccess)
+        return fail(OK_ERR_CUDA, std::string("ok_track_query_host: ") + cudaGetErrorString(err));
     return OK_SUCCESS;
 }
 
@@ -1305,6 +1422,67 @@ int64_t ok_beam_table_bytes(OkEnv *e, int32_t id)
     if (rc)
         return rc;
     return static_cast<int64_t>(e->beams[id]->size());
+}
+
+int ok_pcie_probe(int32_t device, size_t bytes, int32_t iters, int32_t mode, double *gbps_out)
+{
+    if (!gbps_out || bytes < 16 || iters < 1 || mode < 0 || mode > 2)
+        return fail(OK_ERR_INVALID_ARG, "ok_pcie_probe: bad arguments");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+        return fail(OK_ERR_NO_DEVICE, "ok_pcie_probe: no such CUDA device");
+    DeviceGuard  g(device);
+    bytes        = bytes / 16 * 16;
+    void        *h = nullptr, *d = nullptr;
+    cudaStream_t s = nullptr;
+    cudaEvent_t  e0 = nullptr, e1 = nullptr;
+    cudaError_t  err = cudaMallocHost(&h, bytes);
+    if (err == cudaSuccess)
+        err = cudaMalloc(&d, bytes);
+    if (err == cudaSuccess)
+        err = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (err == cudaSuccess)
+        err = cudaEventCreate(&e0);
+    if (err == cudaSuccess)
+        err = cudaEventCreate(&e1);
+    if (err == cudaSuccess)
+    {
+        std::memset(h, 0, bytes);
+        cudaMemsetAsync(d, 1, bytes, s);
+        auto once = [&]() {
+            if (mode == 0)
+                cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s);
+            else if (mode == 2)
+                cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s);
+            else
+                ok::probe_store_kernel<<<296, 512, 0, s>>>(static_cast<const float4 *>(d), static_cast<float4 *>(h), bytes / 16);
+        };
+        for (int i = 0; i < 3; ++i)
+            once();
+        cudaEventRecord(e0, s);
+        for (int i = 0; i < iters; ++i)
+            once();
+        cudaEventRecord(e1, s);
+        err = cudaStreamSynchronize(s);
+        float ms = 0.0f;
+        if (err == cudaSuccess)
+            err = cudaEventElapsedTime(&ms, e0, e1);
+        if (err == cudaSuccess)
+            *gbps_out = static_cast<double>(bytes) * iters / (static_cast<double>(ms) * 1e6);
+    }
+    if (e0)
+        cudaEventDestroy(e0);
+    if (e1)
+        cudaEventDestroy(e1);
+    if (s)
+        cudaStreamDestroy(s);
+    if (d)
+        cudaFree(d);
+    if (h)
+        cudaFreeHost(h);
+    if (err != cudaSuccess)
+        return fail(OK_ERR_CUDA, std::string("ok_pcie_probe: ") + cudaGetErrorString(err));
+    return OK_SUCCESS;
 }
 
 int ok_launch_stats(const OkEnv *e, OkLaunchStats *out)

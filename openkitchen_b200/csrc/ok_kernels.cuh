@@ -77,6 +77,7 @@ struct StepParams
     int32_t      action_source;       // 0 stored/ext, 1 philox
     uint32_t     seed;
     uint64_t     step;
+    uint64_t     id_base;             // OkConfig::agent_id_base: global id of agent 0 (Philox counter)
     int32_t      do_move;             // 0: ok_cast_rays
     // optional mirrors in PINNED HOST memory (ok_step_host): the kernel stores results over PCIe as they are
     // produced, so the device->host transfer overlaps the tick instead of following it
@@ -754,7 +755,8 @@ __device__ __forceinline__ AgentRec agent_pre(const StepParams &p, const uint8_t
         if (p.action_source == 1)
         { // synthetic stream: Philox4x32-10, counter (agent, step), key (seed, 0)
             uint32_t o[4];
-            philox4x32_10(static_cast<uint32_t>(a), static_cast<uint32_t>(static_cast<uint64_t>(a) >> 32),
+            const uint64_t id = p.id_base + static_cast<uint64_t>(a);
+            philox4x32_10(static_cast<uint32_t>(id), static_cast<uint32_t>(id >> 32),
                           static_cast<uint32_t>(p.step), static_cast<uint32_t>(p.step >> 32), p.seed, 0u, o);
             if (p.movement_mode == 1)
             { // GeneticAgent.hpp:22-24 action set
@@ -1636,6 +1638,74 @@ __global__ void genetic_policy_kernel(const StepParams p, const float *__restric
     }
 }
 
+// RaceTrack::findNearestTrackIndexBruteForce / getDistanceToLaneCenter / getNearestDistanceToTrackBoundary
+// (RaceTrack.cpp:16-72) for arbitrary query points: one warp per query, the 32 lanes split the points and combine with
+// the order-independent lexicographic minimum (distance, index) -- the reference's strict '<' keeps the lowest index.
+struct QueryParams
+{
+    const float   *x, *y;
+    const int32_t *track; // nullable: track 0
+    int64_t        n;
+    int32_t        n_tracks;
+    int32_t       *nearest;     // nullable outputs
+    float         *lane_center; // sqrt(min d2) / (w_left + w_right) at the nearest point
+    float         *boundary;    // sqrt(min d2 to the LI / RI points)
+};
+
+__global__ void track_query_kernel(const StepParams p, const QueryParams q)
+{
+    const int     lane = threadIdx.x & 31;
+    const int64_t k    = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (k >= q.n)
+        return;
+    int32_t t = q.track ? q.track[k] : 0;
+    t         = min(max(t, 0), q.n_tracks - 1);
+    const TrackView tv = make_view(p.arena + p.tracks[t].offset);
+    const float     qx = q.x[k], qy = q.y[k];
+    if (q.nearest || q.lane_center)
+    {
+        float     d2;
+        const int idx = nearest_index(tv, qx, qy, lane, 32, d2);
+        if (lane == 0)
+        {
+            if (q.nearest)
+                q.nearest[k] = idx;
+            if (q.lane_center)
+                q.lane_center[k] = __fdiv_rn(__fsqrt_rn(d2), tv.widths[idx]); // widths = w_left + w_right
+        }
+    }
+    if (q.boundary)
+    { // LI / RI points are the start points of the LI / RI segment chains; the last ones start the closure segments
+        const int n    = tv.n_pts;
+        float     best = FLT_MAX;
+        for (int i = lane; i < n; i += 32)
+        {
+            const float4 ls = tv.seg[i < n - 1 ? i : 4 * (n - 1)];
+            const float4 rs = tv.seg[i < n - 1 ? 2 * (n - 1) + i : 4 * (n - 1) + 1];
+            float        ddx = fsub(qx, ls.x), ddy = fsub(qy, ls.y);
+            float        d   = fadd(fmul(ddx, ddx), fmul(ddy, ddy));
+            best             = d < best ? d : best;
+            ddx = fsub(qx, rs.x), ddy = fsub(qy, rs.y);
+            d   = fadd(fmul(ddx, ddx), fmul(ddy, ddy));
+            best = d < best ? d : best;
+        }
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            const float od = __shfl_xor_sync(0xffffffffu, best, o);
+            best           = od < best ? od : best;
+        }
+        if (lane == 0)
+            q.boundary[k] = __fsqrt_rn(best);
+    }
+}
+
+// measurement only (ok_pcie_probe): full-warp 16-byte stores of a device buffer through a host mapping
+__global__ void probe_store_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst, size_t n)
+{
+    for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+        dst[i] = src[i];
+}
+
 __global__ void sincosf_kernel(const float *in, float *s_out, float *c_out, int64_t n)
 {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -1652,8 +1722,9 @@ __global__ void fill_actions_kernel(const StepParams p, int64_t n)
     const int64_t a = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     if (a >= n)
         return;
-    uint32_t o[4];
-    philox4x32_10(static_cast<uint32_t>(a), static_cast<uint32_t>(static_cast<uint64_t>(a) >> 32),
+    uint32_t       o[4];
+    const uint64_t id = p.id_base + static_cast<uint64_t>(a);
+    philox4x32_10(static_cast<uint32_t>(id), static_cast<uint32_t>(id >> 32),
                   static_cast<uint32_t>(p.step), static_cast<uint32_t>(p.step >> 32), p.seed, 0u, o);
     float thr, steer;
     if (p.movement_mode == 1)

@@ -52,9 +52,19 @@ C.pythonapi.PyCapsule_New.restype = C.py_object
 C.pythonapi.PyCapsule_New.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
 
 
+def live_exports(owner) -> int:
+    """DLPack tensors exported from `owner` that some consumer still holds"""
+    return sum(1 for _m, _s, o in _live.values() if o is owner)
+
+
 @_DELETER
 def _release(managed_ptr):
-    _live.pop(C.addressof(managed_ptr.contents), None)
+    rec = _live.pop(C.addressof(managed_ptr.contents), None)
+    if rec is not None:
+        owner = rec[2]
+        # an env whose close() arrived while tensors were still alive is destroyed with its last export
+        if getattr(owner, "_close_pending", False) and live_exports(owner) == 0:
+            owner._destroy_now()
 
 
 @atexit.register
@@ -94,6 +104,22 @@ class DeviceBuffer:
         self.ptr, self.shape, self.dtype = env.buffer_info(name)
 
     def __dlpack__(self, stream=None, **_):
+        """`stream` (DLPack protocol: the consumer's stream; 1 = legacy default, 2 = per-thread default, -1 = no sync):
+        the buffers are produced on torch's current stream of the env's device (where BatchEnv launches), so a consumer
+        on another stream is made to wait for an event recorded there."""
+        if stream is not None and stream != -1:
+            try:
+                import torch
+
+                dev = int(self.env.cfg.device)
+                cur = torch.cuda.current_stream(dev)
+                target = 0 if stream in (0, 1) else int(stream)
+                if stream != 2 and cur.cuda_stream != target:
+                    ev = torch.cuda.Event()
+                    ev.record(cur)
+                    torch.cuda.ExternalStream(target, device=dev).wait_event(ev)
+            except ImportError:
+                pass
         return to_capsule(self.ptr, self.shape, self.dtype, int(self.env.cfg.device), self.env)
 
     def __dlpack_device__(self):

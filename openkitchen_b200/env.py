@@ -78,9 +78,22 @@ class Env:
 
     # ---- lifetime -----------------------------------------------------------------------
     def close(self):
+        """Destroys the OkEnv -- unless DLPack tensors exported from it are still alive: device memory a consumer can
+        still touch is never freed under it; the env is then destroyed when its last export is released."""
+        if not getattr(self, "h", None):
+            return
+        from . import dlpack
+
+        if dlpack.live_exports(self) > 0:
+            self._close_pending = True
+            return
+        self._destroy_now()
+
+    def _destroy_now(self):
         if getattr(self, "h", None):
             self.lib.ok_destroy(self.h)
             self.h = None
+        self._close_pending = False
 
     def __del__(self):
         try:
@@ -192,6 +205,25 @@ class Env:
         """End-to-end tick with HOST buffers (H2D actions, kernel, D2H results, sync)."""
         check(self.lib.ok_step_host(self.h, _vp(thr), _vp(steer), _vp(obs), _vp(reward), _vp(done), stream))
 
+    def track_query(self, x, y, track_id=None, stream=None):
+        """RaceTrack::findNearestTrackIndexBruteForce / getDistanceToLaneCenter / getNearestDistanceToTrackBoundary
+        (RaceTrack.cpp:16-72) for host arrays of points -> (nearest_idx i32[n], dist_lane_center f32[n],
+        dist_boundary f32[n]), computed on the device."""
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        y = np.ascontiguousarray(y, dtype=np.float32)
+        if x.shape != y.shape or x.ndim != 1:
+            raise ValueError("x and y must be 1-d arrays of one length")
+        t = None if track_id is None else np.ascontiguousarray(track_id, dtype=np.int32)
+        idx = np.empty(len(x), dtype=np.int32)
+        lane = np.empty(len(x), dtype=np.float32)
+        bound = np.empty(len(x), dtype=np.float32)
+        check(self.lib.ok_track_query_host(self.h, _vp(x), _vp(y), _vp(t), len(x), _vp(idx), _vp(lane), _vp(bound), stream))
+        return idx, lane, bound
+
+    def track_query_device(self, d_x, d_y, d_track_id, n, d_idx=None, d_lane=None, d_bound=None, stream=None):
+        """device-pointer form (asynchronous on `stream`)"""
+        check(self.lib.ok_track_query(self.h, d_x, d_y, d_track_id, n, d_idx, d_lane, d_bound, stream))
+
     def sync(self, stream=None):
         check(self.lib.ok_sync(self.h, stream))
 
@@ -227,6 +259,14 @@ class Env:
         s = OkLaunchStats()
         check(self.lib.ok_launch_stats(self.h, C.byref(s)))
         return s
+
+
+def pcie_probe(device: int, nbytes: int, iters: int = 50, mode: str = "d2h") -> float:
+    """GB/s of `iters` transfers of `nbytes` between pinned host memory and `device` (measurement only):
+    mode "d2h" = DMA copies, "store" = kernel stores through the host mapping, "h2d" = DMA copies the other way"""
+    g = C.c_double(0.0)
+    check(_capi.load().ok_pcie_probe(device, nbytes, iters, {"d2h": 0, "store": 1, "h2d": 2}[mode], C.byref(g)))
+    return g.value
 
 
 def pinned_array(shape, dtype) -> np.ndarray:

@@ -51,6 +51,8 @@ class OkoConfig(C.Structure):
         ("sensor_offset", C.c_float),
         ("standstill_period", C.c_uint32),
         ("standstill_threshold", C.c_float),
+        ("pad_", C.c_uint32),
+        ("agent_id_base", C.c_uint64),
     ]
 
 
@@ -88,6 +90,7 @@ class Oracle:
         f("config_default", None, [C.POINTER(OkoConfig)])
         f("create", C.c_void_p, [C.POINTER(OkoConfig)])
         f("destroy", None, [C.c_void_p])
+        f("update_config", None, [C.c_void_p, C.POINTER(OkoConfig)])
         f("set_threads", None, [C.c_int])
         f("get_max_threads", C.c_int, [])
         f("add_track", C.c_int, [C.c_void_p] * 5 + [C.c_int])
@@ -135,6 +138,14 @@ class Oracle:
             self.close()
         except Exception:
             pass
+
+    def update_config(self, **cfg):
+        """push self.cfg (after editing it, or with keyword overrides) into the live env"""
+        for k, v in cfg.items():
+            if not hasattr(self.cfg, k):
+                raise AttributeError(k)
+            setattr(self.cfg, k, v)
+        self._update_config(self.h, C.byref(self.cfg))
 
     # ---- tracks -------------------------------------------------------------------------
     def add_track(self, cols) -> int:

@@ -505,6 +505,12 @@ OkoEnv *oko_create(const OkoConfig *cfg)
     return e;
 }
 
+/* change the constants of a live env (the product's ok_update_config) */
+void oko_update_config(OkoEnv *e, const OkoConfig *cfg)
+{
+    e->cfg = *cfg;
+}
+
 static void free_agents(OkoEnv *e)
 {
     for (int i = 0; i < OKO_BUF_COUNT; ++i) {
@@ -891,7 +897,8 @@ void oko_fill_random_actions(OkoEnv *e, uint64_t step, uint32_t seed)
     static const float kSteer[5] = {-4.0f, -1.0f, 0.0f, 1.0f, 4.0f};
     float *thr = F32(e, OKO_BUF_ACT_THROTTLE), *st = F32(e, OKO_BUF_ACT_STEER);
     for (int64_t a = 0; a < e->n; ++a) {
-        uint32_t ctr[4] = {(uint32_t)a, (uint32_t)((uint64_t)a >> 32), (uint32_t)step, (uint32_t)(step >> 32)};
+        const uint64_t id = e->cfg.agent_id_base + (uint64_t)a;
+        uint32_t ctr[4] = {(uint32_t)id, (uint32_t)(id >> 32), (uint32_t)step, (uint32_t)(step >> 32)};
         uint32_t key[2] = {seed, 0u};
         uint32_t o[4];
         oko_philox4x32_10(ctr, key, o);

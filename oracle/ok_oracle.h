@@ -59,6 +59,9 @@ typedef struct OkoConfig {
     float    sensor_offset;        /* Agent.h:61 (0) */
     uint32_t standstill_period;    /* Environment.h:19 (200) */
     float    standstill_threshold; /* Environment.h:20 (20) */
+    uint32_t pad_;
+    uint64_t agent_id_base;        /* global id of agent 0: the Philox counter of the synthetic action stream is
+                                      (agent_id_base + a, step), so a shard reproduces its slice of an unsharded run */
 } OkoConfig;
 
 typedef struct OkoEnv OkoEnv;
@@ -66,6 +69,7 @@ typedef struct OkoEnv OkoEnv;
 void    oko_config_default(OkoConfig *cfg);
 OkoEnv *oko_create(const OkoConfig *cfg);
 void    oko_destroy(OkoEnv *env);
+void    oko_update_config(OkoEnv *env, const OkoConfig *cfg); /* constants of a live env */
 void    oko_set_threads(int n); /* OpenMP threads for the agent loop (1 = the reference's single thread) */
 int     oko_get_max_threads(void);
 

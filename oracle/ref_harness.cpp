@@ -404,6 +404,19 @@ OkrEnv *okr_create(const OkoConfig *cfg)
     return e;
 }
 
+// constants of a live env; the reference's Agent objects keep dt / speed limit / sensor range as compile-time
+// constants (Agent.h:10-12, Agent.cpp:84,110), so only the offset and the movement mode reach them
+void okr_update_config(OkrEnv *e, const OkoConfig *cfg)
+{
+    e->cfg = *cfg;
+    for (auto &ag : e->agents)
+    {
+        ag->sensor_offset_ = e->cfg.sensor_offset;
+        ag->setMovementMode(e->cfg.movement_mode == OKO_MOVE_ACCELERATION ? Agent::MovementMode::ACCELERATION
+                                                                           : Agent::MovementMode::VELOCITY);
+    }
+}
+
 void okr_destroy(OkrEnv *e)
 {
     delete e;
@@ -623,7 +636,8 @@ void okr_fill_random_actions(OkrEnv *e, uint64_t step, uint32_t seed)
     const int64_t      n         = static_cast<int64_t>(e->agents.size());
     for (int64_t a = 0; a < n; ++a)
     {
-        uint32_t ctr[4] = {(uint32_t)a, (uint32_t)((uint64_t)a >> 32), (uint32_t)step, (uint32_t)(step >> 32)};
+        const uint64_t id = e->cfg.agent_id_base + (uint64_t)a;
+        uint32_t ctr[4] = {(uint32_t)id, (uint32_t)(id >> 32), (uint32_t)step, (uint32_t)(step >> 32)};
         uint32_t key[2] = {seed, 0u};
         uint32_t o[4];
         oko_philox4x32_10(ctr, key, o);

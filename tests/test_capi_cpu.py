@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in sorted(declared) if not hasattr(lib, n)]
     assert not missing, f"library does not export: {missing}"
     assert declared == set(_capi.SIGNATURES), "ctypes table and header disagree"
-    assert _capi.load().ok_abi_version() == 1
+    assert _capi.load().ok_abi_version() == 2
 
 
 def test_config_defaults_are_the_reference_constants():

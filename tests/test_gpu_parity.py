@@ -5,16 +5,22 @@ import numpy as np
 import pytest
 
 import openkitchen_b200 as ok
+from oracle.api import have_ref
 from tests.util import ALL_BUFS, assert_same, make_pair, spread_points
 
 pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("mode", [ok.MOVE_VELOCITY, ok.MOVE_ACCELERATION])
-@pytest.mark.parametrize("raycast", [ok.RAYCAST_BEAM, ok.RAYCAST_GRID, ok.RAYCAST_BRUTE])
-def test_rollout_matches_oracle(mode, raycast):
+@pytest.mark.parametrize("raycast,kind", [(ok.RAYCAST_BEAM, "port"), (ok.RAYCAST_GRID, "port"), (ok.RAYCAST_BRUTE, "port"),
+                                          (ok.RAYCAST_BEAM, "reference")])
+def test_rollout_matches_oracle(mode, raycast, kind):
+    """kind = "reference": the checker is oracle/_ref/libokref.so, i.e. the reference's own Agent.cpp / RaceTrack.cpp
+    objects (shipped prebuilt to the GPU box), not the C restatement."""
+    if kind == "reference" and not have_ref():
+        pytest.skip("oracle/_ref/libokref.so not built")
     names = ok.track_names()
-    env, ora, tid = make_pair(names, 23 * 12, 32, movement_mode=mode, raycast_mode=raycast,
+    env, ora, tid = make_pair(names, 23 * 12, 32, kind=kind, movement_mode=mode, raycast_mode=raycast,
                               reward_mode=ok.REWARD_CMAES_PROGRESS, auto_reset=1)
     pts = spread_points(ora, tid)
     env.reset(None, pts)
