@@ -22,7 +22,8 @@ from ._capi import (  # noqa: F401
     REWARD_TRACK_INDEX,
     OkError,
 )
-from .env import Env, pinned_array, ray_fan, release_caches, track_columns, track_names, write_track_csv  # noqa: F401
+from . import dlpack  # noqa: F401
+from .env import Env, pcie_probe, pinned_array, ray_fan, release_caches, track_columns, track_names, write_track_csv  # noqa: F401
 
 __version__ = "0.1.0"
 
