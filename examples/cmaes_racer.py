@@ -35,7 +35,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     rank = dist.get_rank() if world > 1 else 0
     ctrl = PopulationController(args.rays)
-    solver = CmaEs(ctrl.num_params, args.population, device=f"cuda:{local}", generator=torch.Generator(device="cuda").manual_seed(1))
+    # seed: the solver folds the rank in, so every rank draws DIFFERENT candidates for its slice of the population
+    solver = CmaEs(ctrl.num_params, args.population, device=f"cuda:{local}", seed=1)
     n_local = solver.hi - solver.lo
     env = ok.BatchEnv([args.track], n_local, rays=args.rays, device=local, movement_mode=ok.MOVE_VELOCITY,
                       reward_mode=ok.REWARD_CMAES_PROGRESS)
@@ -47,8 +48,8 @@ def main():
         env.step(torch.zeros_like(thr), torch.zeros_like(thr))  # initial observation (zero action)
         ticks = 0
         for ticks in range(1, args.ticks + 1):
-            steer = 5.0 * ctrl.forward(x, env.obs)[:, 0]
-            env.step(thr, steer)
+            ctrl.act(env, x)                      # one kernel: per-candidate MLP -> action buffers
+            env.step()
             if ticks % 50 == 0 and bool(env.crashed.all()):
                 break
         fitness, order = solver.tell(x, env.fitness)

@@ -222,6 +222,15 @@ int ok_track_query_host(OkEnv *env, const float *h_x, const float *h_y, const in
  * bytes per agent). */
 int ok_genetic_policy(OkEnv *env, const float *d_w1, const float *d_w2, int32_t hidden, void *stream);
 
+/* The CMA-ES racer's policy for the whole population: CmaEsAgent::updateAction + Controller::forward
+ * (CovarianceMatrixAdaptationEvolution/main_torch.cpp:61-71, Controller.cpp:16-23).  Candidate i evaluates
+ * tanh(fc3 tanh(fc2 tanh(fc1 obs_i))) with its OWN flat parameter vector d_params[i] (f32[n_params], torch parameters()
+ * order: fc1.weight [16][R], fc1.bias, fc2.weight [8][16], fc2.bias, fc3.weight [1][8], fc3.bias; n_params = 16 R + 169)
+ * and writes ACT_THROTTLE = throttle (100), ACT_STEER = steer_scale (5) * output.  hidden must be 16 (main_torch.cpp:19).
+ * One warp per agent, weights streamed once: HBM bound at 4 * n_params bytes per agent. */
+int ok_cmaes_controller(OkEnv *env, const float *d_params, int32_t n_params, int32_t hidden, float throttle, float steer_scale,
+                        void *stream);
+
 /* End-to-end host call (what the C++ shim's Environment::step and the reference-facing plugin
  * use): H2D of the two action arrays, one tick, D2H of obs / reward / done / crashed (each
  * nullable), then a stream synchronise.  Host buffers should be pinned (ok_host_alloc). */

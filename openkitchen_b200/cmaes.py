@@ -6,7 +6,11 @@ per-candidate host loops turned into batched tensor ops:
 * ``sample``  CmaEsSolverTorch.cpp:48-79  one ``randn [lambda, N]`` and ONE GEMM ``(z * D) @ B^T`` instead of a
   ``matmul`` per candidate;
 * ``tell``    CmaEsSolverTorch.cpp:82-128 the weighted mean and the rank-mu update ``sum_i w_i y_i y_i^T`` as
-  ``Y^T diag(w) Y`` (one SYRK-shaped GEMM) instead of mu outer products.
+  ``Y^T diag(w) Y`` (one SYRK-shaped GEMM) instead of mu outer products.  Like the reference, which promotes every
+  solution to float64 before it touches the sums (CmaEsSolverTorch.cpp:96,116), both sums are computed in BINARY64
+  (a DGEMM: B200 keeps full-rate FP64) and narrowed to the float32 state once -- the reference narrows after every
+  candidate, so the two agree to float32 rounding (tests/test_cmaes_ref_cpu.py states the tolerance), and the
+  eigendecomposition is the reference's float32 ``linalg_eigh`` (CmaEsSolverTorch.cpp:61).
 
 With ``torch.distributed`` initialised every rank holds the candidates it sampled (its slice of the population) and
 only these cross NVLink per generation: the fitness all-gather (f32[lambda]) and the all-reduce of the partial weighted
@@ -23,13 +27,23 @@ import torch.distributed as dist
 from . import dist as okd
 
 
+def _f32(v) -> float:
+    """a value narrowed to binary32, as when the reference stores a binary64 expression into a C++ `float` member"""
+    return float(torch.as_tensor(v, dtype=torch.float64).to(torch.float32))
+
+
 class CmaEs:
     def __init__(self, num_params: int, population_size: int, device="cuda", sigma: float = 0.5,
-                 generator: torch.Generator | None = None):
+                 generator: torch.Generator | None = None, seed: int | None = None, chunk: int = 131072):
+        """``generator`` / ``seed``: the source of the N(0, I) draws.  Every rank must draw DIFFERENT numbers for its
+        slice of the population (the reference draws lambda independent candidates, CmaEsSolverTorch.cpp:73-79): with
+        ``seed`` the solver builds its own generator seeded by (seed, rank); a caller-supplied ``generator`` must
+        already be rank-distinct."""
         self.n, self.lam, self.mu = num_params, population_size, population_size // 2
         self.device = torch.device(device)
-        self.sigma = float(sigma)
+        self.sigma = float(torch.tensor(sigma, dtype=torch.float32))
         self.gen = generator
+        self.chunk = int(chunk)
         f32 = dict(dtype=torch.float32, device=self.device)
         self.mean = torch.zeros(num_params, **f32)
         self.C = torch.eye(num_params, **f32)
@@ -39,13 +53,16 @@ class CmaEs:
         w = (math.log(self.mu + 0.5) - torch.log(i + 1.0)).to(torch.float32)  # CmaEsSolverTorch.cpp:20-25
         w = w / w.sum()
         self.weights = w.to(self.device)
-        self.mu_eff = float(1.0 / (w.pow(2).sum().item()))
+        # learning rates, CmaEsSolverTorch.cpp:30-44 (binary64 arithmetic narrowed to binary32 members)
+        f = _f32
+        self.mu_eff = f(1.0 / (w.pow(2).sum().item()))
         n, me = num_params, self.mu_eff
-        # learning rates, CmaEsSolverTorch.cpp:33-41 (binary64 arithmetic narrowed to binary32 members)
-        f = lambda v: float(torch.tensor(v, dtype=torch.float32))  # noqa: E731
-        self.c_sigma = f((me + 2.0) / (n + me + 5.0))
+        # C++ usual arithmetic conversions in the reference's expressions: `num_params_ + mu_eff_` (int + float) and
+        # `mu_eff_ / num_params_` are FLOAT operations, the rest is binary64
+        n_plus_me, me_over_n = f(f(n) + me), f(torch.tensor(me, dtype=torch.float32) / torch.tensor(float(n), dtype=torch.float32))
+        self.c_sigma = f((me + 2.0) / (n_plus_me + 5.0))
         self.d_sigma = f(1.0 + 2.0 * max(0.0, math.sqrt((me - 1.0) / (n + 1.0)) - 1.0) + self.c_sigma)
-        self.c_c = f((4.0 + me / n) / (n + 4.0 + 2.0 * me / n))
+        self.c_c = f((4.0 + me_over_n) / (n + 4.0 + 2.0 * me / n))
         self.c_1 = f(2.0 / ((n + 1.3) * (n + 1.3) + me))
         self.c_mu = f(min(1.0 - self.c_1, 2.0 * (me - 2.0 + 1.0 / me) / ((n + 2.0) * (n + 2.0) + me)))
         self.chi_n = f(math.sqrt(n) * (1.0 - 1.0 / (4.0 * n) + 1.0 / (21.0 * n * n)))
@@ -54,6 +71,10 @@ class CmaEs:
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
         self.lo, self.hi = okd.shard_bounds(self.lam, self.rank, self.world)
+        if seed is not None:
+            if generator is not None:
+                raise ValueError("pass a generator or a seed, not both")
+            self.gen = torch.Generator(device=self.device).manual_seed(int(seed) * 1_000_003 + self.rank)
 
     # ---- ask -----------------------------------------------------------------------------------
     def sample(self, z: torch.Tensor | None = None) -> torch.Tensor:
@@ -80,14 +101,23 @@ class CmaEs:
         w = w_full[my_rank]  # weight of each local candidate (0 for non-parents)
         old_mean = self.mean.clone()
         x = local_solutions.to(self.device, torch.float32)
-        part_mean = (w[:, None] * x).sum(0)
-        y = (x - old_mean) / self.sigma
-        part_rank_mu = (y * w[:, None]).t() @ y  # sum_i w_i y_i y_i^T
+        # the parents among this rank's candidates, promoted to binary64 chunk by chunk (CmaEsSolverTorch.cpp:96,116)
+        parents = torch.nonzero(w > 0, as_tuple=False).flatten()
+        part_mean = torch.zeros(self.n, device=self.device, dtype=torch.float64)
+        part_rank_mu = torch.zeros(self.n, self.n, device=self.device, dtype=torch.float64)
+        old64, sigma64 = old_mean.double(), float(self.sigma)
+        for c0 in range(0, int(parents.numel()), self.chunk):
+            sel = parents[c0: c0 + self.chunk]
+            xs, ws = x[sel].double(), w[sel].double()
+            part_mean += (ws[:, None] * xs).sum(0)
+            y = (xs - old64) / sigma64
+            part_rank_mu += (y * ws[:, None]).t() @ y  # sum_i w_i y_i y_i^T, a DGEMM
         if self.world > 1:
             buf = torch.cat([part_mean, part_rank_mu.flatten()])
             dist.all_reduce(buf)
             part_mean, part_rank_mu = buf[: self.n], buf[self.n:].view(self.n, self.n)
-        self.mean = part_mean
+        self.mean = part_mean.to(torch.float32)
+        part_rank_mu = part_rank_mu.to(torch.float32)
         y_w = (self.mean - old_mean) / self.sigma
         # evolution paths, equations 31 and 24 of arXiv:1604.00772 (CmaEsSolverTorch.cpp:100-106)
         self.p_sigma = (1.0 - self.c_sigma) * self.p_sigma + math.sqrt(self.c_sigma * (2.0 - self.c_sigma) * self.mu_eff) * (
@@ -97,7 +127,11 @@ class CmaEs:
         self.C = (1.0 - self.c_1 - self.c_mu) * self.C + self.c_1 * torch.outer(self.p_c, self.p_c) + self.c_mu * part_rank_mu
         # step size, equation 37 (CmaEsSolverTorch.cpp:123-127)
         ps_norm = float(self.p_sigma.norm())
-        self.sigma *= math.exp((self.c_sigma / self.d_sigma) * (ps_norm / self.chi_n - 1.0))
+        f = _f32
+        # float / float divisions, then binary64, narrowed into the C++ float `sigma_` (CmaEsSolverTorch.cpp:127)
+        ratio = f(torch.tensor(self.c_sigma, dtype=torch.float32) / torch.tensor(self.d_sigma, dtype=torch.float32))
+        rel = f(torch.tensor(ps_norm, dtype=torch.float32) / torch.tensor(self.chi_n, dtype=torch.float32))
+        self.sigma = f(self.sigma * math.exp(ratio * (rel - 1.0)))
         return fitness, order
 
     def best_solution(self) -> torch.Tensor:
@@ -112,6 +146,14 @@ class PopulationController:
     def __init__(self, inputs: int, hidden: int = 16, outputs: int = 1):
         self.shapes = [(hidden, inputs), (hidden,), (hidden // 2, hidden), (hidden // 2,), (outputs, hidden // 2), (outputs,)]
         self.num_params = sum(int(torch.tensor(s).prod()) for s in self.shapes)
+
+    def act(self, env, flat: torch.Tensor, throttle: float = 100.0, steer_scale: float = 5.0):
+        """CmaEsAgent::updateAction for the whole population in ONE hand-written kernel (ok_cmaes_controller): reads
+        ``env.obs`` and candidate i's parameters ``flat[i]``, writes the env's action buffers (throttle 100,
+        steering 5 * output, main_torch.cpp:68-69).  ``env`` is a BatchEnv; follow with ``env.step()``."""
+        if flat.dtype != torch.float32 or not flat.is_contiguous() or flat.shape != (env.n_agents, self.num_params):
+            raise ValueError("flat must be a contiguous f32[n_agents, num_params] CUDA tensor")
+        env.env.cmaes_controller(flat.data_ptr(), self.num_params, self.shapes[0][0], throttle, steer_scale, env._stream())
 
     def forward(self, flat: torch.Tensor, obs: torch.Tensor) -> torch.Tensor:
         """flat f32[P, num_params], obs f32[P, inputs] -> f32[P, outputs]"""

@@ -1138,6 +1138,27 @@ int ok_genetic_policy(OkEnv *e, const float *d_w1, const float *d_w2, int32_t hi
     return OK_SUCCESS;
 }
 
+int ok_cmaes_controller(OkEnv *e, const float *d_params, int32_t n_params, int32_t hidden, float throttle, float steer_scale,
+                        void *stream)
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    if (!d_params || hidden != 16)
+        return fail(OK_ERR_INVALID_ARG, "parameters must be given and hidden must be 16 (CmaEsAgent::kHiddenSize)");
+    if (n_params != 16 * e->rays + 16 + 8 * 16 + 8 + 8 + 1)
+        return fail(OK_ERR_INVALID_ARG, "n_params must be 16 * rays + 169 (Controller::count_params)");
+    DeviceGuard    g(e->cfg.device);
+    ok::StepParams p = base_params(e);
+    const int      threads = 256;
+    const int64_t  blocks  = (e->n_agents * 32 + threads - 1) / threads;
+    ok::cmaes_controller_kernel<<<static_cast<unsigned>(blocks), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        p, d_params, n_params, throttle, steer_scale, e->n_agents);
+    OK_CUDA(cudaGetLastError());
+    e->launches++;
+    return OK_SUCCESS;
+}
+
 int ok_track_query(OkEnv *e, const float *d_x, const float *d_y, const int32_t *d_track, int64_t n, int32_t *d_idx,
                    float *d_lane, float *d_bound, void *stream)
 {

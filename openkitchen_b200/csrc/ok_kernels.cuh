@@ -1706,6 +1706,127 @@ __global__ void probe_store_kernel(const float4 *__restrict__ src, float4 *__res
         dst[i] = src[i];
 }
 
+// CmaEsAgent::updateAction + Controller::forward for every candidate of a CMA-ES population (main_torch.cpp:61-71,
+// Controller.cpp:16-23): candidate a owns the flat parameter vector params[a] (torch parameters() order: fc1.weight
+// [H][R], fc1.bias [H], fc2.weight [H/2][H], fc2.bias [H/2], fc3.weight [1][H/2], fc3.bias [1]) and evaluates
+// tanh(fc3 tanh(fc2 tanh(fc1 obs))) on its own lidar observation; throttle = `throttle`, steering = out * steer_scale.
+// One warp per agent.  The weights are read exactly once, every row as one coalesced warp load, so the kernel is HBM
+// bound: 4 * (H*R + H + H*H/2 + H/2 + H/2 + 1) bytes per agent (2,692 B at R = 32, H = 16).  Sums are reduced across
+// the warp with shuffles (a different summation order than the reference's sgemv: parity is to 1e-6 on tanh outputs).
+template <int H> __device__ __forceinline__ float warp_reduce_rows(float (&v)[H], const int lane)
+{ // in: v[j] = this lane's partial of row j; out: the full sum of row (lane & (H - 1)) -- H - 1 + (5 - log2 H) shuffles
+    static_assert(H == 16, "written for the reference's 16 hidden units");
+    float a8[8], a4[4], a2[2];
+    {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+        {
+            const float send = hi ? v[j] : v[j + 8];
+            const float keep = hi ? v[j + 8] : v[j];
+            a8[j]            = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            const float send = hi ? a8[j] : a8[j + 4];
+            const float keep = hi ? a8[j + 4] : a8[j];
+            a4[j]            = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool hi = lane & 4;
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+        {
+            const float send = hi ? a4[j] : a4[j + 2];
+            const float keep = hi ? a4[j + 2] : a4[j];
+            a2[j]            = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    const bool  hi   = lane & 2;
+    const float send = hi ? a2[0] : a2[1];
+    const float keep = hi ? a2[1] : a2[0];
+    float       r    = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    r += __shfl_xor_sync(0xffffffffu, r, 1);
+    // lane bits (16, 8, 4, 2) chose row 8*b4 + 4*b3 + 2*b2 + b1: lane l holds row ((l >> 1) & 15)
+    return r;
+}
+
+__global__ void __launch_bounds__(256) cmaes_controller_kernel(const StepParams p, const float *__restrict__ params,
+                                                               const int n_params, const float throttle,
+                                                               const float steer_scale, const int64_t n_agents)
+{
+    constexpr int H = 16, H2 = 8;
+    const int     lane = threadIdx.x & 31;
+    const int64_t a    = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (a >= n_agents)
+        return;
+    const int    R  = p.rays;
+    const float *w  = params + a * n_params;
+    const float *W1 = w, *b1 = w + H * R, *W2 = b1 + H, *b2 = W2 + H2 * H, *W3 = b2 + H2, *b3 = W3 + H2;
+    // the small tail (fc1.bias .. fc3.bias: 16 + 128 + 8 + 8 + 1 = 161 floats) is requested up front
+    const float bias1 = lane < H ? b1[lane] : 0.0f;
+    float       w2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        w2[k] = W2[lane + 32 * k]; // element (row (lane >> 4) + 2k, column lane & 15)
+    const float bias2 = lane < H2 ? b2[lane] : 0.0f;
+    const float w3    = lane < H2 ? W3[lane] : 0.0f;
+    const float bias3 = b3[0];
+    // layer 1: lane = input (mod 32), 16 row partials per lane
+    float acc[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j)
+        acc[j] = 0.0f;
+    for (int r0 = 0; r0 < R; r0 += 32)
+    {
+        const bool  in = r0 + lane < R;
+        const float x  = in ? p.obs[a * R + r0 + lane] : 0.0f;
+        float       wv[H];
+#pragma unroll
+        for (int j = 0; j < H; ++j)
+            wv[j] = in ? W1[j * R + r0 + lane] : 0.0f; // 16 independent coalesced row loads in flight
+#pragma unroll
+        for (int j = 0; j < H; ++j)
+            acc[j] = fmaf(wv[j], x, acc[j]);
+    }
+    const float row = warp_reduce_rows<H>(acc, lane); // lane l: row (l >> 1) & 15
+    // hidden unit i to every lane with (lane & 15) == i
+    const float h1 = tanhf(__shfl_sync(0xffffffffu, row, (lane & 15) << 1) + __shfl_sync(0xffffffffu, bias1, lane & 15));
+    // layer 2: lane holds W2[(lane >> 4) + 2k][lane & 15]; sum over the 16 lanes of a half warp
+    float o2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        o2[k] = w2[k] * h1;
+#pragma unroll
+    for (int s = 8; s > 0; s >>= 1)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            o2[k] += __shfl_xor_sync(0xffffffffu, o2[k], s);
+    // row j of layer 2 sits in o2[j >> 1] of the half warp (j & 1): bring row `lane` to lanes 0..7
+    float h2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        const float v = __shfl_sync(0xffffffffu, o2[k], (lane & 1) << 4);
+        h2            = ((lane >> 1) == k) ? v : h2;
+    }
+    h2 = lane < H2 ? tanhf(h2 + bias2) : 0.0f;
+    float o3 = w3 * h2;
+#pragma unroll
+    for (int s = 4; s > 0; s >>= 1)
+        o3 += __shfl_xor_sync(0xffffffffu, o3, s);
+    if (lane == 0)
+    {
+        p.act_thr[a]   = throttle;                                  // main_torch.cpp:68
+        p.act_steer[a] = fmul(tanhf(o3 + bias3), steer_scale);      // main_torch.cpp:69
+    }
+}
+
 __global__ void sincosf_kernel(const float *in, float *s_out, float *c_out, int64_t n)
 {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;

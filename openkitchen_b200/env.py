@@ -201,6 +201,11 @@ class Env:
         """per-agent shallow MLP -> ACT_* buffers (device weight pointers)"""
         check(self.lib.ok_genetic_policy(self.h, d_w1, d_w2, hidden, stream))
 
+    def cmaes_controller(self, d_params, n_params: int, hidden: int = 16, throttle: float = 100.0, steer_scale: float = 5.0,
+                         stream=None):
+        """per-candidate Controller MLP -> ACT_* buffers (device pointer to f32[N, n_params])"""
+        check(self.lib.ok_cmaes_controller(self.h, d_params, n_params, hidden, throttle, steer_scale, stream))
+
     def step_host(self, thr=None, steer=None, obs=None, reward=None, done=None, stream=None):
         """End-to-end tick with HOST buffers (H2D actions, kernel, D2H results, sync)."""
         check(self.lib.ok_step_host(self.h, _vp(thr), _vp(steer), _vp(obs), _vp(reward), _vp(done), stream))
