@@ -254,6 +254,16 @@ typedef struct OkLaunchStats {
     int32_t  grid_blocks, block_threads, smem_bytes, tiles;
 } OkLaunchStats;
 int ok_launch_stats(const OkEnv *env, OkLaunchStats *out);
+/* Work counters of the beam kernel (profiling aid, off by default): out[0] = rays cast, out[1] = rays its first pass
+ * could not settle from the table entry alone (queued for the second pass), out[2] = rays that fell back to the
+ * uniform-grid walk, since the previous call.  Synchronises the device; enable != 0 keeps counting, 0 stops. */
+int ok_debug_stats(OkEnv *env, uint64_t out[4], int32_t enable);
+/* Timeline of the beam kernel's last launch (profiling aid, off by default): per CTA and per tile it processed, six
+ * 64-bit words {tile | smid << 32, then %globaltimer (ns) at: tile start, end of the thread-per-agent phase, end of the
+ * first ray pass, end of the second ray pass, end of the reward phase}.  Copies min(words available, capacity_words) to
+ * h_out (layout [grid_blocks][tiles_per_cta][6], zero = unused) and returns the count; then re-arms the trace with room
+ * for `tiles_per_cta` tiles per CTA (0 = off).  Synchronises the device. */
+int64_t ok_debug_trace(OkEnv *env, uint64_t *h_out, int64_t capacity_words, int32_t tiles_per_cta);
 /* evaluates the kernels' sincosf (the glibc-2.39 restatement, ok_math.cuh) on `n` host floats: lets a test
  * compare the DEVICE function with libm / the oracle directly (tests/test_gpu_math.py) */
 int ok_eval_sincosf(OkEnv *env, const float *h_in, float *h_sin, float *h_cos, int64_t n);
@@ -271,6 +281,11 @@ int ok_pcie_probe(int32_t device, size_t bytes, int32_t iters, int32_t mode, dou
 #define OK_BEAM_NOT_COVERED (-100)
 int32_t ok_beam_lookup(OkEnv *env, int32_t track_id, float x, float y, float angle_rad, uint16_t *h_items,
                        int32_t capacity, float *d_complete);
+/* the same, also returning what the kernel's first pass works with: *n_inline = how many of the leading candidates are
+ * carried in the table entry itself (at most 4), *d_inline = the distance up to which those are provably the ONLY
+ * contenders (every other listed segment is met at a parameter >= *d_inline by every ray of the cell and bin) */
+int32_t ok_beam_lookup_ex(OkEnv *env, int32_t track_id, float x, float y, float angle_rad, uint16_t *h_items,
+                          int32_t capacity, float *d_complete, float *d_inline, int32_t *n_inline);
 /* size of the track's beam table in bytes (builds it if needed) */
 int64_t ok_beam_table_bytes(OkEnv *env, int32_t track_id);
 /* Beam tables are shared between the envs of a process through a cache (host copies and, per device, the tables the

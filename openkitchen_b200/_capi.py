@@ -113,8 +113,12 @@ SIGNATURES = {
     "ok_write_buffer": (C.c_int, [_P, C.c_int32, _P, C.c_size_t, _P]),
     "ok_sync": (C.c_int, [_P, _P]),
     "ok_launch_stats": (C.c_int, [_P, C.POINTER(OkLaunchStats)]),
+    "ok_debug_stats": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_int32]),
+    "ok_debug_trace": (C.c_int64, [_P, _P, C.c_int64, C.c_int32]),
     "ok_eval_sincosf": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
     "ok_beam_lookup": (C.c_int32, [_P, C.c_int32, C.c_float, C.c_float, C.c_float, _P, C.c_int32, C.POINTER(C.c_float)]),
+    "ok_beam_lookup_ex": (C.c_int32, [_P, C.c_int32, C.c_float, C.c_float, C.c_float, _P, C.c_int32, C.POINTER(C.c_float),
+                                      C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "ok_beam_table_bytes": (C.c_int64, [_P, C.c_int32]),
     "ok_release_caches": (None, []),
     "ok_cmaes_controller": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, _P]),
@@ -143,7 +147,12 @@ def load() -> C.CDLL:
             )
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
-            fn = getattr(lib, name)
+            try:
+                fn = getattr(lib, name)
+            except AttributeError:
+                if os.environ.get("OK_B200_LIB"):  # an experiment build (older ABI) may lack the newest entry points
+                    continue
+                raise
             fn.restype, fn.argtypes = res, args
         _lib = lib
     return _lib

@@ -30,9 +30,10 @@ struct HullRec
 
 struct Row
 {
-    std::vector<uint32_t> meta;  // per bin: count | dq << 16
-    std::vector<uint32_t> first; // per bin: first item of the bin within `items` (multiple of 4)
-    std::vector<uint16_t> items; // chunks of 4
+    std::vector<uint32_t> meta;   // per bin: beam_pack_meta
+    std::vector<uint32_t> inl;    // per bin: 2 words = the four inline candidates
+    std::vector<uint32_t> first;  // per bin: first item of the bin's REST within `items` (multiple of 4)
+    std::vector<uint16_t> items;  // rest lists, chunks of 4
 };
 
 struct Scratch
@@ -142,6 +143,7 @@ struct Builder
         // exact membership: distance from the origin to (S (+) -C) clipped to the bin's cone
         sc.hulls.clear();
         row.meta.assign(nb, 0);
+        row.inl.assign(2 * static_cast<size_t>(nb), 0);
         row.first.assign(nb, 0);
         row.items.clear();
         for (int32_t b = 0; b < nb; ++b)
@@ -177,19 +179,25 @@ struct Builder
                     l.push_back({static_cast<float>(d), static_cast<uint16_t>(c.seg)});
             }
             std::sort(l.begin(), l.end());
-            size_t count = std::min<size_t>(l.size(), 65535);
-            double d     = dc;
+            const size_t cap   = kBeamInline + 4 * static_cast<size_t>(kBeamMaxRest);
+            const size_t count = std::min<size_t>(l.size(), cap);
+            double       d     = dc;
             if (count < l.size())
                 d = std::max(0.0, static_cast<double>(l[count].first) - 1e-3); // truncated: complete only up to here
-            uint32_t dq = 0xffffu;
-            if (d < rb)
-                dq = static_cast<uint32_t>(std::min(65534.0, std::floor(d * 256.0)));
-            row.first[b] = static_cast<uint32_t>(row.items.size());
-            row.meta[b]  = static_cast<uint32_t>(count) | (dq << 16);
-            for (size_t i = 0; i < count; ++i)
+            const uint16_t null_seg = static_cast<uint16_t>(t.n_segments());   // the blob's null segment
+            uint16_t       in4[kBeamInline];
+            for (int i = 0; i < kBeamInline; ++i)
+                in4[i] = static_cast<size_t>(i) < count ? l[i].second : null_seg;
+            row.inl[2 * b]     = in4[0] | (static_cast<uint32_t>(in4[1]) << 16);
+            row.inl[2 * b + 1] = in4[2] | (static_cast<uint32_t>(in4[3]) << 16);
+            row.first[b]       = static_cast<uint32_t>(row.items.size());
+            for (size_t i = kBeamInline; i < count; ++i)
                 row.items.push_back(l[i].second);
             while (row.items.size() % 4)
-                row.items.push_back(static_cast<uint16_t>(t.n_segments())); // the blob's null segment
+                row.items.push_back(null_seg);
+            const uint32_t n_rest = static_cast<uint32_t>((row.items.size() - row.first[b]) / 4);
+            const double   d1     = count > static_cast<size_t>(kBeamInline) ? std::min<double>(l[kBeamInline].first, d) : d;
+            row.meta[b]           = beam_pack_meta(d, d1, d >= rb, n_rest);
         }
     }
 };
@@ -260,8 +268,13 @@ bool beam_plan(const Track &t, const BeamConfig &cfg, BeamPlan &pl, std::string 
     return true;
 }
 
-bool beam_layout(const BeamPlan &pl, const BeamConfig &cfg, size_t n_items, BeamHeader &h, std::string &err)
+bool beam_layout(const BeamPlan &pl, const BeamConfig &cfg, size_t n_items, int32_t n_segments, BeamHeader &h, std::string &err)
 {
+    if (n_segments < 1 || n_segments > 0xffff)
+    {
+        err = "beam tables index segments with 16 bits";
+        return false;
+    }
     if (n_items / 4 >= 0xffffffffull)
     {
         err = "beam table too large";
@@ -273,13 +286,14 @@ bool beam_layout(const BeamPlan &pl, const BeamConfig &cfg, size_t n_items, Beam
     h.nx = pl.nx, h.ny = pl.ny, h.nb = pl.nb;
     h.bin_scale = static_cast<float>(pl.nb / (2.0 * M_PI));
     h.rb        = static_cast<float>(pl.rb);
+    h.tag       = (kBeamFormat << 16) | static_cast<uint32_t>(n_segments);
     h.n_rows    = static_cast<uint32_t>(pl.covered.size());
     h.n_chunks  = static_cast<uint32_t>(n_items / 4);
     size_t off  = sizeof(BeamHeader);
     h.off_rows  = static_cast<uint32_t>(off);
     off += (pl.rows.size() * 4 + 15) / 16 * 16;
     h.off_entries = static_cast<uint32_t>(off);
-    off += (pl.covered.size() * static_cast<size_t>(pl.nb) * 8 + 15) / 16 * 16;
+    off += pl.covered.size() * static_cast<size_t>(pl.nb) * 16;
     h.off_items = static_cast<uint32_t>(off);
     off += (n_items * 2 + 15) / 16 * 16;
     if (off >= 0xffffffffull)
@@ -292,15 +306,15 @@ bool beam_layout(const BeamPlan &pl, const BeamConfig &cfg, size_t n_items, Beam
 }
 
 bool beam_assemble(const BeamPlan &pl, const BeamConfig &cfg, const uint32_t *entries, const uint16_t *items, size_t n_items,
-                   std::vector<uint8_t> &blob, std::string &err)
+                   int32_t n_segments, std::vector<uint8_t> &blob, std::string &err)
 {
     BeamHeader h;
-    if (!beam_layout(pl, cfg, n_items, h, err))
+    if (!beam_layout(pl, cfg, n_items, n_segments, h, err))
         return false;
     blob.assign(h.bytes, 0);
     std::memcpy(blob.data(), &h, sizeof h);
     std::memcpy(blob.data() + h.off_rows, pl.rows.data(), pl.rows.size() * 4);
-    std::memcpy(blob.data() + h.off_entries, entries, pl.covered.size() * static_cast<size_t>(pl.nb) * 8);
+    std::memcpy(blob.data() + h.off_entries, entries, pl.covered.size() * static_cast<size_t>(pl.nb) * 16);
     if (n_items)
         std::memcpy(blob.data() + h.off_items, items, n_items * 2);
     return true;
@@ -359,24 +373,28 @@ bool build_beam_table(const Track &t, const BeamConfig &cfg, std::vector<uint8_t
     size_t n_items = 0;
     for (auto &r : built)
         n_items += r.items.size();
-    std::vector<uint32_t> entries(covered.size() * static_cast<size_t>(b.nb) * 2);
+    std::vector<uint32_t> entries(covered.size() * static_cast<size_t>(b.nb) * 4);
     std::vector<uint16_t> items(n_items);
     size_t                cursor = 0;
     for (size_t r = 0; r < built.size(); ++r)
     {
         for (int32_t k = 0; k < b.nb; ++k)
         {
-            entries[2 * (r * b.nb + k)]     = static_cast<uint32_t>((cursor + built[r].first[k]) / 4);
-            entries[2 * (r * b.nb + k) + 1] = built[r].meta[k];
+            uint32_t *e = &entries[4 * (r * b.nb + k)];
+            e[0]        = built[r].inl[2 * k];
+            e[1]        = built[r].inl[2 * k + 1];
+            e[2]        = static_cast<uint32_t>((cursor + built[r].first[k]) / 4);
+            e[3]        = built[r].meta[k];
         }
         if (!built[r].items.empty())
             std::memcpy(items.data() + cursor, built[r].items.data(), built[r].items.size() * 2);
         cursor += built[r].items.size();
     }
-    return beam_assemble(pl, cfg, entries.data(), items.data(), n_items, blob, err);
+    return beam_assemble(pl, cfg, entries.data(), items.data(), n_items, ns, blob, err);
 }
 
-bool beam_lookup(const std::vector<uint8_t> &blob, float x, float y, float angle, std::vector<uint16_t> &out, float &d_out)
+bool beam_lookup(const std::vector<uint8_t> &blob, float x, float y, float angle, std::vector<uint16_t> &out, float &d_out,
+                 float *d1_out, int32_t *n_inline)
 {
     out.clear();
     if (blob.size() < sizeof(BeamHeader))
@@ -395,12 +413,75 @@ bool beam_lookup(const std::vector<uint8_t> &blob, float x, float y, float angle
     if (row == 0xffffffffu)
         return false;
     const int32_t bin = static_cast<int32_t>(std::floor(angle * h.bin_scale)) & (h.nb - 1);
-    uint32_t      e[2];
-    std::memcpy(e, blob.data() + h.off_entries + 8 * (static_cast<size_t>(row) * h.nb + bin), 8);
-    const uint32_t count = e[1] & 0xffffu, dq = e[1] >> 16;
-    d_out                = dq == 0xffffu ? h.rb : static_cast<float>(dq) * (1.0f / 256.0f);
-    out.resize(count);
-    std::memcpy(out.data(), blob.data() + h.off_items + 2 * (4 * static_cast<size_t>(e[0])), 2 * static_cast<size_t>(count));
+    uint32_t      e[4];
+    std::memcpy(e, blob.data() + h.off_entries + 16 * (static_cast<size_t>(row) * h.nb + bin), 16);
+    const uint32_t dq = e[3] & 0xfffu, d1q = (e[3] >> 12) & 0xfffu, n_rest = e[3] >> 24;
+    d_out             = dq == kBeamDistFull ? h.rb : static_cast<float>(dq) * (1.0f / kBeamDistScale);
+    if (d1_out)
+        *d1_out = n_rest ? static_cast<float>(d1q) * (1.0f / kBeamDistScale) : d_out;
+    if ((h.tag >> 16) != kBeamFormat)
+        return false;
+    const uint16_t null_seg = static_cast<uint16_t>(h.tag & 0xffffu); // padding value: the blob's null segment
+    const uint16_t in4[4]   = {static_cast<uint16_t>(e[0] & 0xffffu), static_cast<uint16_t>(e[0] >> 16),
+                               static_cast<uint16_t>(e[1] & 0xffffu), static_cast<uint16_t>(e[1] >> 16)};
+    for (int i = 0; i < kBeamInline; ++i)
+        if (in4[i] != null_seg)
+            out.push_back(in4[i]);
+    if (n_inline)
+        *n_inline = static_cast<int32_t>(out.size());
+    if (n_rest)
+    {
+        const uint16_t *src = reinterpret_cast<const uint16_t *>(blob.data() + h.off_items) + 4 * static_cast<size_t>(e[2]);
+        for (size_t i = 0; i < 4 * static_cast<size_t>(n_rest); ++i)
+            if (src[i] != null_seg)
+                out.push_back(src[i]);
+    }
+    return true;
+}
+
+bool beam_validate(const std::vector<uint8_t> &blob, int32_t n_segments, std::string &err)
+{
+    auto bad = [&](const char *what) {
+        err = std::string("beam table rejected: ") + what;
+        return false;
+    };
+    if (blob.size() < sizeof(BeamHeader))
+        return bad("too small");
+    BeamHeader h;
+    std::memcpy(&h, blob.data(), sizeof h);
+    if ((h.tag >> 16) != kBeamFormat || static_cast<int32_t>(h.tag & 0xffffu) != n_segments)
+        return bad("format or segment count");
+    if (h.bytes != blob.size() || h.nx < 1 || h.ny < 1 || h.nb < 8 || h.nb > 1024 || (h.nb & (h.nb - 1)))
+        return bad("header");
+    const uint64_t cells = static_cast<uint64_t>(h.nx) * static_cast<uint64_t>(h.ny);
+    if (cells > (1u << 24))
+        return bad("grid");
+    const uint64_t rows_end = static_cast<uint64_t>(h.off_rows) + 4 * cells;
+    const uint64_t ent_end  = static_cast<uint64_t>(h.off_entries) + 16ull * h.n_rows * static_cast<uint64_t>(h.nb);
+    const uint64_t item_end = static_cast<uint64_t>(h.off_items) + 8ull * h.n_chunks;
+    if (h.off_rows < sizeof(BeamHeader) || rows_end > h.off_entries || ent_end > h.off_items || item_end > h.bytes ||
+        (h.off_entries & 15u) || (h.off_items & 7u))
+        return bad("section offsets");
+    const uint32_t *rows = reinterpret_cast<const uint32_t *>(blob.data() + h.off_rows);
+    for (uint64_t c = 0; c < cells; ++c)
+        if (rows[c] != 0xffffffffu && rows[c] >= h.n_rows)
+            return bad("row index");
+    const uint32_t *ent = reinterpret_cast<const uint32_t *>(blob.data() + h.off_entries);
+    const uint64_t  n_e = static_cast<uint64_t>(h.n_rows) * static_cast<uint64_t>(h.nb);
+    for (uint64_t i = 0; i < n_e; ++i)
+    {
+        const uint32_t *e = ent + 4 * i;
+        if ((e[0] & 0xffffu) > static_cast<uint32_t>(n_segments) || (e[0] >> 16) > static_cast<uint32_t>(n_segments) ||
+            (e[1] & 0xffffu) > static_cast<uint32_t>(n_segments) || (e[1] >> 16) > static_cast<uint32_t>(n_segments))
+            return bad("inline segment index");
+        const uint32_t n_rest = e[3] >> 24;
+        if (n_rest && static_cast<uint64_t>(e[2]) + n_rest > h.n_chunks)
+            return bad("chunk range");
+    }
+    const uint16_t *items = reinterpret_cast<const uint16_t *>(blob.data() + h.off_items);
+    for (uint64_t i = 0; i < 4ull * h.n_chunks; ++i)
+        if (items[i] > n_segments)
+            return bad("segment index");
     return true;
 }
 

@@ -30,6 +30,18 @@ namespace ok
 {
 
 // Header of a track's beam blob (device global memory).  Offsets in bytes from the blob start.
+//
+// An ENTRY is 16 bytes and carries the list's first four candidates INLINE, so that one 16-byte load (one 32-byte
+// sector) gives the kernel everything most rays need:
+//   x, y : the four nearest candidates (uint16 segment indices, nearest first, padded with the null segment)
+//   z    : index of the first chunk of the REST of the list (candidates 5, 6, ...: chunks of four uint16, padded)
+//   w    : meta = dq | d1q << 12 | n_rest_chunks << 24
+//          dq  = floor(d * 16)  (12 bits, 0xfff = rb): the list is complete up to d
+//          d1q = floor(d1 * 16) (12 bits): d1 = the lower bound dist(C, b, S) of the first candidate of the REST (= d
+//                when there is no rest).  Every ray from the cell with a direction in the bin meets every segment of
+//                the rest at a parameter >= d1, so a hit among the inline four at t <= d1 - slack is final WITHOUT
+//                looking at the rest (the same argument, with d1 for d, as for the segments the list leaves out).
+//          n_rest_chunks (8 bits): a longer list is cut and d lowered to the first candidate left out.
 struct BeamHeader
 {
     float    x0, y0;     // origin of the beam-cell grid
@@ -37,16 +49,36 @@ struct BeamHeader
     int32_t  nx, ny;     // cells
     int32_t  nb;         // direction bins, a power of two
     float    bin_scale;  // nb / (2 pi): bin = floor(angle * bin_scale) & (nb - 1)
-    float    rb;         // completeness distance of entries flagged complete (dq = 0xffff)
+    float    rb;         // completeness distance of entries flagged complete (dq = 0xfff)
     uint32_t off_rows;   // uint32[nx * ny]: row of the cell in `entries`, 0xffffffff = not covered
-    uint32_t off_entries; // uint2[n_rows * nb]: {first chunk, count | dq << 16}; dq = floor(d * 256), 0xffff = rb
-    uint32_t off_items;  // uint16[]: segment indices in chunks of 4, padded with n_segments (the blob's null segment)
+    uint32_t off_entries; // uint4[n_rows * nb]
+    uint32_t off_items;  // uint16[]: the rest lists, in chunks of 4, padded with n_segments (the blob's null segment)
     uint32_t n_rows;
     uint32_t n_chunks;
     uint32_t bytes;
-    uint32_t pad;
+    uint32_t tag;        // kBeamFormat << 16 | index of the null segment (= n_segments, the padding value)
 };
 static_assert(sizeof(BeamHeader) == 64, "BeamHeader must be 64 bytes");
+
+constexpr uint32_t kBeamFormat      = 2;
+constexpr uint32_t kBeamDistScale   = 16;    // quantisation of d and d1: 1/16 px, rounded DOWN (conservative)
+constexpr uint32_t kBeamDistFull    = 0xfffu; // dq of a list that is complete up to rb
+constexpr uint32_t kBeamMaxRest     = 255;   // chunks of a rest list
+constexpr int      kBeamInline      = 4;     // candidates carried in the entry itself
+
+#if defined(__CUDACC__)
+#define OK_BEAM_HD __host__ __device__ inline
+#else
+#define OK_BEAM_HD inline
+#endif
+// meta word of an entry from the list's completeness distance d, the rest's lower bound d1 (both < rb unless `full`)
+OK_BEAM_HD uint32_t beam_pack_meta(double d, double d1, bool full, uint32_t n_rest)
+{
+    const double   q  = d * kBeamDistScale, q1 = d1 * kBeamDistScale;
+    uint32_t       dq = full ? kBeamDistFull : static_cast<uint32_t>(q < 0.0 ? 0.0 : (q > 4094.0 ? 4094.0 : q));
+    const uint32_t d1q = static_cast<uint32_t>(q1 < 0.0 ? 0.0 : (q1 > 4094.0 ? 4094.0 : q1));
+    return dq | (d1q << 12) | (n_rest << 24);
+}
 
 struct BeamConfig
 {
@@ -58,7 +90,7 @@ struct BeamConfig
 };
 
 // bump when build_beam_table changes what it produces (the on-disk cache is keyed on it)
-constexpr int    kBeamBuildVersion = 1;
+constexpr int    kBeamBuildVersion = 2;
 constexpr double kBeamCellMargin  = 0.0625; // px: the cell is grown by this much on every side
 constexpr double kBeamAngleMargin = 1e-4;   // rad: the bin's cone is widened by this much on both sides
 constexpr float  kBeamSlack       = 0.25f;  // px: a list result is trusted up to d - slack
@@ -74,10 +106,10 @@ struct BeamPlan
 };
 bool beam_plan(const Track &t, const BeamConfig &cfg, BeamPlan &plan, std::string &err);
 // section offsets of a table with n_items uint16 items
-bool beam_layout(const BeamPlan &plan, const BeamConfig &cfg, size_t n_items, BeamHeader &h, std::string &err);
-// entries: 2 x uint32 per (row, bin) = {first chunk, count | dq << 16}; items: uint16 chunks of 4
+bool beam_layout(const BeamPlan &plan, const BeamConfig &cfg, size_t n_items, int32_t n_segments, BeamHeader &h, std::string &err);
+// entries: 4 x uint32 per (row, bin) (see BeamHeader); items: the rest lists, uint16 chunks of 4
 bool beam_assemble(const BeamPlan &plan, const BeamConfig &cfg, const uint32_t *entries, const uint16_t *items, size_t n_items,
-                   std::vector<uint8_t> &blob, std::string &err);
+                   int32_t n_segments, std::vector<uint8_t> &blob, std::string &err);
 
 // Builds the blob on the host.  False (with err) if the configuration is unusable; never throws.
 bool build_beam_table(const Track &t, const BeamConfig &cfg, std::vector<uint8_t> &blob, std::string &err);
@@ -87,9 +119,15 @@ bool build_beam_table(const Track &t, const BeamConfig &cfg, std::vector<uint8_t
 // The blob is left in device memory (*d_blob, cudaMalloc'ed on `device`, owned by the caller).
 bool build_beam_table_device(const Track &t, const BeamConfig &cfg, int device, uint8_t **d_blob, size_t *bytes, std::string &err);
 
-// Host-side lookup used by the CPU tests: the list of (x, y, angle[rad]); returns false when the cell is not
-// covered or the angle is out of range.  d_out = completeness distance.
+// Host-side lookup used by the CPU tests: the list of (x, y, angle[rad]) -- the inline candidates (null padding removed)
+// followed by the rest; returns false when the cell is not covered or the angle is out of range.  d_out = completeness
+// distance, d1_out = lower bound of the rest (= d_out when the list has no rest), n_inline = candidates that came from
+// the entry itself.
 bool beam_lookup(const std::vector<uint8_t> &blob, float x, float y, float angle, std::vector<uint16_t> &items,
-                 float &d_out);
+                 float &d_out, float *d1_out = nullptr, int32_t *n_inline = nullptr);
+
+// Structural check of a table that did not come from this process's builders (the on-disk cache): sizes, offsets,
+// row / chunk / segment indices all within bounds.  The kernels trust a table that passes.
+bool beam_validate(const std::vector<uint8_t> &blob, int32_t n_segments, std::string &err);
 
 } // namespace ok

@@ -46,7 +46,7 @@ struct GpuBuild
     float    *list_d;
     uint16_t *list_s;
     // output
-    uint2              *entries;
+    uint4              *entries;
     uint16_t           *items;
     unsigned long long *item_cursor;
     unsigned long long  item_capacity;
@@ -246,7 +246,9 @@ __global__ void __launch_bounds__(kThreads) beam_build_kernel(const GpuBuild g)
                 dd[j + 1] = vd;
                 ss[j + 1] = vs;
             }
-            const unsigned long long padded = static_cast<unsigned long long>((cnt + 3) & ~3);
+            // the first four candidates travel in the entry itself; the rest goes to the item array in chunks of four
+            const int                rest   = cnt > kBeamInline ? cnt - kBeamInline : 0; // <= kListCap - 4 < 4 * kBeamMaxRest
+            const unsigned long long padded = static_cast<unsigned long long>((rest + 3) & ~3);
             unsigned long long       off    = padded ? atomicAdd(g.item_cursor, padded) : 0ull;
             if (off + padded > g.item_capacity)
             {
@@ -258,12 +260,17 @@ __global__ void __launch_bounds__(kThreads) beam_build_kernel(const GpuBuild g)
             else
             {
                 for (int i = 0; i < static_cast<int>(padded); ++i)
-                    g.items[off + i] = i < cnt ? ss[i] : static_cast<uint16_t>(g.ns); // the blob's null segment
+                    g.items[off + i] = i < rest ? ss[kBeamInline + i] : static_cast<uint16_t>(g.ns); // the blob's null segment
             }
-            uint32_t dq = 0xffffu;
-            if (d < g.rb)
-                dq = static_cast<uint32_t>(fmin(65534.0, floor(d * 256.0)));
-            g.entries[static_cast<size_t>(row) * g.nb + b] = make_uint2(static_cast<uint32_t>(off / 4), static_cast<uint32_t>(cnt) | (dq << 16));
+            const uint32_t null_seg = static_cast<uint32_t>(g.ns);
+            uint32_t       in4[kBeamInline];
+            for (int i = 0; i < kBeamInline; ++i)
+                in4[i] = i < cnt ? ss[i] : null_seg;
+            const int    n_rest = cnt > kBeamInline ? static_cast<int>(padded / 4) : 0;
+            const double d1     = cnt > kBeamInline ? fmin(static_cast<double>(dd[kBeamInline]), d) : d;
+            g.entries[static_cast<size_t>(row) * g.nb + b] =
+                make_uint4(in4[0] | (in4[1] << 16), in4[2] | (in4[3] << 16), static_cast<uint32_t>(off / 4),
+                           beam_pack_meta(d, d1, d >= g.rb, static_cast<uint32_t>(n_rest)));
         }
     }
 }
@@ -308,7 +315,7 @@ static bool build_once(const Track &t, const BeamConfig &cfg, int device, int it
         BEAM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
         const int    grid = static_cast<int>(std::min<size_t>(n_rows, static_cast<size_t>(sms) * 4));
         const size_t per_cta = static_cast<size_t>(ns) * (4 + 2 + 2 + 2) + static_cast<size_t>(nb) * kListCap * (4 + 2);
-        // 24 candidates per (cell, bin) on average; the caller retries with more when the kernel reports the array full
+        // `items_per_entry` rest candidates per (cell, bin) on average; the caller retries with more when the kernel reports the array full
         capacity = static_cast<unsigned long long>(n_rows) * nb * static_cast<unsigned long long>(items_per_entry) + 1024ull;
         GpuBuild g{};
         BEAM_CUDA(cudaMalloc(&d_seg, sizeof(float4) * ns));
@@ -316,7 +323,7 @@ static bool build_once(const Track &t, const BeamConfig &cfg, int device, int it
         BEAM_CUDA(cudaMalloc(&d_cov, 4 * std::max<size_t>(n_rows, 1)));
         BEAM_CUDA(cudaMemcpy(d_cov, pl.covered.data(), 4 * n_rows, cudaMemcpyHostToDevice));
         BEAM_CUDA(cudaMalloc(&d_scratch, per_cta * grid + 256));
-        BEAM_CUDA(cudaMalloc(&d_entries, 8 * std::max<size_t>(n_rows * nb, 1)));
+        BEAM_CUDA(cudaMalloc(&d_entries, 16 * std::max<size_t>(n_rows * nb, 1)));
         BEAM_CUDA(cudaMalloc(&d_items, 2 * capacity));
         BEAM_CUDA(cudaMalloc(&d_ctr, 64));
         BEAM_CUDA(cudaMemset(d_ctr, 0, 64));
@@ -340,7 +347,7 @@ static bool build_once(const Track &t, const BeamConfig &cfg, int device, int it
             p += static_cast<size_t>(grid) * ns * 2;
             g.list_s = reinterpret_cast<uint16_t *>(p);
         }
-        g.entries       = static_cast<uint2 *>(d_entries);
+        g.entries       = static_cast<uint4 *>(d_entries);
         g.items         = static_cast<uint16_t *>(d_items);
         g.item_cursor   = static_cast<unsigned long long *>(d_ctr);
         g.item_capacity = capacity;
@@ -365,14 +372,14 @@ static bool build_once(const Track &t, const BeamConfig &cfg, int device, int it
             goto done;
         }
         // the table in its final layout, assembled on the device: header | rows | entries | items
-        if (!beam_layout(pl, cfg, used, hdr, err))
+        if (!beam_layout(pl, cfg, used, ns, hdr, err))
             goto done;
         BEAM_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_blob), hdr.bytes));
         BEAM_CUDA(cudaMemset(d_blob, 0, hdr.bytes));
         BEAM_CUDA(cudaMemcpy(d_blob, &hdr, sizeof hdr, cudaMemcpyHostToDevice));
         BEAM_CUDA(cudaMemcpy(d_blob + hdr.off_rows, pl.rows.data(), pl.rows.size() * 4, cudaMemcpyHostToDevice));
         if (n_rows)
-            BEAM_CUDA(cudaMemcpy(d_blob + hdr.off_entries, d_entries, 8 * n_rows * nb, cudaMemcpyDeviceToDevice));
+            BEAM_CUDA(cudaMemcpy(d_blob + hdr.off_entries, d_entries, 16 * n_rows * nb, cudaMemcpyDeviceToDevice));
         if (used)
             BEAM_CUDA(cudaMemcpy(d_blob + hdr.off_items, d_items, 2 * used, cudaMemcpyDeviceToDevice));
         BEAM_CUDA(cudaDeviceSynchronize());
@@ -401,7 +408,7 @@ done:
 
 bool build_beam_table_device(const Track &t, const BeamConfig &cfg, int device, uint8_t **d_blob, size_t *bytes, std::string &err)
 {
-    for (int per = 24; per <= 384; per *= 4)
+    for (int per = 8; per <= 512; per *= 4)
     {
         bool full = false;
         if (build_once(t, cfg, device, per, d_blob, bytes, err, full))

@@ -151,8 +151,12 @@ struct OkEnv
     int32_t              n_tiles_beam{0};
     int32_t              batch_agents_beam{0};
     int32_t              grid_beam{0};
+    int32_t              ctas_per_sm_beam{1};
     uint16_t            *d_ray_order{nullptr};
     int32_t             *d_sched{nullptr};
+    unsigned long long  *d_stats{nullptr}; // ok_debug_stats: allocated on first use
+    unsigned long long  *d_trace{nullptr}; // ok_debug_trace
+    int32_t              trace_tiles{0};
     int                  smem_optin{0};
     std::vector<int32_t> h_track_id;
     // staging for the *_host entry points
@@ -192,6 +196,11 @@ void free_agents(OkEnv *e)
         cudaFree(e->d_ray_order);
     if (e->d_sched)
         cudaFree(e->d_sched);
+    if (e->d_stats)
+        cudaFree(e->d_stats);
+    if (e->d_trace)
+        cudaFree(e->d_trace);
+    e->d_stats = nullptr, e->d_trace = nullptr, e->trace_tiles = 0;
     e->d_slab = nullptr, e->d_ray_deg = nullptr, e->d_tiles = nullptr, e->d_ray_order = nullptr, e->d_sched = nullptr;
     for (auto &b : e->d_buf)
         b = nullptr;
@@ -236,22 +245,25 @@ std::string beam_cache_dir()
 
 struct BeamFileHeader
 {
-    char     magic[8]; // "OKBEAM01"
+    char     magic[8]; // "OKBEAM02"
     uint64_t bytes, checksum;
 };
 
-bool beam_file_load(const std::string &path, std::vector<uint8_t> &blob)
+bool beam_file_load(const std::string &path, std::vector<uint8_t> &blob, int32_t n_segments)
 {
     FILE *f = std::fopen(path.c_str(), "rb");
     if (!f)
         return false;
     BeamFileHeader h{};
-    bool           ok = std::fread(&h, sizeof h, 1, f) == 1 && std::memcmp(h.magic, "OKBEAM01", 8) == 0 && h.bytes >= sizeof(ok::BeamHeader) &&
+    bool           ok = std::fread(&h, sizeof h, 1, f) == 1 && std::memcmp(h.magic, "OKBEAM02", 8) == 0 && h.bytes >= sizeof(ok::BeamHeader) &&
               h.bytes < (1ull << 32);
     if (ok)
     {
         blob.resize(h.bytes);
         ok = std::fread(blob.data(), 1, h.bytes, f) == h.bytes && fnv1a(blob.data(), blob.size()) == h.checksum;
+        // the kernels trust a table's indices: one that did not come from this process is checked structurally first
+        std::string why;
+        ok = ok && ok::beam_validate(blob, n_segments, why);
     }
     std::fclose(f);
     if (!ok)
@@ -266,7 +278,7 @@ void beam_file_save(const std::string &path, const std::vector<uint8_t> &blob)
     if (!f)
         return;
     BeamFileHeader h{};
-    std::memcpy(h.magic, "OKBEAM01", 8);
+    std::memcpy(h.magic, "OKBEAM02", 8);
     h.bytes    = blob.size();
     h.checksum = fnv1a(blob.data(), blob.size());
     const bool ok = std::fwrite(&h, sizeof h, 1, f) == 1 && std::fwrite(blob.data(), 1, blob.size(), f) == blob.size();
@@ -324,7 +336,7 @@ std::shared_ptr<const std::vector<uint8_t>> beam_table_for(const ok::Track &t, c
     bool              locked = false;
     if (!path.empty())
     {
-        if (beam_file_load(path, *blob))
+        if (beam_file_load(path, *blob, t.n_segments()))
             return beam_remember(key, blob);
         const int fd = ::open(lock.c_str(), O_CREAT | O_EXCL | O_WRONLY, 0600);
         if (fd >= 0)
@@ -346,10 +358,10 @@ std::shared_ptr<const std::vector<uint8_t>> beam_table_for(const ok::Track &t, c
                 for (int i = 0; i < 2400 && ::stat(lock.c_str(), &st) == 0; ++i) // up to two minutes
                 {
                     std::this_thread::sleep_for(std::chrono::milliseconds(50));
-                    if (beam_file_load(path, *blob))
+                    if (beam_file_load(path, *blob, t.n_segments()))
                         return beam_remember(key, blob);
                 }
-            if (beam_file_load(path, *blob))
+            if (beam_file_load(path, *blob, t.n_segments()))
                 return beam_remember(key, blob);
         }
     }
@@ -473,6 +485,11 @@ int ensure_arena(OkEnv *e)
         {
             r.has_beam    = 1;
             r.beam_offset = reinterpret_cast<uint64_t>(e->beams_dev[i]->ptr); // absolute: the table is its own allocation
+            ok::BeamHeader h{};
+            OK_CUDA(cudaMemcpy(&h, e->beams_dev[i]->ptr, sizeof h, cudaMemcpyDeviceToHost));
+            r.bx0 = h.x0, r.by0 = h.y0, r.binv_h = h.inv_h, r.bbin_scale = h.bin_scale, r.brb = h.rb;
+            r.bnx = h.nx, r.bny = h.ny, r.bnb = h.nb;
+            r.boff_rows = h.off_rows, r.boff_entries = h.off_entries, r.boff_items = h.off_items;
         }
         refs.push_back(r);
         total += (t.blob.size() + 127) / 128 * 128;
@@ -531,6 +548,9 @@ ok::StepParams base_params(OkEnv *e)
     p.smem_blob_bytes   = static_cast<uint32_t>((e->max_blob_used + 127) / 128 * 128);
     p.ray_order         = e->d_ray_order;
     p.sched             = e->d_sched;
+    p.stats             = e->d_stats;
+    p.trace             = e->d_trace;
+    p.trace_tiles       = e->trace_tiles;
     p.movement_mode     = e->cfg.movement_mode;
     p.reward_mode       = e->cfg.reward_mode;
     p.raycast_mode      = e->cfg.raycast_mode;
@@ -565,8 +585,8 @@ int arm_shared_memory_limit(OkEnv *e)
     OK_CUDA(cudaFuncGetAttributes(&fa, ok::step_kernel<kBlock, false>));
     OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<kBlock, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  e->smem_optin - static_cast<int>(fa.sharedSizeBytes)));
-    OK_CUDA(cudaFuncGetAttributes(&fa, ok::step_kernel<kBlock, true>));
-    OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<kBlock, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    OK_CUDA(cudaFuncGetAttributes(&fa, ok::step_kernel<ok::kBeamBlock, true>));
+    OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<ok::kBeamBlock, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  e->smem_optin - static_cast<int>(fa.sharedSizeBytes)));
     return OK_SUCCESS;
 }
@@ -583,7 +603,7 @@ int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
         p.tiles        = e->d_tiles_beam;
         p.n_tiles      = e->n_tiles_beam;
         p.batch_agents = e->batch_agents_beam;
-        ok::step_kernel<kBlock, true><<<e->grid_beam, kBlock, e->smem_beam, s>>>(p);
+        ok::step_kernel<ok::kBeamBlock, true><<<e->grid_beam, ok::kBeamBlock, e->smem_beam, s>>>(p);
     }
     else
         ok::step_kernel<kBlock, false><<<e->grid, kBlock, e->smem, s>>>(p);
@@ -867,8 +887,8 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
         const size_t avail = static_cast<size_t>(e->smem_optin) > blob + 4096 ? e->smem_optin - blob - 4096 : 0;
         const size_t per   = ok::batch_smem_bytes(1, rays);
         int64_t      a     = static_cast<int64_t>(avail / per);
-        if (avail < 32768)
-            a = 0; // the beam kernel keeps 24 KB of per-thread scratch in static shared memory
+        if (avail < static_cast<size_t>(ok::kBeamStaticSmem) + 4096)
+            a = 0; // the beam kernel keeps per-thread scratch and its ray queue in static shared memory
         int          cap   = kMaxBatchAgents;
         if (const char *env = std::getenv("OK_BATCH_AGENTS"))
             cap = std::max(1, std::atoi(env));
@@ -879,21 +899,28 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
             return fail(OK_ERR_CAPACITY, "shared memory cannot hold one agent's rays next to the largest track");
         e->batch_agents = static_cast<int32_t>(a);
         e->smem         = blob + ok::batch_smem_bytes(e->batch_agents, rays);
-        // beam kernel: one 64-byte record per agent; phases 1 / 4 run a thread per agent, so at most kBlock agents.
-        // Bigger batches mean fewer barriers but coarser scheduling: 256 unless every SM gets several larger ones.
-        int64_t ab = static_cast<int64_t>((avail - 28672) / sizeof(ok::AgentRec));
-        // measured at 1,048,576 agents: 1.736 ms/tick with 256-agent batches, 1.643 with 512, 1.606 with 1,024
-        int capb = kMaxBatchAgents;
-        if (2 * n >= static_cast<int64_t>(e->num_sms) * 1024 * 3)
-            capb = 1024;
-        else if (2 * n >= static_cast<int64_t>(e->num_sms) * 512 * 3)
-            capb = 512;
+        // beam kernel: one 64-byte record per agent; phases 1 / 4 run a thread per agent, so at most kBeamBlock agents
+        int64_t ab;
+        int     capb;
+        if (ok::kBeamStage)
+        { // one 1,024-thread CTA per SM behind the staged track: as many agents per tile as the shared memory behind the
+          // largest track holds (the balanced tiling then sizes the tiles: about one per CTA and wave)
+            ab   = static_cast<int64_t>((avail - ok::kBeamStaticSmem) / sizeof(ok::AgentRec));
+            capb = ok::kBeamBlock;
+        }
+        else
+        { // several small CTAs per SM, nothing staged: small tiles, the SM's other CTAs hide a tile's serial phases
+            ab   = ok::kBeamBlock;
+            capb = OK_BEAM_TILE;
+        }
+        ab = std::min<int64_t>(ab, 65535 / rays); // tile-local ray indices are 16 bits (the kernel's ray queue)
         if (const char *env = std::getenv("OK_BEAM_BATCH_AGENTS"))
             capb = std::max(1, std::atoi(env));
-        ab = std::min<int64_t>({ab, capb, kBlock});
-        ab = std::min<int64_t>(ab, std::max<int64_t>(1, (n + e->num_sms - 1) / std::max(1, e->num_sms)));
+        ab = std::min<int64_t>({ab, capb, ok::kBeamBlock});
+        if (!ok::kBeamStage)
+            ab = std::min<int64_t>(ab, std::max<int64_t>(1, (n + e->num_sms - 1) / std::max(1, e->num_sms)));
         e->batch_agents_beam = static_cast<int32_t>(std::max<int64_t>(1, ab));
-        e->smem_beam         = blob + ok::beam_smem_bytes(e->batch_agents_beam);
+        e->smem_beam         = (ok::kBeamStage ? blob : 0) + ok::beam_smem_bytes(e->batch_agents_beam);
         // The limit is an attribute of the FUNCTION on this device, not of the env: it is raised to the opt-in maximum
         // (minus the kernel's static shared memory), so that envs of different sizes can interleave their launches.
         if (int rc = arm_shared_memory_limit(e))
@@ -935,9 +962,10 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
     // tiles: maximal runs of one track, cut into batches.  Guided self-scheduling: CTAs pull tiles in
     // list order, so full-size batches come first and a tail of quarter-size ones (about half a big
     // batch per SM) evens out the finish.
-    auto build_tiles = [&](int big, ok::Tile **d_out, int32_t *n_out) -> int {
-        const int     small = std::max(1, big / 4);
-        const int64_t tail_agents = std::min<int64_t>(n / 2, static_cast<int64_t>(e->num_sms) * big / 2);
+    auto build_tiles = [&](int big, int ctas, int tail_div, ok::Tile **d_out, int32_t *n_out) -> int {
+        // tail_div = 0: uniform tiles; otherwise the last tiles (about half a big batch per CTA) are 1 / tail_div the size
+        const int     small = std::max(1, big / std::max(1, tail_div));
+        const int64_t tail_agents = tail_div > 1 ? std::min<int64_t>(n / 2, static_cast<int64_t>(ctas) * big / 2) : 0;
         std::vector<ok::Tile> tiles, tail;
         for (int64_t i = 0; i < n;)
         {
@@ -966,12 +994,77 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
         OK_CUDA(cudaMemcpy(*d_out, tiles.data(), sizeof(ok::Tile) * tiles.size(), cudaMemcpyHostToDevice));
         return OK_SUCCESS;
     };
-    if (int rc = build_tiles(e->batch_agents, &e->d_tiles, &e->n_tiles))
+    // Balanced tiling (staged beam kernel).  The kernel's cost per ray is nearly uniform, but a tile pays ~15 us of serial
+    // latency (thread-per-agent phases, second ray pass, barriers) whatever its size: the fewer, larger and more equal
+    // the tiles, the better.  Tiles = CTAs x waves, dealt to the track runs in proportion to their length, every run
+    // cut into equal parts, largest first.
+    auto build_tiles_balanced = [&](int max_tile, int ctas, ok::Tile **d_out, int32_t *n_out) -> int {
+        struct Run
+        {
+            int32_t track;
+            int64_t begin, len;
+            int64_t k;
+        };
+        std::vector<Run> runs;
+        for (int64_t i = 0; i < n;)
+        {
+            int64_t j = i;
+            while (j < n && e->h_track_id[j] == e->h_track_id[i])
+                ++j;
+            runs.push_back({e->h_track_id[i], i, j - i, (j - i + max_tile - 1) / max_tile});
+            i = j;
+        }
+        int64_t have = 0;
+        for (auto &r : runs)
+            have += r.k;
+        const int64_t waves  = std::max<int64_t>(1, (n + static_cast<int64_t>(ctas) * max_tile - 1) / (static_cast<int64_t>(ctas) * max_tile));
+        const int64_t target = static_cast<int64_t>(ctas) * waves;
+        for (; have < target; ++have)
+        { // one more tile for the run whose tiles are the largest
+            Run *best = nullptr;
+            for (auto &r : runs)
+                if (r.len > r.k && (!best || r.len * best->k > best->len * r.k))
+                    best = &r;
+            if (!best)
+                break;
+            best->k++;
+        }
+        std::vector<ok::Tile> tiles;
+        for (const auto &r : runs)
+            for (int64_t t = 0; t < r.k; ++t)
+            {
+                const int64_t b0 = r.begin + r.len * t / r.k, b1 = r.begin + r.len * (t + 1) / r.k;
+                if (b1 > b0)
+                    tiles.push_back({r.track, static_cast<int32_t>(b1 - b0), b0});
+            }
+        std::stable_sort(tiles.begin(), tiles.end(), [](const ok::Tile &a, const ok::Tile &b) { return a.count > b.count; });
+        *n_out = static_cast<int32_t>(tiles.size());
+        OK_CUDA(cudaMalloc(d_out, sizeof(ok::Tile) * tiles.size()));
+        OK_CUDA(cudaMemcpy(*d_out, tiles.data(), sizeof(ok::Tile) * tiles.size(), cudaMemcpyHostToDevice));
+        return OK_SUCCESS;
+    };
+    {
+        int per_sm = 1;
+        if (!ok::kBeamStage)
+            OK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ok::step_kernel<ok::kBeamBlock, true>, ok::kBeamBlock,
+                                                                  e->smem_beam));
+        e->ctas_per_sm_beam = std::max(1, per_sm);
+    }
+    if (int rc = build_tiles(e->batch_agents, e->num_sms, 4, &e->d_tiles, &e->n_tiles))
         return rc;
-    if (int rc = build_tiles(e->batch_agents_beam, &e->d_tiles_beam, &e->n_tiles_beam))
-        return rc;
+    {
+        // the unstaged beam kernel's small tiles cost about the same serial latency whatever their size (the thread-per-
+        // agent phases, the second ray pass): shrinking them further only adds tiles
+        int tail_div = ok::kBeamStage ? -1 : 0; // -1: balanced tiling
+        if (const char *env = std::getenv("OK_BEAM_TAIL"))
+            tail_div = std::atoi(env);
+        const int rc = tail_div < 0 ? build_tiles_balanced(e->batch_agents_beam, e->num_sms * e->ctas_per_sm_beam, &e->d_tiles_beam, &e->n_tiles_beam)
+                                    : build_tiles(e->batch_agents_beam, e->num_sms * e->ctas_per_sm_beam, tail_div, &e->d_tiles_beam, &e->n_tiles_beam);
+        if (rc)
+            return rc;
+    }
     e->grid      = std::max(1, std::min(e->num_sms, e->n_tiles));
-    e->grid_beam = std::max(1, std::min(e->num_sms, e->n_tiles_beam));
+    e->grid_beam = std::max(1, std::min(e->num_sms * e->ctas_per_sm_beam, e->n_tiles_beam));
 
     // every agent starts where `Environment::resetAgent(agent, false)` puts it: RaceTrack::kStartingIdx
     std::vector<int32_t> pt(static_cast<size_t>(n));
@@ -1416,12 +1509,18 @@ static int host_beam(OkEnv *e, int32_t id)
 int32_t ok_beam_lookup(OkEnv *e, int32_t id, float x, float y, float angle, uint16_t *h_items, int32_t capacity,
                        float *d_complete)
 {
+    return ok_beam_lookup_ex(e, id, x, y, angle, h_items, capacity, d_complete, nullptr, nullptr);
+}
+
+int32_t ok_beam_lookup_ex(OkEnv *e, int32_t id, float x, float y, float angle, uint16_t *h_items, int32_t capacity,
+                          float *d_complete, float *d_inline, int32_t *n_inline)
+{
     int rc = host_beam(e, id);
     if (rc)
         return rc;
     std::vector<uint16_t> items;
     float                 d = 0.0f;
-    if (!ok::beam_lookup(*e->beams[id], x, y, angle, items, d))
+    if (!ok::beam_lookup(*e->beams[id], x, y, angle, items, d, d_inline, n_inline))
         return OK_BEAM_NOT_COVERED;
     if (d_complete)
         *d_complete = d;
@@ -1506,13 +1605,70 @@ int ok_pcie_probe(int32_t device, size_t bytes, int32_t iters, int32_t mode, dou
     return OK_SUCCESS;
 }
 
+int ok_debug_stats(OkEnv *e, uint64_t out[4], int32_t enable)
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    DeviceGuard g(e->cfg.device);
+    if (out)
+    {
+        out[0] = out[1] = out[2] = out[3] = 0;
+        if (e->d_stats)
+            OK_CUDA(cudaMemcpy(out, e->d_stats, 32, cudaMemcpyDeviceToHost));
+    }
+    if (enable && !e->d_stats)
+    {
+        OK_CUDA(cudaMalloc(&e->d_stats, 32));
+    }
+    if (e->d_stats)
+        OK_CUDA(cudaMemset(e->d_stats, 0, 32));
+    if (!enable && e->d_stats)
+    {
+        OK_CUDA(cudaDeviceSynchronize());
+        cudaFree(e->d_stats);
+        e->d_stats = nullptr;
+    }
+    return OK_SUCCESS;
+}
+
+int64_t ok_debug_trace(OkEnv *e, uint64_t *h_out, int64_t capacity_words, int32_t tiles_per_cta)
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    DeviceGuard  g(e->cfg.device);
+    const size_t words = static_cast<size_t>(e->grid_beam) * static_cast<size_t>(std::max(e->trace_tiles, 0)) * 6;
+    int64_t      got   = 0;
+    OK_CUDA(cudaDeviceSynchronize());
+    if (h_out && e->d_trace && words)
+    {
+        got = static_cast<int64_t>(std::min<size_t>(words, static_cast<size_t>(std::max<int64_t>(capacity_words, 0))));
+        OK_CUDA(cudaMemcpy(h_out, e->d_trace, 8 * static_cast<size_t>(got), cudaMemcpyDeviceToHost));
+    }
+    if (e->d_trace && tiles_per_cta != e->trace_tiles)
+    {
+        cudaFree(e->d_trace);
+        e->d_trace = nullptr, e->trace_tiles = 0;
+    }
+    if (tiles_per_cta > 0)
+    {
+        const size_t bytes = 8 * static_cast<size_t>(e->grid_beam) * tiles_per_cta * 6;
+        if (!e->d_trace)
+            OK_CUDA(cudaMalloc(&e->d_trace, bytes));
+        OK_CUDA(cudaMemset(e->d_trace, 0, bytes));
+        e->trace_tiles = tiles_per_cta;
+    }
+    return got;
+}
+
 int ok_launch_stats(const OkEnv *e, OkLaunchStats *out)
 {
     if (!e || !out)
         return fail(OK_ERR_INVALID_ARG, "NULL argument");
     out->kernel_launches = e->launches;
     out->grid_blocks     = e->cfg.raycast_mode == OK_RAYCAST_BEAM ? e->grid_beam : e->grid;
-    out->block_threads   = kBlock;
+    out->block_threads   = e->cfg.raycast_mode == OK_RAYCAST_BEAM ? ok::kBeamBlock : kBlock;
     out->smem_bytes      = static_cast<int32_t>(e->cfg.raycast_mode == OK_RAYCAST_BEAM ? e->smem_beam : e->smem);
     out->tiles           = e->cfg.raycast_mode == OK_RAYCAST_BEAM ? e->n_tiles_beam : e->n_tiles;
     return OK_SUCCESS;

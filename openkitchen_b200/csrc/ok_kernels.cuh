@@ -46,7 +46,13 @@ struct TrackRef
     uint32_t bytes;       // blob_bytes
     uint32_t has_beam;    // the track has a beam table
     uint64_t beam_offset; // device address of its beam table (ok_beam.hpp), its own allocation
+    // the table's header, copied here by the host: a tile start reads this 64-byte record (L2 resident, 23 of them)
+    // instead of chasing the header at the front of a multi-hundred-MB table that no cache holds
+    float    bx0, by0, binv_h, bbin_scale, brb;
+    int32_t  bnx, bny, bnb;
+    uint32_t boff_rows, boff_entries, boff_items, pad;
 };
+static_assert(sizeof(TrackRef) == 72, "TrackRef layout");
 
 struct StepParams
 {
@@ -72,6 +78,9 @@ struct StepParams
     uint32_t       smem_blob_bytes; // offset of the batch scratch behind the staged track
     const uint16_t *ray_order;      // ray indices sorted by |angle|: pool order, long (central) rays first
     int32_t       *sched;           // {next tile, CTAs finished}: dynamic tile scheduler
+    unsigned long long *stats;      // nullable: {rays cast, rays queued for pass B, rays sent to the grid walk} (beam kernel)
+    unsigned long long *trace;      // nullable: per CTA and tile, globaltimer at the phase boundaries (profiling aid, beam kernel)
+    int32_t             trace_tiles; // tiles per CTA the trace buffer has room for
     // this launch
     const float *ext_thr, *ext_steer; // nullable: actions supplied by the caller
     int32_t      action_source;       // 0 stored/ext, 1 philox
@@ -566,22 +575,22 @@ enum : uint32_t
 struct BeamView
 {
     const uint32_t *rows;
-    const uint2    *entries;
-    const uint2    *chunks; // 4 x uint16 segment indices per chunk
+    const uint4    *entries; // {inline candidates 0-1, 2-3, first rest chunk, meta}: ok_beam.hpp
+    const uint2    *chunks;  // rest lists: 4 x uint16 segment indices per chunk
     float           x0, y0, inv_h, bin_scale, rb;
     int32_t         nx, ny, nb;
     bool            valid;
 };
 
-__device__ __forceinline__ BeamView make_beam_view(const uint8_t *blob)
+__device__ __forceinline__ BeamView make_beam_view(const TrackRef &tr)
 {
-    BeamView          v;
-    const BeamHeader *h = reinterpret_cast<const BeamHeader *>(blob);
-    v.rows              = reinterpret_cast<const uint32_t *>(blob + h->off_rows);
-    v.entries           = reinterpret_cast<const uint2 *>(blob + h->off_entries);
-    v.chunks            = reinterpret_cast<const uint2 *>(blob + h->off_items);
-    v.x0 = h->x0, v.y0 = h->y0, v.inv_h = h->inv_h, v.bin_scale = h->bin_scale, v.rb = h->rb;
-    v.nx = h->nx, v.ny = h->ny, v.nb = h->nb;
+    BeamView       v;
+    const uint8_t *blob = reinterpret_cast<const uint8_t *>(tr.beam_offset);
+    v.rows              = reinterpret_cast<const uint32_t *>(blob + tr.boff_rows);
+    v.entries           = reinterpret_cast<const uint4 *>(blob + tr.boff_entries);
+    v.chunks            = reinterpret_cast<const uint2 *>(blob + tr.boff_items);
+    v.x0 = tr.bx0, v.y0 = tr.by0, v.inv_h = tr.binv_h, v.bin_scale = tr.bbin_scale, v.rb = tr.brb;
+    v.nx = tr.bnx, v.ny = tr.bny, v.nb = tr.bnb;
     v.valid = true;
     return v;
 }
@@ -603,14 +612,6 @@ __device__ __forceinline__ unsigned long long beam_key(float t, int idx)
     return (static_cast<unsigned long long>(tb) << 32) | static_cast<uint32_t>(0x7fffffff - idx);
 }
 
-// a candidate that survived the screens and sits comfortably inside the segment (s in [0,1] and t > 0 hold
-// without a division): only the order of its exact t matters
-__device__ __forceinline__ void beam_flush(const float4 *segs, int idx, float ox, float oy, float dx, float dy,
-                                           unsigned long long *key)
-{
-    atomicMin(key, beam_key(exact_t(segs[idx], ox, oy, dx, dy), idx));
-}
-
 // One candidate, written without branches (a warp's lanes hold unrelated rays, so every branch here would be
 // taken by a few lanes while the others wait) and free of dependences on the other candidates of the chunk, so
 // the four evaluations of a chunk interleave.  Returns the approximate quotient tq = a * rcp(ad)
@@ -620,7 +621,7 @@ __device__ __forceinline__ void beam_flush(const float4 *segs, int idx, float ox
 //   lit -- on an edge of the segment or at the origin (rare): needs the reference's literal predicate.
 // Everything else fails the reference's predicate (sufficient conditions, see test_segment).
 __device__ __forceinline__ float beam_eval(const float4 *segs, const int idx, const float ox, const float oy,
-                                           const float dx, const float dy, bool &el, bool &lit)
+                                           const float dx, const float dy, bool &el, bool &lit, float &a_out, float &ad_out)
 {
     const float4   sg    = segs[idx];
     const float    ex    = fsub(sg.x, ox);
@@ -640,14 +641,16 @@ __device__ __forceinline__ float beam_eval(const float4 *segs, const int idx, co
     lit                  = !rej & !comfy;
     // a * rcp(ad): rcp.approx is within 1 ulp and the product adds half an ulp, inside the 2^-21 bound; where
     // `el` holds, ad < 2^60 and a >= 2^-60, so nothing is flushed or overflows
+    // the exact quotient of a winner is a / ad: RN(tn / denom) bit for bit (both signs were flipped together)
+    a_out = a, ad_out = ad;
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(ad));
     return fmul(a, r);
 }
 
-// literal predicate of the reference (CollisionChecker.cu:25-33) for a candidate flagged `lit`
-__device__ __noinline__ void beam_literal(const float4 *segs, int idx, float ox, float oy, float dx, float dy,
-                                          unsigned long long *key)
+// literal predicate of the reference (CollisionChecker.cu:25-33) for a candidate flagged `lit`:
+// returns the candidate's key (all ones = rejected)
+__device__ __noinline__ unsigned long long beam_literal_key(const float4 *segs, int idx, float ox, float oy, float dx, float dy)
 {
     const float4 sg    = segs[idx];
     const float  ex    = fsub(sg.x, ox);
@@ -656,11 +659,65 @@ __device__ __noinline__ void beam_literal(const float4 *segs, int idx, float ox,
     const float  sn    = fsub(fmul(ex, dy), fmul(ey, dx));
     const float  tn    = fsub(fmul(ex, sg.w), fmul(ey, sg.z));
     if (fabsf(denom) < 1e-8f)
-        return;
-    const float t = __fdiv_rn(tn, denom);
+        return ~0ull;
+    const float t  = __fdiv_rn(tn, denom);
     const float s2 = __fdiv_rn(sn, denom);
-    if ((s2 >= 0.0f) && (s2 <= 1.0f) && (t >= 0.0f))
-        atomicMin(key, beam_key(t, idx));
+    return ((s2 >= 0.0f) && (s2 <= 1.0f) && (t >= 0.0f)) ? beam_key(t, idx) : ~0ull;
+}
+
+__device__ __forceinline__ unsigned long long key_min(unsigned long long a, unsigned long long b)
+{
+    return a < b ? a : b;
+}
+
+// Four candidates (two packed words of uint16 segment indices) of ONE ray, entirely in registers: the best of them by
+// the reference's rule folded into `key` ((exact t) << 32 | (0x7fffffff - segment), see beam_key).  `bound` = the
+// ray's incumbent exact t (its key's high word, or the sensor range): a candidate whose approximate quotient is
+// clearly beyond it is dropped without a division.  Every candidate is either strictly beaten by another one (the two
+// quotients differ by more than both error bounds) or reaches the key with its exact IEEE quotient.
+__device__ __forceinline__ unsigned long long beam_chunk_key(const float4 *segs, const uint32_t c01, const uint32_t c23,
+                                                             const float ox, const float oy, const float dx, const float dy,
+                                                             const float bound, unsigned long long key)
+{
+    int   idx[4];
+    float tq[4], a[4], ad[4];
+    bool  el[4], lit[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+    {
+        // chunks are padded with the index of the track's null segment (zero length: denom = 0 fails the reference's
+        // parallel test), so padding needs no special case
+        idx[u] = static_cast<int>(((u < 2 ? c01 : c23) >> (16 * (u & 1))) & 0xffffu);
+        tq[u]  = beam_eval(segs, idx[u], ox, oy, dx, dy, el[u], lit[u], a[u], ad[u]);
+    }
+    float tq_b  = bound, a_b = 0.0f, ad_b = 1.0f;
+    int   idx_b = -1;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+    {
+        const bool cand = el[u] & !(tq[u] > fmul(tq_b, 1.000003814697265625f));
+        if (cand & !(tq[u] < fmul(tq_b, 0.999996185302734375f)) & (idx_b >= 0))
+            key = key_min(key, beam_key(__fdiv_rn(a_b, ad_b), idx_b)); // near tie (rare): the displaced one keeps its claim
+        tq_b  = cand ? tq[u] : tq_b;
+        a_b   = cand ? a[u] : a_b;
+        ad_b  = cand ? ad[u] : ad_b;
+        idx_b = cand ? idx[u] : idx_b;
+    }
+    if (idx_b >= 0)
+        key = key_min(key, beam_key(__fdiv_rn(a_b, ad_b), idx_b));
+    if (lit[0] | lit[1] | lit[2] | lit[3])
+    {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (lit[u])
+                key = key_min(key, beam_literal_key(segs, idx[u], ox, oy, dx, dy));
+    }
+    return key;
+}
+
+__device__ __forceinline__ float beam_meta_dist(const uint32_t q, const float rb)
+{ // 12-bit distance field of an entry's meta word (ok_beam.hpp): 1/16 px, all ones = complete up to rb
+    return q == kBeamDistFull ? rb : static_cast<float>(q) * (1.0f / kBeamDistScale);
 }
 
 // The rare ray a beam list cannot decide: uniform-grid walk from t_start with the best listed hit (best, min_t)
@@ -1007,35 +1064,84 @@ __device__ __forceinline__ void agent_post(const StepParams &p, const TrackView 
 #define OK_UNITS 4
 #endif
 constexpr int kUnitsPerRefill = OK_UNITS; // units of work a lane does between two looks at the pool
+// The beam kernel (kBeam = true) runs SEVERAL SMALL CTAs per SM instead of one that owns the SM: its narrow phase reads
+// four listed segments per ray, not the whole track, so nothing is staged in shared memory -- segments, centre line and
+// the (rarely walked) grid come from the track's blob in global memory through L1 / L2 (a fan's rays touch the same few
+// 128-byte lines) -- and a CTA needs only its agents' records.  While one CTA sits at a phase barrier, fetches its next
+// tile or runs the thread-per-agent phases, the SM's other CTAs cast rays: the 1,024-thread kernel of round 1 spent
+// 24 % of its warp time at barriers and issued on 49 % of the cycles.  OK_BEAM_STAGE=1 keeps the staged variant.
+#ifndef OK_BEAM_BLOCK
+#define OK_BEAM_BLOCK 256
+#endif
+#ifndef OK_BEAM_MIN_CTAS
+#define OK_BEAM_MIN_CTAS (1024 / OK_BEAM_BLOCK) // 64 registers per thread fill the register file
+#endif
+#ifndef OK_BEAM_STAGE
+#define OK_BEAM_STAGE 1
+#endif
+#ifndef OK_BEAM_PREFETCH
+#define OK_BEAM_PREFETCH 0 // measured: an L2 prefetch of the queued rays' rest chunks costs 12 % (0.129 vs 0.115 ms)
+#endif
+#ifndef OK_BEAM_TILE
+#define OK_BEAM_TILE 64 // agents per tile of the unstaged beam kernel
+#endif
+constexpr int  kBeamBlock = OK_BEAM_STAGE ? 1024 : OK_BEAM_BLOCK;
+constexpr bool kBeamStage = OK_BEAM_STAGE != 0;
+// beam kernel: capacity of the CTA's queue of rays pass A leaves to pass B.  Tile-local ray indices are 16 bits, so a
+// beam tile holds at most 65,535 rays (the host caps the batch); a full queue only costs speed (see pass A).
+constexpr int kPendCap = kBeamStage ? 8192 : 2048;
+// static shared memory of step_kernel<., true> besides the staged track and the agent records (host: batch sizing)
+constexpr int kBeamStaticSmem = kBeamBlock * (16 + 8) + 2 * kPendCap + 4 * (kPendCap / 32) + 128;
 
-template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) step_kernel(const StepParams p)
+__device__ __forceinline__ unsigned long long global_timer()
 {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// trace record of one tile: {tile | smid << 32, t_start, t_phase1_done, t_passA_done, t_passB_done, t_phase4_done}
+#define OK_TRACE(slot)                                                                                                 \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        if (kBeam && p.trace && tid == 0 && n_done < p.trace_tiles)                                                    \
+            p.trace[(static_cast<size_t>(blockIdx.x) * p.trace_tiles + n_done) * 6 + (slot)] = global_timer();         \
+    } while (0)
+
+template <int kBlock, bool kBeam>
+__global__ void __launch_bounds__(kBlock, (kBeam && !kBeamStage) ? OK_BEAM_MIN_CTAS : 1) step_kernel(const StepParams p)
+{
+    constexpr bool kStage = !kBeam || kBeamStage; // the track is staged in shared memory with one TMA bulk copy
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint16_t                      s_order[1024]; // pool order of the rays (p.ray_order)
+    __shared__ uint16_t                      s_order[kBeam ? 1 : 1024]; // pool order of the rays (p.ray_order)
     __shared__ __align__(8) uint64_t         bar;
-    __shared__ int                           s_tile, s_pool;
+    __shared__ int                           s_tile, s_pool, s_pool2, s_npend, s_adone;
+    __shared__ int                           s_ready[kBeam ? kPendCap / 32 : 1]; // entries written, per 32-ray chunk of the queue
+    __shared__ uint16_t                      s_pend[kBeam ? kPendCap : 1]; // tile-local indices of the rays pass A left open
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int     R      = p.rays;
 
     uint8_t  *blob    = smem;
-    AgentRec *recs    = reinterpret_cast<AgentRec *>(smem + p.smem_blob_bytes);
+    AgentRec *recs    = reinterpret_cast<AgentRec *>(smem + (kStage ? p.smem_blob_bytes : 0u));
     float2   *dirs    = reinterpret_cast<float2 *>(recs + p.batch_agents); // !kBeam
     // kBeam: per-thread ray parameters and result keys of the group a warp is working on
     __shared__ __align__(16) float4             s_wray[kBeam ? kBlock : 1];
     __shared__ __align__(8) unsigned long long s_wkey[kBeam ? kBlock : 1];
 
-    if (tid == 0)
+    if (kStage && tid == 0)
         mbar_init(&bar, 1);
-    for (int i = tid; i < R; i += kBlock)
-        s_order[i] = p.ray_order[i];
+    if (!kBeam)
+        for (int i = tid; i < R; i += kBlock)
+            s_order[i] = p.ray_order[i];
     __syncthreads();
 
     int      staged = -1;
+    int      n_done = 0; // tiles this CTA has finished (trace slot)
     uint32_t phase  = 0;
     const float inv_R = 1.0f / static_cast<float>(R);
+    // the first tile of a CTA is its own index: no trip to the global cursor before any work can start
     if (tid == 0)
-        s_tile = atomicAdd(p.sched, 1);
+        s_tile = static_cast<int>(blockIdx.x);
 
     for (;;)
     {
@@ -1046,21 +1152,30 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
         const int tile = s_tile;
         if (tile >= p.n_tiles)
             break;
+        if (kBeam && p.trace && tid == 0 && n_done < p.trace_tiles)
+        {
+            unsigned smid;
+            asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+            p.trace[(static_cast<size_t>(blockIdx.x) * p.trace_tiles + n_done) * 6] =
+                static_cast<unsigned long long>(tile) | (static_cast<unsigned long long>(smid) << 32);
+        }
+        OK_TRACE(1);
 
         const Tile     tl = p.tiles[tile];
         const TrackRef tr = p.tracks[tl.track];
         // the bulk copy of the track runs under phase 1, which reads no staged data; it is awaited before the rays
-        const bool restage = tl.track != staged;
+        const uint8_t *gblob   = p.arena + tr.offset;
+        const bool     restage = kStage && tl.track != staged;
         if (restage && tid == 0)
         {
             fence_proxy_async();
             mbar_expect_tx(&bar, tr.bytes);
-            tma_bulk_g2s(blob, p.arena + tr.offset, tr.bytes, &bar);
+            tma_bulk_g2s(blob, gblob, tr.bytes, &bar);
         }
         BeamView bv;
         bv.valid = false;
         if (kBeam && tr.has_beam)
-            bv = make_beam_view(reinterpret_cast<const uint8_t *>(tr.beam_offset));
+            bv = make_beam_view(tr);
         const int       count    = tl.count;
         const int       n_rays   = count * R;
         const float     inv_cnt  = 1.0f / static_cast<float>(count);
@@ -1069,9 +1184,12 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
         // phase 1 -- one thread per agent: optional reset, kinematics, standstill (Environment.cpp:128-143)
         // =====================================================================================
         if (tid < count)
-            recs[tid] = agent_pre(p, p.arena + tr.offset, bv, tl.begin + tid);
+            recs[tid] = agent_pre(p, gblob, bv, tl.begin + tid);
         if (tid == 0)
-            s_pool = 0;
+            s_pool = 0, s_pool2 = 0, s_npend = 0, s_adone = 0;
+        if (kBeam)
+            for (int i = tid; i < kPendCap / 32; i += kBlock)
+                s_ready[i] = 0;
         if (restage)
         {
             mbar_wait(&bar, phase);
@@ -1079,8 +1197,10 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
             staged = tl.track;
         }
         __syncthreads();
-        const TrackView tv = make_view(blob);
-        const int64_t ray_base = tl.begin * R; // global index of the batch's first ray
+        OK_TRACE(2);
+        const uint8_t  *track    = kStage ? blob : gblob; // where this tile reads its track from
+        const TrackView tv       = make_view(track);
+        const int64_t   ray_base = tl.begin * R; // global index of the batch's first ray
         if (!kBeam)
         {
 
@@ -1225,10 +1345,14 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
         else
         {
             // =================================================================================
-            // beam phase -- warps pull groups of 32 consecutive rays (lane = ray): direction, table lookup,
-            // balanced test of the listed candidates, outputs.  A ray the table cannot decide (cell not
-            // covered, hit beyond the list's completeness distance: ~0.1 %) continues with the grid walk
-            // from where its list stopped, in place.
+            // beam phase.  PASS A -- warps pull groups of 32 consecutive rays (lane = ray): direction, ONE 16-byte table
+            // entry (fetched a group ahead), the entry's four inline candidates tested in registers.  A ray whose hit
+            // lies within the distance up to which those four are provably the only contenders (d1, ok_beam.hpp) is
+            // finished on the spot with coalesced stores; the others (longer lists, hit beyond the list's completeness
+            // distance, cell not covered) are queued.  PASS B -- the queued rays of the whole CTA, 32 at a time: the
+            // rest of each list is dealt evenly over the warp's lanes (chunks of four, owner found by a shuffle binary
+            // search), results meet in a 64-bit atomicMin key per ray; what even that cannot decide (~0.1 %) continues
+            // with the uniform-grid walk from where its list stopped.
             // =================================================================================
             const int                n_groups = (n_rays + 31) >> 5;
             const unsigned long long key_none =
@@ -1236,14 +1360,13 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
             const float inf = __int_as_float(0x7f800000);
             float4             *w_ray = s_wray + (tid & ~31);
             unsigned long long *w_key = s_wkey + (tid & ~31);
-            // ray `lane` of group g: agent, angle and its table entry (fetched one group ahead)
-            auto locate = [&](int g, int &al, float &ang, bool &active, bool &cov, uint2 &ent) {
-                const int q = (g << 5) + lane;
+            // tile-local ray q: agent, angle and its table entry
+            auto locate = [&](const int q, const bool valid, int &al, float &ang, bool &active, bool &cov, uint4 &ent) {
                 active = false, cov = false;
                 al  = 0;
                 ang = 0.0f;
-                ent = make_uint2(0u, 0u);
-                if (g < n_groups && q < n_rays)
+                ent = make_uint4(0u, 0u, 0u, 0u);
+                if (valid)
                 {
                     al                  = __float2int_rz((static_cast<float>(q) + 0.5f) * inv_R);
                     const AgentRec &rec = recs[al];
@@ -1257,76 +1380,24 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                     }
                 }
             };
-            int g = 0;
-            if (lane == 0)
-                g = atomicAdd(&s_pool, 1);
-            g = __shfl_sync(0xffffffffu, g, 0);
-            int   al;
-            float ang;
-            bool  active, cov;
-            uint2 ent;
-            locate(g, al, ang, active, cov, ent);
-            while (g < n_groups)
-            {
-                int g_next = 0;
-                if (lane == 0)
-                    g_next = atomicAdd(&s_pool, 1);
-                g_next = __shfl_sync(0xffffffffu, g_next, 0);
-                int   al_n;
-                float ang_n;
-                bool  active_n, cov_n;
-                uint2 ent_n;
-                locate(g_next, al_n, ang_n, active_n, cov_n, ent_n);
-
-                const int  q   = (g << 5) + lane;
-                const bool has = q < n_rays;
-                // every ray's FIRST chunk (the nearest candidates: the winner is among them for ~9 rays in 10) is
-                // tested by the ray's own lane -- no owner search, ray parameters in registers; only the chunks
-                // beyond the first are dealt across the warp
-                const uint32_t cnt  = cov ? (ent.y & 0xffffu) : 0u;
-                uint2          it_0 = make_uint2(0u, 0u);
-                if (cnt)
-                    it_0 = __ldg(bv.chunks + ent.x);
+            // The full treatment of up to 32 queued rays (lane = ray `q`, `has` = the lane holds one): inline chunk on
+            // the ray's own lane, the rest dealt across the warp, grid-walk fallback, outputs.  Warp-collective.
+            auto process_full = [&](const int q, const bool has) {
+                int   al;
+                float ang;
+                bool  active, cov;
+                uint4 ent;
+                locate(q, has, al, ang, active, cov, ent);
                 float dx = 0.0f, dy = 0.0f;
                 if (active)
                     sincosf(ang, dy, dx); // cosf/sinf of CollisionChecker.cu:47-48
                 const float rox = recs[al].ox, roy = recs[al].oy;
                 w_ray[lane]     = make_float4(rox, roy, dx, dy);
-                w_key[lane]     = key_none;
-                if (cnt)
-                {
-                    unsigned long long *key = w_key + lane;
-                    int                 idx[4];
-                    float               tq[4];
-                    bool                el[4], lit[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                    {
-                        idx[u] = static_cast<int>(((u < 2 ? it_0.x : it_0.y) >> (16 * (u & 1))) & 0xffffu);
-                        tq[u]  = beam_eval(tv.seg, idx[u], rox, roy, dx, dy, el[u], lit[u]);
-                    }
-                    float tq_b  = p.sensor_range;
-                    int   idx_b = -1;
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                    {
-                        const bool cand = el[u] & !(tq[u] > fmul(tq_b, 1.000003814697265625f));
-                        if (cand & !(tq[u] < fmul(tq_b, 0.999996185302734375f)) & (idx_b >= 0))
-                            beam_flush(tv.seg, idx_b, rox, roy, dx, dy, key); // near tie (rare)
-                        tq_b  = cand ? tq[u] : tq_b;
-                        idx_b = cand ? idx[u] : idx_b;
-                    }
-                    if (idx_b >= 0)
-                        beam_flush(tv.seg, idx_b, rox, roy, dx, dy, key);
-                    if (lit[0] | lit[1] | lit[2] | lit[3])
-                    {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (lit[u])
-                                beam_literal(tv.seg, idx[u], rox, roy, dx, dy, key);
-                    }
-                }
-                const uint32_t nch = cnt ? ((cnt + 3u) >> 2) - 1u : 0u; // chunks beyond the first
+                unsigned long long key0 = key_none;
+                if (cov)
+                    key0 = beam_chunk_key(tv.seg, ent.x, ent.y, rox, roy, dx, dy, p.sensor_range, key_none);
+                w_key[lane]        = key0;
+                const uint32_t nch = cov ? (ent.w >> 24) : 0u; // chunks of the rest of the list
                 uint32_t       inc = nch;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1)
@@ -1336,9 +1407,9 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                         inc += v;
                 }
                 const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-                const uint32_t first = ent.x + 1u - (inc - nch); // chunk j of the rest is chunk (first + j) of the table
+                const uint32_t first = ent.z - (inc - nch); // chunk j of the warp's rest chunks is chunk (first + j) of the table
                 __syncwarp();
-                // chunk j of the group belongs to the lane `owner` whose prefix range contains j
+                // chunk j belongs to the lane `owner` whose prefix range contains j
                 auto find_chunk = [&](uint32_t j, int &owner) -> uint32_t {
                     owner = 0;
 #pragma unroll
@@ -1374,87 +1445,179 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
                     {
                         const float4        ray = w_ray[owner];
                         unsigned long long *key = w_key + owner;
-                        const float         m   = __uint_as_float(reinterpret_cast<const uint32_t *>(key)[1]);
-                        int                 idx[4];
-                        float               tq[4];
-                        bool                el[4], lit[4];
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                        {
-                            // chunks are padded with the index of the track's null segment (zero length: denom = 0
-                            // fails the reference's parallel test), so padding needs no special case
-                            idx[u] = static_cast<int>(((u < 2 ? it.x : it.y) >> (16 * (u & 1))) & 0xffffu);
-                            tq[u]  = beam_eval(tv.seg, idx[u], ray.x, ray.y, ray.z, ray.w, el[u], lit[u]);
-                        }
-                        // the chunk's best by approximate quotient, starting from the ray's incumbent (exact t = m,
-                        // already in the key).  Every candidate is either strictly beaten by another one (the two
-                        // quotients differ by more than both error bounds) or reaches the key with its exact t.
-                        float tq_b  = m;
-                        int   idx_b = -1;
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                        {
-                            const bool cand = el[u] & !(tq[u] > fmul(tq_b, 1.000003814697265625f));
-                            if (cand & !(tq[u] < fmul(tq_b, 0.999996185302734375f)) & (idx_b >= 0))
-                                beam_flush(tv.seg, idx_b, ray.x, ray.y, ray.z, ray.w, key); // near tie (rare)
-                            tq_b  = cand ? tq[u] : tq_b;
-                            idx_b = cand ? idx[u] : idx_b;
-                        }
-                        if (idx_b >= 0)
-                            beam_flush(tv.seg, idx_b, ray.x, ray.y, ray.z, ray.w, key);
-                        if (lit[0] | lit[1] | lit[2] | lit[3])
-                        {
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                if (lit[u])
-                                    beam_literal(tv.seg, idx[u], ray.x, ray.y, ray.z, ray.w, key);
-                        }
+                        // the ray's incumbent exact t (already in the key) bounds what is worth a division
+                        const float              m = __uint_as_float(reinterpret_cast<const uint32_t *>(key)[1]);
+                        const unsigned long long k = beam_chunk_key(tv.seg, it.x, it.y, ray.x, ray.y, ray.z, ray.w, m, ~0ull);
+                        if (k != ~0ull)
+                            atomicMin(key, k);
                     }
                     owner = owner_n;
                     it    = it_n;
                 }
                 __syncwarp();
-                float sq = inf;
                 if (has)
                 {
                     const AgentRec          &rec   = recs[al];
                     const unsigned long long key   = w_key[lane];
                     int                      best  = static_cast<int>(0x7fffffffu - static_cast<uint32_t>(key));
                     const float              min_t = __uint_as_float(static_cast<uint32_t>(key >> 32));
-                    const uint32_t           dq    = ent.y >> 16;
-                    const float              d_eff = dq == 0xffffu ? bv.rb : static_cast<float>(dq) * 0.00390625f;
+                    const float              d_eff = beam_meta_dist(ent.w & 0xfffu, bv.rb);
                     float t_known = min_t; // the key holds the exact t of `best`
                     if (active && !(cov && min_t <= d_eff - kBeamSlack))
                     { // undecided: everything nearer than d_eff - 1 is settled, the grid walk covers the rest
-                        best = beam_walk_fallback(blob, rec.ox, rec.oy, dx, dy, p.sensor_range,
+                        best = beam_walk_fallback(track, rec.ox, rec.oy, dx, dy, p.sensor_range,
                                                   cov ? fmaxf(d_eff - 1.0f, 0.0f) : 0.0f, best, min_t);
                         t_known = 0.0f;
+                        if (p.stats)
+                            atomicAdd(p.stats + 2, 1ull);
                     }
-                    sq = finish_ray(p, tv.seg, rec, ray_base + q, dx, dy, best, t_known);
+                    const float sq = finish_ray(p, tv.seg, rec, ray_base + q, dx, dy, best, t_known);
+                    // min_dist2 of CollisionChecker.cu:150,162-165: `if (sq < min) min = sq` skips NaN, and so does a
+                    // signed-int min over the bit patterns of values >= +0 (a NaN made here is 0x7fffffff)
+                    if (sq == sq)
+                        atomicMin(&recs[al].min_d2_bits, __float_as_int(sq));
                 }
-                // min_dist2 of CollisionChecker.cu:150,162-165: `if (sq < min) min = sq` skips NaN, and so
-                // does a signed-int min over the bit patterns of values >= +0 (a NaN made here is 0x7fffffff)
+                __syncwarp(); // w_ray / w_key are reused by the next call
+            };
+
+            // ---------------------------------- pass A ----------------------------------
+            int g = 0;
+            if (lane == 0)
+                g = atomicAdd(&s_pool, 1);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            int   al;
+            float ang;
+            bool  active, cov;
+            uint4 ent;
+            locate((g << 5) + lane, g < n_groups && (g << 5) + lane < n_rays, al, ang, active, cov, ent);
+            while (g < n_groups)
+            {
+                int g_next = 0;
+                if (lane == 0)
+                    g_next = atomicAdd(&s_pool, 1);
+                g_next = __shfl_sync(0xffffffffu, g_next, 0);
+                int   al_n;
+                float ang_n;
+                bool  active_n, cov_n;
+                uint4 ent_n;
+                locate((g_next << 5) + lane, g_next < n_groups && (g_next << 5) + lane < n_rays, al_n, ang_n, active_n, cov_n, ent_n);
+
+                const int  q   = (g << 5) + lane;
+                const bool has = q < n_rays;
+                float dx = 0.0f, dy = 0.0f;
+                if (active)
+                    sincosf(ang, dy, dx); // cosf/sinf of CollisionChecker.cu:47-48
+                const AgentRec &rec = recs[al];
+                unsigned long long key = key_none;
+                if (cov)
+                    key = beam_chunk_key(tv.seg, ent.x, ent.y, rec.ox, rec.oy, dx, dy, p.sensor_range, key_none);
+                const float min_t = __uint_as_float(static_cast<uint32_t>(key >> 32));
+                // d1: up to there the inline four are the only contenders (= the list's completeness distance when it
+                // has no rest).  The key holds the exact t of its segment, or the sensor range when nothing was hit.
+                const float d1      = beam_meta_dist((ent.w >> 12) & 0xfffu, bv.rb);
+                const bool  settled = cov && (min_t <= d1 - kBeamSlack);
+                const bool  queue   = has && active && !settled;
+                float       sq      = inf;
+                if (has && !queue)
+                    sq = finish_ray(p, tv.seg, rec, ray_base + q, dx, dy, static_cast<int>(0x7fffffffu - static_cast<uint32_t>(key)),
+                                    min_t);
+                const unsigned qm = __ballot_sync(0xffffffffu, queue);
+                if (qm)
+                { // warp-aggregated append to the CTA's queue of undecided rays
+                    const int cnt  = __popc(qm);
+                    int       base = 0;
+                    if (lane == 0)
+                        base = atomicAdd(&s_npend, cnt);
+                    base          = __shfl_sync(0xffffffffu, base, 0);
+                    const int pos = base + __popc(qm & ((1u << lane) - 1u));
+                    if (queue && pos < kPendCap)
+                        s_pend[pos] = static_cast<uint16_t>(q);
+                    __syncwarp();
+                    if (lane == 0)
+                    { // publish: a 32-ray chunk of the queue may be taken by pass B as soon as all of it is written
+                        const int lo = min(base, kPendCap), hi = min(base + cnt, kPendCap);
+                        if (hi > lo)
+                        {
+                            __threadfence_block();
+                            const int c0 = lo >> 5, c1 = (hi - 1) >> 5;
+                            if (c0 == c1)
+                                atomicAdd(&s_ready[c0], hi - lo);
+                            else
+                            {
+                                atomicAdd(&s_ready[c0], ((c0 + 1) << 5) - lo);
+                                atomicAdd(&s_ready[c1], hi - (c1 << 5));
+                            }
+                        }
+                    }
+                    if (base + cnt > kPendCap) // queue full (warp-uniform): these rays get the full treatment now
+                        process_full(q, queue && pos >= kPendCap);
+                }
+                // min_dist2 of CollisionChecker.cu:150,162-165 over the rays finished here (see process_full)
                 if ((R & 31) == 0)
-                {
-                    float m = (sq == sq) ? sq : inf;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1)
-                        m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                { // a warp's 32 rays belong to one agent: one warp-wide integer min (REDUX), one atomic per warp
+                    const int m = __reduce_min_sync(0xffffffffu, __float_as_int((sq == sq) ? sq : inf));
                     if (has && lane == 0)
-                        atomicMin(&recs[al].min_d2_bits, __float_as_int(m));
+                        atomicMin(&recs[al].min_d2_bits, m);
                 }
-                else if (has && sq == sq)
+                else if (has && !queue && sq == sq)
                     atomicMin(&recs[al].min_d2_bits, __float_as_int(sq));
                 g = g_next, al = al_n, ang = ang_n, active = active_n, cov = cov_n, ent = ent_n;
+            }
+            // ---------------------------------- pass B ----------------------------------
+            // No CTA barrier between the passes: a warp that runs out of groups starts on the queue right away.  It
+            // claims the queue's next 32-ray chunk and waits until that chunk is completely written (s_ready) or every
+            // warp has left pass A (s_adone), which makes the queue's length final.
+            __syncwarp();
+            if (lane == 0)
+            {
+                __threadfence_block();
+                atomicAdd(&s_adone, 1);
+            }
+            for (;;)
+            {
+                int j = 0, size = 0;
+                if (lane == 0)
+                {
+                    j = atomicAdd(&s_pool2, 1);
+                    if (j < kPendCap / 32)
+                        for (;;)
+                        {
+                            if (*reinterpret_cast<volatile int *>(&s_ready[j]) >= 32)
+                            {
+                                size = 32;
+                                break;
+                            }
+                            if (*reinterpret_cast<volatile int *>(&s_adone) == kBlock / 32)
+                            { // every append is complete and visible: what the chunk holds now is all it will ever hold
+                                const int n = min(*reinterpret_cast<volatile int *>(&s_npend), kPendCap);
+                                size        = max(0, min(32, n - (j << 5)));
+                                break;
+                            }
+                            __nanosleep(100);
+                        }
+                    __threadfence_block();
+                }
+                j    = __shfl_sync(0xffffffffu, j, 0);
+                size = __shfl_sync(0xffffffffu, size, 0);
+                if (size <= 0)
+                    break;
+                const bool has = lane < size;
+                process_full(has ? static_cast<int>(s_pend[(j << 5) + lane]) : 0, has);
             }
             // claim the next batch now: late enough to keep the schedule dynamic (see the loop top), early enough
             // for the atomic's latency to hide behind the other warps' last groups and phase 4
             if (tid == 0)
-                s_tile = atomicAdd(p.sched, 1); // every thread read the old value before phase 1
+                s_tile = static_cast<int>(gridDim.x) + atomicAdd(p.sched, 1); // every thread read the old value before phase 1
         }
         __syncthreads();
+        OK_TRACE(4);
+        if (kBeam && p.stats && tid == 0)
+        {
+            atomicAdd(p.stats, static_cast<unsigned long long>(n_rays));
+            atomicAdd(p.stats + 1, static_cast<unsigned long long>(s_npend));
+        }
         if (!kBeam && tid == 0)
-            s_tile = atomicAdd(p.sched, 1); // every thread read the old value long ago; visible after the loop-top barrier
+            s_tile = static_cast<int>(gridDim.x) + atomicAdd(p.sched, 1); // every thread read the old value long ago; visible after the loop-top barrier
 
         // =====================================================================================
         // phase 4 -- four lanes (small batches) or one thread per agent: crash flag, centre-line search, reward, done
@@ -1471,6 +1634,8 @@ template <int kBlock, bool kBeam> __global__ void __launch_bounds__(kBlock, 1) s
             const bool valid = tid < count;
             agent_post<1>(p, tv, recs[valid ? tid : 0], tl.begin + (valid ? tid : 0), valid, lane);
         }
+        OK_TRACE(5); // thread 0's own phase 4 (the CTA-wide end is the next tile's start)
+        ++n_done;
     }
 
     // last CTA out re-arms the tile scheduler for the next launch on this stream

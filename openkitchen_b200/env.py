@@ -161,6 +161,17 @@ class Env:
         check(self.lib.ok_beam_lookup(self.h, t, x, y, angle_rad, _vp(items), n, C.byref(d)))
         return items[:n], float(d.value)
 
+    def beam_lookup_ex(self, t: int, x: float, y: float, angle_rad: float):
+        """beam_lookup plus the first pass's view: (items, d_complete, d_inline, n_inline) or None"""
+        d, d1, ni = C.c_float(0.0), C.c_float(0.0), C.c_int32(0)
+        n = self.lib.ok_beam_lookup_ex(self.h, t, x, y, angle_rad, None, 0, C.byref(d), C.byref(d1), C.byref(ni))
+        if n == -100:
+            return None
+        check(n)
+        items = np.empty(max(n, 1), dtype=np.uint16)
+        check(self.lib.ok_beam_lookup_ex(self.h, t, x, y, angle_rad, _vp(items), n, C.byref(d), C.byref(d1), C.byref(ni)))
+        return items[:n], float(d.value), float(d1.value), int(ni.value)
+
     def beam_table_bytes(self, t: int) -> int:
         return check(self.lib.ok_beam_table_bytes(self.h, t))
 
@@ -259,6 +270,21 @@ class Env:
         s, c = np.empty_like(x), np.empty_like(x)
         check(self.lib.ok_eval_sincosf(self.h, _vp(x), _vp(s), _vp(c), x.size))
         return s, c
+
+    def debug_stats(self, enable: bool = True):
+        """(rays cast, rays queued for the second pass, rays sent to the grid walk) since the previous call"""
+        out = (C.c_uint64 * 4)()
+        check(self.lib.ok_debug_stats(self.h, out, 1 if enable else 0))
+        return int(out[0]), int(out[1]), int(out[2])
+
+    def debug_trace(self, tiles_per_cta: int = 0):
+        """timeline of the last beam-kernel launch as u64[grid, tiles, 6] (None if tracing was off); then re-arms the
+        trace for `tiles_per_cta` tiles per CTA (0 = off)"""
+        grid = self.launch_stats().grid_blocks
+        cap = grid * 64 * 6
+        buf = np.zeros(cap, dtype=np.uint64)
+        got = check(self.lib.ok_debug_trace(self.h, _vp(buf), cap, tiles_per_cta))
+        return buf[:got].reshape(grid, -1, 6) if got else None
 
     def launch_stats(self) -> OkLaunchStats:
         s = OkLaunchStats()

@@ -21,10 +21,11 @@ def _first_hits(seg, ox, oy, ang):
     s = (ex * dy - ey * dx) / den
     valid = ok_den & (t >= 0) & (t <= 200.0) & (s >= 0) & (s <= 1)
     if not valid.any():
-        return 200.0, -1
+        return 200.0, -1, np.zeros(0), np.zeros(0, dtype=np.int64)
     tt = np.where(valid, t, np.inf)
     tmin = tt.min()
-    return float(tmin), int(np.flatnonzero(tt == tmin).max())
+    hit = np.flatnonzero(valid)
+    return float(tmin), int(np.flatnonzero(tt == tmin).max()), t[hit], hit
 
 
 @pytest.mark.parametrize("name,cell,bins", [("Monza", 8.0, 64), ("Spa", 8.0, 64), ("Zandvoort", 6.0, 32)])
@@ -32,14 +33,20 @@ def test_beam_lists_contain_the_reference_winner(name, cell, bins):
     check_beam_lists(ok.Env(device=-1, beam_cell=cell, beam_bins=bins), name)
 
 
-def check_beam_lists(env, name):
+def test_default_resolution_settles_most_rays_in_the_first_pass():
+    """at the default 2 px x 256 bins the four inline candidates decide most rays without the rest of the list"""
+    first_pass, decided, mean_len = check_beam_lists(ok.Env(device=-1, beam_cell=2.0, beam_bins=256), "Monza", n_rays=800)
+    assert first_pass > 0.7 and decided > 0.99 and mean_len < 12
+
+
+def check_beam_lists(env, name, n_rays=1500):
     """shared with tests/test_gpu_beam_builder.py (the same property for tables built by the device builder)"""
     t = env.add_named_track(name)
     seg = env.track_array(t, "segments").astype(np.float64)
     x, y, head = env.track_array(t, "x"), env.track_array(t, "y"), env.track_array(t, "heading")
     li, ri = env.track_array(t, "li"), env.track_array(t, "ri")
     rng = np.random.default_rng(7)
-    n_rays, decided, covered = 1500, 0, 0
+    decided, covered, first_pass = 0, 0, 0
     lengths = []
     for _ in range(n_rays):
         i = int(rng.integers(0, len(x)))
@@ -47,22 +54,33 @@ def check_beam_lists(env, name):
         ox = np.float32(a * li[i, 0] + (1 - a) * ri[i, 0])
         oy = np.float32(a * li[i, 1] + (1 - a) * ri[i, 1])
         ang = np.float32(np.deg2rad(head[i] + rng.uniform(-180, 180)))
-        got = env.beam_lookup(t, float(ox), float(oy), float(ang))
+        got = env.beam_lookup_ex(t, float(ox), float(oy), float(ang))
         if got is None:
             continue
         covered += 1
-        items, d = got
+        items, d, d_inline, n_inline = got
+        assert env.beam_lookup(t, float(ox), float(oy), float(ang))[0].tolist() == items.tolist()
+        assert 0 <= n_inline <= min(4, len(items)) and d_inline <= d + 1e-6
         lengths.append(len(items))
-        tmin, best = _first_hits(seg, float(ox), float(oy), float(ang))
+        tmin, best, all_t, all_idx = _first_hits(seg, float(ox), float(oy), float(ang))
         if tmin <= d - 0.25:
             decided += 1
             if best >= 0:
                 assert best in items, f"{name}: winner {best} (t={tmin:.3f}) missing from the list (d={d:.3f})"
+        # what the kernel's first pass relies on: up to d_inline the entry's inline candidates are the ONLY contenders,
+        # i.e. EVERY segment the ray crosses before d_inline - slack is one of them (not just the winner)
+        inline = set(items[:n_inline].tolist())
+        early = all_idx[all_t <= d_inline - 0.25]
+        assert set(early.tolist()) <= inline, f"{name}: segments {sorted(set(early.tolist()) - inline)} are crossed before d_inline={d_inline:.3f}"
+        if tmin <= d_inline - 0.25:
+            first_pass += 1
         # the list is sorted by a lower bound of the distance and never names a segment twice
         assert len(set(items.tolist())) == len(items)
     assert covered > 0.99 * n_rays, "points inside the lane must be covered by the table"
     assert decided > 0.97 * covered, "the lists should decide almost every ray"
     assert np.mean(lengths) < 60
+    assert first_pass > 0
+    return first_pass / covered, decided / covered, float(np.mean(lengths))
     assert env.beam_table_bytes(t) > 0
 
 

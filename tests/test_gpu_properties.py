@@ -74,13 +74,18 @@ def test_full_size_sampled_slice_matches_oracle():
         assert np.array_equal(env.read(name)[sel].view(np.uint8), want.view(np.uint8)), name + " (fused random actions)"
 
 
-def test_large_batches_give_the_same_bits(monkeypatch):
-    """large populations use batches of up to 1,024 agents (phase 4 then runs one thread per agent instead of four
-    lanes): force that layout at 65,536 agents and compare with the default 256-agent batches"""
+def test_tile_schedules_give_the_same_bits(monkeypatch):
+    """the results do not depend on how the agents are cut into tiles: the default balanced tiling (about one large tile
+    per CTA), small 96-agent tiles (phase 4 then runs four lanes per agent instead of one thread) and the guided
+    schedule with a tail of quarter-size tiles must agree bit for bit"""
     ticks = 20
     a = _run(ok.RAYCAST_BEAM, ticks)
-    monkeypatch.setenv("OK_BEAM_BATCH_AGENTS", "1024")
+    monkeypatch.setenv("OK_BEAM_BATCH_AGENTS", "96")
     b = _run(ok.RAYCAST_BEAM, ticks)
-    assert b.launch_stats().tiles < a.launch_stats().tiles
+    monkeypatch.setenv("OK_BEAM_BATCH_AGENTS", "256")
+    monkeypatch.setenv("OK_BEAM_TAIL", "4")
+    c = _run(ok.RAYCAST_BEAM, ticks)
+    assert b.launch_stats().tiles > c.launch_stats().tiles > a.launch_stats().tiles
     for name in ok.BUFFERS:
-        assert np.array_equal(a.read(name).view(np.uint8), b.read(name).view(np.uint8)), f"1,024-agent batches: {name}"
+        assert np.array_equal(a.read(name).view(np.uint8), b.read(name).view(np.uint8)), f"96-agent tiles: {name}"
+        assert np.array_equal(a.read(name).view(np.uint8), c.read(name).view(np.uint8)), f"quarter-size tail: {name}"
