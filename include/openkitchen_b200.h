@@ -231,11 +231,54 @@ int ok_genetic_policy(OkEnv *env, const float *d_w1, const float *d_w2, int32_t 
 int ok_cmaes_controller(OkEnv *env, const float *d_params, int32_t n_params, int32_t hidden, float throttle, float steer_scale,
                         void *stream);
 
+/* The PPO racers' policy step for every agent in ONE kernel: PPOAgent::updateAction + Actor::forward
+ * (RLRacers/PPO/PPOAgent.hpp:79-102, Actor.hpp:9-26): probs = softmax(W2 relu(W1 obs + b1) + b2) clamped to
+ * [1e-8, 1 - 1e-8]; an action index drawn with torch::multinomial's distribution (inverse CDF on one uniform per agent:
+ * d_uniform[N] if given, else Philox keyed by (agent_id_base + a, step) with `seed`), or the argmax when greedy != 0;
+ * log-probability of the choice; (throttle, steering) = d_action_table[action] into the ACT_* buffers
+ * (PPOAgent::kActionMap).  Weights are device pointers in torch.nn.Linear layout, shared by all agents: d_w1 [hidden][R],
+ * d_b1 [hidden], d_w2 [n_actions][hidden], d_b2 [n_actions]; n_actions <= 8.  Nullable outputs (rows of a rollout
+ * buffer): d_action i32[N], d_log_prob f32[N], d_probs f32[N][n_actions], d_obs f32[N][R] (the observation the action
+ * was chosen from), d_prev_reward f32[N] / d_prev_done u8[N] (REWARD / DONE of the tick before this call).
+ * With d_w1 == NULL only the d_prev_* record is made (the flush after a rollout's last tick). */
+typedef struct OkActorIO {
+    const float *d_w1, *d_b1, *d_w2, *d_b2;
+    int32_t      hidden, n_actions;
+    const float *d_action_table;
+    const float *d_uniform;
+    int32_t      greedy, reserved;
+    int32_t     *d_action;
+    float       *d_log_prob, *d_probs, *d_obs;
+    float       *d_prev_reward;
+    uint8_t     *d_prev_done;
+} OkActorIO;
+int ok_ppo_actor(OkEnv *env, const OkActorIO *io, uint64_t step, uint32_t seed, void *stream);
+/* ExperienceBuffer::calculateDiscountedRewards (RLRacers/PPO/ExperienceBuffer.hpp:45-62) for all agents: d_rewards
+ * f32[steps][N] -> d_out f32[steps][N], ret[t] = r[t] + gamma * ret[t + 1] in binary32 with the reference's operation
+ * order; d_done u8[steps][N] (nullable) restarts the sum where an episode ended.  No env needed beyond its device. */
+int ok_discounted_returns(OkEnv *env, const float *d_rewards, const uint8_t *d_done, float *d_out, int32_t steps, int64_t n,
+                          float gamma, void *stream);
+
 /* End-to-end host call (what the C++ shim's Environment::step and the reference-facing plugin
  * use): H2D of the two action arrays, one tick, D2H of obs / reward / done / crashed (each
  * nullable), then a stream synchronise.  Host buffers should be pinned (ok_host_alloc). */
 int ok_step_host(OkEnv *env, const float *h_act_throttle, const float *h_act_steer, float *h_obs, float *h_reward,
                  uint8_t *h_done, void *stream);
+/* The object-model tick in ONE upload, one launch and two downloads (what the C++ shim's Environment::step and
+ * CollisionChecker::checkCollision use; round 1 made ~24 synchronous buffer copies per tick).  The env's first thirteen
+ * buffers (OK_BUF_POS_X .. OK_BUF_SS_Y: pose, speed, acceleration, action, flags, standstill record) are adjacent in
+ * device memory; h_state is a byte-for-byte host image of that block (layout from ok_packed_layout).  The call copies
+ * h_state to the device, runs one tick (move != 0: ok_launch_step with the actions in the block; 0: ok_cast_rays), copies
+ * the block back into h_state and HIT_ABS + HIT_REL into h_hits, and synchronises `stream` once.  Pinned buffers
+ * (ok_host_alloc) make the three copies asynchronous. */
+typedef struct OkPackedLayout {
+    size_t state_bytes;      /* bytes of the state block */
+    size_t state_offset[13]; /* byte offset of OK_BUF_POS_X ... OK_BUF_SS_Y (enum order) inside it */
+    size_t hits_bytes;       /* bytes of the hits block */
+    size_t hit_abs_offset, hit_rel_offset;
+} OkPackedLayout;
+int ok_packed_layout(const OkEnv *env, OkPackedLayout *out);
+int ok_step_packed(OkEnv *env, void *h_state, void *h_hits, int32_t move, void *stream);
 int ok_host_alloc(void **h_ptr, size_t bytes); /* cudaMallocHost */
 int ok_host_free(void *h_ptr);
 

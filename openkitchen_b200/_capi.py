@@ -80,6 +80,22 @@ class OkLaunchStats(C.Structure):
     ]
 
 
+class OkPackedLayout(C.Structure):
+    _fields_ = [("state_bytes", C.c_size_t), ("state_offset", C.c_size_t * 13), ("hits_bytes", C.c_size_t),
+                ("hit_abs_offset", C.c_size_t), ("hit_rel_offset", C.c_size_t)]
+
+
+class OkActorIO(C.Structure):
+    _fields_ = [
+        ("d_w1", C.c_void_p), ("d_b1", C.c_void_p), ("d_w2", C.c_void_p), ("d_b2", C.c_void_p),
+        ("hidden", C.c_int32), ("n_actions", C.c_int32),
+        ("d_action_table", C.c_void_p), ("d_uniform", C.c_void_p),
+        ("greedy", C.c_int32), ("reserved", C.c_int32),
+        ("d_action", C.c_void_p), ("d_log_prob", C.c_void_p), ("d_probs", C.c_void_p), ("d_obs", C.c_void_p),
+        ("d_prev_reward", C.c_void_p), ("d_prev_done", C.c_void_p),
+    ]
+
+
 # every symbol include/openkitchen_b200.h declares: (restype, argtypes)
 _P = C.c_void_p
 SIGNATURES = {
@@ -106,6 +122,8 @@ SIGNATURES = {
     "ok_fill_random_actions": (C.c_int, [_P, C.c_uint64, C.c_uint32, _P]),
     "ok_genetic_policy": (C.c_int, [_P, _P, _P, C.c_int32, _P]),
     "ok_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "ok_packed_layout": (C.c_int, [_P, C.POINTER(OkPackedLayout)]),
+    "ok_step_packed": (C.c_int, [_P, _P, _P, C.c_int32, _P]),
     "ok_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),
     "ok_host_free": (C.c_int, [_P]),
     "ok_get_buffer": (C.c_int, [_P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
@@ -122,6 +140,8 @@ SIGNATURES = {
     "ok_beam_table_bytes": (C.c_int64, [_P, C.c_int32]),
     "ok_release_caches": (None, []),
     "ok_cmaes_controller": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, _P]),
+    "ok_ppo_actor": (C.c_int, [_P, C.POINTER(OkActorIO), C.c_uint64, C.c_uint32, _P]),
+    "ok_discounted_returns": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int64, C.c_float, _P]),
     "ok_track_query": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "ok_track_query_host": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "ok_pcie_probe": (C.c_int, [C.c_int32, C.c_size_t, C.c_int32, C.c_int32, C.POINTER(C.c_double)]),

@@ -142,6 +142,7 @@ struct OkEnv
     int32_t              rays{0};
     uint8_t             *d_slab{nullptr};
     void                *d_buf[OK_BUF_COUNT]{};
+    size_t               buf_off[OK_BUF_COUNT]{}; // offsets of the buffers inside the slab
     float               *d_ray_deg{nullptr};
     ok::Tile            *d_tiles{nullptr};
     int32_t              n_tiles{0};
@@ -152,6 +153,8 @@ struct OkEnv
     int32_t              batch_agents_beam{0};
     int32_t              grid_beam{0};
     int32_t              ctas_per_sm_beam{1};
+    bool                 beam_staged{true}; // which shape of the beam kernel this population runs (ok_kernels.cuh)
+    int32_t              beam_block{1024};
     uint16_t            *d_ray_order{nullptr};
     int32_t             *d_sched{nullptr};
     unsigned long long  *d_stats{nullptr}; // ok_debug_stats: allocated on first use
@@ -585,8 +588,8 @@ int arm_shared_memory_limit(OkEnv *e)
     OK_CUDA(cudaFuncGetAttributes(&fa, ok::step_kernel<kBlock, false>));
     OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<kBlock, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  e->smem_optin - static_cast<int>(fa.sharedSizeBytes)));
-    OK_CUDA(cudaFuncGetAttributes(&fa, ok::step_kernel<ok::kBeamBlock, true>));
-    OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<ok::kBeamBlock, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    OK_CUDA(cudaFuncGetAttributes(&fa, ok::step_kernel<ok::kBeamBlockStaged, true, true>));
+    OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<ok::kBeamBlockStaged, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  e->smem_optin - static_cast<int>(fa.sharedSizeBytes)));
     return OK_SUCCESS;
 }
@@ -603,7 +606,10 @@ int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
         p.tiles        = e->d_tiles_beam;
         p.n_tiles      = e->n_tiles_beam;
         p.batch_agents = e->batch_agents_beam;
-        ok::step_kernel<ok::kBeamBlock, true><<<e->grid_beam, ok::kBeamBlock, e->smem_beam, s>>>(p);
+        if (e->beam_staged)
+            ok::step_kernel<ok::kBeamBlockStaged, true, true><<<e->grid_beam, ok::kBeamBlockStaged, e->smem_beam, s>>>(p);
+        else
+            ok::step_kernel<ok::kBeamBlockUnstaged, true, false><<<e->grid_beam, ok::kBeamBlockUnstaged, e->smem_beam, s>>>(p);
     }
     else
         ok::step_kernel<kBlock, false><<<e->grid, kBlock, e->smem, s>>>(p);
@@ -887,7 +893,7 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
         const size_t avail = static_cast<size_t>(e->smem_optin) > blob + 4096 ? e->smem_optin - blob - 4096 : 0;
         const size_t per   = ok::batch_smem_bytes(1, rays);
         int64_t      a     = static_cast<int64_t>(avail / per);
-        if (avail < static_cast<size_t>(ok::kBeamStaticSmem) + 4096)
+        if (avail < static_cast<size_t>(ok::beam_static_smem(true)) + 4096)
             a = 0; // the beam kernel keeps per-thread scratch and its ray queue in static shared memory
         int          cap   = kMaxBatchAgents;
         if (const char *env = std::getenv("OK_BATCH_AGENTS"))
@@ -899,28 +905,34 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
             return fail(OK_ERR_CAPACITY, "shared memory cannot hold one agent's rays next to the largest track");
         e->batch_agents = static_cast<int32_t>(a);
         e->smem         = blob + ok::batch_smem_bytes(e->batch_agents, rays);
-        // beam kernel: one 64-byte record per agent; phases 1 / 4 run a thread per agent, so at most kBeamBlock agents
+        // beam kernel: one 64-byte record per agent; phases 1 / 4 run a thread per agent, so at most one block of agents.
+        // Which shape (ok_kernels.cuh): the staged one for throughput, the unstaged one when the population is too small
+        // to give every SM a worthwhile tile (OK_BEAM_KERNEL = staged | unstaged overrides).
+        e->beam_staged = n >= 2048; // measured (tools/bench_small.py): the unstaged shape is ahead only below ~2,000 agents
+        if (const char *env = std::getenv("OK_BEAM_KERNEL"))
+            e->beam_staged = std::strcmp(env, "unstaged") != 0 && (std::strcmp(env, "staged") == 0 || e->beam_staged);
+        e->beam_block = e->beam_staged ? ok::kBeamBlockStaged : ok::kBeamBlockUnstaged;
         int64_t ab;
         int     capb;
-        if (ok::kBeamStage)
+        if (e->beam_staged)
         { // one 1,024-thread CTA per SM behind the staged track: as many agents per tile as the shared memory behind the
           // largest track holds (the balanced tiling then sizes the tiles: about one per CTA and wave)
-            ab   = static_cast<int64_t>((avail - ok::kBeamStaticSmem) / sizeof(ok::AgentRec));
-            capb = ok::kBeamBlock;
+            ab   = static_cast<int64_t>((avail - ok::beam_static_smem(true)) / sizeof(ok::AgentRec));
+            capb = e->beam_block;
         }
         else
         { // several small CTAs per SM, nothing staged: small tiles, the SM's other CTAs hide a tile's serial phases
-            ab   = ok::kBeamBlock;
+            ab   = e->beam_block;
             capb = OK_BEAM_TILE;
         }
         ab = std::min<int64_t>(ab, 65535 / rays); // tile-local ray indices are 16 bits (the kernel's ray queue)
         if (const char *env = std::getenv("OK_BEAM_BATCH_AGENTS"))
             capb = std::max(1, std::atoi(env));
-        ab = std::min<int64_t>({ab, capb, ok::kBeamBlock});
-        if (!ok::kBeamStage)
+        ab = std::min<int64_t>({ab, capb, e->beam_block});
+        if (!e->beam_staged) // small populations: spread over all SMs rather than filling a few tiles
             ab = std::min<int64_t>(ab, std::max<int64_t>(1, (n + e->num_sms - 1) / std::max(1, e->num_sms)));
         e->batch_agents_beam = static_cast<int32_t>(std::max<int64_t>(1, ab));
-        e->smem_beam         = (ok::kBeamStage ? blob : 0) + ok::beam_smem_bytes(e->batch_agents_beam);
+        e->smem_beam         = (e->beam_staged ? blob : 0) + ok::beam_smem_bytes(e->batch_agents_beam);
         // The limit is an attribute of the FUNCTION on this device, not of the env: it is raised to the opt-in maximum
         // (minus the kernel's static shared memory), so that envs of different sizes can interleave their launches.
         if (int rc = arm_shared_memory_limit(e))
@@ -937,7 +949,10 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
     OK_CUDA(cudaMalloc(&e->d_slab, total));
     OK_CUDA(cudaMemset(e->d_slab, 0, total));
     for (int b = 0; b < OK_BUF_COUNT; ++b)
-        e->d_buf[b] = e->d_slab + offs[b];
+    {
+        e->d_buf[b]   = e->d_slab + offs[b];
+        e->buf_off[b] = offs[b];
+    }
     OK_CUDA(cudaMalloc(&e->d_ray_deg, sizeof(float) * rays));
     OK_CUDA(cudaMemcpy(e->d_ray_deg, h_ray_deg, sizeof(float) * rays, cudaMemcpyHostToDevice));
     e->h_track_id.assign(static_cast<size_t>(n), 0);
@@ -1045,9 +1060,9 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
     };
     {
         int per_sm = 1;
-        if (!ok::kBeamStage)
-            OK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ok::step_kernel<ok::kBeamBlock, true>, ok::kBeamBlock,
-                                                                  e->smem_beam));
+        if (!e->beam_staged)
+            OK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ok::step_kernel<ok::kBeamBlockUnstaged, true, false>,
+                                                                  ok::kBeamBlockUnstaged, e->smem_beam));
         e->ctas_per_sm_beam = std::max(1, per_sm);
     }
     if (int rc = build_tiles(e->batch_agents, e->num_sms, 4, &e->d_tiles, &e->n_tiles))
@@ -1055,7 +1070,7 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
     {
         // the unstaged beam kernel's small tiles cost about the same serial latency whatever their size (the thread-per-
         // agent phases, the second ray pass): shrinking them further only adds tiles
-        int tail_div = ok::kBeamStage ? -1 : 0; // -1: balanced tiling
+        int tail_div = e->beam_staged ? -1 : 0; // -1: balanced tiling
         if (const char *env = std::getenv("OK_BEAM_TAIL"))
             tail_div = std::atoi(env);
         const int rc = tail_div < 0 ? build_tiles_balanced(e->batch_agents_beam, e->num_sms * e->ctas_per_sm_beam, &e->d_tiles_beam, &e->n_tiles_beam)
@@ -1252,6 +1267,68 @@ int ok_cmaes_controller(OkEnv *e, const float *d_params, int32_t n_params, int32
     return OK_SUCCESS;
 }
 
+int ok_ppo_actor(OkEnv *e, const OkActorIO *io, uint64_t step, uint32_t seed, void *stream)
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    if (!io)
+        return fail(OK_ERR_INVALID_ARG, "io is NULL");
+    ok::ActorParams q{};
+    q.act = io->d_w1 != nullptr;
+    if (q.act)
+    {
+        if (!io->d_b1 || !io->d_w2 || !io->d_b2 || !io->d_action_table)
+            return fail(OK_ERR_INVALID_ARG, "weights, biases and the action table must all be given");
+        if (io->hidden < 1 || io->hidden > 1024 || io->n_actions < 1 || io->n_actions > ok::kActorMaxActs)
+            return fail(OK_ERR_INVALID_ARG, "1 <= hidden <= 1024 and 1 <= n_actions <= 8");
+    }
+    else if (!io->d_prev_reward && !io->d_prev_done)
+        return OK_SUCCESS;
+    q.w1 = io->d_w1, q.b1 = io->d_b1, q.w2 = io->d_w2, q.b2 = io->d_b2;
+    q.hidden = io->hidden, q.n_actions = io->n_actions;
+    q.table = io->d_action_table, q.uniform = io->d_uniform, q.greedy = io->greedy;
+    q.action_out = io->d_action, q.log_prob_out = io->d_log_prob, q.probs_out = io->d_probs, q.obs_out = io->d_obs;
+    q.prev_reward_out = io->d_prev_reward, q.prev_done_out = io->d_prev_done;
+    DeviceGuard    g(e->cfg.device);
+    ok::StepParams p = base_params(e);
+    p.step           = step;
+    p.seed           = seed;
+    const size_t smem = q.act ? sizeof(float) * (static_cast<size_t>(q.hidden) * e->rays + q.hidden +
+                                                 static_cast<size_t>(q.n_actions) * q.hidden + q.n_actions)
+                              : 0;
+    if (smem > static_cast<size_t>(e->smem_optin))
+        return fail(OK_ERR_CAPACITY, "the actor's weights do not fit in shared memory");
+    if (smem > 48 * 1024)
+        OK_CUDA(cudaFuncSetAttribute(ok::ppo_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const int     threads = 256;
+    const int64_t blocks  = (e->n_agents * ok::kActorLanes + threads - 1) / threads;
+    ok::ppo_actor_kernel<<<static_cast<unsigned>(blocks), threads, smem, static_cast<cudaStream_t>(stream)>>>(p, q, e->n_agents);
+    OK_CUDA(cudaGetLastError());
+    e->launches++;
+    return OK_SUCCESS;
+}
+
+int ok_discounted_returns(OkEnv *e, const float *d_rewards, const uint8_t *d_done, float *d_out, int32_t steps, int64_t n,
+                          float gamma, void *stream)
+{
+    if (!e)
+        return fail(OK_ERR_INVALID_ARG, "env is NULL");
+    if (!e->has_device)
+        return fail(OK_ERR_NO_DEVICE, "this env was created without a CUDA device (device = -1)");
+    if (!d_rewards || !d_out || steps < 0 || n < 0)
+        return fail(OK_ERR_INVALID_ARG, "bad arguments");
+    if (steps == 0 || n == 0)
+        return OK_SUCCESS;
+    DeviceGuard g(e->cfg.device);
+    const int   threads = 128;
+    ok::discounted_returns_kernel<<<static_cast<unsigned>((n + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        d_rewards, d_done, d_out, steps, n, gamma);
+    OK_CUDA(cudaGetLastError());
+    e->launches++;
+    return OK_SUCCESS;
+}
+
 int ok_track_query(OkEnv *e, const float *d_x, const float *d_y, const int32_t *d_track, int64_t n, int32_t *d_idx,
                    float *d_lane, float *d_bound, void *stream)
 {
@@ -1375,6 +1452,48 @@ int ok_step_host(OkEnv *e, const float *h_thr, const float *h_steer, float *h_ob
         OK_CUDA(cudaMemcpyAsync(h_reward, e->d_buf[OK_BUF_REWARD], 4 * n, cudaMemcpyDeviceToHost, s));
     if (h_done && !p.host_done)
         OK_CUDA(cudaMemcpyAsync(h_done, e->d_buf[OK_BUF_DONE], n, cudaMemcpyDeviceToHost, s));
+    OK_CUDA(cudaStreamSynchronize(s));
+    return OK_SUCCESS;
+}
+
+int ok_packed_layout(const OkEnv *e, OkPackedLayout *out)
+{
+    if (!e || !out)
+        return fail(OK_ERR_INVALID_ARG, "NULL argument");
+    if (e->n_agents <= 0)
+        return fail(OK_ERR_STATE, "ok_alloc_agents has not been called");
+    static_assert(OK_BUF_POS_X == 0 && OK_BUF_SS_Y == 12 && OK_BUF_HIT_REL == OK_BUF_HIT_ABS + 1, "packed blocks follow the enum order");
+    for (int b = 0; b <= OK_BUF_SS_Y; ++b)
+        out->state_offset[b] = e->buf_off[b] - e->buf_off[OK_BUF_POS_X];
+    out->state_bytes    = e->buf_off[OK_BUF_SS_Y] + buffer_bytes(e, OK_BUF_SS_Y) - e->buf_off[OK_BUF_POS_X];
+    out->hit_abs_offset = 0;
+    out->hit_rel_offset = e->buf_off[OK_BUF_HIT_REL] - e->buf_off[OK_BUF_HIT_ABS];
+    out->hits_bytes     = out->hit_rel_offset + buffer_bytes(e, OK_BUF_HIT_REL);
+    return OK_SUCCESS;
+}
+
+int ok_step_packed(OkEnv *e, void *h_state, void *h_hits, int32_t move, void *stream)
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    if (!h_state)
+        return fail(OK_ERR_INVALID_ARG, "h_state is NULL");
+    OkPackedLayout lay;
+    rc = ok_packed_layout(e, &lay);
+    if (rc)
+        return rc;
+    DeviceGuard  g(e->cfg.device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    OK_CUDA(cudaMemcpyAsync(e->d_buf[OK_BUF_POS_X], h_state, lay.state_bytes, cudaMemcpyHostToDevice, s));
+    ok::StepParams p = base_params(e);
+    p.do_move        = move ? 1 : 0;
+    rc               = launch_step(e, p, s);
+    if (rc)
+        return rc;
+    OK_CUDA(cudaMemcpyAsync(h_state, e->d_buf[OK_BUF_POS_X], lay.state_bytes, cudaMemcpyDeviceToHost, s));
+    if (h_hits)
+        OK_CUDA(cudaMemcpyAsync(h_hits, e->d_buf[OK_BUF_HIT_ABS], lay.hits_bytes, cudaMemcpyDeviceToHost, s));
     OK_CUDA(cudaStreamSynchronize(s));
     return OK_SUCCESS;
 }
@@ -1668,7 +1787,7 @@ int ok_launch_stats(const OkEnv *e, OkLaunchStats *out)
         return fail(OK_ERR_INVALID_ARG, "NULL argument");
     out->kernel_launches = e->launches;
     out->grid_blocks     = e->cfg.raycast_mode == OK_RAYCAST_BEAM ? e->grid_beam : e->grid;
-    out->block_threads   = e->cfg.raycast_mode == OK_RAYCAST_BEAM ? ok::kBeamBlock : kBlock;
+    out->block_threads   = e->cfg.raycast_mode == OK_RAYCAST_BEAM ? e->beam_block : kBlock;
     out->smem_bytes      = static_cast<int32_t>(e->cfg.raycast_mode == OK_RAYCAST_BEAM ? e->smem_beam : e->smem);
     out->tiles           = e->cfg.raycast_mode == OK_RAYCAST_BEAM ? e->n_tiles_beam : e->n_tiles;
     return OK_SUCCESS;

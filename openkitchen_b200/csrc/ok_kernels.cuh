@@ -1064,20 +1064,21 @@ __device__ __forceinline__ void agent_post(const StepParams &p, const TrackView 
 #define OK_UNITS 4
 #endif
 constexpr int kUnitsPerRefill = OK_UNITS; // units of work a lane does between two looks at the pool
-// The beam kernel (kBeam = true) runs SEVERAL SMALL CTAs per SM instead of one that owns the SM: its narrow phase reads
-// four listed segments per ray, not the whole track, so nothing is staged in shared memory -- segments, centre line and
-// the (rarely walked) grid come from the track's blob in global memory through L1 / L2 (a fan's rays touch the same few
-// 128-byte lines) -- and a CTA needs only its agents' records.  While one CTA sits at a phase barrier, fetches its next
-// tile or runs the thread-per-agent phases, the SM's other CTAs cast rays: the 1,024-thread kernel of round 1 spent
-// 24 % of its warp time at barriers and issued on 49 % of the cycles.  OK_BEAM_STAGE=1 keeps the staged variant.
+// The beam kernel comes in two shapes, chosen by the host from the population size (ok_capi.cu, OK_BEAM_KERNEL):
+//  * STAGED (kStaged = true): one 1,024-thread CTA per SM behind the track staged in shared memory with ONE TMA bulk
+//    copy; about one large tile per CTA and wave (balanced tiling).  The throughput shape: a tile pays ~15 us of serial
+//    latency (thread-per-agent phases, second ray pass) whatever its size, so tiles are made as large and as equal as the
+//    shared memory and the SM count allow;
+//  * UNSTAGED (kStaged = false): several 256-thread CTAs per SM, nothing staged -- the narrow phase reads four listed
+//    segments per ray, not the whole track, so segments, centre line and the (rarely walked) grid come from the track's
+//    blob in global memory through L1 / L2 (a fan's rays touch the same few 128-byte lines) and a CTA needs only its
+//    agents' records.  The latency shape for small populations: no 75-140 KB staging copy, 8-warp barriers, and while
+//    one CTA sits in a serial phase the SM's other CTAs cast rays.
 #ifndef OK_BEAM_BLOCK
 #define OK_BEAM_BLOCK 256
 #endif
 #ifndef OK_BEAM_MIN_CTAS
 #define OK_BEAM_MIN_CTAS (1024 / OK_BEAM_BLOCK) // 64 registers per thread fill the register file
-#endif
-#ifndef OK_BEAM_STAGE
-#define OK_BEAM_STAGE 1
 #endif
 #ifndef OK_BEAM_PREFETCH
 #define OK_BEAM_PREFETCH 0 // measured: an L2 prefetch of the queued rays' rest chunks costs 12 % (0.129 vs 0.115 ms)
@@ -1085,13 +1086,19 @@ constexpr int kUnitsPerRefill = OK_UNITS; // units of work a lane does between t
 #ifndef OK_BEAM_TILE
 #define OK_BEAM_TILE 64 // agents per tile of the unstaged beam kernel
 #endif
-constexpr int  kBeamBlock = OK_BEAM_STAGE ? 1024 : OK_BEAM_BLOCK;
-constexpr bool kBeamStage = OK_BEAM_STAGE != 0;
-// beam kernel: capacity of the CTA's queue of rays pass A leaves to pass B.  Tile-local ray indices are 16 bits, so a
-// beam tile holds at most 65,535 rays (the host caps the batch); a full queue only costs speed (see pass A).
-constexpr int kPendCap = kBeamStage ? 8192 : 2048;
-// static shared memory of step_kernel<., true> besides the staged track and the agent records (host: batch sizing)
-constexpr int kBeamStaticSmem = kBeamBlock * (16 + 8) + 2 * kPendCap + 4 * (kPendCap / 32) + 128;
+constexpr int kBeamBlockStaged   = 1024;
+constexpr int kBeamBlockUnstaged = OK_BEAM_BLOCK;
+// capacity of the CTA's queue of rays pass A leaves to pass B.  Tile-local ray indices are 16 bits, so a beam tile holds
+// at most 65,535 rays (the host caps the batch); a full queue only costs speed (see pass A).
+__host__ __device__ constexpr int beam_pend_cap(bool staged)
+{
+    return staged ? 8192 : 2048;
+}
+// static shared memory of the beam kernel besides the staged track and the agent records (host: batch sizing)
+__host__ __device__ constexpr int beam_static_smem(bool staged)
+{
+    return (staged ? kBeamBlockStaged : kBeamBlockUnstaged) * (16 + 8) + 2 * beam_pend_cap(staged) + 4 * (beam_pend_cap(staged) / 32) + 128;
+}
 
 __device__ __forceinline__ unsigned long long global_timer()
 {
@@ -1107,10 +1114,11 @@ __device__ __forceinline__ unsigned long long global_timer()
             p.trace[(static_cast<size_t>(blockIdx.x) * p.trace_tiles + n_done) * 6 + (slot)] = global_timer();         \
     } while (0)
 
-template <int kBlock, bool kBeam>
-__global__ void __launch_bounds__(kBlock, (kBeam && !kBeamStage) ? OK_BEAM_MIN_CTAS : 1) step_kernel(const StepParams p)
+template <int kBlock, bool kBeam, bool kStaged = true>
+__global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS : 1) step_kernel(const StepParams p)
 {
-    constexpr bool kStage = !kBeam || kBeamStage; // the track is staged in shared memory with one TMA bulk copy
+    constexpr bool kStage   = !kBeam || kStaged; // the track is staged in shared memory with one TMA bulk copy
+    constexpr int  kPendCap = beam_pend_cap(kStaged);
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint16_t                      s_order[kBeam ? 1 : 1024]; // pool order of the rays (p.ray_order)
     __shared__ __align__(8) uint64_t         bar;
@@ -1139,7 +1147,9 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kBeamStage) ? OK_BEAM_MIN_C
     int      n_done = 0; // tiles this CTA has finished (trace slot)
     uint32_t phase  = 0;
     const float inv_R = 1.0f / static_cast<float>(R);
-    // the first tile of a CTA is its own index: no trip to the global cursor before any work can start
+    // the first tile of a CTA is its own index: no trip to the global cursor before any work can start; and when the
+    // grid covers every tile (the balanced tiling's single wave, small populations) the cursor is never touched
+    const bool single_wave = p.n_tiles <= static_cast<int>(gridDim.x);
     if (tid == 0)
         s_tile = static_cast<int>(blockIdx.x);
 
@@ -1607,7 +1617,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kBeamStage) ? OK_BEAM_MIN_C
             // claim the next batch now: late enough to keep the schedule dynamic (see the loop top), early enough
             // for the atomic's latency to hide behind the other warps' last groups and phase 4
             if (tid == 0)
-                s_tile = static_cast<int>(gridDim.x) + atomicAdd(p.sched, 1); // every thread read the old value before phase 1
+                s_tile = single_wave ? p.n_tiles : static_cast<int>(gridDim.x) + atomicAdd(p.sched, 1); // every thread read the old value before phase 1
         }
         __syncthreads();
         OK_TRACE(4);
@@ -1617,7 +1627,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kBeamStage) ? OK_BEAM_MIN_C
             atomicAdd(p.stats + 1, static_cast<unsigned long long>(s_npend));
         }
         if (!kBeam && tid == 0)
-            s_tile = static_cast<int>(gridDim.x) + atomicAdd(p.sched, 1); // every thread read the old value long ago; visible after the loop-top barrier
+            s_tile = single_wave ? p.n_tiles : static_cast<int>(gridDim.x) + atomicAdd(p.sched, 1); // every thread read the old value long ago; visible after the loop-top barrier
 
         // =====================================================================================
         // phase 4 -- four lanes (small batches) or one thread per agent: crash flag, centre-line search, reward, done
@@ -1629,6 +1639,13 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kBeamStage) ? OK_BEAM_MIN_C
             if ((warp << 3) < count) // warp-uniform: this warp has at least one agent
                 agent_post<4>(p, tv, recs[valid ? al : 0], tl.begin + (valid ? al : 0), valid, lane);
         }
+        else if (count <= kBlock / 2)
+        { // the balanced tiling's large tiles (about 450 agents at the bench workload): two lanes per agent
+            const int  al    = tid >> 1;
+            const bool valid = al < count;
+            if ((warp << 4) < count)
+                agent_post<2>(p, tv, recs[valid ? al : 0], tl.begin + (valid ? al : 0), valid, lane);
+        }
         else if ((warp << 5) < count)
         {
             const bool valid = tid < count;
@@ -1639,7 +1656,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kBeamStage) ? OK_BEAM_MIN_C
     }
 
     // last CTA out re-arms the tile scheduler for the next launch on this stream
-    if (tid == 0)
+    if (tid == 0 && !single_wave)
     {
         __threadfence();
         if (atomicAdd(p.sched + 1, 1) == static_cast<int>(gridDim.x) - 1)
@@ -1989,6 +2006,178 @@ __global__ void __launch_bounds__(256) cmaes_controller_kernel(const StepParams 
     {
         p.act_thr[a]   = throttle;                                  // main_torch.cpp:68
         p.act_steer[a] = fmul(tanhf(o3 + bias3), steer_scale);      // main_torch.cpp:69
+    }
+}
+
+// PPOAgent::updateAction + Actor::forward for every agent (RLRacers/PPO/PPOAgent.hpp:79-102, Actor.hpp:9-26): ONE
+// kernel per tick does observation -> Linear(R, H) -> relu -> Linear(H, A) -> softmax -> clamp [1e-8, 1 - 1e-8] ->
+// sample an action (torch::multinomial's distribution: inverse CDF of the clamped probabilities on a uniform draw) ->
+// log-probability -> kActionMap lookup into the action buffers.  The weights are shared by all agents and staged in
+// shared memory; kActorLanes lanes share an agent (each takes every kActorLanes-th hidden unit), logits meet by shuffles.
+// It also records: the observation the action was chosen from, and the PREVIOUS tick's reward / done (so a rollout costs
+// two launches per tick: this kernel and the step kernel).
+struct ActorParams
+{
+    const float *w1, *b1, *w2, *b2; // torch Linear layouts: w1 [H][R], w2 [A][H]
+    int32_t      hidden, n_actions;
+    const float *table;   // [A][2] = (throttle, steering) per action, PPOAgent::kActionMap
+    const float *uniform; // nullable: explicit draws in [0, 1), one per agent (tests); else Philox (id_base + a, step)
+    int32_t      greedy;  // != 0: argmax instead of sampling
+    int32_t     *action_out; // nullable outputs, one row of a rollout buffer each
+    float       *log_prob_out, *probs_out, *obs_out;
+    float       *prev_reward_out; // nullable: reward / done of the tick BEFORE this call (the env's buffers as they are)
+    uint8_t     *prev_done_out;
+    int32_t      act; // 0: only record prev_reward / prev_done (the flush after the last tick)
+};
+constexpr int kActorLanes   = 8;
+constexpr int kActorMaxActs = 8;
+
+__global__ void __launch_bounds__(256) ppo_actor_kernel(const StepParams p, const ActorParams q, const int64_t n_agents)
+{
+    extern __shared__ float s_w[]; // w1 | b1 | w2 | b2
+    const int R = p.rays, H = q.hidden, A = q.n_actions;
+    float    *s_w1 = s_w, *s_b1 = s_w1 + H * R, *s_w2 = s_b1 + H, *s_b2 = s_w2 + A * H;
+    if (q.act)
+    {
+        for (int i = threadIdx.x; i < H * R; i += blockDim.x)
+            s_w1[i] = q.w1[i];
+        for (int i = threadIdx.x; i < H; i += blockDim.x)
+            s_b1[i] = q.b1[i];
+        for (int i = threadIdx.x; i < A * H; i += blockDim.x)
+            s_w2[i] = q.w2[i];
+        for (int i = threadIdx.x; i < A; i += blockDim.x)
+            s_b2[i] = q.b2[i];
+    }
+    __syncthreads();
+    const int     sub = threadIdx.x & (kActorLanes - 1);
+    const int64_t a   = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / kActorLanes;
+    const bool    has = a < n_agents;
+    const int64_t ac  = has ? a : 0;
+    if (has && sub == 0)
+    { // the tick before this call
+        if (q.prev_reward_out)
+            q.prev_reward_out[a] = p.reward[a];
+        if (q.prev_done_out)
+            q.prev_done_out[a] = p.done[a];
+    }
+    if (!q.act)
+        return;
+    const float *obs = p.obs + ac * R;
+    float        logit[kActorMaxActs];
+#pragma unroll
+    for (int k = 0; k < kActorMaxActs; ++k)
+        logit[k] = 0.0f;
+    for (int h = sub; h < H; h += kActorLanes)
+    {
+        float        acc = s_b1[h];
+        const float *row = s_w1 + h * R;
+        for (int r = 0; r < R; ++r)
+            acc = fmaf(row[r], __ldg(obs + r), acc);
+        acc = fmaxf(acc, 0.0f); // relu
+#pragma unroll
+        for (int k = 0; k < kActorMaxActs; ++k)
+            if (k < A)
+                logit[k] = fmaf(s_w2[k * H + h], acc, logit[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < kActorMaxActs; ++k)
+#pragma unroll
+        for (int o = kActorLanes >> 1; o > 0; o >>= 1)
+            logit[k] += __shfl_xor_sync(0xffffffffu, logit[k], o);
+    if (!has || sub != 0)
+        return;
+    // softmax (max-subtracted, as torch::softmax), clamp of PPOAgent.hpp:82-83 (the bounds narrow to float: 1e-8f, 1.0f)
+    float mx = -FLT_MAX;
+#pragma unroll
+    for (int k = 0; k < kActorMaxActs; ++k)
+        if (k < A)
+        {
+            logit[k] += s_b2[k];
+            mx = fmaxf(mx, logit[k]);
+        }
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kActorMaxActs; ++k)
+        if (k < A)
+        {
+            logit[k] = expf(logit[k] - mx);
+            sum += logit[k];
+        }
+    float total = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kActorMaxActs; ++k)
+        if (k < A)
+        {
+            logit[k] = fminf(fmaxf(__fdiv_rn(logit[k], sum), 1e-8f), 1.0f);
+            total += logit[k];
+            if (q.probs_out)
+                q.probs_out[a * A + k] = logit[k];
+        }
+    int act = 0;
+    if (q.greedy)
+    {
+#pragma unroll
+        for (int k = 1; k < kActorMaxActs; ++k)
+            if (k < A && logit[k] > logit[act])
+                act = k;
+    }
+    else
+    { // torch::multinomial(probs, 1): index k with probability probs[k] / sum(probs)
+        float u;
+        if (q.uniform)
+            u = q.uniform[a];
+        else
+        {
+            uint32_t       o[4];
+            const uint64_t id = p.id_base + static_cast<uint64_t>(a);
+            philox4x32_10(static_cast<uint32_t>(id), static_cast<uint32_t>(id >> 32), static_cast<uint32_t>(p.step),
+                          static_cast<uint32_t>(p.step >> 32), p.seed, 0x50504fu /* "PPO": a stream of its own */, o);
+            u = static_cast<float>(o[0] >> 8) * 0x1p-24f;
+        }
+        const float target = u * total;
+        float       cum    = 0.0f;
+        act                = A - 1;
+#pragma unroll
+        for (int k = 0; k < kActorMaxActs; ++k)
+            if (k < A)
+            {
+                cum += logit[k];
+                if (target < cum && act == A - 1 && k < A - 1)
+                    act = k;
+            }
+    }
+    float pa = logit[0];
+#pragma unroll
+    for (int k = 1; k < kActorMaxActs; ++k)
+        pa = (k == act) ? logit[k] : pa;
+    if (q.action_out)
+        q.action_out[a] = act;
+    if (q.log_prob_out)
+        q.log_prob_out[a] = logf(pa);
+    if (q.obs_out)
+        for (int r = 0; r < R; ++r)
+            q.obs_out[a * R + r] = obs[r];
+    p.act_thr[a]   = q.table[2 * act];     // PPOAgent.hpp:95-96
+    p.act_steer[a] = q.table[2 * act + 1];
+}
+
+// ExperienceBuffer::calculateDiscountedRewards (RLRacers/PPO/ExperienceBuffer.hpp:45-62) for every agent: one thread per
+// agent scans its column of rewards[T][N] backwards in binary32 with the reference's operation order
+// (cum = r + gamma * cum, no contraction); done[t][a] != 0 cuts the scan where an episode ended at tick t.
+__global__ void discounted_returns_kernel(const float *__restrict__ rewards, const uint8_t *__restrict__ done, float *__restrict__ out,
+                                          const int32_t steps, const int64_t n_agents, const float gamma)
+{
+    const int64_t a = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (a >= n_agents)
+        return;
+    float cum = 0.0f;
+    for (int32_t t = steps - 1; t >= 0; --t)
+    {
+        const int64_t i = static_cast<int64_t>(t) * n_agents + a;
+        if (done && done[i])
+            cum = 0.0f;
+        cum    = fadd(rewards[i], fmul(gamma, cum));
+        out[i] = cum;
     }
 }
 

@@ -217,6 +217,13 @@ class Env:
         """per-candidate Controller MLP -> ACT_* buffers (device pointer to f32[N, n_params])"""
         check(self.lib.ok_cmaes_controller(self.h, d_params, n_params, hidden, throttle, steer_scale, stream))
 
+    def ppo_actor(self, io, step: int = 0, seed: int = 0x0C17C4E2, stream=None):
+        """obs -> actor MLP -> softmax -> sample -> action buffers, one kernel (io: _capi.OkActorIO of device pointers)"""
+        check(self.lib.ok_ppo_actor(self.h, C.byref(io), step, seed, stream))
+
+    def discounted_returns(self, d_rewards, d_done, d_out, steps: int, n: int, gamma: float = 0.99, stream=None):
+        check(self.lib.ok_discounted_returns(self.h, d_rewards, d_done, d_out, steps, n, gamma, stream))
+
     def step_host(self, thr=None, steer=None, obs=None, reward=None, done=None, stream=None):
         """End-to-end tick with HOST buffers (H2D actions, kernel, D2H results, sync)."""
         check(self.lib.ok_step_host(self.h, _vp(thr), _vp(steer), _vp(obs), _vp(reward), _vp(done), stream))

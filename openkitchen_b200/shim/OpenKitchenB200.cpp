@@ -6,6 +6,8 @@
 #include <algorithm>
 #include <cctype>
 #include <limits>
+#include <map>
+#include <mutex>
 
 namespace
 {
@@ -74,12 +76,13 @@ void Agent::move()
 }
 
 // ---- RaceTrack ---------------------------------------------------------------------------------------
-RaceTrack::RaceTrack(const OkEnv *env, int track_id, const std::string &name) : track_name_{name}
+RaceTrack::RaceTrack(const OkEnv *env, int track_id, const std::string &track_csv_path)
+    : track_name_{upper_stem(track_csv_path)}, source_path_{track_csv_path}
 {
     fill(env, track_id);
 }
 
-RaceTrack::RaceTrack(const std::string &track_csv_path) : track_name_{upper_stem(track_csv_path)}
+RaceTrack::RaceTrack(const std::string &track_csv_path) : track_name_{upper_stem(track_csv_path)}, source_path_{track_csv_path}
 {
     OkConfig cfg;
     ok_config_default(&cfg);
@@ -149,6 +152,197 @@ float RaceTrack::getDistanceToLaneCenter(const Vec2d &q) const
     return std::sqrt(d) / (track_data_points_.w_tr_left_m[i] + track_data_points_.w_tr_right_m[i]);
 }
 
+// ---- the engine: one OkEnv + the packed tick --------------------------------------------------------------
+namespace okshim
+{
+struct Engine
+{
+    OkEnv               *ok{nullptr};
+    std::vector<Agent *> agents;
+    std::vector<DisplacementStats> *stats{nullptr}; // the Environment's standstill records (nullptr: stand-alone checker)
+    std::vector<DisplacementStats>  own_stats;
+    OkPackedLayout       lay{};
+    uint8_t             *h_state{nullptr}, *h_hits{nullptr}; // pinned images of the device blocks
+    std::vector<Ray_>    rays;
+    size_t               n_rays{0};
+
+    Engine(const std::string &track_csv_path, const std::vector<Agent *> &agents_in) : agents(agents_in)
+    {
+        if (agents.empty())
+            throw std::invalid_argument("at least one agent is needed");
+        OkConfig cfg;
+        ok_config_default(&cfg);
+        cfg.movement_mode = agents[0]->movement_mode_ == Agent::MovementMode::ACCELERATION ? OK_MOVE_ACCELERATION : OK_MOVE_VELOCITY;
+        cfg.sensor_offset = agents[0]->sensor_offset_;
+        cfg.sensor_range  = agents[0]->sensor_range_;
+        must(ok_create(&cfg, &ok), "ok_create");
+        try
+        {
+            int32_t track = -1;
+            must(ok_load_track_csv(ok, track_csv_path.c_str(), &track), "ok_load_track_csv");
+            // the reference sizes everything from agents[0]'s fan (CollisionChecker.cu:82) and silently assumes the
+            // others match; here a mismatch is an error
+            const auto &fan = agents[0]->sensor_ray_angles_;
+            for (const Agent *a : agents)
+                if (a->sensor_ray_angles_ != fan)
+                    throw std::invalid_argument("all agents of one Environment must share one sensor_ray_angles_ fan");
+            n_rays = fan.size();
+            must(ok_alloc_agents(ok, static_cast<int64_t>(agents.size()), static_cast<int32_t>(fan.size()), fan.data(), nullptr),
+                 "ok_alloc_agents");
+            must(ok_packed_layout(ok, &lay), "ok_packed_layout");
+            must(ok_host_alloc(reinterpret_cast<void **>(&h_state), lay.state_bytes), "ok_host_alloc");
+            must(ok_host_alloc(reinterpret_cast<void **>(&h_hits), lay.hits_bytes), "ok_host_alloc");
+            std::fill(h_state, h_state + lay.state_bytes, 0);
+        }
+        catch (...)
+        {
+            release();
+            throw;
+        }
+        rays.assign(agents.size() * n_rays, Ray_{});
+        own_stats.resize(agents.size());
+        stats = &own_stats;
+    }
+    Engine(const Engine &)            = delete;
+    Engine &operator=(const Engine &) = delete;
+    ~Engine() { release(); }
+
+    void release()
+    {
+        if (h_state)
+            ok_host_free(h_state);
+        if (h_hits)
+            ok_host_free(h_hits);
+        if (ok)
+            ok_destroy(ok);
+        h_state = h_hits = nullptr;
+        ok               = nullptr;
+    }
+
+    template <typename T> T *col(int buffer) { return reinterpret_cast<T *>(h_state + lay.state_offset[buffer]); }
+
+    // Environment::step (Environment.cpp:125-149 minus the render) or CollisionChecker::checkCollision: the Agent objects'
+    // fields go up in one block, one kernel runs, pose / flags / standstill record and the hits come back in two blocks
+    void run(bool move)
+    {
+        // Agent::setMovementMode may be called at any time (Agent.h:46-49); the reference reads it per move()
+        const int mode = agents[0]->movement_mode_ == Agent::MovementMode::ACCELERATION ? OK_MOVE_ACCELERATION : OK_MOVE_VELOCITY;
+        for (const Agent *a : agents)
+        {
+            if (a->movement_mode_ == Agent::MovementMode::MANUAL)
+                throw std::logic_error("MovementMode::MANUAL (keyboard) is not supported");
+            if ((a->movement_mode_ == Agent::MovementMode::ACCELERATION ? OK_MOVE_ACCELERATION : OK_MOVE_VELOCITY) != mode)
+                throw std::logic_error("all agents of one Environment must use the same MovementMode");
+        }
+        OkConfig cfg;
+        must(ok_get_config(ok, &cfg), "ok_get_config");
+        if (cfg.movement_mode != mode)
+        {
+            cfg.movement_mode = mode;
+            must(ok_update_config(ok, &cfg), "ok_update_config");
+        }
+        const size_t n = agents.size();
+        float *x = col<float>(OK_BUF_POS_X), *y = col<float>(OK_BUF_POS_Y), *rot = col<float>(OK_BUF_ROT);
+        float *speed = col<float>(OK_BUF_SPEED), *accel = col<float>(OK_BUF_ACCEL);
+        float *thr = col<float>(OK_BUF_ACT_THROTTLE), *steer = col<float>(OK_BUF_ACT_STEER);
+        uint8_t  *crashed = col<uint8_t>(OK_BUF_CRASHED), *timed_out = col<uint8_t>(OK_BUF_TIMED_OUT), *done = col<uint8_t>(OK_BUF_DONE);
+        uint32_t *ctr = col<uint32_t>(OK_BUF_SS_CTR);
+        float    *ssx = col<float>(OK_BUF_SS_X), *ssy = col<float>(OK_BUF_SS_Y);
+        for (size_t i = 0; i < n; ++i)
+        {
+            const Agent *a = agents[i];
+            x[i] = a->pos_.x, y[i] = a->pos_.y, rot[i] = a->rot_, speed[i] = a->speed_, accel[i] = a->acceleration_;
+            thr[i] = a->current_action_.throttle_delta, steer[i] = a->current_action_.steering_delta;
+            crashed[i] = a->crashed_, timed_out[i] = a->timed_out_, done[i] = a->crashed_;
+            const DisplacementStats &ds = (*stats)[i];
+            ctr[i] = ds.displacement_ctr, ssx[i] = ds.init_pos.x, ssy[i] = ds.init_pos.y;
+        }
+        must(ok_step_packed(ok, h_state, h_hits, move ? 1 : 0, nullptr), "ok_step_packed");
+        const float *hit_abs = reinterpret_cast<const float *>(h_hits + lay.hit_abs_offset);
+        const float *hit_rel = reinterpret_cast<const float *>(h_hits + lay.hit_rel_offset);
+        const size_t R = n_rays;
+        for (size_t i = 0; i < n; ++i)
+        {
+            Agent *a = agents[i];
+            if (move)
+            {
+                a->pos_ = Vec2d{x[i], y[i]};
+                a->rot_ = rot[i], a->speed_ = speed[i], a->acceleration_ = accel[i];
+                DisplacementStats &ds     = (*stats)[i];
+                ds.displacement_ctr       = ctr[i];
+                ds.init_pos               = Vec2d{ssx[i], ssy[i]};
+                ds.displacement_timed_out = timed_out[i] != 0;
+            }
+            a->crashed_   = crashed[i] != 0;
+            a->timed_out_ = timed_out[i] != 0;
+            a->sensor_hits_.resize(R);
+            for (size_t r = 0; r < R; ++r)
+            {
+                const size_t k     = i * R + r;
+                a->sensor_hits_[r] = Vec2d{hit_rel[2 * k], hit_rel[2 * k + 1]};
+                Ray_ &ray          = rays[k];
+                ray.x              = a->pos_.x + a->sensor_offset_ * std::cos(kDeg2Rad * a->rot_);
+                ray.y              = a->pos_.y + a->sensor_offset_ * std::sin(kDeg2Rad * a->rot_);
+                ray.angle          = kDeg2Rad * (a->rot_ + a->sensor_ray_angles_[r]);
+                ray.hit_x          = hit_abs[2 * k];
+                ray.hit_y          = hit_abs[2 * k + 1];
+                ray.active         = !a->crashed_;
+            }
+        }
+    }
+};
+} // namespace okshim
+
+// ---- TrackSegments -----------------------------------------------------------------------------------
+namespace
+{
+std::mutex                                  g_seg_mu;
+std::map<const void *, const TrackSegments *> g_segments; // handle -> owner
+} // namespace
+
+TrackSegments::TrackSegments(const RaceTrack &race_track) : host_(race_track.segments_), source_path_(race_track.source_path_)
+{
+    GOX_ASSERT(!host_.empty()); // TrackSegments.cu:72
+    std::lock_guard<std::mutex> lock(g_seg_mu);
+    g_segments[&handle_] = this;
+}
+
+TrackSegments::~TrackSegments()
+{
+    std::lock_guard<std::mutex> lock(g_seg_mu);
+    g_segments.erase(&handle_);
+}
+
+// ---- CollisionChecker --------------------------------------------------------------------------------
+CollisionChecker::CollisionChecker(const Segment2d *d_segments, size_t num_segments, const std::vector<Agent *> &agents)
+{
+    std::string path;
+    {
+        std::lock_guard<std::mutex> lock(g_seg_mu);
+        const auto                  it = g_segments.find(d_segments);
+        if (it == g_segments.end() || it->second->getNumSegments() != num_segments)
+            throw std::invalid_argument("CollisionChecker: d_segments must be what a live TrackSegments::getDeviceSegments() returned");
+        path = it->second->sourcePath();
+    }
+    engine_ = std::make_shared<okshim::Engine>(path, agents);
+}
+
+CollisionChecker::CollisionChecker(std::shared_ptr<okshim::Engine> engine) : engine_(std::move(engine)) {}
+CollisionChecker::~CollisionChecker() = default;
+
+void CollisionChecker::checkCollision()
+{
+    engine_->run(false);
+}
+const Ray_ *CollisionChecker::getHostRays() const
+{
+    return engine_->rays.data();
+}
+size_t CollisionChecker::getNumRays() const
+{
+    return engine_->rays.size();
+}
+
 // ---- Environment -------------------------------------------------------------------------------------
 Environment::Environment(const std::string &race_track_path, const std::vector<Agent *> &agents, const bool draw_rays,
                          const bool hidden_window)
@@ -156,59 +350,23 @@ Environment::Environment(const std::string &race_track_path, const std::vector<A
 {
     if (agents.empty())
         throw std::invalid_argument("Environment needs at least one agent");
-    OkConfig cfg;
-    ok_config_default(&cfg);
-    cfg.movement_mode = agents[0]->movement_mode_ == Agent::MovementMode::ACCELERATION ? OK_MOVE_ACCELERATION : OK_MOVE_VELOCITY;
-    cfg.sensor_offset = agents[0]->sensor_offset_;
-    cfg.sensor_range  = agents[0]->sensor_range_;
-    must(ok_create(&cfg, &ok_), "ok_create");
-    int32_t track = -1;
-    if (ok_load_track_csv(ok_, race_track_path.c_str(), &track) < 0)
-    {
-        ok_destroy(ok_);
-        ok_ = nullptr;
-        raise("ok_load_track_csv");
-    }
-    race_track_     = std::make_unique<RaceTrack>(ok_, track, upper_stem(race_track_path));
+    engine_         = std::make_shared<okshim::Engine>(race_track_path, agents);
+    race_track_     = std::make_unique<RaceTrack>(engine_->ok, 0, race_track_path);
     track_segments_ = std::make_unique<TrackSegments>(*race_track_);
     visualizer_     = std::make_unique<env::Visualizer>(hidden_window);
     screen_grabber_ = std::make_unique<ScreenGrabber>(kScreenWidth, kScreenHeight);
     agents_         = agents;
     displacement_stats_.resize(agents.size());
-
-    // the reference sizes everything from agents[0]'s fan (CollisionChecker.cu:82) and silently assumes the
-    // others match; here a mismatch is an error
-    const auto &fan = agents[0]->sensor_ray_angles_;
-    for (const Agent *a : agents)
-        if (a->sensor_ray_angles_ != fan)
-        {
-            ok_destroy(ok_);
-            ok_ = nullptr;
-            throw std::invalid_argument("all agents of one Environment must share one sensor_ray_angles_ fan");
-        }
-    if (ok_alloc_agents(ok_, static_cast<int64_t>(agents.size()), static_cast<int32_t>(fan.size()), fan.data(), nullptr) < 0)
-    {
-        ok_destroy(ok_);
-        ok_ = nullptr;
-        raise("ok_alloc_agents");
-    }
-    collision_checker_ = std::make_unique<CollisionChecker>(this);
-    collision_checker_->rays_.assign(agents.size() * fan.size(), Ray_{});
-    for (auto &v : f_)
-        v.resize(agents.size());
-    for (auto &v : b_)
-        v.resize(agents.size());
-    ctr_.resize(agents.size());
-    hits_.resize(agents.size() * fan.size() * 2);
-    hit_abs_.resize(agents.size() * fan.size() * 2);
+    engine_->stats = &displacement_stats_;
+    collision_checker_.reset(new CollisionChecker(engine_));
 }
 
-Environment::~Environment()
+Environment::~Environment() = default;
+
+OkEnv *Environment::handle() const
 {
-    if (ok_)
-        ok_destroy(ok_);
+    return engine_->ok;
 }
-
 int32_t Environment::pickRandomResetTrackIdx() const
 { // Environment.cpp:74-77 (GetRandomValue(0, n-1) -> a seedable generator)
     std::uniform_int_distribution<int32_t> d(0, static_cast<int32_t>(race_track_->track_data_points_.x_m.size()) - 1);
@@ -239,106 +397,7 @@ void Environment::resetAgent(Agent *agent, const bool pick_random_point, const b
     agent->reset(start, race_track_->headings_[idx] + heading_offset);
 }
 
-void Environment::upload()
-{
-    const size_t n = agents_.size();
-    for (size_t i = 0; i < n; ++i)
-    {
-        const Agent *a = agents_[i];
-        f_[0][i] = a->pos_.x, f_[1][i] = a->pos_.y, f_[2][i] = a->rot_, f_[3][i] = a->speed_, f_[4][i] = a->acceleration_;
-        f_[5][i] = a->current_action_.throttle_delta, f_[6][i] = a->current_action_.steering_delta;
-        b_[0][i] = a->crashed_, b_[1][i] = a->timed_out_;
-        ctr_[i]  = displacement_stats_[i].displacement_ctr;
-        f_[7][i] = displacement_stats_[i].init_pos.x;
-    }
-    static const int kF[7] = {OK_BUF_POS_X, OK_BUF_POS_Y, OK_BUF_ROT, OK_BUF_SPEED, OK_BUF_ACCEL, OK_BUF_ACT_THROTTLE, OK_BUF_ACT_STEER};
-    for (int k = 0; k < 7; ++k)
-        must(ok_write_buffer(ok_, kF[k], f_[k].data(), 4 * n, nullptr), "ok_write_buffer");
-    must(ok_write_buffer(ok_, OK_BUF_CRASHED, b_[0].data(), n, nullptr), "ok_write_buffer");
-    must(ok_write_buffer(ok_, OK_BUF_TIMED_OUT, b_[1].data(), n, nullptr), "ok_write_buffer");
-    must(ok_write_buffer(ok_, OK_BUF_SS_CTR, ctr_.data(), 4 * n, nullptr), "ok_write_buffer");
-    must(ok_write_buffer(ok_, OK_BUF_SS_X, f_[7].data(), 4 * n, nullptr), "ok_write_buffer");
-    for (size_t i = 0; i < n; ++i)
-        f_[7][i] = displacement_stats_[i].init_pos.y;
-    must(ok_write_buffer(ok_, OK_BUF_SS_Y, f_[7].data(), 4 * n, nullptr), "ok_write_buffer");
-}
-
-void Environment::download(bool moved)
-{
-    const size_t n = agents_.size(), R = agents_[0]->sensor_ray_angles_.size();
-    static const int kF[5] = {OK_BUF_POS_X, OK_BUF_POS_Y, OK_BUF_ROT, OK_BUF_SPEED, OK_BUF_ACCEL};
-    if (moved)
-        for (int k = 0; k < 5; ++k)
-            must(ok_read_buffer(ok_, kF[k], f_[k].data(), 4 * n, nullptr), "ok_read_buffer");
-    must(ok_read_buffer(ok_, OK_BUF_CRASHED, b_[0].data(), n, nullptr), "ok_read_buffer");
-    must(ok_read_buffer(ok_, OK_BUF_TIMED_OUT, b_[1].data(), n, nullptr), "ok_read_buffer");
-    must(ok_read_buffer(ok_, OK_BUF_HIT_REL, hits_.data(), 4 * hits_.size(), nullptr), "ok_read_buffer");
-    must(ok_read_buffer(ok_, OK_BUF_HIT_ABS, hit_abs_.data(), 4 * hit_abs_.size(), nullptr), "ok_read_buffer");
-    if (moved)
-    {
-        must(ok_read_buffer(ok_, OK_BUF_SS_CTR, ctr_.data(), 4 * n, nullptr), "ok_read_buffer");
-        must(ok_read_buffer(ok_, OK_BUF_SS_X, f_[5].data(), 4 * n, nullptr), "ok_read_buffer");
-        must(ok_read_buffer(ok_, OK_BUF_SS_Y, f_[6].data(), 4 * n, nullptr), "ok_read_buffer");
-    }
-    for (size_t i = 0; i < n; ++i)
-    {
-        Agent *a = agents_[i];
-        if (moved)
-        {
-            a->pos_ = Vec2d{f_[0][i], f_[1][i]};
-            a->rot_ = f_[2][i], a->speed_ = f_[3][i], a->acceleration_ = f_[4][i];
-            DisplacementStats &ds = displacement_stats_[i];
-            ds.displacement_ctr   = ctr_[i];
-            ds.init_pos           = Vec2d{f_[5][i], f_[6][i]};
-            ds.displacement_timed_out = b_[1][i] != 0;
-        }
-        a->crashed_   = b_[0][i] != 0;
-        a->timed_out_ = b_[1][i] != 0;
-        a->sensor_hits_.resize(R);
-        for (size_t r = 0; r < R; ++r)
-        {
-            const size_t k      = i * R + r;
-            a->sensor_hits_[r]  = Vec2d{hits_[2 * k], hits_[2 * k + 1]};
-            Ray_ &ray           = collision_checker_->rays_[k];
-            ray.x               = a->pos_.x + a->sensor_offset_ * std::cos(kDeg2Rad * a->rot_);
-            ray.y               = a->pos_.y + a->sensor_offset_ * std::sin(kDeg2Rad * a->rot_);
-            ray.angle           = kDeg2Rad * (a->rot_ + a->sensor_ray_angles_[r]);
-            ray.hit_x           = hit_abs_[2 * k];
-            ray.hit_y           = hit_abs_[2 * k + 1];
-            ray.active          = !a->crashed_;
-        }
-    }
-}
-
-void Environment::run(bool move)
-{
-    // Agent::setMovementMode may be called at any time (Agent.h:46-49); the reference reads it per move()
-    OkConfig cfg;
-    must(ok_get_config(ok_, &cfg), "ok_get_config");
-    const int mode = agents_[0]->movement_mode_ == Agent::MovementMode::ACCELERATION ? OK_MOVE_ACCELERATION : OK_MOVE_VELOCITY;
-    for (const Agent *a : agents_)
-    {
-        if (a->movement_mode_ == Agent::MovementMode::MANUAL)
-            throw std::logic_error("MovementMode::MANUAL (keyboard) is not supported");
-        if ((a->movement_mode_ == Agent::MovementMode::ACCELERATION ? OK_MOVE_ACCELERATION : OK_MOVE_VELOCITY) != mode)
-            throw std::logic_error("all agents of one Environment must use the same MovementMode");
-    }
-    if (cfg.movement_mode != mode)
-    {
-        cfg.movement_mode = mode;
-        must(ok_update_config(ok_, &cfg), "ok_update_config");
-    }
-    upload();
-    must(move ? ok_launch_step(ok_, nullptr, nullptr, nullptr) : ok_cast_rays(ok_, nullptr), "launch");
-    download(move);
-}
-
 void Environment::step()
 { // Environment.cpp:125-149 minus the render
-    run(true);
-}
-
-void CollisionChecker::checkCollision()
-{
-    env_->run(false);
+    engine_->run(true);
 }

@@ -24,6 +24,10 @@
 #include <vector>
 
 struct OkEnv;
+namespace okshim
+{
+struct Engine; // one OkEnv + the pinned staging blocks of the packed tick (OpenKitchenB200.cpp)
+}
 
 // ---- Typedefs.h ------------------------------------------------------------------------------------
 constexpr int   kScreenWidth  = 1600;
@@ -181,7 +185,7 @@ class RaceTrack
 
     RaceTrack() = delete;
     explicit RaceTrack(const std::string &track_csv_path); // stand-alone: builds through a host-only OkEnv
-    RaceTrack(const OkEnv *env, int track_id, const std::string &name);
+    RaceTrack(const OkEnv *env, int track_id, const std::string &track_csv_path);
 
     size_t findNearestTrackIndexBruteForce(const Vec2d &query_pt) const;
     float  getNearestDistanceToTrackBoundary(const Vec2d &query_pt) const;
@@ -194,39 +198,52 @@ class RaceTrack
     std::vector<Vec2d> start_line_, finish_line_;
     std::vector<float> headings_{};
     std::vector<Segment2d> segments_; // TrackSegments order (not in the reference's RaceTrack; used by the shim)
+    std::string            source_path_; // the CSV this track was built from (not in the reference; TrackSegments carries it on)
 
   private:
     void fill(const OkEnv *env, int track_id);
 };
 
 // ---- TrackSegments.h -------------------------------------------------------------------------------
+// Same interface as the reference (TrackSegments.h:11-26).  The device copy of the segments lives inside an OkEnv's track
+// arena, so getDeviceSegments() hands out an opaque, non-null HANDLE with the reference's type: like the reference's device
+// pointer it must not be dereferenced on the host; its one consumer, CollisionChecker's constructor, resolves it.
 class TrackSegments
 {
   public:
-    explicit TrackSegments(const RaceTrack &race_track) : host_(race_track.segments_) {}
-    // the device copy lives inside the OkEnv's track arena; there is no separate device array to hand out
-    const Segment2d *getDeviceSegments() const { return nullptr; }
-    const Segment2d *getHostSegments() const { return host_.data(); }
+    explicit TrackSegments(const RaceTrack &race_track);
+    ~TrackSegments();
+    TrackSegments(const TrackSegments &)            = delete;
+    TrackSegments &operator=(const TrackSegments &) = delete;
+
+    const Segment2d *getDeviceSegments() const { return reinterpret_cast<const Segment2d *>(&handle_); }
     size_t           getNumSegments() const { return host_.size(); }
+    const Segment2d *getHostSegments() const { return host_.data(); } // not in the reference
+    const std::string &sourcePath() const { return source_path_; }   // not in the reference
 
   private:
     std::vector<Segment2d> host_;
+    std::string            source_path_;
+    char                   handle_{0}; // its address is the handle
 };
 
 // ---- CollisionChecker.h ----------------------------------------------------------------------------
+// Same interface as the reference (CollisionChecker.h:8-24): built from the segment handle and the agents, it casts
+// every agent's rays on checkCollision() (CollisionChecker.cu:96-100) -- lidar + crash flags, no movement.
 class Environment;
 class CollisionChecker
 {
   public:
-    explicit CollisionChecker(Environment *env) : env_(env) {}
-    void        checkCollision(); // lidar + crash flags on the current poses, no movement (ok_cast_rays)
-    const Ray_ *getHostRays() const { return rays_.data(); }
-    size_t      getNumRays() const { return rays_.size(); }
+    CollisionChecker(const Segment2d *d_segments, size_t num_segments, const std::vector<Agent *> &agents);
+    ~CollisionChecker();
+    void        checkCollision();
+    const Ray_ *getHostRays() const;
+    size_t      getNumRays() const;
 
   private:
     friend class Environment;
-    Environment      *env_;
-    std::vector<Ray_> rays_;
+    explicit CollisionChecker(std::shared_ptr<okshim::Engine> engine); // the Environment's own checker shares its engine
+    std::shared_ptr<okshim::Engine> engine_;
 };
 
 // ---- Visualizer.h / ScreenGrabber.h: inert -----------------------------------------------------------
@@ -299,7 +316,7 @@ class Environment
 
     // not in the reference: its resets draw from raylib's never-seeded global RNG (Environment.cpp:76,92,111)
     void   seed(uint64_t s) { rng_.seed(s); }
-    OkEnv *handle() const { return ok_; }
+    OkEnv *handle() const;
 
   public:
     std::unique_ptr<RaceTrack>        race_track_;
@@ -312,16 +329,7 @@ class Environment
     bool                              draw_rays_{false};
 
   private:
-    friend class CollisionChecker;
-    void upload();               // Agent objects -> device buffers
-    void download(bool moved);   // device buffers -> Agent objects (+ host rays)
-    void run(bool move);
-
-    OkEnv               *ok_{nullptr};
-    mutable std::mt19937 rng_{0x0C17C4E2u};
-    size_t               heading_ctr_{0};
-    std::vector<float>   f_[8];
-    std::vector<uint8_t> b_[2];
-    std::vector<uint32_t> ctr_;
-    std::vector<float>   hits_, hit_abs_;
+    std::shared_ptr<okshim::Engine> engine_; // OkEnv + packed staging: ONE upload, one launch, two downloads per step
+    mutable std::mt19937            rng_{0x0C17C4E2u};
+    size_t                          heading_ctr_{0};
 };

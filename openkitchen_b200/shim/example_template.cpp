@@ -83,6 +83,23 @@ int main(int argc, char **argv)
                 std::printf("S %d %d %.9g %.9g %.9g %d %d %.9g %.9g\n", s, a->id_, a->pos_.x, a->pos_.y, a->rot_,
                             a->crashed_ ? 1 : 0, a->timed_out_ ? 1 : 0, a->sensor_hits_[2].x, a->sensor_hits_[2].y);
     }
+    // the lidar alone, the way Environment.cpp:49-54 wires it: RaceTrack -> TrackSegments -> CollisionChecker(device
+    // segments, count, agents) -> checkCollision() on the agents' current poses (reference signatures throughout)
+    if (trace)
+    {
+        RaceTrack        track(argv[1]);
+        TrackSegments    segments(track);
+        CollisionChecker checker(segments.getDeviceSegments(), segments.getNumSegments(), createBaseAgentPtrs(agents));
+        for (auto &a : agents)
+            a->crashed_ = false; // cast for everyone
+        checker.checkCollision();
+        const Ray_ *rays = checker.getHostRays();
+        for (size_t k = 0; k < checker.getNumRays(); ++k)
+            std::printf("R %zu %.9g %.9g %.9g %.9g %.9g %d\n", k, rays[k].x, rays[k].y, rays[k].angle, rays[k].hit_x, rays[k].hit_y,
+                        rays[k].active ? 1 : 0);
+        for (auto &a : agents)
+            std::printf("C %d %d %.9g %.9g\n", a->id_, a->crashed_ ? 1 : 0, a->sensor_hits_[0].x, a->sensor_hits_[0].y);
+    }
     int         episodes = 0;
     const auto &rt       = *env.race_track_;
     for (auto &a : agents)

@@ -55,6 +55,22 @@ def test_template_app_trace_replays_through_oracle(tmp_path):
             assert (ora.buffer("crashed")[a], ora.buffer("timed_out")[a]) == (crashed, tout), (s, a)
             assert tuple(ora.buffer("hit_rel")[a, 2]) == (hx, hy), (s, a)
     assert resets >= n  # at least the initial resets; crashes add more
+    # the stand-alone lidar with the reference's signatures (RaceTrack -> TrackSegments -> CollisionChecker(d_segments, n,
+    # agents) -> checkCollision(), CollisionChecker.h:8-24): same hits and crash flags as the oracle's cast on those poses
+    ora.buffer("crashed")[:] = 0
+    ora.cast_rays()
+    rays = [ln.split() for ln in out.stdout.splitlines() if ln.startswith("R ")]
+    flags = [ln.split() for ln in out.stdout.splitlines() if ln.startswith("C ")]
+    assert len(rays) == n * 5 and len(flags) == n
+    hit_abs = ora.buffer("hit_abs").reshape(-1, 2)
+    for f in rays:
+        k = int(f[1])
+        assert (np.float32(f[5]), np.float32(f[6])) == tuple(hit_abs[k]), k
+        assert (np.float32(f[2]), np.float32(f[3])) == (ora.buffer("pos_x")[k // 5], ora.buffer("pos_y")[k // 5])
+    for f in flags:
+        a = int(f[1])
+        assert int(f[2]) == int(ora.buffer("crashed")[a])
+        assert (np.float32(f[3]), np.float32(f[4])) == tuple(ora.buffer("hit_rel")[a, 0])
 
 
 def test_pybind_module_is_a_drop_in(tmp_path):

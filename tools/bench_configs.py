@@ -172,6 +172,32 @@ def c4():
                               "crashed_fraction": float(ro.dones.float().mean())})
 
 
+    # the policy step as ONE hand-written kernel (ok_ppo_actor) + the step kernel: two launches per tick in one graph,
+    # returns by the discounted-return kernel (openkitchen_b200.rollout.FusedActorRollout)
+    from openkitchen_b200.rollout import FusedActorRollout, discounted_returns_fused
+
+    env3 = ok.BatchEnv(["Monza"], n, rays=[-70, -30, 0, 30, 70], reward_mode=ok.REWARD_CONSTANT, auto_reset=1)
+    fr = FusedActorRollout(env3, actor[0], actor[2], table, steps, sample=True)
+    env3.reset_random()
+    env3.cast_rays()
+    fr.capture()
+    fr.run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(reps):
+        fr.run()
+        ret = discounted_returns_fused(env3, fr.rewards, 0.99, fr.dones)
+    e1.record()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    report("C4 PPO rollout 4096 envs x 256 steps, fused actor kernel + step kernel as one CUDA graph (FusedActorRollout) + return kernel",
+           n, rays, 1e3 * dt / steps, {"env_steps": n * steps, "env_steps_per_sec": n * steps / dt, "wall_s": dt,
+                                       "device_ms_per_tick": e0.elapsed_time(e1) / reps / steps,
+                                       "crashed_fraction": float(fr.dones.float().mean())})
+
+
 def c5s():
     n, rays = 1_048_576, 32
     env = ok.BatchEnv(ok.track_names(), n, rays=rays, reward_mode=ok.REWARD_CMAES_PROGRESS, auto_reset=1)
