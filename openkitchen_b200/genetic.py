@@ -46,16 +46,50 @@ class GeneticPopulation:
         return thr.float(), steer.float(), z
 
     # ---- mating --------------------------------------------------------------------------------
-    def _mate_selective(self, dom_w, sub_w, count):
-        """mate2AgentsSelective for `count` offspring at once: dom_w / sub_w f32[count, ...]"""
-        u1 = torch.rand(dom_w.shape, device=self.device, generator=self.gen)
-        u2 = torch.rand(dom_w.shape, device=self.device, generator=self.gen)
-        u3 = torch.rand(dom_w.shape, device=self.device, generator=self.gen)
-        mutated = (u3 - 0.5) * 2.0
-        return torch.where(u1 < P_MUTATE, mutated, torch.where(u2 < P_DOMINANT, dom_w, sub_w))
+    def _mate_selective(self, dom_w, sub_w, draws=None):
+        """mate2AgentsSelective (Mating.hpp:52-104) for a batch of offspring: dom_w / sub_w f32[count, ...] are the
+        superior / inferior parent's weights.  Exactly the reference's two uniform draws per coefficient: r1 < 0.1 mutates
+        to (r2 - 0.5) * 2, otherwise r2 < 0.75 takes the superior parent's coefficient.  draws: f32[count, ..., 2]
+        (injected, for the parity test) or None (torch's generator)."""
+        if draws is None:
+            draws = torch.rand(*dom_w.shape, 2, device=self.device, generator=self.gen)
+        r1, r2 = draws[..., 0], draws[..., 1]
+        return torch.where(r1 < P_MUTATE, (r2 - 0.5) * 2.0, torch.where(r2 < P_DOMINANT, dom_w, sub_w))
+
+    def _roulette(self, top_val, m):
+        """(first, second != first) parents with probability proportional to the score (std::discrete_distribution with
+        rejection of first == second, Mating.hpp:138-149 -- the same joint distribution, drawn without the loop)"""
+        probs = top_val.clamp_min(0) + 1e-12
+        first = torch.multinomial(probs.expand(max(m, 1), -1), 1, generator=self.gen)[:, 0]
+        p2 = probs.expand(max(m, 1), -1).clone()
+        p2.scatter_(1, first[:, None], 0.0)
+        second = torch.multinomial(p2, 1, generator=self.gen)[:, 0]
+        return first, second
+
+    def mate_from_draws(self, pw1, pw2, top_val, first, second, draws_w1=None, draws_w2=None, with_elite=True):
+        """chooseAndMateAgents (Mating.hpp:113-166) as a pure function of its random draws.  pw1 / pw2: the five parents'
+        weights in score order, top_val their scores; first / second i64[m]: the roulette's parent indices for the m
+        mated offspring; draws_w1 f32[k, inputs, hidden, 2], draws_w2 f32[k, hidden, 6, 2] with k = m (+ 1 leading row for
+        the best agent's self-mutation when with_elite) or None.  Returns the new colony's (w1, w2): with_elite puts the
+        best agent's clone in slot 0 and its self-mutation in slot 1 (Mating.hpp:127-131)."""
+        m = int(first.numel())
+        # "superior agent" = agent_1 only when its score is strictly greater (Mating.hpp:58-61): a tie favours agent_2
+        first_wins = top_val[first] > top_val[second]
+        dom, sub = torch.where(first_wins, first, second), torch.where(first_wins, second, first)
+        off = 1 if with_elite else 0
+        d1 = None if draws_w1 is None else draws_w1[off:off + m]
+        d2 = None if draws_w2 is None else draws_w2[off:off + m]
+        new1 = self._mate_selective(pw1[dom], pw1[sub], d1)
+        new2 = self._mate_selective(pw2[dom], pw2[sub], d2)
+        if not with_elite:
+            return new1, new2
+        s1 = self._mate_selective(pw1[:1], pw1[:1], None if draws_w1 is None else draws_w1[:1])
+        s2 = self._mate_selective(pw2[:1], pw2[:1], None if draws_w2 is None else draws_w2[:1])
+        return torch.cat([pw1[:1], s1, new1]), torch.cat([pw2[:1], s2, new2])
 
     def mate(self, scores: torch.Tensor):
-        """scores f32[n_local] (higher is better, e.g. the nearest track index: MiscUtils.hpp:64-71)"""
+        """scores f32[n_local] (higher is better, e.g. the nearest track index: MiscUtils.hpp:64-71).  Every rank must own
+        a generator seeded differently (or the ranks breed identical offspring): pass e.g. seed * world + rank."""
         world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         rank = dist.get_rank() if world > 1 else 0
         n_total = self.n * world if world > 1 else self.n
@@ -71,21 +105,8 @@ class GeneticPopulation:
             dist.all_reduce(pw2)
         else:
             pw1, pw2 = self.w1[top_idx].clone(), self.w2[top_idx].clone()
-        # roulette: P(parent) proportional to its score (std::discrete_distribution), second parent != first
-        m = self.n - 2 if rank == 0 else self.n
-        probs = top_val.clamp_min(0) + 1e-12
-        first = torch.multinomial(probs.expand(max(m, 1), -1), 1, generator=self.gen)[:, 0]
-        p2 = probs.expand(max(m, 1), -1).clone()
-        p2.scatter_(1, first[:, None], 0.0)
-        second = torch.multinomial(p2, 1, generator=self.gen)[:, 0]
-        dom = torch.where(top_val[first] > top_val[second], first, second)  # "superior agent", Mating.hpp:58-61
-        sub = torch.where(top_val[first] > top_val[second], second, first)
-        new1 = self._mate_selective(pw1[dom], pw1[sub], m)
-        new2 = self._mate_selective(pw2[dom], pw2[sub], m)
-        if rank == 0:  # the global colony's slots 0 and 1 (Mating.hpp:127-131)
-            zero = torch.zeros(1, dtype=torch.long, device=self.device)
-            self.w1 = torch.cat([pw1[:1], self._mate_selective(pw1[zero], pw1[zero], 1), new1[:m]])
-            self.w2 = torch.cat([pw2[:1], self._mate_selective(pw2[zero], pw2[zero], 1), new2[:m]])
-        else:
-            self.w1, self.w2 = new1, new2
+        elite = rank == 0  # the global colony's slots 0 and 1 live on rank 0
+        m = self.n - 2 if elite else self.n
+        first, second = self._roulette(top_val, m)
+        self.w1, self.w2 = self.mate_from_draws(pw1, pw2, top_val, first[:m], second[:m], with_elite=elite)
         return top_val, top_idx
