@@ -468,11 +468,13 @@ def main():
         if dist is not None and (i + 1) % gen_every == 0:
             # the generation boundary of the population learners: every rank needs every candidate's fitness and the
             # same ranking (CmaEsSolverTorch.cpp:81-96, Mating.hpp:108-119) -- the ONLY exchange on the data path
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0, gm, g1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             g0.record(stream)
-            okdist.global_ranking(fit_view, n * world)
+            gathered = okdist.all_gather_fitness(fit_view, n * world)  # NCCL over NVLink
+            gm.record(stream)
+            torch.sort(gathered, descending=True, stable=True)        # the ranking every rank derives (ties by global id)
             g1.record(stream)
-            gens.append((g0, g1))
+            gens.append((g0, g1, gm))
     barrier()
     t_wall = time.perf_counter() - t_wall
     if rank == 0:
@@ -480,7 +482,8 @@ def main():
     launches = env.launch_stats().kernel_launches - launches0
     ms = np.array([a.elapsed_time(b) for a, b in zip(starts, stops)], dtype=np.float64)
     ms_tick = float(ms.mean())
-    gen_ms = float(np.mean([a.elapsed_time(b) for a, b in gens])) if gens else 0.0
+    gen_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in gens])) if gens else 0.0
+    gather_ms = float(np.mean([a.elapsed_time(m) for a, _, m in gens])) if gens else 0.0
     ms_per_step = ms_tick + gen_ms * len(gens) / args.steps
     crashed_frac = float(env.read("crashed", sp).mean())
     step_base += args.steps
@@ -612,6 +615,7 @@ def main():
         if dist is not None:
             line["generation"] = {
                 "every_ticks": gen_every, "exchanges_timed": len(gens), "collective_us": 1e3 * gen_ms,
+                "allgather_us": 1e3 * gather_ms, "ranking_sort_us": 1e3 * (gen_ms - gather_ms),
                 "what": "NCCL all-gather of f32 fitness[agents x ranks] + stable global ranking (sort), on the step stream, inside the timed region",
                 "bytes_gathered_per_rank": 4 * n * world, "ms_per_tick_without": ms_tick,
                 "value_without_collective": total_agents / (ms_tick * 1e-3),

@@ -301,6 +301,10 @@ int ok_launch_stats(const OkEnv *env, OkLaunchStats *out);
  * could not settle from the table entry alone (queued for the second pass), out[2] = rays that fell back to the
  * uniform-grid walk, since the previous call.  Synchronises the device; enable != 0 keeps counting, 0 stops. */
 int ok_debug_stats(OkEnv *env, uint64_t out[4], int32_t enable);
+/* Index self-checks: a library built with -DOK_CHECKED=1 (tools/checked_build.sh) counts every table row, chunk,
+ * segment, ray or agent index that would leave its array; *count is the total since the library was loaded (always 0 for
+ * the product build, whose *checks_compiled_in is 0).  Synchronises the device. */
+int ok_debug_violations(OkEnv *env, uint64_t *count, int32_t *checks_compiled_in);
 /* Timeline of the beam kernel's last launch (profiling aid, off by default): per CTA and per tile it processed, six
  * 64-bit words {tile | smid << 32, then %globaltimer (ns) at: tile start, end of the thread-per-agent phase, end of the
  * first ray pass, end of the second ray pass, end of the reward phase}.  Copies min(words available, capacity_words) to

@@ -493,6 +493,7 @@ int ensure_arena(OkEnv *e)
             r.bx0 = h.x0, r.by0 = h.y0, r.binv_h = h.inv_h, r.bbin_scale = h.bin_scale, r.brb = h.rb;
             r.bnx = h.nx, r.bny = h.ny, r.bnb = h.nb;
             r.boff_rows = h.off_rows, r.boff_entries = h.off_entries, r.boff_items = h.off_items;
+            r.bn_rows = h.n_rows, r.bn_chunks = h.n_chunks;
         }
         refs.push_back(r);
         total += (t.blob.size() + 127) / 128 * 128;
@@ -1748,6 +1749,21 @@ int ok_debug_stats(OkEnv *e, uint64_t out[4], int32_t enable)
         cudaFree(e->d_stats);
         e->d_stats = nullptr;
     }
+    return OK_SUCCESS;
+}
+
+int ok_debug_violations(OkEnv *e, uint64_t *count, int32_t *checks_compiled_in)
+{
+    if (!e || !e->has_device)
+        return fail(OK_ERR_NO_DEVICE, "no device");
+    DeviceGuard g(e->cfg.device);
+    OK_CUDA(cudaDeviceSynchronize());
+    unsigned long long v = 0;
+    OK_CUDA(cudaMemcpyFromSymbol(&v, ok::g_violations, sizeof v));
+    if (count)
+        *count = v;
+    if (checks_compiled_in)
+        *checks_compiled_in = OK_CHECKED;
     return OK_SUCCESS;
 }
 

@@ -33,6 +33,24 @@
 namespace ok
 {
 
+// Self-checks (the pool's compute-sanitizer is closed, profiles/r2_sanitizer_closed.log): a build with -DOK_CHECKED=1
+// counts every index that leaves its array instead of using it (tools/checked_build.sh runs the parity suite on it and
+// requires the count to stay zero).  Compiled out of the product build.
+#ifndef OK_CHECKED
+#define OK_CHECKED 0
+#endif
+__device__ unsigned long long g_violations = 0;
+#if OK_CHECKED
+#define OK_CHECK(cond)                                                                                                 \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        if (!(cond))                                                                                                   \
+            atomicAdd(&g_violations, 1ull);                                                                            \
+    } while (0)
+#else
+#define OK_CHECK(cond) ((void)0)
+#endif
+
 struct Tile
 {
     int32_t track;
@@ -50,9 +68,9 @@ struct TrackRef
     // instead of chasing the header at the front of a multi-hundred-MB table that no cache holds
     float    bx0, by0, binv_h, bbin_scale, brb;
     int32_t  bnx, bny, bnb;
-    uint32_t boff_rows, boff_entries, boff_items, pad;
+    uint32_t boff_rows, boff_entries, boff_items, bn_rows, bn_chunks, pad;
 };
-static_assert(sizeof(TrackRef) == 72, "TrackRef layout");
+static_assert(sizeof(TrackRef) == 80, "TrackRef layout");
 
 struct StepParams
 {
@@ -579,6 +597,7 @@ struct BeamView
     const uint2    *chunks;  // rest lists: 4 x uint16 segment indices per chunk
     float           x0, y0, inv_h, bin_scale, rb;
     int32_t         nx, ny, nb;
+    uint32_t        n_rows, n_chunks; // OK_CHECKED builds only
     bool            valid;
 };
 
@@ -591,6 +610,7 @@ __device__ __forceinline__ BeamView make_beam_view(const TrackRef &tr)
     v.chunks            = reinterpret_cast<const uint2 *>(blob + tr.boff_items);
     v.x0 = tr.bx0, v.y0 = tr.by0, v.inv_h = tr.binv_h, v.bin_scale = tr.bbin_scale, v.rb = tr.brb;
     v.nx = tr.bnx, v.ny = tr.bny, v.nb = tr.bnb;
+    v.n_rows = tr.bn_rows, v.n_chunks = tr.bn_chunks;
     v.valid = true;
     return v;
 }
@@ -677,7 +697,7 @@ __device__ __forceinline__ unsigned long long key_min(unsigned long long a, unsi
 // quotients differ by more than both error bounds) or reaches the key with its exact IEEE quotient.
 __device__ __forceinline__ unsigned long long beam_chunk_key(const float4 *segs, const uint32_t c01, const uint32_t c23,
                                                              const float ox, const float oy, const float dx, const float dy,
-                                                             const float bound, unsigned long long key)
+                                                             const float bound, unsigned long long key, const int n_seg = 0x7fffffff)
 {
     int   idx[4];
     float tq[4], a[4], ad[4];
@@ -688,6 +708,7 @@ __device__ __forceinline__ unsigned long long beam_chunk_key(const float4 *segs,
         // chunks are padded with the index of the track's null segment (zero length: denom = 0 fails the reference's
         // parallel test), so padding needs no special case
         idx[u] = static_cast<int>(((u < 2 ? c01 : c23) >> (16 * (u & 1))) & 0xffffu);
+        OK_CHECK(idx[u] <= n_seg); // n_seg itself is the null segment
         tq[u]  = beam_eval(segs, idx[u], ox, oy, dx, dy, el[u], lit[u], a[u], ad[u]);
     }
     float tq_b  = bound, a_b = 0.0f, ad_b = 1.0f;
@@ -762,6 +783,7 @@ __device__ __forceinline__ float finish_ray(const StepParams &p, const float4 *s
     }
     else
         hit = reinterpret_cast<const float2 *>(p.hit_abs)[gi]; // stale hit of a crashed agent
+    OK_CHECK(gi >= 0 && seg >= -1);
     const float xt = fsub(hit.x, rec.ox), yt = fsub(hit.y, rec.oy);
     float2      rel;
     rel.x          = fsub(fmul(xt, rec.rc), fmul(yt, rec.rs));
@@ -1379,13 +1401,16 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                 if (valid)
                 {
                     al                  = __float2int_rz((static_cast<float>(q) + 0.5f) * inv_R);
+                    OK_CHECK(q >= 0 && q < n_rays && al >= 0 && al < count && q - al * R >= 0 && q - al * R < R);
                     const AgentRec &rec = recs[al];
                     ang                 = fmul(OK_DEG2RAD, fadd(rec.rot, __ldg(p.ray_deg + (q - al * R))));
                     active              = !(rec.flags & kFlagCrashed);
                     if (active && rec.row >= 0 && fabsf(ang) < kBeamMaxAngle)
                     {
                         const int bin = __float2int_rd(fmul(ang, bv.bin_scale)) & (bv.nb - 1);
+                        OK_CHECK(static_cast<uint32_t>(rec.row) < bv.n_rows);
                         ent           = __ldg(bv.entries + static_cast<size_t>(rec.row) * bv.nb + bin);
+                        OK_CHECK((ent.w >> 24) == 0 || ent.z + (ent.w >> 24) <= bv.n_chunks);
                         cov           = true;
                     }
                 }
@@ -1405,7 +1430,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                 w_ray[lane]     = make_float4(rox, roy, dx, dy);
                 unsigned long long key0 = key_none;
                 if (cov)
-                    key0 = beam_chunk_key(tv.seg, ent.x, ent.y, rox, roy, dx, dy, p.sensor_range, key_none);
+                    key0 = beam_chunk_key(tv.seg, ent.x, ent.y, rox, roy, dx, dy, p.sensor_range, key_none, tv.n_seg);
                 w_key[lane]        = key0;
                 const uint32_t nch = cov ? (ent.w >> 24) : 0u; // chunks of the rest of the list
                 uint32_t       inc = nch;
@@ -1437,7 +1462,10 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                 {
                     const uint32_t ch = find_chunk(lane, owner);
                     if (static_cast<uint32_t>(lane) < total)
+                    {
+                        OK_CHECK(ch < bv.n_chunks);
                         it = __ldg(bv.chunks + ch);
+                    }
                 }
                 for (uint32_t base = 0; base < total; base += 32)
                 {
@@ -1457,7 +1485,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                         unsigned long long *key = w_key + owner;
                         // the ray's incumbent exact t (already in the key) bounds what is worth a division
                         const float              m = __uint_as_float(reinterpret_cast<const uint32_t *>(key)[1]);
-                        const unsigned long long k = beam_chunk_key(tv.seg, it.x, it.y, ray.x, ray.y, ray.z, ray.w, m, ~0ull);
+                        const unsigned long long k = beam_chunk_key(tv.seg, it.x, it.y, ray.x, ray.y, ray.z, ray.w, m, ~0ull, tv.n_seg);
                         if (k != ~0ull)
                             atomicMin(key, k);
                     }
@@ -1520,7 +1548,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                 const AgentRec &rec = recs[al];
                 unsigned long long key = key_none;
                 if (cov)
-                    key = beam_chunk_key(tv.seg, ent.x, ent.y, rec.ox, rec.oy, dx, dy, p.sensor_range, key_none);
+                    key = beam_chunk_key(tv.seg, ent.x, ent.y, rec.ox, rec.oy, dx, dy, p.sensor_range, key_none, tv.n_seg);
                 const float min_t = __uint_as_float(static_cast<uint32_t>(key >> 32));
                 // d1: up to there the inline four are the only contenders (= the list's completeness distance when it
                 // has no rest).  The key holds the exact t of its segment, or the sensor range when nothing was hit.

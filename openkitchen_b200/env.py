@@ -284,6 +284,12 @@ class Env:
         check(self.lib.ok_debug_stats(self.h, out, 1 if enable else 0))
         return int(out[0]), int(out[1]), int(out[2])
 
+    def debug_violations(self):
+        """(out-of-range indices counted by an OK_CHECKED build, whether this library was built with the checks)"""
+        n, on = C.c_uint64(0), C.c_int32(0)
+        check(self.lib.ok_debug_violations(self.h, C.byref(n), C.byref(on)))
+        return int(n.value), bool(on.value)
+
     def debug_trace(self, tiles_per_cta: int = 0):
         """timeline of the last beam-kernel launch as u64[grid, tiles, 6] (None if tracing was off); then re-arms the
         trace for `tiles_per_cta` tiles per CTA (0 = off)"""
