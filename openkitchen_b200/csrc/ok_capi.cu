@@ -610,7 +610,7 @@ int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
         if (e->beam_staged)
             ok::step_kernel<ok::kBeamBlockStaged, true, true><<<e->grid_beam, ok::kBeamBlockStaged, e->smem_beam, s>>>(p);
         else
-            ok::step_kernel<ok::kBeamBlockUnstaged, true, false><<<e->grid_beam, ok::kBeamBlockUnstaged, e->smem_beam, s>>>(p);
+            OK_CUDA(ok::launch_step_unstaged(p, e->grid_beam, e->smem_beam, s));
     }
     else
         ok::step_kernel<kBlock, false><<<e->grid, kBlock, e->smem, s>>>(p);
@@ -1062,8 +1062,7 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
     {
         int per_sm = 1;
         if (!e->beam_staged)
-            OK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ok::step_kernel<ok::kBeamBlockUnstaged, true, false>,
-                                                                  ok::kBeamBlockUnstaged, e->smem_beam));
+            OK_CUDA(ok::occupancy_step_unstaged(e->smem_beam, &per_sm));
         e->ctas_per_sm_beam = std::max(1, per_sm);
     }
     if (int rc = build_tiles(e->batch_agents, e->num_sms, 4, &e->d_tiles, &e->n_tiles))
@@ -1758,10 +1757,11 @@ int ok_debug_violations(OkEnv *e, uint64_t *count, int32_t *checks_compiled_in)
         return fail(OK_ERR_NO_DEVICE, "no device");
     DeviceGuard g(e->cfg.device);
     OK_CUDA(cudaDeviceSynchronize());
-    unsigned long long v = 0;
+    unsigned long long v = 0, u = 0;
     OK_CUDA(cudaMemcpyFromSymbol(&v, ok::g_violations, sizeof v));
+    OK_CUDA(ok::violations_step_unstaged(&u));
     if (count)
-        *count = v;
+        *count = v + u;
     if (checks_compiled_in)
         *checks_compiled_in = OK_CHECKED;
     return OK_SUCCESS;

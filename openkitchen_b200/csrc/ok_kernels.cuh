@@ -39,7 +39,7 @@ namespace ok
 #ifndef OK_CHECKED
 #define OK_CHECKED 0
 #endif
-__device__ unsigned long long g_violations = 0;
+static __device__ unsigned long long g_violations = 0; // one per translation unit (ok_capi.cu, ok_step_unstaged.cu)
 #if OK_CHECKED
 #define OK_CHECK(cond)                                                                                                 \
     do                                                                                                                 \
@@ -670,7 +670,7 @@ __device__ __forceinline__ float beam_eval(const float4 *segs, const int idx, co
 
 // literal predicate of the reference (CollisionChecker.cu:25-33) for a candidate flagged `lit`:
 // returns the candidate's key (all ones = rejected)
-__device__ __noinline__ unsigned long long beam_literal_key(const float4 *segs, int idx, float ox, float oy, float dx, float dy)
+static __device__ __noinline__ unsigned long long beam_literal_key(const float4 *segs, int idx, float ox, float oy, float dx, float dy)
 {
     const float4 sg    = segs[idx];
     const float  ex    = fsub(sg.x, ox);
@@ -744,7 +744,7 @@ __device__ __forceinline__ float beam_meta_dist(const uint32_t q, const float rb
 // The rare ray a beam list cannot decide: uniform-grid walk from t_start with the best listed hit (best, min_t)
 // as the incumbent.  Out of line on purpose: the walk's state would otherwise count against the registers of
 // the hot loop around the call.
-__device__ __noinline__ int beam_walk_fallback(const uint8_t *blob, float ox, float oy, float dx, float dy, float range,
+static __device__ __noinline__ int beam_walk_fallback(const uint8_t *blob, float ox, float oy, float dx, float dy, float range,
                                                float t_start, int best, float min_t)
 {
     const TrackView tv = make_view(blob);
@@ -1171,7 +1171,10 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
     const float inv_R = 1.0f / static_cast<float>(R);
     // the first tile of a CTA is its own index: no trip to the global cursor before any work can start; and when the
     // grid covers every tile (the balanced tiling's single wave, small populations) the cursor is never touched
-    const bool single_wave = p.n_tiles <= static_cast<int>(gridDim.x);
+#ifndef OK_SINGLE_WAVE
+#define OK_SINGLE_WAVE 1
+#endif
+    const bool single_wave = OK_SINGLE_WAVE && p.n_tiles <= static_cast<int>(gridDim.x);
     if (tid == 0)
         s_tile = static_cast<int>(blockIdx.x);
 
@@ -1696,6 +1699,11 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
     }
 }
 
+
+// Everything below is compiled into ok_capi.cu only.  ok_step_unstaged.cu (-DOK_STEP_KERNEL_ONLY) instantiates the
+// unstaged beam kernel in a translation unit of its own: with both shapes in one unit ptxas shares the out-of-line
+// device functions between them and the staged kernel lost a third of its speed (0.139 vs 0.095 ms per tick).
+#ifndef OK_STEP_KERNEL_ONLY
 
 // Environment::resetAgent (Environment.cpp:79-122) + Agent::reset (Agent.cpp:123-135), one thread
 // per request, reading the track blobs from global memory.
@@ -2244,5 +2252,12 @@ __global__ void fill_actions_kernel(const StepParams p, int64_t n)
     p.act_thr[a]   = thr;
     p.act_steer[a] = steer;
 }
+
+#endif // OK_STEP_KERNEL_ONLY
+
+// the unstaged beam kernel's launcher, occupancy and self-check counter (ok_step_unstaged.cu)
+cudaError_t launch_step_unstaged(const StepParams &p, int grid, size_t smem_bytes, cudaStream_t stream);
+cudaError_t occupancy_step_unstaged(size_t smem_bytes, int *ctas_per_sm);
+cudaError_t violations_step_unstaged(unsigned long long *count);
 
 } // namespace ok
