@@ -150,6 +150,9 @@ struct OkEnv
     // the beam kernel's batches are not limited by per-ray scratch: its own batch size, tile table and grid
     ok::Tile            *d_tiles_beam{nullptr};
     int32_t              n_tiles_beam{0};
+    // ok_step_host's tiling: several tiles per CTA, so that a tile's observations cross PCIe while the next one is computed
+    ok::Tile            *d_tiles_e2e{nullptr};
+    int32_t              n_tiles_e2e{0}, grid_e2e{0};
     int32_t              batch_agents_beam{0};
     int32_t              grid_beam{0};
     int32_t              ctas_per_sm_beam{1};
@@ -194,7 +197,9 @@ void free_agents(OkEnv *e)
         cudaFree(e->d_tiles);
     if (e->d_tiles_beam)
         cudaFree(e->d_tiles_beam);
-    e->d_tiles_beam = nullptr, e->n_tiles_beam = 0;
+    if (e->d_tiles_e2e)
+        cudaFree(e->d_tiles_e2e);
+    e->d_tiles_beam = nullptr, e->n_tiles_beam = 0, e->d_tiles_e2e = nullptr, e->n_tiles_e2e = 0;
     if (e->d_ray_order)
         cudaFree(e->d_ray_order);
     if (e->d_sched)
@@ -607,8 +612,15 @@ int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
         p.tiles        = e->d_tiles_beam;
         p.n_tiles      = e->n_tiles_beam;
         p.batch_agents = e->batch_agents_beam;
+        int grid       = e->grid_beam;
+        if (p.host_obs && e->d_tiles_e2e)
+        { // results stream to a host buffer: several tiles per CTA, each flushed while the next is computed
+            p.tiles   = e->d_tiles_e2e;
+            p.n_tiles = e->n_tiles_e2e;
+            grid      = e->grid_e2e;
+        }
         if (e->beam_staged)
-            ok::step_kernel<ok::kBeamBlockStaged, true, true><<<e->grid_beam, ok::kBeamBlockStaged, e->smem_beam, s>>>(p);
+            ok::step_kernel<ok::kBeamBlockStaged, true, true><<<grid, ok::kBeamBlockStaged, e->smem_beam, s>>>(p);
         else
             OK_CUDA(ok::launch_step_unstaged(p, e->grid_beam, e->smem_beam, s));
     }
@@ -1014,7 +1026,7 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
     // latency (thread-per-agent phases, second ray pass, barriers) whatever its size: the fewer, larger and more equal
     // the tiles, the better.  Tiles = CTAs x waves, dealt to the track runs in proportion to their length, every run
     // cut into equal parts, largest first.
-    auto build_tiles_balanced = [&](int max_tile, int ctas, ok::Tile **d_out, int32_t *n_out) -> int {
+    auto build_tiles_balanced = [&](int max_tile, int ctas, ok::Tile **d_out, int32_t *n_out, int min_waves = 1) -> int {
         struct Run
         {
             int32_t track;
@@ -1033,7 +1045,7 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
         int64_t have = 0;
         for (auto &r : runs)
             have += r.k;
-        const int64_t waves  = std::max<int64_t>(1, (n + static_cast<int64_t>(ctas) * max_tile - 1) / (static_cast<int64_t>(ctas) * max_tile));
+        const int64_t waves  = std::max<int64_t>(min_waves, (n + static_cast<int64_t>(ctas) * max_tile - 1) / (static_cast<int64_t>(ctas) * max_tile));
         const int64_t target = static_cast<int64_t>(ctas) * waves;
         for (; have < target; ++have)
         { // one more tile for the run whose tiles are the largest
@@ -1080,6 +1092,15 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
     }
     e->grid      = std::max(1, std::min(e->num_sms, e->n_tiles));
     e->grid_beam = std::max(1, std::min(e->num_sms * e->ctas_per_sm_beam, e->n_tiles_beam));
+    if (e->beam_staged)
+    { // the end-to-end tiling (see ok_step_host): OK_E2E_TILES tiles per CTA (default 4)
+        int per_cta = 4;
+        if (const char *env = std::getenv("OK_E2E_TILES"))
+            per_cta = std::max(1, std::atoi(env));
+        if (int rc = build_tiles_balanced(e->batch_agents_beam, e->num_sms, &e->d_tiles_e2e, &e->n_tiles_e2e, per_cta))
+            return rc;
+        e->grid_e2e = std::max(1, std::min(e->num_sms, e->n_tiles_e2e));
+    }
 
     // every agent starts where `Environment::resetAgent(agent, false)` puts it: RaceTrack::kStartingIdx
     std::vector<int32_t> pt(static_cast<size_t>(n));
@@ -1419,10 +1440,14 @@ int ok_step_host(OkEnv *e, const float *h_thr, const float *h_steer, float *h_ob
     p.do_move        = 1;
     // Pinned buffers are used in place: the kernel reads the actions and writes obs / reward / done straight
     // through the host mapping, so both transfers overlap the tick.  Pageable buffers fall back to staged copies.
+    static const bool act_by_copy = [] { // OK_HOST_ACT=copy: DMA the two action arrays instead of reading them through the mapping
+        const char *v = std::getenv("OK_HOST_ACT");
+        return v && std::strcmp(v, "copy") == 0;
+    }();
     const float *a_thr = pinned_alias(h_thr), *a_steer = pinned_alias(h_steer);
     if (h_thr)
     {
-        if (a_thr && a_steer)
+        if (a_thr && a_steer && !act_by_copy)
         {
             p.ext_thr   = a_thr;
             p.ext_steer = a_steer;
@@ -1433,16 +1458,21 @@ int ok_step_host(OkEnv *e, const float *h_thr, const float *h_steer, float *h_ob
             OK_CUDA(cudaMemcpyAsync(e->d_buf[OK_BUF_ACT_STEER], h_steer, 4 * n, cudaMemcpyHostToDevice, s));
         }
     }
-    // only the lidar goes through the mapping (full 128-byte warp stores); reward / done are one element per warp,
-    // which would be 2 tiny PCIe writes per agent -- a 0.3 MB copy after the kernel is cheaper
-    // OK_HOST_OBS=copy: a DMA copy after the kernel instead of stores through the host mapping
+    // OK_HOST_OBS=copy: DMA copies after the kernel instead of stores through the host mapping.
+    // OK_HOST_SMALL=copy: only reward / done by DMA (round 1's choice: one element per agent makes small PCIe writes);
+    // round 2 measures the mapped stores ahead: they cost 8,192 sector-sized writes per tick and save two copy
+    // operations on the critical path after the kernel.
     static const bool obs_by_copy = [] {
         const char *v = std::getenv("OK_HOST_OBS");
         return v && std::strcmp(v, "copy") == 0;
     }();
+    static const bool small_by_copy = [] {
+        const char *v = std::getenv("OK_HOST_SMALL");
+        return v && std::strcmp(v, "copy") == 0;
+    }();
     p.host_obs    = obs_by_copy ? nullptr : pinned_alias(h_obs);
-    p.host_reward = nullptr;
-    p.host_done   = nullptr;
+    p.host_reward = (obs_by_copy || small_by_copy) ? nullptr : pinned_alias(h_reward);
+    p.host_done   = (obs_by_copy || small_by_copy) ? nullptr : pinned_alias(h_done);
     rc            = launch_step(e, p, s);
     if (rc)
         return rc;

@@ -766,7 +766,7 @@ static __device__ __noinline__ int beam_walk_fallback(const uint8_t *blob, float
 // segment is `seg` (-1 = none); returns the squared norm of the relative hit
 // t_known != 0: the winner's exact t is already at hand (the beam key holds it; a zero is recomputed because the
 // key does not keep its sign)
-template <typename Rec>
+template <bool kHostStore = true, typename Rec>
 __device__ __forceinline__ float finish_ray(const StepParams &p, const float4 *segs, const Rec &rec, const int64_t gi,
                                             const float dx, const float dy, const int seg, const float t_known = 0.0f)
 {
@@ -792,7 +792,7 @@ __device__ __forceinline__ float finish_ray(const StepParams &p, const float4 *s
     reinterpret_cast<float2 *>(p.hit_rel)[gi] = rel;
     const float ob = __fdiv_rn(__fsqrt_rn(sq), p.sensor_range);
     p.obs[gi]      = ob;
-    if (p.host_obs)
+    if (kHostStore && p.host_obs) // (the beam kernel copies a whole tile's observations at once, see its tile flush)
         p.host_obs[gi] = ob;
     return sq;
 }
@@ -1512,7 +1512,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                         if (p.stats)
                             atomicAdd(p.stats + 2, 1ull);
                     }
-                    const float sq = finish_ray(p, tv.seg, rec, ray_base + q, dx, dy, best, t_known);
+                    const float sq = finish_ray<false>(p, tv.seg, rec, ray_base + q, dx, dy, best, t_known);
                     // min_dist2 of CollisionChecker.cu:150,162-165: `if (sq < min) min = sq` skips NaN, and so does a
                     // signed-int min over the bit patterns of values >= +0 (a NaN made here is 0x7fffffff)
                     if (sq == sq)
@@ -1560,7 +1560,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                 const bool  queue   = has && active && !settled;
                 float       sq      = inf;
                 if (has && !queue)
-                    sq = finish_ray(p, tv.seg, rec, ray_base + q, dx, dy, static_cast<int>(0x7fffffffu - static_cast<uint32_t>(key)),
+                    sq = finish_ray<false>(p, tv.seg, rec, ray_base + q, dx, dy, static_cast<int>(0x7fffffffu - static_cast<uint32_t>(key)),
                                     min_t);
                 const unsigned qm = __ballot_sync(0xffffffffu, queue);
                 if (qm)
@@ -1652,6 +1652,21 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
         }
         __syncthreads();
         OK_TRACE(4);
+        if (kBeam && p.host_obs)
+        { // End-to-end path (ok_step_host): this tile's observations are complete in device memory; they go to the pinned
+          // HOST buffer now, as full 16-byte-per-lane stores through the mapping.  (The second ray pass finishes rays in
+          // no particular order: storing them one by one reached the host as scattered 4-byte PCIe writes, 0.39 ms per
+          // tick instead of 0.24.)  ok_step_host cuts the population into several tiles per CTA, so this copy drains
+          // while the next tile is computed; trickling it through the next tile's ray loop instead measured the same.
+            const float *src = p.obs + ray_base;
+            float       *dst = p.host_obs + ray_base;
+            if (((ray_base | n_rays) & 3) == 0)
+                for (int i = tid; i < (n_rays >> 2); i += kBlock)
+                    reinterpret_cast<float4 *>(dst)[i] = __ldcg(reinterpret_cast<const float4 *>(src) + i);
+            else
+                for (int i = tid; i < n_rays; i += kBlock)
+                    dst[i] = __ldcg(src + i);
+        }
         if (kBeam && p.stats && tid == 0)
         {
             atomicAdd(p.stats, static_cast<unsigned long long>(n_rays));
