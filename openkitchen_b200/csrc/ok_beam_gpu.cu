@@ -408,7 +408,7 @@ done:
 
 bool build_beam_table_device(const Track &t, const BeamConfig &cfg, int device, uint8_t **d_blob, size_t *bytes, std::string &err)
 {
-    for (int per = 8; per <= 512; per *= 4)
+    for (int per = 16; per <= 1024; per *= 4) // rest candidates per entry the item array is sized for (3-10 on the 23 tracks)
     {
         bool full = false;
         if (build_once(t, cfg, device, per, d_blob, bytes, err, full))

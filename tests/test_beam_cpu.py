@@ -130,3 +130,46 @@ def test_disk_cache_is_shared_between_processes(tmp_path):
     fresh = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(envv, OK_BEAM_CACHE="0"), capture_output=True,
                            text=True, timeout=300)
     assert again.returncode == 0 and fresh.returncode == 0 and again.stdout == outs[0] == fresh.stdout
+
+
+def _fnv1a(data: bytes) -> int:
+    h = 1469598103934665603
+    for b in data:
+        h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+def test_planted_cache_file_is_rejected(tmp_path, monkeypatch):
+    """round-1 advisor finding: a table from the on-disk cache steers device reads.  A file whose checksum is right but
+    whose indices leave their arrays (here: a rest-chunk range past the end) must be rejected by the structural check
+    and rebuilt; a cache directory other users can write is not used at all."""
+    import os
+    import struct
+
+    monkeypatch.setenv("OK_BEAM_CACHE_DIR", str(tmp_path))
+    monkeypatch.setenv("OK_BEAM_CACHE", "1")
+
+    def lookup():
+        ok.release_caches()
+        env = ok.Env(device=-1, beam_cell=8.0, beam_bins=32)
+        t = env.add_named_track("Zandvoort")
+        x, y = env.track_array(t, "x"), env.track_array(t, "y")
+        return [env.beam_lookup(t, float(x[i]), float(y[i]), 0.3 * i)[0].tolist() for i in range(0, 200, 10)]
+
+    good = lookup()
+    files = [f for f in os.listdir(tmp_path) if f.endswith(".bin")]
+    assert len(files) == 1
+    path = os.path.join(tmp_path, files[0])
+    raw = bytearray(open(path, "rb").read())
+    magic, nbytes, checksum = raw[:8], struct.unpack_from("<Q", raw, 8)[0], struct.unpack_from("<Q", raw, 16)[0]
+    blob = raw[24:24 + nbytes]
+    assert _fnv1a(bytes(blob)) == checksum
+    off_entries = struct.unpack_from("<I", blob, 40)[0]
+    struct.pack_into("<I", blob, off_entries + 8, 0xFFFFFFF0)  # entry 0: first rest chunk far past the item array
+    struct.pack_into("<I", blob, off_entries + 12, struct.unpack_from("<I", blob, off_entries + 12)[0] | (3 << 24))  # ... with 3 chunks
+    open(path, "wb").write(bytes(magic) + struct.pack("<QQ", nbytes, _fnv1a(bytes(blob))) + bytes(blob))
+    assert lookup() == good  # rejected (bounds), rebuilt
+    os.chmod(tmp_path, 0o777)  # a directory anybody can write is not trusted: the table is built, nothing is read or written
+    os.remove(path)
+    assert lookup() == good
+    assert not [f for f in os.listdir(tmp_path) if f.endswith(".bin")]
