@@ -278,3 +278,25 @@ def test_host_step_delivers_every_buffer(n, rays):
     for name in ok.BUFFERS:
         assert np.array_equal(a.read(name).view(np.uint8), b.read(name).view(np.uint8)), name
     assert (a.read("reset_pt") != 3).any() or n < 1000, "nobody ever crashed: test too weak"
+
+
+@pytest.mark.parametrize("kernel", ["staged", "unstaged"])
+@pytest.mark.parametrize("mode", [ok.MOVE_VELOCITY, ok.MOVE_ACCELERATION])
+def test_both_beam_kernel_shapes_match_the_oracle(monkeypatch, kernel, mode):
+    """The beam kernel has two shapes (staged: one 1,024-thread CTA per SM behind the TMA-staged track; unstaged: several
+    256-thread CTAs per SM reading the track from global memory) and the host picks one by population size.  Forced
+    either way on the same small population -- with a sensor offset, auto-reset and all 23 tracks -- both must be the
+    oracle, bit for bit."""
+    monkeypatch.setenv("OK_BEAM_KERNEL", kernel)
+    names = ok.track_names()
+    env, ora, tid = make_pair(names, 23 * 9, 32, movement_mode=mode, reward_mode=ok.REWARD_Q_PROGRESS, auto_reset=1, sensor_offset=2.5)
+    assert env.launch_stats().block_threads == (1024 if kernel == "staged" else 256)
+    pts = spread_points(ora, tid)
+    env.reset(None, pts)
+    ora.reset(None, pts)
+    for step in range(150):
+        env.launch_steps_random(step, 1)
+        ora.fill_random_actions(step)
+        ora.step()
+        if step % 50 == 49:
+            assert_same(env, ora, ctx=f"{kernel} kernel, step {step}")
