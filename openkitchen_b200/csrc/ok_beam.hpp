@@ -118,6 +118,8 @@ bool build_beam_table(const Track &t, const BeamConfig &cfg, std::vector<uint8_t
 // construction, binary64 on the device; libm differences may move a list boundary by an ulp, never its validity.
 // The blob is left in device memory (*d_blob, cudaMalloc'ed on `device`, owned by the caller).
 bool build_beam_table_device(const Track &t, const BeamConfig &cfg, int device, uint8_t **d_blob, size_t *bytes, std::string &err);
+// frees the device builder's scratch pool (kept between tracks)
+void beam_builder_release();
 
 // Host-side lookup used by the CPU tests: the list of (x, y, angle[rad]) -- the inline candidates (null padding removed)
 // followed by the rest; returns false when the cell is not covered or the angle is out of range.  d_out = completeness

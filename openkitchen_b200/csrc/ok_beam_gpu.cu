@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 namespace ok
 {
@@ -42,7 +43,7 @@ struct GpuBuild
     int32_t         n_rows;
     // scratch, per CTA
     float    *cand_lb;
-    uint16_t *cand_seg, *cand_b0, *cand_bn;
+    uint16_t *cand_seg, *cand_b0, *cand_bn, *cand_act;
     float    *list_d;
     uint16_t *list_s;
     // output
@@ -61,12 +62,18 @@ __global__ void __launch_bounds__(kThreads) beam_build_kernel(const GpuBuild g)
     unsigned int *hit_bits = reinterpret_cast<unsigned int *>(dir_xy + 4 * g.nb); // [2 * nb][5] first hit per sample ray
     float        *dcomp    = reinterpret_cast<float *>(hit_bits + 10 * g.nb); // [nb]
     int          *bin_cnt  = reinterpret_cast<int *>(dcomp + g.nb);           // [nb]
-    __shared__ int s_row, s_ncand;
+    double       *edge     = reinterpret_cast<double *>(bin_cnt + g.nb);      // [nb][4]: the widened cone's two half-plane normals
+    __shared__ int s_row, s_ncand, s_nact;
+    // candidates are shared by GROUPS of kGroup lanes (the work per candidate -- bins it can be seen in -- varies from 3 to
+    // all of them: a thread per candidate left 7 of 32 lanes busy and 69 % of the warp time at the barriers)
+    constexpr int kGroup = 8, kGroups = kThreads / kGroup;
+    const int     gid = threadIdx.x / kGroup, sub = threadIdx.x % kGroup;
 
     const int    tid   = threadIdx.x;
     const size_t slot  = blockIdx.x;
     float       *c_lb  = g.cand_lb + slot * g.ns;
     uint16_t    *c_seg = g.cand_seg + slot * g.ns, *c_b0 = g.cand_b0 + slot * g.ns, *c_bn = g.cand_bn + slot * g.ns;
+    uint16_t    *c_act = g.cand_act + slot * g.ns;
     float       *l_d   = g.list_d + slot * static_cast<size_t>(g.nb) * kListCap;
     uint16_t    *l_s   = g.list_s + slot * static_cast<size_t>(g.nb) * kListCap;
     const double two_pi = 2.0 * M_PI, dbin = two_pi / g.nb;
@@ -74,6 +81,13 @@ __global__ void __launch_bounds__(kThreads) beam_build_kernel(const GpuBuild g)
     { // bin edges (even j) and bin centres (odd j)
         dir_xy[2 * j]     = cos(0.5 * j * dbin);
         dir_xy[2 * j + 1] = sin(0.5 * j * dbin);
+    }
+    for (int b = tid; b < g.nb; b += kThreads)
+    { // half planes of bin b's cone, widened by dth on both sides (the same expressions the per-pair code used)
+        edge[4 * b]     = cos(b * dbin - g.dth);
+        edge[4 * b + 1] = sin(b * dbin - g.dth);
+        edge[4 * b + 2] = -cos((b + 1) * dbin + g.dth);
+        edge[4 * b + 3] = -sin((b + 1) * dbin + g.dth);
     }
     const float miss = static_cast<float>(2.0 * g.rb);
 
@@ -84,6 +98,7 @@ __global__ void __launch_bounds__(kThreads) beam_build_kernel(const GpuBuild g)
         {
             s_row   = atomicAdd(g.row_cursor, 1);
             s_ncand = 0;
+            s_nact  = 0;
         }
         __syncthreads();
         const int row = s_row;
@@ -134,30 +149,28 @@ __global__ void __launch_bounds__(kThreads) beam_build_kernel(const GpuBuild g)
         // ---- 2. completeness distance: rays from the four corners and the centre, bin edges and centres.  A thread
         // takes a candidate and tries the sample rays of the bins it can be seen in; the first hit of a ray is a
         // shared-memory minimum (bit patterns of non-negative floats order like the floats) ----
-        for (int c = tid; c < ncand; c += kThreads)
-        {
+        for (int c = gid; c < ncand; c += kGroups)
+        { // a group per candidate, its lanes over the (sample direction, origin) pairs
             const float4 sg = g.seg[c_seg[c]];
             const double sx = static_cast<double>(sg.z) - sg.x, sy = static_cast<double>(sg.w) - sg.y;
             const int    b0 = c_b0[c], bn = c_bn[c];
-            for (int k = 0; k < 2 * bn; ++k)
+            for (int m = sub; m < 10 * bn; m += kGroup)
             {
+                const int    k = m / 5, o = m - 5 * k;
                 const int    j  = (2 * b0 + k) & (2 * g.nb - 1);
                 const double dx = dir_xy[2 * j], dy = dir_xy[2 * j + 1];
                 const double den = dx * sy - dy * sx;
                 if (fabs(den) < 1e-12)
                     continue;
-                for (int o = 0; o < 5; ++o)
-                {
-                    const double ox = o == 4 ? ccx : ((o & 1) ? bx1 : bx0), oy = o == 4 ? ccy : ((o & 2) ? by1 : by0);
-                    const double ex = sg.x - ox, ey = sg.y - oy;
-                    const double tt = (ex * sy - ey * sx) / den, ss = (ex * dy - ey * dx) / den;
-                    if (tt >= 0 && ss >= 0 && ss <= 1 && tt < miss)
-                    { // rounded UP to binary32: the sampled distance is never understated
-                        float bf = static_cast<float>(tt);
-                        if (static_cast<double>(bf) < tt)
-                            bf = nextafterf(bf, 3.0e38f);
-                        atomicMin(&hit_bits[5 * j + o], __float_as_uint(bf));
-                    }
+                const double ox = o == 4 ? ccx : ((o & 1) ? bx1 : bx0), oy = o == 4 ? ccy : ((o & 2) ? by1 : by0);
+                const double ex = sg.x - ox, ey = sg.y - oy;
+                const double tt = (ex * sy - ey * sx) / den, ss = (ex * dy - ey * dx) / den;
+                if (tt >= 0 && ss >= 0 && ss <= 1 && tt < miss)
+                { // rounded UP to binary32: the sampled distance is never understated
+                    float bf = static_cast<float>(tt);
+                    if (static_cast<double>(bf) < tt)
+                        bf = nextafterf(bf, 3.0e38f);
+                    atomicMin(&hit_bits[5 * j + o], __float_as_uint(bf));
                 }
             }
         }
@@ -180,14 +193,22 @@ __global__ void __launch_bounds__(kThreads) beam_build_kernel(const GpuBuild g)
 
         // ---- 3. membership ----
         for (int c = tid; c < ncand; c += kThreads)
-        {
+        { // the candidates that can be in any list at all (most are beyond every completeness distance)
             const float lb = c_lb[c];
             const int   b0 = c_b0[c], bn = c_bn[c];
             bool        any = false;
             for (int k = 0; k < bn && !any; ++k)
                 any = lb <= dcomp[(b0 + k) & (g.nb - 1)];
-            if (!any)
-                continue;
+            if (any)
+                c_act[atomicAdd(&s_nact, 1)] = static_cast<uint16_t>(c);
+        }
+        __syncthreads();
+        const int nact = s_nact;
+        for (int i = gid; i < nact; i += kGroups)
+        { // a group per candidate: every lane builds the (same) hull, then the lanes take the bins
+            const int    c  = c_act[i];
+            const float  lb = c_lb[c];
+            const int    b0 = c_b0[c], bn = c_bn[c];
             const float4 sg = g.seg[c_seg[c]];
             V2           pts[8], hull[9];
             int          np = 0;
@@ -195,13 +216,13 @@ __global__ void __launch_bounds__(kThreads) beam_build_kernel(const GpuBuild g)
                 for (int k = 0; k < 4; ++k)
                     pts[np++] = {(e ? sg.z : sg.x) - ((k & 1) ? bx1 : bx0), (e ? sg.w : sg.y) - ((k & 2) ? by1 : by0)};
             const int nh = convex_hull8(pts, np, hull);
-            for (int k = 0; k < bn; ++k)
+            for (int k = sub; k < bn; k += kGroup)
             {
                 const int b = (b0 + k) & (g.nb - 1);
                 if (lb > dcomp[b])
                     continue;
-                const V2 lo  = {cos(b * dbin - g.dth), sin(b * dbin - g.dth)};
-                const V2 hi  = {-cos((b + 1) * dbin + g.dth), -sin((b + 1) * dbin + g.dth)};
+                const V2 lo = {edge[4 * b], edge[4 * b + 1]};
+                const V2 hi = {edge[4 * b + 2], edge[4 * b + 3]};
                 V2       c1[12], c2[14];
                 const int    n1 = clip_half_plane(hull, nh, lo, c1);
                 const int    n2 = clip_half_plane(c1, n1, hi, c2);
@@ -287,10 +308,65 @@ __global__ void __launch_bounds__(kThreads) beam_build_kernel(const GpuBuild g)
     } while (0)
 } // namespace
 
+// The builder's three large scratch areas (candidate / list scratch, entries, items: ~0.6 GB together at the default
+// resolution) are kept between tracks: a process builds 23 tables back to back, and cudaMalloc / cudaFree of that much
+// memory per track cost about as much as a third of the kernel.  beam_builder_release() (ok_release_caches) frees them.
+namespace
+{
+struct Pool
+{
+    void  *ptr{nullptr};
+    size_t bytes{0};
+    int    device{-1};
+};
+Pool       g_pool[3];
+std::mutex g_pool_mu;
+
+cudaError_t pool_get(int which, int device, size_t bytes, void **out)
+{ // caller holds g_pool_mu and has made `device` current
+    Pool &p = g_pool[which];
+    if (p.ptr && (p.device != device || p.bytes < bytes))
+    {
+        cudaFree(p.ptr);
+        p = Pool{};
+    }
+    if (!p.ptr)
+    {
+        const cudaError_t e = cudaMalloc(&p.ptr, bytes);
+        if (e != cudaSuccess)
+        {
+            p = Pool{};
+            return e;
+        }
+        p.bytes  = bytes;
+        p.device = device;
+    }
+    *out = p.ptr;
+    return cudaSuccess;
+}
+} // namespace
+
+void beam_builder_release()
+{
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    for (auto &p : g_pool)
+        if (p.ptr)
+        {
+            int prev = -1;
+            cudaGetDevice(&prev);
+            cudaSetDevice(p.device);
+            cudaFree(p.ptr);
+            if (prev >= 0)
+                cudaSetDevice(prev);
+            p = Pool{};
+        }
+}
+
 static bool build_once(const Track &t, const BeamConfig &cfg, int device, int items_per_entry, uint8_t **d_blob_out,
                        size_t *bytes_out, std::string &err, bool &full)
 {
     full = false;
+    std::lock_guard<std::mutex> pool_lock(g_pool_mu); // one build at a time per process: the scratch pool is shared
     const auto t_begin = std::chrono::steady_clock::now();
     BeamPlan   pl;
     if (!beam_plan(t, cfg, pl, err))
@@ -314,7 +390,7 @@ static bool build_once(const Track &t, const BeamConfig &cfg, int device, int it
         BEAM_CUDA(cudaSetDevice(device));
         BEAM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
         const int    grid = static_cast<int>(std::min<size_t>(n_rows, static_cast<size_t>(sms) * 4));
-        const size_t per_cta = static_cast<size_t>(ns) * (4 + 2 + 2 + 2) + static_cast<size_t>(nb) * kListCap * (4 + 2);
+        const size_t per_cta = static_cast<size_t>(ns) * (4 + 2 + 2 + 2 + 2) + static_cast<size_t>(nb) * kListCap * (4 + 2);
         // `items_per_entry` rest candidates per (cell, bin) on average; the caller retries with more when the kernel reports the array full
         capacity = static_cast<unsigned long long>(n_rows) * nb * static_cast<unsigned long long>(items_per_entry) + 1024ull;
         GpuBuild g{};
@@ -322,9 +398,9 @@ static bool build_once(const Track &t, const BeamConfig &cfg, int device, int it
         BEAM_CUDA(cudaMemcpy(d_seg, t.segments.data(), sizeof(float4) * ns, cudaMemcpyHostToDevice));
         BEAM_CUDA(cudaMalloc(&d_cov, 4 * std::max<size_t>(n_rows, 1)));
         BEAM_CUDA(cudaMemcpy(d_cov, pl.covered.data(), 4 * n_rows, cudaMemcpyHostToDevice));
-        BEAM_CUDA(cudaMalloc(&d_scratch, per_cta * grid + 256));
-        BEAM_CUDA(cudaMalloc(&d_entries, 16 * std::max<size_t>(n_rows * nb, 1)));
-        BEAM_CUDA(cudaMalloc(&d_items, 2 * capacity));
+        BEAM_CUDA(pool_get(0, device, per_cta * grid + 256, &d_scratch));
+        BEAM_CUDA(pool_get(1, device, 16 * std::max<size_t>(n_rows * nb, 1), &d_entries));
+        BEAM_CUDA(pool_get(2, device, 2 * capacity, &d_items));
         BEAM_CUDA(cudaMalloc(&d_ctr, 64));
         BEAM_CUDA(cudaMemset(d_ctr, 0, 64));
         g.seg = static_cast<const float4 *>(d_seg);
@@ -345,6 +421,8 @@ static bool build_once(const Track &t, const BeamConfig &cfg, int device, int it
             p += static_cast<size_t>(grid) * ns * 2;
             g.cand_bn = reinterpret_cast<uint16_t *>(p);
             p += static_cast<size_t>(grid) * ns * 2;
+            g.cand_act = reinterpret_cast<uint16_t *>(p);
+            p += static_cast<size_t>(grid) * ns * 2;
             g.list_s = reinterpret_cast<uint16_t *>(p);
         }
         g.entries       = static_cast<uint4 *>(d_entries);
@@ -356,7 +434,7 @@ static bool build_once(const Track &t, const BeamConfig &cfg, int device, int it
         const auto t_k0 = std::chrono::steady_clock::now();
         if (n_rows)
         {
-            const size_t smem = static_cast<size_t>(nb) * (32 + 40 + 8);
+            const size_t smem = static_cast<size_t>(nb) * (32 + 40 + 8 + 32);
             BEAM_CUDA(cudaFuncSetAttribute(beam_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             beam_build_kernel<<<grid, kThreads, smem>>>(g);
             BEAM_CUDA(cudaGetLastError());
@@ -393,7 +471,7 @@ static bool build_once(const Track &t, const BeamConfig &cfg, int device, int it
         }
     }
 done:
-    cudaFree(d_seg), cudaFree(d_cov), cudaFree(d_scratch), cudaFree(d_entries), cudaFree(d_items), cudaFree(d_ctr);
+    cudaFree(d_seg), cudaFree(d_cov), cudaFree(d_ctr); // (scratch, entries and items stay in the pool)
     if (ok)
     {
         *d_blob_out = d_blob;

@@ -482,6 +482,7 @@ int ensure_arena(OkEnv *e)
                     if (!e->beams_dev[i] && (pass == 1 || !err.empty()))
                         return fail(OK_ERR_INVALID_ARG, "beam table: " + err);
                 }
+        ok::beam_builder_release(); // the device builder's scratch pool (kept from track to track) is no longer needed
     }
     for (size_t i = 0; i < e->tracks.size(); ++i)
     {
@@ -1683,6 +1684,7 @@ void ok_release_caches(void)
     std::lock_guard<std::mutex> lock(g_beam_mu);
     g_beam_cache.clear();
     g_beam_dev_cache.clear(); // tables still referenced by live envs stay alive until those envs are destroyed
+    ok::beam_builder_release();
 }
 
 int64_t ok_beam_table_bytes(OkEnv *e, int32_t id)
