@@ -71,3 +71,30 @@ def test_views_alive_at_interpreter_exit_do_not_crash():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
     assert "done" in r.stdout and r.returncode == 0, (r.returncode, r.stderr[-500:])
+
+
+def test_views_outlive_close_and_keep_their_memory():
+    """round-1 advisor finding: BatchEnv.close() destroyed the OkEnv under live DLPack views.  Now a tensor the caller
+    still holds keeps the device memory alive: the env is destroyed when its last export is released."""
+    import gc
+
+    from openkitchen_b200 import dlpack
+
+    env = ok.BatchEnv(["Monza"], 64, rays=15)
+    env.step_random(5)
+    torch.cuda.synchronize()
+    keep = env.obs            # the caller's own reference
+    want = keep.clone()
+    inner = env.env
+    env.close()
+    assert env.obs is None and inner.h is not None, "the env must survive while a view is alive"
+    assert torch.equal(keep, want)               # still valid memory
+    other = ok.BatchEnv(["Spa"], 4096, rays=32)  # allocations in between must not land on it
+    other.step_random(2)
+    torch.cuda.synchronize()
+    assert torch.equal(keep, want)
+    other.close()
+    del keep, want
+    gc.collect()
+    torch.cuda.synchronize()
+    assert dlpack.live_exports(inner) == 0 and inner.h is None, "released with its last view"
