@@ -184,6 +184,19 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// shared-memory atomic add as ONE instruction (ATOMS.ADD).  The CUDA atomicAdd() here sits behind `if (lane == 0)` inside
+// a loop, and nvcc wraps it in its automatic warp aggregation (match / vote / popc / elect / shuffle, ~30 instructions for
+// a single active lane): 9 % of the beam kernel's warp instructions in round 2's first profile.
+__device__ __forceinline__ int smem_add(int *addr, int v)
+{
+    int old;
+    asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(addr)), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void smem_min(int *addr, int v)
+{
+    asm volatile("red.shared.min.s32 [%0], %1;" ::"r"(smem_u32(addr)), "r"(v) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1516,16 +1529,16 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                     // min_dist2 of CollisionChecker.cu:150,162-165: `if (sq < min) min = sq` skips NaN, and so does a
                     // signed-int min over the bit patterns of values >= +0 (a NaN made here is 0x7fffffff)
                     if (sq == sq)
-                        atomicMin(&recs[al].min_d2_bits, __float_as_int(sq));
+                        smem_min(&recs[al].min_d2_bits, __float_as_int(sq));
                 }
                 __syncwarp(); // w_ray / w_key are reused by the next call
             };
 
             // ---------------------------------- pass A ----------------------------------
-            int g = 0;
-            if (lane == 0)
-                g = atomicAdd(&s_pool, 1);
-            g = __shfl_sync(0xffffffffu, g, 0);
+            // groups are dealt to the warps round-robin: every group costs the same here (the uneven part is queued), so
+            // a shared cursor would only add an atomic and a shuffle per group
+            constexpr int kWarps = kBlock / 32;
+            int           g      = warp;
             int   al;
             float ang;
             bool  active, cov;
@@ -1533,10 +1546,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
             locate((g << 5) + lane, g < n_groups && (g << 5) + lane < n_rays, al, ang, active, cov, ent);
             while (g < n_groups)
             {
-                int g_next = 0;
-                if (lane == 0)
-                    g_next = atomicAdd(&s_pool, 1);
-                g_next = __shfl_sync(0xffffffffu, g_next, 0);
+                const int g_next = g + kWarps;
                 int   al_n;
                 float ang_n;
                 bool  active_n, cov_n;
@@ -1568,7 +1578,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                     const int cnt  = __popc(qm);
                     int       base = 0;
                     if (lane == 0)
-                        base = atomicAdd(&s_npend, cnt);
+                        base = smem_add(&s_npend, cnt);
                     base          = __shfl_sync(0xffffffffu, base, 0);
                     const int pos = base + __popc(qm & ((1u << lane) - 1u));
                     if (queue && pos < kPendCap)
@@ -1582,11 +1592,11 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                             __threadfence_block();
                             const int c0 = lo >> 5, c1 = (hi - 1) >> 5;
                             if (c0 == c1)
-                                atomicAdd(&s_ready[c0], hi - lo);
+                                smem_add(&s_ready[c0], hi - lo);
                             else
                             {
-                                atomicAdd(&s_ready[c0], ((c0 + 1) << 5) - lo);
-                                atomicAdd(&s_ready[c1], hi - (c1 << 5));
+                                smem_add(&s_ready[c0], ((c0 + 1) << 5) - lo);
+                                smem_add(&s_ready[c1], hi - (c1 << 5));
                             }
                         }
                     }
@@ -1598,10 +1608,10 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                 { // a warp's 32 rays belong to one agent: one warp-wide integer min (REDUX), one atomic per warp
                     const int m = __reduce_min_sync(0xffffffffu, __float_as_int((sq == sq) ? sq : inf));
                     if (has && lane == 0)
-                        atomicMin(&recs[al].min_d2_bits, m);
+                        smem_min(&recs[al].min_d2_bits, m);
                 }
                 else if (has && !queue && sq == sq)
-                    atomicMin(&recs[al].min_d2_bits, __float_as_int(sq));
+                    smem_min(&recs[al].min_d2_bits, __float_as_int(sq));
                 g = g_next, al = al_n, ang = ang_n, active = active_n, cov = cov_n, ent = ent_n;
             }
             // ---------------------------------- pass B ----------------------------------
@@ -1612,14 +1622,14 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
             if (lane == 0)
             {
                 __threadfence_block();
-                atomicAdd(&s_adone, 1);
+                smem_add(&s_adone, 1);
             }
             for (;;)
             {
                 int j = 0, size = 0;
                 if (lane == 0)
                 {
-                    j = atomicAdd(&s_pool2, 1);
+                    j = smem_add(&s_pool2, 1);
                     if (j < kPendCap / 32)
                         for (;;)
                         {
