@@ -157,6 +157,8 @@ struct OkEnv
     int32_t              grid_beam{0};
     int32_t              ctas_per_sm_beam{1};
     bool                 beam_staged{true}; // which shape of the beam kernel this population runs (ok_kernels.cuh)
+    bool                 beam_seg{false};   // ... the segment-staged one (two CTAs per SM); implies beam_staged
+    int                  smem_per_sm{0}, smem_reserved{1024};
     int32_t              beam_block{1024};
     uint16_t            *d_ray_order{nullptr};
     int32_t             *d_sched{nullptr};
@@ -501,6 +503,7 @@ int ensure_arena(OkEnv *e)
             r.boff_rows = h.off_rows, r.boff_entries = h.off_entries, r.boff_items = h.off_items;
             r.bn_rows = h.n_rows, r.bn_chunks = h.n_chunks;
         }
+        r.seg_bytes = reinterpret_cast<const ok::TrackHeader *>(t.blob.data())->off_words; // header + segments
         refs.push_back(r);
         total += (t.blob.size() + 127) / 128 * 128;
         e->max_blob_used = std::max(e->max_blob_used, t.blob.size());
@@ -598,6 +601,7 @@ int arm_shared_memory_limit(OkEnv *e)
     OK_CUDA(cudaFuncGetAttributes(&fa, ok::step_kernel<ok::kBeamBlockStaged, true, true>));
     OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<ok::kBeamBlockStaged, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  e->smem_optin - static_cast<int>(fa.sharedSizeBytes)));
+    OK_CUDA(ok::arm_step_segstaged(e->smem_optin));
     return OK_SUCCESS;
 }
 
@@ -620,7 +624,9 @@ int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
             p.n_tiles = e->n_tiles_e2e;
             grid      = e->grid_e2e;
         }
-        if (e->beam_staged)
+        if (e->beam_seg)
+            OK_CUDA(ok::launch_step_segstaged(p, grid, e->smem_beam, s));
+        else if (e->beam_staged)
             ok::step_kernel<ok::kBeamBlockStaged, true, true><<<grid, ok::kBeamBlockStaged, e->smem_beam, s>>>(p);
         else
             OK_CUDA(ok::launch_step_unstaged(p, e->grid_beam, e->smem_beam, s));
@@ -731,6 +737,8 @@ int ok_create(const OkConfig *cfg, OkEnv **out)
         e->has_device = true;
         e->num_sms    = sms;
         e->smem_optin = optin;
+        cudaDeviceGetAttribute(&e->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c.device);
+        cudaDeviceGetAttribute(&e->smem_reserved, cudaDevAttrReservedSharedMemoryPerBlock, c.device);
         e->max_blob   = optin > 65536 ? static_cast<size_t>(optin) - 40960 : 0; // room for the batch scratch
     }
     else
@@ -901,6 +909,14 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
 {
     e->n_agents = n;
     e->rays     = rays;
+    // the segment-staged shape (two 512-thread CTAs per SM): populations that give every CTA a worthwhile tile, tracks
+    // whose segments leave room for at least 64 agent records in half an SM's shared memory
+    const int64_t seg_budget = static_cast<int64_t>(e->smem_per_sm) / ok::kBeamSegCtasPerSm - e->smem_reserved -
+                               ok::beam_static_smem(true, true) - 256;
+    auto seg_cap_of = [&](int32_t track) -> int64_t {
+        const int64_t sb = (static_cast<int64_t>(reinterpret_cast<const ok::TrackHeader *>(e->tracks[track].blob.data())->off_words) + 127) / 128 * 128;
+        return std::min<int64_t>({(seg_budget - sb) / static_cast<int64_t>(sizeof(ok::AgentRec)), ok::kBeamBlockSeg, 65535 / rays});
+    };
     // batch = the agents a CTA keeps in flight: as many as fit behind the largest staged track
     {
         const size_t blob  = (e->max_blob_used + 127) / 128 * 128;
@@ -923,12 +939,25 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
         // Which shape (ok_kernels.cuh): the staged one for throughput, the unstaged one when the population is too small
         // to give every SM a worthwhile tile (OK_BEAM_KERNEL = staged | unstaged overrides).
         e->beam_staged = n >= 2048; // measured (tools/bench_small.py): the unstaged shape is ahead only below ~2,000 agents
+        e->beam_seg = e->beam_staged && n >= static_cast<int64_t>(e->num_sms) * ok::kBeamSegCtasPerSm * 64;
         if (const char *env = std::getenv("OK_BEAM_KERNEL"))
-            e->beam_staged = std::strcmp(env, "unstaged") != 0 && (std::strcmp(env, "staged") == 0 || e->beam_staged);
-        e->beam_block = e->beam_staged ? ok::kBeamBlockStaged : ok::kBeamBlockUnstaged;
+        {
+            e->beam_staged = std::strcmp(env, "unstaged") != 0 && (std::strcmp(env, "staged") == 0 || std::strcmp(env, "segstaged") == 0 || e->beam_staged);
+            e->beam_seg    = std::strcmp(env, "segstaged") == 0 || (e->beam_seg && e->beam_staged && std::strcmp(env, "staged") != 0);
+        }
+        if (e->beam_seg)
+            for (size_t t = 0; t < e->tracks.size(); ++t)
+                if (seg_cap_of(static_cast<int32_t>(t)) < 64)
+                    e->beam_seg = false; // a track too large for half an SM: the one-CTA-per-SM shape stages whole blobs
+        e->beam_block = e->beam_seg ? ok::kBeamBlockSeg : (e->beam_staged ? ok::kBeamBlockStaged : ok::kBeamBlockUnstaged);
         int64_t ab;
         int     capb;
-        if (e->beam_staged)
+        if (e->beam_seg)
+        { // provisional: the tiling below sizes every track's tiles by what fits behind ITS segments
+            ab   = ok::kBeamBlockSeg;
+            capb = ok::kBeamBlockSeg;
+        }
+        else if (e->beam_staged)
         { // one 1,024-thread CTA per SM behind the staged track: as many agents per tile as the shared memory behind the
           // largest track holds (the balanced tiling then sizes the tiles: about one per CTA and wave)
             ab   = static_cast<int64_t>((avail - ok::beam_static_smem(true)) / sizeof(ok::AgentRec));
@@ -946,7 +975,7 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
         if (!e->beam_staged) // small populations: spread over all SMs rather than filling a few tiles
             ab = std::min<int64_t>(ab, std::max<int64_t>(1, (n + e->num_sms - 1) / std::max(1, e->num_sms)));
         e->batch_agents_beam = static_cast<int32_t>(std::max<int64_t>(1, ab));
-        e->smem_beam         = (e->beam_staged ? blob : 0) + ok::beam_smem_bytes(e->batch_agents_beam);
+        e->smem_beam         = ((e->beam_staged && !e->beam_seg) ? blob : 0) + ok::beam_smem_bytes(e->batch_agents_beam); // (segment-staged: set by the tiling)
         // The limit is an attribute of the FUNCTION on this device, not of the env: it is raised to the opt-in maximum
         // (minus the kernel's static shared memory), so that envs of different sizes can interleave their launches.
         if (int rc = arm_shared_memory_limit(e))
@@ -1027,7 +1056,8 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
     // latency (thread-per-agent phases, second ray pass, barriers) whatever its size: the fewer, larger and more equal
     // the tiles, the better.  Tiles = CTAs x waves, dealt to the track runs in proportion to their length, every run
     // cut into equal parts, largest first.
-    auto build_tiles_balanced = [&](int max_tile, int ctas, ok::Tile **d_out, int32_t *n_out, int min_waves = 1) -> int {
+    size_t seg_smem_need = 0; // segment-staged shape: the largest (segments + records) of any tile built below
+    auto   build_tiles_balanced = [&](int max_tile, int ctas, ok::Tile **d_out, int32_t *n_out, int min_waves = 1) -> int {
         struct Run
         {
             int32_t track;
@@ -1040,13 +1070,16 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
             int64_t j = i;
             while (j < n && e->h_track_id[j] == e->h_track_id[i])
                 ++j;
-            runs.push_back({e->h_track_id[i], i, j - i, (j - i + max_tile - 1) / max_tile});
+            // (segment-staged shape: a track's tiles are capped by what fits behind ITS segments)
+            const int64_t cap = e->beam_seg ? std::min<int64_t>(max_tile, seg_cap_of(e->h_track_id[i])) : max_tile;
+            runs.push_back({e->h_track_id[i], i, j - i, (j - i + cap - 1) / cap});
             i = j;
         }
         int64_t have = 0;
         for (auto &r : runs)
             have += r.k;
-        const int64_t waves  = std::max<int64_t>(min_waves, (n + static_cast<int64_t>(ctas) * max_tile - 1) / (static_cast<int64_t>(ctas) * max_tile));
+        const int64_t waves  = std::max<int64_t>({static_cast<int64_t>(min_waves), (n + static_cast<int64_t>(ctas) * max_tile - 1) / (static_cast<int64_t>(ctas) * max_tile),
+                                                  e->beam_seg ? (have + ctas - 1) / ctas : int64_t{1}});
         const int64_t target = static_cast<int64_t>(ctas) * waves;
         for (; have < target; ++have)
         { // one more tile for the run whose tiles are the largest
@@ -1064,7 +1097,12 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
             {
                 const int64_t b0 = r.begin + r.len * t / r.k, b1 = r.begin + r.len * (t + 1) / r.k;
                 if (b1 > b0)
+                {
                     tiles.push_back({r.track, static_cast<int32_t>(b1 - b0), b0});
+                    if (e->beam_seg)
+                        seg_smem_need = std::max(seg_smem_need, (static_cast<size_t>(reinterpret_cast<const ok::TrackHeader *>(e->tracks[r.track].blob.data())->off_words) + 127) / 128 * 128 +
+                                                                    ok::beam_smem_bytes(static_cast<int>(b1 - b0)));
+                }
             }
         std::stable_sort(tiles.begin(), tiles.end(), [](const ok::Tile &a, const ok::Tile &b) { return a.count > b.count; });
         *n_out = static_cast<int32_t>(tiles.size());
@@ -1076,6 +1114,8 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
         int per_sm = 1;
         if (!e->beam_staged)
             OK_CUDA(ok::occupancy_step_unstaged(e->smem_beam, &per_sm));
+        if (e->beam_seg)
+            per_sm = ok::kBeamSegCtasPerSm;
         e->ctas_per_sm_beam = std::max(1, per_sm);
     }
     if (int rc = build_tiles(e->batch_agents, e->num_sms, 4, &e->d_tiles, &e->n_tiles))
@@ -1094,13 +1134,22 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
     e->grid      = std::max(1, std::min(e->num_sms, e->n_tiles));
     e->grid_beam = std::max(1, std::min(e->num_sms * e->ctas_per_sm_beam, e->n_tiles_beam));
     if (e->beam_staged)
-    { // the end-to-end tiling (see ok_step_host): OK_E2E_TILES tiles per CTA (default 4)
-        int per_cta = 4;
+    { // the end-to-end tiling (see ok_step_host): OK_E2E_TILES tiles per CTA (default 4; 2 for the two-CTAs-per-SM shape)
+        int per_cta = e->beam_seg ? 2 : 4;
         if (const char *env = std::getenv("OK_E2E_TILES"))
             per_cta = std::max(1, std::atoi(env));
-        if (int rc = build_tiles_balanced(e->batch_agents_beam, e->num_sms, &e->d_tiles_e2e, &e->n_tiles_e2e, per_cta))
+        if (int rc = build_tiles_balanced(e->batch_agents_beam, e->num_sms * e->ctas_per_sm_beam, &e->d_tiles_e2e, &e->n_tiles_e2e, per_cta))
             return rc;
-        e->grid_e2e = std::max(1, std::min(e->num_sms, e->n_tiles_e2e));
+        e->grid_e2e = std::max(1, std::min(e->num_sms * e->ctas_per_sm_beam, e->n_tiles_e2e));
+    }
+    if (e->beam_seg)
+    { // both tilings are built: the launch's dynamic shared memory is the largest tile's need; two CTAs must fit an SM
+        e->smem_beam = seg_smem_need;
+        int per_sm   = 0;
+        OK_CUDA(ok::occupancy_step_segstaged(e->smem_beam, &per_sm));
+        if (per_sm < ok::kBeamSegCtasPerSm)
+            return fail(OK_ERR_CAPACITY, "segment-staged beam kernel: " + std::to_string(e->smem_beam) + " bytes of shared memory per CTA do not give " +
+                                             std::to_string(ok::kBeamSegCtasPerSm) + " CTAs per SM (set OK_BEAM_KERNEL=staged)");
     }
 
     // every agent starts where `Environment::resetAgent(agent, false)` puts it: RaceTrack::kStartingIdx
@@ -1792,6 +1841,9 @@ int ok_debug_violations(OkEnv *e, uint64_t *count, int32_t *checks_compiled_in)
     unsigned long long v = 0, u = 0;
     OK_CUDA(cudaMemcpyFromSymbol(&v, ok::g_violations, sizeof v));
     OK_CUDA(ok::violations_step_unstaged(&u));
+    unsigned long long w = 0;
+    OK_CUDA(ok::violations_step_segstaged(&w));
+    u += w;
     if (count)
         *count = v + u;
     if (checks_compiled_in)

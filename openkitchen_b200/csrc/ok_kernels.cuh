@@ -68,7 +68,8 @@ struct TrackRef
     // instead of chasing the header at the front of a multi-hundred-MB table that no cache holds
     float    bx0, by0, binv_h, bbin_scale, brb;
     int32_t  bnx, bny, bnb;
-    uint32_t boff_rows, boff_entries, boff_items, bn_rows, bn_chunks, pad;
+    uint32_t boff_rows, boff_entries, boff_items, bn_rows, bn_chunks;
+    uint32_t seg_bytes;   // header + segments (+ the null segment) = the blob's prefix up to the grid words, multiple of 16
 };
 static_assert(sizeof(TrackRef) == 80, "TrackRef layout");
 
@@ -143,6 +144,24 @@ __device__ __forceinline__ TrackView make_view(const uint8_t *blob)
     v.widths   = reinterpret_cast<const float *>(blob + h->off_widths);
     v.headings = reinterpret_cast<const float *>(blob + h->off_headings);
     v.safe     = reinterpret_cast<const float *>(blob + h->off_safe);
+    v.n_pts = h->n_points, v.n_seg = h->n_segments, v.nx = h->grid_nx, v.ny = h->grid_ny;
+    v.gx0 = h->grid_x0, v.gy0 = h->grid_y0, v.cell = h->cell, v.inv_cell = h->inv_cell;
+    return v;
+}
+
+// the SEGMENT-STAGED shape: header + segments from the staged prefix of the blob, everything else from the global blob
+__device__ __forceinline__ TrackView make_view_split(const uint8_t *staged_prefix, const uint8_t *gblob)
+{
+    const TrackHeader *h = reinterpret_cast<const TrackHeader *>(staged_prefix);
+    TrackView          v;
+    v.seg      = reinterpret_cast<const float4 *>(staged_prefix + h->off_segments);
+    v.words    = reinterpret_cast<const uint2 *>(gblob + h->off_words);
+    v.starts   = reinterpret_cast<const uint32_t *>(gblob + h->off_starts);
+    v.items    = reinterpret_cast<const uint16_t *>(gblob + h->off_items);
+    v.pts      = reinterpret_cast<const float2 *>(gblob + h->off_points);
+    v.widths   = reinterpret_cast<const float *>(gblob + h->off_widths);
+    v.headings = reinterpret_cast<const float *>(gblob + h->off_headings);
+    v.safe     = reinterpret_cast<const float *>(gblob + h->off_safe);
     v.n_pts = h->n_points, v.n_seg = h->n_segments, v.nx = h->grid_nx, v.ny = h->grid_ny;
     v.gx0 = h->grid_x0, v.gy0 = h->grid_y0, v.cell = h->cell, v.inv_cell = h->inv_cell;
     return v;
@@ -613,6 +632,22 @@ struct BeamView
     uint32_t        n_rows, n_chunks; // OK_CHECKED builds only
     bool            valid;
 };
+
+// The table constants the ray loop needs, in SHARED memory (beam kernel): they are uniform over a tile, and ptxas, short
+// of registers, used to spill them to local memory -- where a CTA's 64 KB of stack frames thrash the ~23 KB of L1 this
+// kernel leaves, so that every reload in the hot loop was a trip to the L2 (ncu: 328,000 local loads per launch, 1.7 %
+// L1 hits).  Read through ld_hot() at the point of use: one LDS instead.
+struct BeamHot
+{
+    const uint4 *entries;
+    const uint2 *chunks;
+    float        bin_scale, rb;
+    int32_t      nb_mask, nb;
+};
+template <typename T> __device__ __forceinline__ T ld_hot(const T &field)
+{
+    return *const_cast<const volatile T *>(&field);
+}
 
 __device__ __forceinline__ BeamView make_beam_view(const TrackRef &tr)
 {
@@ -1121,18 +1156,28 @@ constexpr int kUnitsPerRefill = OK_UNITS; // units of work a lane does between t
 #ifndef OK_BEAM_TILE
 #define OK_BEAM_TILE 64 // agents per tile of the unstaged beam kernel
 #endif
+//  * SEGMENT-STAGED (kStaged = true, kSegOnly = true): TWO 512-thread CTAs per SM, each behind its own track's header +
+//    SEGMENTS only (47-90 KB of the blob's 77-143 KB, the only part the narrow phase reads per candidate); centre line,
+//    widths, headings and the rarely walked grid come from the global blob.  Twice as many, half as large tiles: while
+//    one CTA sits in a thread-per-agent phase the SM's other CTA casts rays, and the tiles-per-track quantisation halves.
+#ifndef OK_BEAM_BLOCK_SEG
+#define OK_BEAM_BLOCK_SEG 512
+#endif
 constexpr int kBeamBlockStaged   = 1024;
 constexpr int kBeamBlockUnstaged = OK_BEAM_BLOCK;
+constexpr int kBeamBlockSeg      = OK_BEAM_BLOCK_SEG;
+constexpr int kBeamSegCtasPerSm  = 1024 / OK_BEAM_BLOCK_SEG; // 64 registers per thread fill the register file
 // capacity of the CTA's queue of rays pass A leaves to pass B.  Tile-local ray indices are 16 bits, so a beam tile holds
 // at most 65,535 rays (the host caps the batch); a full queue only costs speed (see pass A).
-__host__ __device__ constexpr int beam_pend_cap(bool staged)
+__host__ __device__ constexpr int beam_pend_cap(bool staged, bool seg_only = false)
 {
-    return staged ? 8192 : 2048;
+    return (staged && !seg_only) ? 8192 : 2048;
 }
 // static shared memory of the beam kernel besides the staged track and the agent records (host: batch sizing)
-__host__ __device__ constexpr int beam_static_smem(bool staged)
+__host__ __device__ constexpr int beam_static_smem(bool staged, bool seg_only = false)
 {
-    return (staged ? kBeamBlockStaged : kBeamBlockUnstaged) * (16 + 8) + 2 * beam_pend_cap(staged) + 4 * (beam_pend_cap(staged) / 32) + 128;
+    return (staged ? (seg_only ? kBeamBlockSeg : kBeamBlockStaged) : kBeamBlockUnstaged) * (16 + 8) + 2 * beam_pend_cap(staged, seg_only) +
+           4 * (beam_pend_cap(staged, seg_only) / 32) + 128;
 }
 
 __device__ __forceinline__ unsigned long long global_timer()
@@ -1149,11 +1194,12 @@ __device__ __forceinline__ unsigned long long global_timer()
             p.trace[(static_cast<size_t>(blockIdx.x) * p.trace_tiles + n_done) * 6 + (slot)] = global_timer();         \
     } while (0)
 
-template <int kBlock, bool kBeam, bool kStaged = true>
-__global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS : 1) step_kernel(const StepParams p)
+template <int kBlock, bool kBeam, bool kStaged = true, bool kSegOnly = false>
+__global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS : (kSegOnly ? 1024 / kBlock : 1)) step_kernel(const StepParams p)
 {
-    constexpr bool kStage   = !kBeam || kStaged; // the track is staged in shared memory with one TMA bulk copy
-    constexpr int  kPendCap = beam_pend_cap(kStaged);
+    static_assert(!kSegOnly || (kBeam && kStaged), "the segment-staged shape is a beam kernel");
+    constexpr bool kStage   = !kBeam || kStaged; // the track (kSegOnly: its header + segments) is staged in shared memory with one TMA bulk copy
+    constexpr int  kPendCap = beam_pend_cap(kStaged, kSegOnly);
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint16_t                      s_order[kBeam ? 1 : 1024]; // pool order of the rays (p.ray_order)
     __shared__ __align__(8) uint64_t         bar;
@@ -1168,6 +1214,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
     AgentRec *recs    = reinterpret_cast<AgentRec *>(smem + (kStage ? p.smem_blob_bytes : 0u));
     float2   *dirs    = reinterpret_cast<float2 *>(recs + p.batch_agents); // !kBeam
     // kBeam: per-thread ray parameters and result keys of the group a warp is working on
+    __shared__ BeamHot                         s_hot;
     __shared__ __align__(16) float4             s_wray[kBeam ? kBlock : 1];
     __shared__ __align__(8) unsigned long long s_wkey[kBeam ? kBlock : 1];
 
@@ -1214,11 +1261,14 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
         // the bulk copy of the track runs under phase 1, which reads no staged data; it is awaited before the rays
         const uint8_t *gblob   = p.arena + tr.offset;
         const bool     restage = kStage && tl.track != staged;
+        const uint32_t stage_bytes = kSegOnly ? tr.seg_bytes : tr.bytes;
+        if (kSegOnly) // the records follow THIS track's segments (tracks differ by a factor of two: a fixed offset would waste it)
+            recs = reinterpret_cast<AgentRec *>(smem + ((tr.seg_bytes + 127u) & ~127u));
         if (restage && tid == 0)
         {
             fence_proxy_async();
-            mbar_expect_tx(&bar, tr.bytes);
-            tma_bulk_g2s(blob, gblob, tr.bytes, &bar);
+            mbar_expect_tx(&bar, stage_bytes);
+            tma_bulk_g2s(blob, gblob, stage_bytes, &bar);
         }
         BeamView bv;
         bv.valid = false;
@@ -1234,7 +1284,15 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
         if (tid < count)
             recs[tid] = agent_pre(p, gblob, bv, tl.begin + tid);
         if (tid == 0)
+        {
             s_pool = 0, s_pool2 = 0, s_npend = 0, s_adone = 0;
+            if (kBeam)
+            {
+                s_hot.entries = bv.entries, s_hot.chunks = bv.chunks;
+                s_hot.bin_scale = bv.bin_scale, s_hot.rb = bv.rb;
+                s_hot.nb = bv.nb, s_hot.nb_mask = bv.nb - 1;
+            }
+        }
         if (kBeam)
             for (int i = tid; i < kPendCap / 32; i += kBlock)
                 s_ready[i] = 0;
@@ -1246,8 +1304,8 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
         }
         __syncthreads();
         OK_TRACE(2);
-        const uint8_t  *track    = kStage ? blob : gblob; // where this tile reads its track from
-        const TrackView tv       = make_view(track);
+        const uint8_t  *track    = (kStage && !kSegOnly) ? blob : gblob; // where this tile reads its (whole) track from
+        const TrackView tv       = kSegOnly ? make_view_split(blob, gblob) : make_view(track);
         const int64_t   ray_base = tl.begin * R; // global index of the batch's first ray
         if (!kBeam)
         {
@@ -1423,9 +1481,9 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                     active              = !(rec.flags & kFlagCrashed);
                     if (active && rec.row >= 0 && fabsf(ang) < kBeamMaxAngle)
                     {
-                        const int bin = __float2int_rd(fmul(ang, bv.bin_scale)) & (bv.nb - 1);
+                        const int bin = __float2int_rd(fmul(ang, ld_hot(s_hot.bin_scale))) & ld_hot(s_hot.nb_mask);
                         OK_CHECK(static_cast<uint32_t>(rec.row) < bv.n_rows);
-                        ent           = __ldg(bv.entries + static_cast<size_t>(rec.row) * bv.nb + bin);
+                        ent           = __ldg(ld_hot(s_hot.entries) + static_cast<size_t>(rec.row) * ld_hot(s_hot.nb) + bin);
                         OK_CHECK((ent.w >> 24) == 0 || ent.z + (ent.w >> 24) <= bv.n_chunks);
                         cov           = true;
                     }
@@ -1480,7 +1538,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                     if (static_cast<uint32_t>(lane) < total)
                     {
                         OK_CHECK(ch < bv.n_chunks);
-                        it = __ldg(bv.chunks + ch);
+                        it = __ldg(ld_hot(s_hot.chunks) + ch);
                     }
                 }
                 for (uint32_t base = 0; base < total; base += 32)
@@ -1493,7 +1551,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                         const uint32_t jn = base + 32 + lane;
                         const uint32_t ch = find_chunk(jn, owner_n);
                         if (jn < total)
-                            it_n = __ldg(bv.chunks + ch);
+                            it_n = __ldg(ld_hot(s_hot.chunks) + ch);
                     }
                     if (base + lane < total)
                     {
@@ -1515,7 +1573,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                     const unsigned long long key   = w_key[lane];
                     int                      best  = static_cast<int>(0x7fffffffu - static_cast<uint32_t>(key));
                     const float              min_t = __uint_as_float(static_cast<uint32_t>(key >> 32));
-                    const float              d_eff = beam_meta_dist(ent.w & 0xfffu, bv.rb);
+                    const float              d_eff = beam_meta_dist(ent.w & 0xfffu, ld_hot(s_hot.rb));
                     float t_known = min_t; // the key holds the exact t of `best`
                     if (active && !(cov && min_t <= d_eff - kBeamSlack))
                     { // undecided: everything nearer than d_eff - 1 is settled, the grid walk covers the rest
@@ -1565,7 +1623,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                 const float min_t = __uint_as_float(static_cast<uint32_t>(key >> 32));
                 // d1: up to there the inline four are the only contenders (= the list's completeness distance when it
                 // has no rest).  The key holds the exact t of its segment, or the sensor range when nothing was hit.
-                const float d1      = beam_meta_dist((ent.w >> 12) & 0xfffu, bv.rb);
+                const float d1      = beam_meta_dist((ent.w >> 12) & 0xfffu, ld_hot(s_hot.rb));
                 const bool  settled = cov && (min_t <= d1 - kBeamSlack);
                 const bool  queue   = has && active && !settled;
                 float       sq      = inf;
@@ -2284,5 +2342,10 @@ __global__ void fill_actions_kernel(const StepParams p, int64_t n)
 cudaError_t launch_step_unstaged(const StepParams &p, int grid, size_t smem_bytes, cudaStream_t stream);
 cudaError_t occupancy_step_unstaged(size_t smem_bytes, int *ctas_per_sm);
 cudaError_t violations_step_unstaged(unsigned long long *count);
+// the segment-staged beam kernel's (ok_step_segstaged.cu)
+cudaError_t launch_step_segstaged(const StepParams &p, int grid, size_t smem_bytes, cudaStream_t stream);
+cudaError_t arm_step_segstaged(int smem_optin);
+cudaError_t occupancy_step_segstaged(size_t smem_bytes, int *ctas_per_sm);
+cudaError_t violations_step_segstaged(unsigned long long *count);
 
 } // namespace ok
