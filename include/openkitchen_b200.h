@@ -311,6 +311,16 @@ int ok_debug_violations(OkEnv *env, uint64_t *count, int32_t *checks_compiled_in
  * h_out (layout [grid_blocks][tiles_per_cta][6], zero = unused) and returns the count; then re-arms the trace with room
  * for `tiles_per_cta` tiles per CTA (0 = off).  Synchronises the device. */
 int64_t ok_debug_trace(OkEnv *env, uint64_t *h_out, int64_t capacity_words, int32_t tiles_per_cta);
+/* Feedback tiling of the staged beam kernels.  The kernel leaves every tile's time (ray phase / rest) in a small device
+ * buffer; this call synchronises `stream`, reads it and re-cuts the tiles so that a tile's MEASURED cost -- not its agent
+ * count -- is equal across the SMs (tracks differ by up to 15 % per agent).  Results never depend on the tiling.  The
+ * library does this on its own after the 16th, 64th and 256th launch of an env and every 4,096 launches from then on
+ * (never inside a stream capture; OK_AUTO_BALANCE=0 turns that off); call it yourself after a change of workload.
+ * out[0] / out[1] (nullable): slowest tile over mean tile before (measured) and after (predicted). */
+int ok_balance_schedule(OkEnv *env, void *stream, float out[2]);
+/* The beam kernel's tiling of the population (profiling aid; ok_debug_trace's tile ids index it): copies up to `capacity`
+ * tiles as {track, count, first agent} to h_out[capacity][3] and returns the number of tiles. */
+int64_t ok_debug_tiles(OkEnv *env, int64_t *h_out, int64_t capacity);
 /* evaluates the kernels' sincosf (the glibc-2.39 restatement, ok_math.cuh) on `n` host floats: lets a test
  * compare the DEVICE function with libm / the oracle directly (tests/test_gpu_math.py) */
 int ok_eval_sincosf(OkEnv *env, const float *h_in, float *h_sin, float *h_cos, int64_t n);

@@ -134,6 +134,8 @@ SIGNATURES = {
     "ok_debug_stats": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_int32]),
     "ok_debug_violations": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
     "ok_debug_trace": (C.c_int64, [_P, _P, C.c_int64, C.c_int32]),
+    "ok_debug_tiles": (C.c_int64, [_P, _P, C.c_int64]),
+    "ok_balance_schedule": (C.c_int, [_P, _P, _P]),
     "ok_eval_sincosf": (C.c_int, [_P, _P, _P, _P, C.c_int64]),
     "ok_beam_lookup": (C.c_int32, [_P, C.c_int32, C.c_float, C.c_float, C.c_float, _P, C.c_int32, C.POINTER(C.c_float)]),
     "ok_beam_lookup_ex": (C.c_int32, [_P, C.c_int32, C.c_float, C.c_float, C.c_float, _P, C.c_int32, C.POINTER(C.c_float),

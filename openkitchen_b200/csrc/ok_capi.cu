@@ -150,6 +150,26 @@ struct OkEnv
     // the beam kernel's batches are not limited by per-ray scratch: its own batch size, tile table and grid
     ok::Tile            *d_tiles_beam{nullptr};
     int32_t              n_tiles_beam{0};
+    // cost feedback for the beam tiling (ok_balance_schedule): the kernel leaves every tile's ray-phase / other time here
+    struct TileRun
+    {
+        int32_t track;
+        int64_t begin, len, cap; // cap: most agents a tile of this run may hold
+        double  w;               // measured cost per agent (ns in the ray phase), 1 before any measurement
+        int64_t k;               // tiles
+    };
+    std::vector<TileRun>  beam_runs;
+    std::vector<ok::Tile> h_tiles_beam;
+    bool                  beam_launches_weighted{false};
+    int32_t               tiles_beam_target{0}, tiles_beam_capacity{0};
+    uint32_t             *d_tile_ns{nullptr};
+    std::vector<ok::TrackRef> h_track_refs;     // host copy of d_track_refs
+    ok::FirstTile            *d_first_beam{nullptr}; // the first tile of every CTA with its track record (ok_kernels.cuh)
+    int32_t                   first_capacity{0};
+    bool                      first_dirty{true};
+    uint64_t              beam_launches{0};
+    int                   auto_balance{1};
+    float                 balance_before{0.0f}, balance_after{0.0f}; // predicted slowest-tile / mean-tile cost of the last rebalancing
     // ok_step_host's tiling: several tiles per CTA, so that a tile's observations cross PCIe while the next one is computed
     ok::Tile            *d_tiles_e2e{nullptr};
     int32_t              n_tiles_e2e{0}, grid_e2e{0};
@@ -202,6 +222,12 @@ void free_agents(OkEnv *e)
     if (e->d_tiles_e2e)
         cudaFree(e->d_tiles_e2e);
     e->d_tiles_beam = nullptr, e->n_tiles_beam = 0, e->d_tiles_e2e = nullptr, e->n_tiles_e2e = 0;
+    if (e->d_tile_ns)
+        cudaFree(e->d_tile_ns);
+    if (e->d_first_beam)
+        cudaFree(e->d_first_beam);
+    e->d_first_beam = nullptr, e->first_capacity = 0, e->first_dirty = true;
+    e->d_tile_ns = nullptr, e->beam_launches = 0, e->beam_launches_weighted = false, e->beam_runs.clear(), e->h_tiles_beam.clear();
     if (e->d_ray_order)
         cudaFree(e->d_ray_order);
     if (e->d_sched)
@@ -503,7 +529,11 @@ int ensure_arena(OkEnv *e)
             r.boff_rows = h.off_rows, r.boff_entries = h.off_entries, r.boff_items = h.off_items;
             r.bn_rows = h.n_rows, r.bn_chunks = h.n_chunks;
         }
-        r.seg_bytes = reinterpret_cast<const ok::TrackHeader *>(t.blob.data())->off_words; // header + segments
+        {
+            const ok::TrackHeader *th = reinterpret_cast<const ok::TrackHeader *>(t.blob.data());
+            r.seg_bytes = th->off_words; // header + segments
+            r.n_points = th->n_points, r.off_points = th->off_points, r.off_headings = th->off_headings;
+        }
         refs.push_back(r);
         total += (t.blob.size() + 127) / 128 * 128;
         e->max_blob_used = std::max(e->max_blob_used, t.blob.size());
@@ -516,6 +546,8 @@ int ensure_arena(OkEnv *e)
     OK_CUDA(cudaMalloc(&e->d_track_refs, sizeof(ok::TrackRef) * std::max<size_t>(refs.size(), 1)));
     OK_CUDA(cudaMemcpy(e->d_arena, host.data(), total, cudaMemcpyHostToDevice));
     OK_CUDA(cudaMemcpy(e->d_track_refs, refs.data(), sizeof(ok::TrackRef) * refs.size(), cudaMemcpyHostToDevice));
+    e->h_track_refs = refs;
+    e->first_dirty  = true;
     e->arena_bytes = total;
     e->arena_dirty = false;
     return OK_SUCCESS;
@@ -605,6 +637,120 @@ int arm_shared_memory_limit(OkEnv *e)
     return OK_SUCCESS;
 }
 
+// Cost-aware balanced tiling.  A tile of `count` agents of run r costs about c0 + w_r * count (c0: the thread-per-agent
+// phases and barriers, whatever the size; w_r: the ray phase, which differs from track to track by up to 15 %).  Tiles go
+// to the runs greedily -- one more for the run whose tiles are the most expensive -- which minimises the slowest tile;
+// every run is cut into equal parts, most expensive first (CTAs take tiles in list order).  With w = 1, c0 = 0 this is the
+// plain balanced tiling by agent count.
+std::vector<ok::Tile> cost_balanced_tiles(std::vector<OkEnv::TileRun> &runs, int64_t target, double c0, float *slowest_over_mean)
+{
+    int64_t have = 0;
+    for (auto &r : runs)
+    {
+        r.k = std::max<int64_t>(1, (r.len + r.cap - 1) / r.cap);
+        have += r.k;
+    }
+    auto cost = [&](const OkEnv::TileRun &r) { return c0 + r.w * static_cast<double>((r.len + r.k - 1) / r.k); };
+    for (; have < target; ++have)
+    {
+        OkEnv::TileRun *best = nullptr;
+        for (auto &r : runs)
+            if (r.len > r.k && (!best || cost(r) > cost(*best)))
+                best = &r;
+        if (!best)
+            break;
+        best->k++;
+    }
+    struct Costed
+    {
+        ok::Tile t;
+        double   c;
+    };
+    std::vector<Costed> tiles;
+    double              sum = 0.0, worst = 0.0;
+    for (const auto &r : runs)
+        for (int64_t t = 0; t < r.k; ++t)
+        {
+            const int64_t b0 = r.begin + r.len * t / r.k, b1 = r.begin + r.len * (t + 1) / r.k;
+            if (b1 > b0)
+            {
+                const double c = c0 + r.w * static_cast<double>(b1 - b0);
+                tiles.push_back({{r.track, static_cast<int32_t>(b1 - b0), b0}, c});
+                sum += c, worst = std::max(worst, c);
+            }
+        }
+    std::stable_sort(tiles.begin(), tiles.end(), [](const Costed &a, const Costed &b) { return a.c > b.c; });
+    if (slowest_over_mean)
+        *slowest_over_mean = tiles.empty() ? 1.0f : static_cast<float>(worst * static_cast<double>(tiles.size()) / sum);
+    std::vector<ok::Tile> out;
+    out.reserve(tiles.size());
+    for (const auto &t : tiles)
+        out.push_back(t.t);
+    return out;
+}
+
+// Re-cuts the beam tiling from the per-tile times the last launch on `s` left in d_tile_ns.  Results do not depend on the
+// tiling (tests/test_gpu_properties.py); only the finish times of the SMs do.  Synchronises `s`.
+int rebalance_beam_tiles(OkEnv *e, cudaStream_t s)
+{
+    if (!e->d_tile_ns || e->h_tiles_beam.empty() || e->beam_runs.empty())
+        return OK_SUCCESS;
+    OK_CUDA(cudaStreamSynchronize(s));
+    std::vector<uint32_t> ns(2 * e->h_tiles_beam.size());
+    OK_CUDA(cudaMemcpy(ns.data(), e->d_tile_ns, sizeof(uint32_t) * ns.size(), cudaMemcpyDeviceToHost));
+    // per run: ns of ray phase per agent; c0: the median of what a tile spends outside the ray phase
+    std::vector<double>   ray_ns(e->beam_runs.size(), 0.0), agents(e->beam_runs.size(), 0.0);
+    std::vector<uint32_t> rest;
+    for (size_t i = 0; i < e->h_tiles_beam.size(); ++i)
+    {
+        if (ns[2 * i] == 0 || ns[2 * i] > 1000000000u) // never ran (or a wrapped timer): no information
+            continue;
+        const ok::Tile &t = e->h_tiles_beam[i];
+        for (size_t r = 0; r < e->beam_runs.size(); ++r)
+            if (t.begin >= e->beam_runs[r].begin && t.begin < e->beam_runs[r].begin + e->beam_runs[r].len)
+            {
+                ray_ns[r] += ns[2 * i], agents[r] += t.count;
+                break;
+            }
+        rest.push_back(ns[2 * i + 1]);
+    }
+    if (rest.size() * 2 < e->h_tiles_beam.size())
+        return OK_SUCCESS; // too few tiles measured
+    std::nth_element(rest.begin(), rest.begin() + rest.size() / 2, rest.end());
+    const double c0 = rest[rest.size() / 2];
+    double       w_sum = 0.0, a_sum = 0.0;
+    for (size_t r = 0; r < e->beam_runs.size(); ++r)
+        w_sum += ray_ns[r], a_sum += agents[r];
+    const double w_mean = a_sum > 0 ? w_sum / a_sum : 1.0;
+    // what the CURRENT tiling costs under the measured model (for the report)
+    {
+        double sum = 0.0, worst = 0.0;
+        for (size_t i = 0; i < e->h_tiles_beam.size(); ++i)
+        {
+            const double c = static_cast<double>(ns[2 * i]) + ns[2 * i + 1];
+            sum += c, worst = std::max(worst, c);
+        }
+        e->balance_before = sum > 0 ? static_cast<float>(worst * e->h_tiles_beam.size() / sum) : 1.0f;
+    }
+    for (size_t r = 0; r < e->beam_runs.size(); ++r)
+    { // damped: half way from the weight in use to the measured one (a tile's time also depends on who shares its SM)
+        const double measured = agents[r] > 0 ? ray_ns[r] / agents[r] : w_mean;
+        const double prev     = e->beam_launches_weighted ? e->beam_runs[r].w : w_mean;
+        e->beam_runs[r].w     = 0.5 * (prev + measured);
+    }
+    e->beam_launches_weighted = true;
+    std::vector<ok::Tile> tiles = cost_balanced_tiles(e->beam_runs, e->tiles_beam_target, c0, &e->balance_after);
+    if (tiles.empty() || static_cast<int32_t>(tiles.size()) > e->tiles_beam_capacity)
+        return OK_SUCCESS;
+    OK_CUDA(cudaMemcpy(e->d_tiles_beam, tiles.data(), sizeof(ok::Tile) * tiles.size(), cudaMemcpyHostToDevice));
+    OK_CUDA(cudaMemset(e->d_tile_ns, 0, sizeof(uint32_t) * 2 * static_cast<size_t>(e->tiles_beam_capacity)));
+    e->h_tiles_beam = std::move(tiles);
+    e->first_dirty  = true;
+    e->n_tiles_beam = static_cast<int32_t>(e->h_tiles_beam.size());
+    e->grid_beam    = std::max(1, std::min(e->num_sms * e->ctas_per_sm_beam, e->n_tiles_beam));
+    return OK_SUCCESS;
+}
+
 int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
 {
     int rc = ensure_arena(e);
@@ -614,11 +760,57 @@ int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
     p.tracks     = e->d_track_refs;
     if (e->cfg.raycast_mode == OK_RAYCAST_BEAM)
     {
+        const bool e2e = p.host_obs && e->d_tiles_e2e;
+        if (!e2e && e->auto_balance && e->d_tile_ns)
+        { // feedback tiling: re-cut the tiles from the measured tile times, a few times early on, then now and then
+            const uint64_t k = e->beam_launches++;
+            if (k == 16 || k == 64 || k == 256 || (k & 4095) == 4095)
+            {
+                cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+                if (cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone)
+                    if (int rc2 = rebalance_beam_tiles(e, s))
+                        return rc2;
+            }
+        }
         p.tiles        = e->d_tiles_beam;
         p.n_tiles      = e->n_tiles_beam;
         p.batch_agents = e->batch_agents_beam;
+        p.tile_ns      = e2e ? nullptr : e->d_tile_ns;
         int grid       = e->grid_beam;
-        if (p.host_obs && e->d_tiles_e2e)
+        p.first        = nullptr;
+        if (!e2e && !e->h_tiles_beam.empty())
+        { // the CTAs' first tiles with their track records side by side (rebuilt when the tiling or the arena changed)
+            if (e->first_dirty)
+            {
+                cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+                if (cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone)
+                {
+                    const int32_t nf = std::min<int32_t>(grid, static_cast<int32_t>(e->h_tiles_beam.size()));
+                    if (nf > e->first_capacity)
+                    {
+                        OK_CUDA(cudaStreamSynchronize(s));
+                        if (e->d_first_beam)
+                            cudaFree(e->d_first_beam);
+                        e->d_first_beam = nullptr, e->first_capacity = 0;
+                        OK_CUDA(cudaMalloc(&e->d_first_beam, sizeof(ok::FirstTile) * static_cast<size_t>(nf)));
+                        e->first_capacity = nf;
+                    }
+                    std::vector<ok::FirstTile> first(static_cast<size_t>(nf));
+                    for (int32_t i = 0; i < nf; ++i)
+                    {
+                        first[i].tile = e->h_tiles_beam[i];
+                        first[i].ref  = e->h_track_refs[e->h_tiles_beam[i].track];
+                        std::memset(first[i].pad, 0, sizeof first[i].pad);
+                    }
+                    OK_CUDA(cudaStreamSynchronize(s)); // (a launch in flight may still read the old records)
+                    OK_CUDA(cudaMemcpy(e->d_first_beam, first.data(), sizeof(ok::FirstTile) * first.size(), cudaMemcpyHostToDevice));
+                    e->first_dirty = false;
+                }
+            }
+            if (!e->first_dirty)
+                p.first = e->d_first_beam;
+        }
+        if (e2e)
         { // results stream to a host buffer: several tiles per CTA, each flushed while the next is computed
             p.tiles   = e->d_tiles_e2e;
             p.n_tiles = e->n_tiles_e2e;
@@ -939,7 +1131,8 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
         // Which shape (ok_kernels.cuh): the staged one for throughput, the unstaged one when the population is too small
         // to give every SM a worthwhile tile (OK_BEAM_KERNEL = staged | unstaged overrides).
         e->beam_staged = n >= 2048; // measured (tools/bench_small.py): the unstaged shape is ahead only below ~2,000 agents
-        e->beam_seg = e->beam_staged && n >= static_cast<int64_t>(e->num_sms) * ok::kBeamSegCtasPerSm * 64;
+        e->beam_seg = false; // opt-in (OK_BEAM_KERNEL=segstaged): 1 % ahead at 65,536 agents with tiles of equal agent counts, but its tile times
+                             // depend on the CTA that shares the SM, so the feedback tiling gains nothing there (0.092 vs 0.085 ms per tick)
         if (const char *env = std::getenv("OK_BEAM_KERNEL"))
         {
             e->beam_staged = std::strcmp(env, "unstaged") != 0 && (std::strcmp(env, "staged") == 0 || std::strcmp(env, "segstaged") == 0 || e->beam_staged);
@@ -1056,15 +1249,14 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
     // latency (thread-per-agent phases, second ray pass, barriers) whatever its size: the fewer, larger and more equal
     // the tiles, the better.  Tiles = CTAs x waves, dealt to the track runs in proportion to their length, every run
     // cut into equal parts, largest first.
-    size_t seg_smem_need = 0; // segment-staged shape: the largest (segments + records) of any tile built below
-    auto   build_tiles_balanced = [&](int max_tile, int ctas, ok::Tile **d_out, int32_t *n_out, int min_waves = 1) -> int {
-        struct Run
-        {
-            int32_t track;
-            int64_t begin, len;
-            int64_t k;
-        };
-        std::vector<Run> runs;
+    size_t seg_smem_need = 0; // segment-staged shape: the most (segments + records) any tile of any tiling may need
+    // Balanced tiling (staged beam kernels).  The kernel's cost per ray is nearly uniform, but a tile pays ~15 us of serial
+    // latency (thread-per-agent phases, second ray pass, barriers) whatever its size: the fewer, larger and more equal
+    // the tiles, the better.  Tiles = CTAs x waves, dealt to the track runs in proportion to their length (and, once the
+    // kernel has reported tile times, to their measured cost: cost_balanced_tiles / rebalance_beam_tiles).
+    auto build_tiles_balanced = [&](int max_tile, int ctas, ok::Tile **d_out, int32_t *n_out, int min_waves = 1, bool feedback = false) -> int {
+        std::vector<OkEnv::TileRun> runs;
+        int64_t                     have = 0;
         for (int64_t i = 0; i < n;)
         {
             int64_t j = i;
@@ -1072,42 +1264,28 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
                 ++j;
             // (segment-staged shape: a track's tiles are capped by what fits behind ITS segments)
             const int64_t cap = e->beam_seg ? std::min<int64_t>(max_tile, seg_cap_of(e->h_track_id[i])) : max_tile;
-            runs.push_back({e->h_track_id[i], i, j - i, (j - i + cap - 1) / cap});
+            runs.push_back({e->h_track_id[i], i, j - i, cap, 1.0, 0});
+            have += (j - i + cap - 1) / cap;
+            if (e->beam_seg)
+                seg_smem_need = std::max(seg_smem_need, (static_cast<size_t>(reinterpret_cast<const ok::TrackHeader *>(e->tracks[e->h_track_id[i]].blob.data())->off_words) + 127) / 128 * 128 +
+                                                            ok::beam_smem_bytes(static_cast<int>(std::min<int64_t>(cap, j - i))));
             i = j;
         }
-        int64_t have = 0;
-        for (auto &r : runs)
-            have += r.k;
         const int64_t waves  = std::max<int64_t>({static_cast<int64_t>(min_waves), (n + static_cast<int64_t>(ctas) * max_tile - 1) / (static_cast<int64_t>(ctas) * max_tile),
-                                                  e->beam_seg ? (have + ctas - 1) / ctas : int64_t{1}});
+                                                  (have + ctas - 1) / ctas});
         const int64_t target = static_cast<int64_t>(ctas) * waves;
-        for (; have < target; ++have)
-        { // one more tile for the run whose tiles are the largest
-            Run *best = nullptr;
-            for (auto &r : runs)
-                if (r.len > r.k && (!best || r.len * best->k > best->len * r.k))
-                    best = &r;
-            if (!best)
-                break;
-            best->k++;
-        }
-        std::vector<ok::Tile> tiles;
-        for (const auto &r : runs)
-            for (int64_t t = 0; t < r.k; ++t)
-            {
-                const int64_t b0 = r.begin + r.len * t / r.k, b1 = r.begin + r.len * (t + 1) / r.k;
-                if (b1 > b0)
-                {
-                    tiles.push_back({r.track, static_cast<int32_t>(b1 - b0), b0});
-                    if (e->beam_seg)
-                        seg_smem_need = std::max(seg_smem_need, (static_cast<size_t>(reinterpret_cast<const ok::TrackHeader *>(e->tracks[r.track].blob.data())->off_words) + 127) / 128 * 128 +
-                                                                    ok::beam_smem_bytes(static_cast<int>(b1 - b0)));
-                }
-            }
-        std::stable_sort(tiles.begin(), tiles.end(), [](const ok::Tile &a, const ok::Tile &b) { return a.count > b.count; });
+        std::vector<ok::Tile> tiles = cost_balanced_tiles(runs, target, 0.0, nullptr);
+        const size_t capacity = std::max<size_t>(tiles.size(), static_cast<size_t>(target));
         *n_out = static_cast<int32_t>(tiles.size());
-        OK_CUDA(cudaMalloc(d_out, sizeof(ok::Tile) * tiles.size()));
+        OK_CUDA(cudaMalloc(d_out, sizeof(ok::Tile) * capacity));
         OK_CUDA(cudaMemcpy(*d_out, tiles.data(), sizeof(ok::Tile) * tiles.size(), cudaMemcpyHostToDevice));
+        if (feedback)
+        {
+            e->beam_runs = runs, e->h_tiles_beam = tiles, e->first_dirty = true;
+            e->tiles_beam_target = static_cast<int32_t>(target), e->tiles_beam_capacity = static_cast<int32_t>(capacity);
+            OK_CUDA(cudaMalloc(&e->d_tile_ns, sizeof(uint32_t) * 2 * capacity));
+            OK_CUDA(cudaMemset(e->d_tile_ns, 0, sizeof(uint32_t) * 2 * capacity));
+        }
         return OK_SUCCESS;
     };
     {
@@ -1126,7 +1304,15 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
         int tail_div = e->beam_staged ? -1 : 0; // -1: balanced tiling
         if (const char *env = std::getenv("OK_BEAM_TAIL"))
             tail_div = std::atoi(env);
-        const int rc = tail_div < 0 ? build_tiles_balanced(e->batch_agents_beam, e->num_sms * e->ctas_per_sm_beam, &e->d_tiles_beam, &e->n_tiles_beam)
+        int waves = 1; // balanced tiling: tiles per CTA (OK_BEAM_WAVES)
+        if (const char *env = std::getenv("OK_BEAM_WAVES"))
+            waves = std::max(1, std::atoi(env));
+        if (e->beam_seg)
+            tail_div = -1; // (the guided schedule knows nothing of the per-track tile caps of the segment-staged shape)
+        e->auto_balance = 1; // OK_AUTO_BALANCE=0: keep the tiling by agent count
+        if (const char *env = std::getenv("OK_AUTO_BALANCE"))
+            e->auto_balance = std::atoi(env);
+        const int rc = tail_div < 0 ? build_tiles_balanced(e->batch_agents_beam, e->num_sms * e->ctas_per_sm_beam, &e->d_tiles_beam, &e->n_tiles_beam, waves, true)
                                     : build_tiles(e->batch_agents_beam, e->num_sms * e->ctas_per_sm_beam, tail_div, &e->d_tiles_beam, &e->n_tiles_beam);
         if (rc)
             return rc;
@@ -1849,6 +2035,35 @@ int ok_debug_violations(OkEnv *e, uint64_t *count, int32_t *checks_compiled_in)
     if (checks_compiled_in)
         *checks_compiled_in = OK_CHECKED;
     return OK_SUCCESS;
+}
+
+int ok_balance_schedule(OkEnv *e, void *stream, float out[2])
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    DeviceGuard g(e->cfg.device);
+    if (e->cfg.raycast_mode == OK_RAYCAST_BEAM)
+        if ((rc = rebalance_beam_tiles(e, static_cast<cudaStream_t>(stream))))
+            return rc;
+    if (out)
+        out[0] = e->balance_before, out[1] = e->balance_after;
+    return OK_SUCCESS;
+}
+
+int64_t ok_debug_tiles(OkEnv *e, int64_t *h_out, int64_t capacity)
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    if (e->cfg.raycast_mode != OK_RAYCAST_BEAM || !e->d_tiles_beam)
+        return 0;
+    DeviceGuard           g(e->cfg.device);
+    std::vector<ok::Tile> tiles(static_cast<size_t>(e->n_tiles_beam));
+    OK_CUDA(cudaMemcpy(tiles.data(), e->d_tiles_beam, sizeof(ok::Tile) * tiles.size(), cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; h_out && i < std::min<int64_t>(capacity, e->n_tiles_beam); ++i)
+        h_out[3 * i] = tiles[i].track, h_out[3 * i + 1] = tiles[i].count, h_out[3 * i + 2] = tiles[i].begin;
+    return e->n_tiles_beam;
 }
 
 int64_t ok_debug_trace(OkEnv *e, uint64_t *h_out, int64_t capacity_words, int32_t tiles_per_cta)

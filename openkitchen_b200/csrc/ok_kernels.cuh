@@ -70,8 +70,19 @@ struct TrackRef
     int32_t  bnx, bny, bnb;
     uint32_t boff_rows, boff_entries, boff_items, bn_rows, bn_chunks;
     uint32_t seg_bytes;   // header + segments (+ the null segment) = the blob's prefix up to the grid words, multiple of 16
+    // what a crashed agent's auto-reset needs of the blob's header (phase 1 reads the GLOBAL blob: one trip to memory less)
+    int32_t  n_points;
+    uint32_t off_points, off_headings, pad;
 };
-static_assert(sizeof(TrackRef) == 80, "TrackRef layout");
+static_assert(sizeof(TrackRef) == 96, "TrackRef layout");
+// a CTA's FIRST tile with its track record next to it: one trip to memory instead of two before any work can start
+struct FirstTile
+{
+    Tile     tile;
+    TrackRef ref;
+    uint32_t pad[4];
+};
+static_assert(sizeof(FirstTile) == 128, "FirstTile layout");
 
 struct StepParams
 {
@@ -91,6 +102,7 @@ struct StepParams
     const uint8_t *arena;
     const TrackRef *tracks;
     const Tile    *tiles;
+    const FirstTile *first; // nullable: tiles[b] and its track record for b < gridDim.x
     int32_t        n_tiles;
     int32_t        rays;
     int32_t        batch_agents;    // agents per tile (shared-memory scratch is sized for this many)
@@ -100,6 +112,7 @@ struct StepParams
     unsigned long long *stats;      // nullable: {rays cast, rays queued for pass B, rays sent to the grid walk} (beam kernel)
     unsigned long long *trace;      // nullable: per CTA and tile, globaltimer at the phase boundaries (profiling aid, beam kernel)
     int32_t             trace_tiles; // tiles per CTA the trace buffer has room for
+    uint32_t           *tile_ns;     // nullable (beam kernel): per tile {ns in the ray phase, ns in the rest of the tile}: feedback for the host's tiling
     // this launch
     const float *ext_thr, *ext_steer; // nullable: actions supplied by the caller
     int32_t      action_source;       // 0 stored/ext, 1 philox
@@ -860,10 +873,12 @@ __host__ __device__ inline size_t beam_smem_bytes(int agents)
 // returns the record the ray and reward phases work from.
 // `gblob` is the track's blob in the GLOBAL arena: only a crashed agent's auto-reset reads it (centre line, headings),
 // so phase 1 does not have to wait for the blob to be staged in shared memory.
-__device__ __forceinline__ AgentRec agent_pre(const StepParams &p, const uint8_t *gblob, const BeamView &bv, const int64_t a)
+__device__ __forceinline__ AgentRec agent_pre(const StepParams &p, const uint8_t *gblob, const TrackRef &tr, const BeamView &bv, const int64_t a)
 {
     float    x = p.x[a], y = p.y[a], rot = p.rot[a], speed = p.speed[a], accel = p.accel[a];
     bool     crashed = p.crashed[a] != 0, timed_out = p.timed_out[a] != 0;
+    // (auto-reset) the reset point is requested with the rest of the state, not after the crash flag has arrived
+    const int32_t reset_pt0 = (p.auto_reset && p.do_move) ? p.reset_pt[a] : 0;
     // the standstill record is read up front with the rest of the state: a load issued only after the kinematics
     // would add a second trip to memory to the latency of this (latency-bound) phase
     const uint32_t ss_ctr0 = p.ss_ctr[a];
@@ -912,11 +927,9 @@ __device__ __forceinline__ AgentRec agent_pre(const StepParams &p, const uint8_t
         // prev / nearest / fitness are finalised in phase 4 (they need a centre-line search).
         if (p.auto_reset && crashed)
         {
-            const TrackView tv = make_view(gblob);
-            const int32_t   pt =
-                static_cast<int32_t>((static_cast<int64_t>(p.reset_pt[a]) + p.auto_reset_stride) % tv.n_pts);
-            const float2 c = tv.pts[pt];
-            x = c.x, y = c.y, rot = tv.headings[pt];
+            const int32_t pt = static_cast<int32_t>((static_cast<int64_t>(reset_pt0) + p.auto_reset_stride) % tr.n_points);
+            const float2  c  = reinterpret_cast<const float2 *>(gblob + tr.off_points)[pt];
+            x = c.x, y = c.y, rot = reinterpret_cast<const float *>(gblob + tr.off_headings)[pt];
             accel = 0.0f, speed = 0.0f;
             crashed = false, timed_out = false;
             thr = 0.0f, steer = 0.0f; // Agent::reset zeroes current_action_
@@ -1215,6 +1228,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
     float2   *dirs    = reinterpret_cast<float2 *>(recs + p.batch_agents); // !kBeam
     // kBeam: per-thread ray parameters and result keys of the group a warp is working on
     __shared__ BeamHot                         s_hot;
+    __shared__ unsigned long long              s_tns[3];
     __shared__ __align__(16) float4             s_wray[kBeam ? kBlock : 1];
     __shared__ __align__(8) unsigned long long s_wkey[kBeam ? kBlock : 1];
 
@@ -1255,9 +1269,21 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                 static_cast<unsigned long long>(tile) | (static_cast<unsigned long long>(smid) << 32);
         }
         OK_TRACE(1);
+        if (kBeam && p.tile_ns && tid == 0) // thread 0: this tile's cost, for the host's tiling (ok_balance_schedule); kept in shared memory
+            s_tns[0] = global_timer();
 
-        const Tile     tl = p.tiles[tile];
-        const TrackRef tr = p.tracks[tl.track];
+        Tile     tl;
+        TrackRef tr;
+        if (p.first && n_done == 0)
+        { // (the first tile of a CTA is its block index)
+            tl = p.first[tile].tile;
+            tr = p.first[tile].ref;
+        }
+        else
+        {
+            tl = p.tiles[tile];
+            tr = p.tracks[tl.track];
+        }
         // the bulk copy of the track runs under phase 1, which reads no staged data; it is awaited before the rays
         const uint8_t *gblob   = p.arena + tr.offset;
         const bool     restage = kStage && tl.track != staged;
@@ -1282,7 +1308,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
         // phase 1 -- one thread per agent: optional reset, kinematics, standstill (Environment.cpp:128-143)
         // =====================================================================================
         if (tid < count)
-            recs[tid] = agent_pre(p, gblob, bv, tl.begin + tid);
+            recs[tid] = agent_pre(p, gblob, tr, bv, tl.begin + tid);
         if (tid == 0)
         {
             s_pool = 0, s_pool2 = 0, s_npend = 0, s_adone = 0;
@@ -1296,6 +1322,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
         if (kBeam)
             for (int i = tid; i < kPendCap / 32; i += kBlock)
                 s_ready[i] = 0;
+        OK_TRACE(3); // thread 0's own phase 1 is done; what follows is the wait for the staged track and for the other threads
         if (restage)
         {
             mbar_wait(&bar, phase);
@@ -1304,6 +1331,8 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
         }
         __syncthreads();
         OK_TRACE(2);
+        if (kBeam && p.tile_ns && tid == 0)
+            s_tns[1] = global_timer();
         const uint8_t  *track    = (kStage && !kSegOnly) ? blob : gblob; // where this tile reads its (whole) track from
         const TrackView tv       = kSegOnly ? make_view_split(blob, gblob) : make_view(track);
         const int64_t   ray_base = tl.begin * R; // global index of the batch's first ray
@@ -1720,6 +1749,8 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
         }
         __syncthreads();
         OK_TRACE(4);
+        if (kBeam && p.tile_ns && tid == 0)
+            s_tns[2] = global_timer();
         if (kBeam && p.host_obs)
         { // End-to-end path (ok_step_host): this tile's observations are complete in device memory; they go to the pinned
           // HOST buffer now, as full 16-byte-per-lane stores through the mapping.  (The second ray pass finishes rays in
@@ -1766,6 +1797,12 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
             agent_post<1>(p, tv, recs[valid ? tid : 0], tl.begin + (valid ? tid : 0), valid, lane);
         }
         OK_TRACE(5); // thread 0's own phase 4 (the CTA-wide end is the next tile's start)
+        if (kBeam && p.tile_ns && tid == 0)
+        {
+            const unsigned long long t_end = global_timer(), rays_ns = s_tns[2] - s_tns[1];
+            p.tile_ns[2 * tile]     = static_cast<uint32_t>(rays_ns);
+            p.tile_ns[2 * tile + 1] = static_cast<uint32_t>((t_end - s_tns[0]) - rays_ns);
+        }
         ++n_done;
     }
 

@@ -299,6 +299,20 @@ class Env:
         got = check(self.lib.ok_debug_trace(self.h, _vp(buf), cap, tiles_per_cta))
         return buf[:got].reshape(grid, -1, 6) if got else None
 
+    def balance_schedule(self, stream: int = 0):
+        """re-cuts the beam kernel's tiles from the tile times of the last launch (ok_balance_schedule); returns
+        (slowest tile / mean tile before, predicted after).  The library also does this on its own early in a run."""
+        out = (C.c_float * 2)()
+        check(self.lib.ok_balance_schedule(self.h, C.c_void_p(stream), out))
+        return float(out[0]), float(out[1])
+
+    def debug_tiles(self) -> np.ndarray:
+        """the beam kernel's tiling as i64[tiles, 3] = {track, count, first agent} (ok_debug_trace's tile ids index it)"""
+        n = check(self.lib.ok_debug_tiles(self.h, None, 0))
+        buf = np.zeros((max(n, 1), 3), dtype=np.int64)
+        check(self.lib.ok_debug_tiles(self.h, _vp(buf), n))
+        return buf[:n]
+
     def launch_stats(self) -> OkLaunchStats:
         s = OkLaunchStats()
         check(self.lib.ok_launch_stats(self.h, C.byref(s)))

@@ -85,7 +85,41 @@ def test_tile_schedules_give_the_same_bits(monkeypatch):
     monkeypatch.setenv("OK_BEAM_BATCH_AGENTS", "256")
     monkeypatch.setenv("OK_BEAM_TAIL", "4")
     c = _run(ok.RAYCAST_BEAM, ticks)
-    assert b.launch_stats().tiles > c.launch_stats().tiles > a.launch_stats().tiles
+    assert b.launch_stats().tiles > a.launch_stats().tiles and c.launch_stats().tiles > a.launch_stats().tiles
     for name in ok.BUFFERS:
         assert np.array_equal(a.read(name).view(np.uint8), b.read(name).view(np.uint8)), f"96-agent tiles: {name}"
         assert np.array_equal(a.read(name).view(np.uint8), c.read(name).view(np.uint8)), f"quarter-size tail: {name}"
+
+
+@pytest.mark.parametrize("kernel", ["staged", "segstaged"])
+def test_feedback_tiling_changes_the_schedule_not_the_bits(monkeypatch, kernel):
+    """ok_balance_schedule re-cuts the tiles from the tile times the kernel measured (the library also does it on its own
+    after the 16th and 64th launch): the tiling changes, tiles stay within their tracks and cover every agent once, and
+    the results are those of a run that never re-balanced, bit for bit"""
+    monkeypatch.setenv("OK_BEAM_KERNEL", kernel)
+    ticks = 80
+    monkeypatch.setenv("OK_AUTO_BALANCE", "0")
+    a = _run(ok.RAYCAST_BEAM, ticks)
+    monkeypatch.setenv("OK_AUTO_BALANCE", "1")
+    b = _run(ok.RAYCAST_BEAM, ticks)  # re-balanced by the library at launches 16 and 64
+    monkeypatch.setenv("OK_AUTO_BALANCE", "0")
+    c = ok.Env(device=0, movement_mode=ok.MOVE_VELOCITY, reward_mode=ok.REWARD_CMAES_PROGRESS, auto_reset=1)
+    tid = bench.build_workload(ok, c, N)
+    before = c.debug_tiles().copy()
+    for t in range(ticks):
+        c.launch_steps_random(t, 1)
+        if t in (5, 30, 31):
+            worst_before, worst_after = c.balance_schedule()
+            assert worst_before >= 1.0 and 1.0 <= worst_after < worst_before + 0.05
+    c.sync()
+    for env in (b, c):
+        tiles = env.debug_tiles()
+        assert not np.array_equal(tiles, a.debug_tiles()), "the tiling never changed"
+        order = np.argsort(tiles[:, 2])
+        tr, cnt, beg = tiles[order].T
+        assert beg[0] == 0 and (beg[1:] == beg[:-1] + cnt[:-1]).all() and beg[-1] + cnt[-1] == N, "tiles do not partition the agents"
+        assert all((tid[b0:b0 + n] == t).all() for t, n, b0 in tiles), "a tile spans two tracks"
+        assert cnt.max() <= env.launch_stats().block_threads
+        for name in ok.BUFFERS:
+            assert np.array_equal(a.read(name).view(np.uint8), env.read(name).view(np.uint8)), name
+    assert len(before) == len(a.debug_tiles())

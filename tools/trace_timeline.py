@@ -53,7 +53,8 @@ for rep in range(5):
         "event_ms": e0.elapsed_time(e1), "span_us": float(np.where(used, p4, 0).max()), "ctas": int(tr.shape[0]),
         "tiles": int(used.sum()), "tiles_per_cta_mean": float(tiles_per_cta.mean()), "tiles_per_cta_max": int(tiles_per_cta.max()),
         "first_tile_start_us_mean": float(first_start[first_start < 1e8].mean()), "first_tile_start_us_max": float(first_start[first_start < 1e8].max()),
-        "phase1_us_mean": float((p1 - start)[used].mean()), "rays_us_mean": float((pb - p1)[used].mean()),
+        "phase1_us_mean": float((p1 - start)[used].mean()), "phase1_thread0_us_mean": float((pa - start)[used].mean()),
+        "rays_us_mean": float((pb - p1)[used].mean()),
         "phase4_us_mean": float((p4 - pb)[used].mean()),
         "tile_us_mean": float((p4 - start)[used].mean()),
         "between_tiles_us_mean": float(gap[:, 1:][used[:, 1:]].mean()) if used[:, 1:].any() else None,
@@ -61,5 +62,21 @@ for rep in range(5):
                       "p90": float(np.percentile(ends, 90)), "max": float(ends.max())},
         "sm_idle_tail_frac": float(1.0 - ends.mean() / ends.max()),
     })
+# per track (last repetition): tiles, agents per tile, where the time goes
+tiles = env.debug_tiles()
+tile_id = (tr[:, :, 0] & np.uint64(0xFFFFFFFF)).astype(np.int64)
+per_track = {}
+for c in range(tr.shape[0]):
+    for k in range(tr.shape[1]):
+        if used[c, k]:
+            trk, cnt, _ = tiles[tile_id[c, k]]
+            per_track.setdefault(int(trk), []).append((int(cnt), float(p1[c, k] - start[c, k]), float(pa[c, k] - p1[c, k]), float(pb[c, k] - pa[c, k]),
+                                                       float(p4[c, k] - pb[c, k]), float(p4[c, k])))
+names = ok.track_names()
+res[-1]["per_track"] = {names[t]: {"tiles": len(v), "agents_per_tile": round(float(np.mean([x[0] for x in v])), 1),
+                                   "phase1_us": round(float(np.mean([x[1] for x in v])), 1), "passA_us": round(float(np.mean([x[2] for x in v])), 1),
+                                   "passB_tail_us": round(float(np.mean([x[3] for x in v])), 1), "phase4_us": round(float(np.mean([x[4] for x in v])), 1),
+                                   "end_us_mean": round(float(np.mean([x[5] for x in v])), 1), "end_us_max": round(float(np.max([x[5] for x in v])), 1)}
+                        for t, v in sorted(per_track.items())}
 print(json.dumps(res[-1], indent=1))
 print(json.dumps({"event_ms_all": [r["event_ms"] for r in res], "span_us_all": [r["span_us"] for r in res]}))
