@@ -319,7 +319,7 @@ struct Pool
     size_t bytes{0};
     int    device{-1};
 };
-Pool       g_pool[3];
+Pool       g_pool[6]; // scratch, entries, items, segments, covered cells, counters
 std::mutex g_pool_mu;
 
 cudaError_t pool_get(int which, int device, size_t bytes, void **out)
@@ -331,7 +331,9 @@ cudaError_t pool_get(int which, int device, size_t bytes, void **out)
         p = Pool{};
     }
     if (!p.ptr)
-    {
+    { // a quarter of headroom: the next, slightly larger track must not trigger a cudaFree + cudaMalloc of its own (on this
+      // pool's boxes a cudaFree in the middle of a build sporadically took 200-800 ms: 2.7 of 4.3 s of set-up)
+        bytes = bytes + bytes / 4 + 4096;
         const cudaError_t e = cudaMalloc(&p.ptr, bytes);
         if (e != cudaSuccess)
         {
@@ -371,6 +373,7 @@ static bool build_once(const Track &t, const BeamConfig &cfg, int device, int it
     BeamPlan   pl;
     if (!beam_plan(t, cfg, pl, err))
         return false;
+    const auto    t_plan = std::chrono::steady_clock::now();
     const int32_t ns = t.n_segments(), nb = pl.nb;
     const size_t  n_rows = pl.covered.size();
     int           prev = -1, sms = 0;
@@ -394,14 +397,14 @@ static bool build_once(const Track &t, const BeamConfig &cfg, int device, int it
         // `items_per_entry` rest candidates per (cell, bin) on average; the caller retries with more when the kernel reports the array full
         capacity = static_cast<unsigned long long>(n_rows) * nb * static_cast<unsigned long long>(items_per_entry) + 1024ull;
         GpuBuild g{};
-        BEAM_CUDA(cudaMalloc(&d_seg, sizeof(float4) * ns));
+        BEAM_CUDA(pool_get(3, device, sizeof(float4) * ns, &d_seg));
         BEAM_CUDA(cudaMemcpy(d_seg, t.segments.data(), sizeof(float4) * ns, cudaMemcpyHostToDevice));
-        BEAM_CUDA(cudaMalloc(&d_cov, 4 * std::max<size_t>(n_rows, 1)));
+        BEAM_CUDA(pool_get(4, device, 4 * std::max<size_t>(n_rows, 1), &d_cov));
         BEAM_CUDA(cudaMemcpy(d_cov, pl.covered.data(), 4 * n_rows, cudaMemcpyHostToDevice));
         BEAM_CUDA(pool_get(0, device, per_cta * grid + 256, &d_scratch));
         BEAM_CUDA(pool_get(1, device, 16 * std::max<size_t>(n_rows * nb, 1), &d_entries));
         BEAM_CUDA(pool_get(2, device, 2 * capacity, &d_items));
-        BEAM_CUDA(cudaMalloc(&d_ctr, 64));
+        BEAM_CUDA(pool_get(5, device, 64, &d_ctr));
         BEAM_CUDA(cudaMemset(d_ctr, 0, 64));
         g.seg = static_cast<const float4 *>(d_seg);
         g.ns  = ns;
@@ -453,7 +456,9 @@ static bool build_once(const Track &t, const BeamConfig &cfg, int device, int it
         if (!beam_layout(pl, cfg, used, ns, hdr, err))
             goto done;
         BEAM_CUDA(cudaMalloc(reinterpret_cast<void **>(&d_blob), hdr.bytes));
-        BEAM_CUDA(cudaMemset(d_blob, 0, hdr.bytes));
+        // (only the padding behind the rows and behind the items is not overwritten below)
+        BEAM_CUDA(cudaMemset(d_blob + hdr.off_entries - 16, 0, 16));
+        BEAM_CUDA(cudaMemset(d_blob + hdr.bytes - 16, 0, 16));
         BEAM_CUDA(cudaMemcpy(d_blob, &hdr, sizeof hdr, cudaMemcpyHostToDevice));
         BEAM_CUDA(cudaMemcpy(d_blob + hdr.off_rows, pl.rows.data(), pl.rows.size() * 4, cudaMemcpyHostToDevice));
         if (n_rows)
@@ -466,12 +471,11 @@ static bool build_once(const Track &t, const BeamConfig &cfg, int device, int it
         {
             const auto t_a1 = std::chrono::steady_clock::now();
             auto       ms   = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-            std::fprintf(stderr, "[ok_beam_gpu] rows %zu bins %d: setup %.1f ms, kernel %.1f ms, assemble %.1f ms, %.1f MB, %d lists overflowed\n",
-                         n_rows, nb, ms(t_begin, t_k0), ms(t_k0, t_k1), ms(t_k1, t_a1), hdr.bytes / 1e6, counters[0]);
+            std::fprintf(stderr, "[ok_beam_gpu] rows %zu bins %d: plan %.1f ms, setup %.1f ms, kernel %.1f ms, assemble %.1f ms, free %.1f ms, %.1f MB, %d lists overflowed\n",
+                         n_rows, nb, ms(t_begin, t_plan), ms(t_plan, t_k0), ms(t_k0, t_k1), ms(t_k1, t_a1), ms(t_a1, std::chrono::steady_clock::now()), hdr.bytes / 1e6, counters[0]);
         }
     }
-done:
-    cudaFree(d_seg), cudaFree(d_cov), cudaFree(d_ctr); // (scratch, entries and items stay in the pool)
+done: // (every scratch buffer stays in the pool: beam_builder_release)
     if (ok)
     {
         *d_blob_out = d_blob;

@@ -499,6 +499,8 @@ int ensure_arena(OkEnv *e)
     size_t                    total = 0;
     e->max_blob_used                = 0;
     e->beams_dev.resize(e->tracks.size());
+    const bool verbose = std::getenv("OK_BEAM_VERBOSE") != nullptr;
+    const auto t_0     = std::chrono::steady_clock::now();
     if (want_beams)
     { // (host-built tables only) first every table nobody else is building, then the ones other ranks were busy with
         for (int pass = 0; pass < 2; ++pass)
@@ -510,7 +512,11 @@ int ensure_arena(OkEnv *e)
                     if (!e->beams_dev[i] && (pass == 1 || !err.empty()))
                         return fail(OK_ERR_INVALID_ARG, "beam table: " + err);
                 }
+        const auto t_1 = std::chrono::steady_clock::now();
         ok::beam_builder_release(); // the device builder's scratch pool (kept from track to track) is no longer needed
+        if (verbose)
+            std::fprintf(stderr, "[ensure_arena] tables %.1f ms, pool release %.1f ms\n", std::chrono::duration<double, std::milli>(t_1 - t_0).count(),
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_1).count());
     }
     for (size_t i = 0; i < e->tracks.size(); ++i)
     {
@@ -588,6 +594,7 @@ ok::StepParams base_params(OkEnv *e)
     p.tracks    = e->d_track_refs;
     p.tiles     = e->d_tiles;
     p.n_tiles   = e->n_tiles;
+    p.n_agents  = e->n_agents;
     p.rays      = e->rays;
     p.batch_agents      = e->batch_agents;
     p.smem_blob_bytes   = static_cast<uint32_t>((e->max_blob_used + 127) / 128 * 128);
@@ -1078,12 +1085,22 @@ int ok_alloc_agents(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, c
         if (h_track_id[i] < 0 || h_track_id[i] >= static_cast<int32_t>(e->tracks.size()))
             return fail(OK_ERR_INVALID_ARG, "track id out of range for agent " + std::to_string(i));
     DeviceGuard g(e->cfg.device);
+    const bool  verbose = std::getenv("OK_BEAM_VERBOSE") != nullptr;
+    const auto  t_0     = std::chrono::steady_clock::now();
     // everything that can fail without touching the current agents comes first
     int rc0 = ensure_arena(e);
     if (rc0)
         return rc0;
+    const auto t_1 = std::chrono::steady_clock::now();
     free_agents(e);
     const int rc1 = alloc_agents_impl(e, n, rays, h_ray_deg, h_track_id);
+    if (verbose)
+    {
+        cudaDeviceSynchronize();
+        const auto t_2 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[ok_alloc_agents] tables + arena %.1f ms, agents + tiles + reset %.1f ms\n",
+                     std::chrono::duration<double, std::milli>(t_1 - t_0).count(), std::chrono::duration<double, std::milli>(t_2 - t_1).count());
+    }
     if (rc1)
     { // never leave a half-built set behind: n_agents = 0 makes every entry point report OK_ERR_STATE
         const std::string msg = g_last_error;

@@ -103,6 +103,7 @@ struct StepParams
     const TrackRef *tracks;
     const Tile    *tiles;
     const FirstTile *first; // nullable: tiles[b] and its track record for b < gridDim.x
+    int64_t        n_agents;
     int32_t        n_tiles;
     int32_t        rays;
     int32_t        batch_agents;    // agents per tile (shared-memory scratch is sized for this many)
@@ -883,9 +884,21 @@ __device__ __forceinline__ AgentRec agent_pre(const StepParams &p, const uint8_t
     // would add a second trip to memory to the latency of this (latency-bound) phase
     const uint32_t ss_ctr0 = p.ss_ctr[a];
     const float    ss_x0 = p.ss_x[a], ss_y0 = p.ss_y[a];
+#ifdef OK_PRE_PROBE // experiment build: where does a thread's phase 1 spend its time?  (slots 3-5 of the tile trace, thread 0)
+#define OK_PROBE(slot, dep)                                                                                            \
+    if (p.trace && threadIdx.x == 0)                                                                                   \
+    {                                                                                                                  \
+        unsigned long long t_;                                                                                         \
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_) : "r"(__float_as_int(dep)) : "memory");                  \
+        p.trace[static_cast<size_t>(blockIdx.x) * p.trace_tiles * 6 + (slot)] = t_;                                    \
+    }
+#else
+#define OK_PROBE(slot, dep)
+#endif
     uint32_t flags = 0;
     float    rx = 0.0f, ry = 0.0f;
     float    hs = 0.0f, hc = 0.0f; // sin / cos of the heading, when the move already computed them
+    OK_PROBE(3, x + y + rot + speed + accel + (crashed ? 1.0f : 0.0f) + static_cast<float>(ss_ctr0) + ss_x0)
     bool     have_sc = false;
     int32_t  hint = p.nearest[a], prev_idx = 0;
     float    fitness = 0.0f;
@@ -1000,7 +1013,9 @@ __device__ __forceinline__ AgentRec agent_pre(const StepParams &p, const uint8_t
     rec.rc = rc, rec.rs = rs, rec.rot = rot, rec.x = x, rec.y = y, rec.rx = rx, rec.ry = ry;
     rec.min_d2_bits = __float_as_int(fmul(p.sensor_range, p.sensor_range));
     rec.flags       = flags | (crashed ? kFlagCrashed : 0u) | (timed_out ? kFlagTimedOut : 0u);
+    OK_PROBE(4, rec.ox + rec.oy)
     rec.row         = beam_row(bv, rec.ox, rec.oy); // -1 when bv is not valid
+    OK_PROBE(5, static_cast<float>(rec.row))
     rec.prev = prev_idx, rec.fitness = fitness, rec.hint = hint, rec.pad = 0;
     return rec;
 }
@@ -1200,10 +1215,15 @@ __device__ __forceinline__ unsigned long long global_timer()
     return t;
 }
 // trace record of one tile: {tile | smid << 32, t_start, t_phase1_done, t_passA_done, t_passB_done, t_phase4_done}
+#ifdef OK_PRE_PROBE
+#define OK_TRACE_ON(slot) ((slot) < 3)
+#else
+#define OK_TRACE_ON(slot) true
+#endif
 #define OK_TRACE(slot)                                                                                                 \
     do                                                                                                                 \
     {                                                                                                                  \
-        if (kBeam && p.trace && tid == 0 && n_done < p.trace_tiles)                                                    \
+        if (kBeam && OK_TRACE_ON(slot) && p.trace && tid == 0 && n_done < p.trace_tiles)                                                    \
             p.trace[(static_cast<size_t>(blockIdx.x) * p.trace_tiles + n_done) * 6 + (slot)] = global_timer();         \
     } while (0)
 
