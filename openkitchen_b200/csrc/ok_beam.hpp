@@ -118,6 +118,10 @@ bool build_beam_table(const Track &t, const BeamConfig &cfg, std::vector<uint8_t
 // construction, binary64 on the device; libm differences may move a list boundary by an ulp, never its validity.
 // The blob is left in device memory (*d_blob, cudaMalloc'ed on `device`, owned by the caller).
 bool build_beam_table_device(const Track &t, const BeamConfig &cfg, int device, uint8_t **d_blob, size_t *bytes, std::string &err);
+// Several tables back to back, pipelined (the host sizes / allocates / assembles table i - 1 while the kernel of table i
+// runs).  blobs[i] stays null for a track that needs the one-track path above (item array too small, any failure).
+void build_beam_tables_device(const std::vector<const Track *> &tracks, const BeamConfig &cfg, int device, std::vector<uint8_t *> &blobs,
+                              std::vector<size_t> &bytes);
 // frees the device builder's scratch pool (kept between tracks)
 void beam_builder_release();
 

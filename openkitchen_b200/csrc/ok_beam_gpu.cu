@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 namespace ok
 {
@@ -319,7 +320,7 @@ struct Pool
     size_t bytes{0};
     int    device{-1};
 };
-Pool       g_pool[6]; // scratch, entries, items, segments, covered cells, counters
+Pool       g_pool[8]; // scratch, entries, items, segments, covered cells, counters, second entries, second items (pipelined builds)
 std::mutex g_pool_mu;
 
 cudaError_t pool_get(int which, int device, size_t bytes, void **out)
@@ -499,6 +500,194 @@ bool build_beam_table_device(const Track &t, const BeamConfig &cfg, int device, 
             return false;
     }
     return false;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Several tables back to back, pipelined: while the kernel of track i runs, the host sizes, allocates and assembles the
+// table of track i - 1 on a second stream (the cudaMalloc of a 120-430 MB table sporadically takes 50-100 ms on this
+// pool's boxes; hidden behind the kernel it costs nothing).  Entries and items are double-buffered for that.  A track
+// whose item array turns out too small (or anything else that fails) is left to the caller: blobs[i] stays null.
+// ---------------------------------------------------------------------------------------------------------------------
+void build_beam_tables_device(const std::vector<const Track *> &tracks, const BeamConfig &cfg, int device, std::vector<uint8_t *> &blobs,
+                              std::vector<size_t> &bytes)
+{
+    const size_t n = tracks.size();
+    blobs.assign(n, nullptr);
+    bytes.assign(n, 0);
+    if (!n)
+        return;
+    std::lock_guard<std::mutex> pool_lock(g_pool_mu);
+    int                         prev = -1, sms = 0;
+    if (cudaGetDevice(&prev) != cudaSuccess || cudaSetDevice(device) != cudaSuccess)
+    {
+        cudaGetLastError();
+        return;
+    }
+    struct Job
+    {
+        BeamPlan            pl;
+        int32_t             ns{0};
+        size_t              n_rows{0};
+        unsigned long long  capacity{0};
+        void               *d_entries{nullptr}, *d_items{nullptr};
+        bool                launched{false};
+    };
+    std::vector<Job>    jobs(n);
+    cudaStream_t        sk = nullptr, sc = nullptr;
+    cudaEvent_t         ev_kernel[2] = {nullptr, nullptr}, ev_copy[2] = {nullptr, nullptr};
+    unsigned long long *h_ctr = nullptr; // pinned: 2 x 8 words {items used, -, overflow[0..1]}
+    std::string         err;
+    const auto          t_begin = std::chrono::steady_clock::now();
+    bool                ready = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess &&
+                 cudaStreamCreateWithFlags(&sk, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&sc, cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaMallocHost(reinterpret_cast<void **>(&h_ctr), 2 * 64) == cudaSuccess;
+    for (int k = 0; ready && k < 2; ++k)
+        ready = cudaEventCreateWithFlags(&ev_kernel[k], cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&ev_copy[k], cudaEventDisableTiming) == cudaSuccess;
+    bool copy_pending[2] = {false, false};
+
+    // stage 1 of track i: plan, upload, kernel, counters back -- all on stream sk, nothing waits
+    auto launch = [&](size_t i) -> bool {
+        Job &j = jobs[i];
+        const Track &t = *tracks[i];
+        const int    set = static_cast<int>(i & 1);
+        if (!beam_plan(t, cfg, j.pl, err))
+            return false;
+        j.ns = t.n_segments(), j.n_rows = j.pl.covered.size();
+        const int32_t nb = j.pl.nb;
+        if (!j.n_rows)
+            return false;
+        const int    grid    = static_cast<int>(std::min<size_t>(j.n_rows, static_cast<size_t>(sms) * 4));
+        const size_t per_cta = static_cast<size_t>(j.ns) * (4 + 2 + 2 + 2 + 2) + static_cast<size_t>(nb) * kListCap * (4 + 2);
+        j.capacity           = static_cast<unsigned long long>(j.n_rows) * nb * 16ull + 1024ull;
+        void *d_seg = nullptr, *d_cov = nullptr, *d_scratch = nullptr, *d_ctr = nullptr;
+        if (copy_pending[set])
+        { // the copies of track i - 2 read this set's entries and items
+            if (cudaEventSynchronize(ev_copy[set]) != cudaSuccess)
+                return false;
+            copy_pending[set] = false;
+        }
+        // (the shared scratch, segments, cells and counters are only touched by work on sk, which is ordered)
+        if (pool_get(0, device, per_cta * grid + 256, &d_scratch) != cudaSuccess || pool_get(3, device, sizeof(float4) * j.ns, &d_seg) != cudaSuccess ||
+            pool_get(4, device, 4 * j.n_rows, &d_cov) != cudaSuccess || pool_get(5, device, 64, &d_ctr) != cudaSuccess ||
+            pool_get(set ? 6 : 1, device, 16 * j.n_rows * nb, &j.d_entries) != cudaSuccess || pool_get(set ? 7 : 2, device, 2 * j.capacity, &j.d_items) != cudaSuccess)
+            return false;
+        GpuBuild g{};
+        if (cudaMemcpyAsync(d_seg, t.segments.data(), sizeof(float4) * j.ns, cudaMemcpyHostToDevice, sk) != cudaSuccess ||
+            cudaMemcpyAsync(d_cov, j.pl.covered.data(), 4 * j.n_rows, cudaMemcpyHostToDevice, sk) != cudaSuccess || cudaMemsetAsync(d_ctr, 0, 64, sk) != cudaSuccess)
+            return false;
+        g.seg = static_cast<const float4 *>(d_seg);
+        g.ns  = j.ns;
+        g.x0 = j.pl.x0, g.y0 = j.pl.y0, g.h = j.pl.h, g.rb = j.pl.rb, g.range = cfg.range, g.pad = cfg.pad, g.dth = kBeamAngleMargin;
+        g.nx = j.pl.nx, g.nb = nb;
+        g.covered = static_cast<const uint32_t *>(d_cov);
+        g.n_rows  = static_cast<int32_t>(j.n_rows);
+        {
+            uint8_t *p = static_cast<uint8_t *>(d_scratch);
+            g.cand_lb  = reinterpret_cast<float *>(p);
+            p += static_cast<size_t>(grid) * j.ns * 4;
+            g.list_d = reinterpret_cast<float *>(p);
+            p += static_cast<size_t>(grid) * nb * kListCap * 4;
+            g.cand_seg = reinterpret_cast<uint16_t *>(p);
+            p += static_cast<size_t>(grid) * j.ns * 2;
+            g.cand_b0 = reinterpret_cast<uint16_t *>(p);
+            p += static_cast<size_t>(grid) * j.ns * 2;
+            g.cand_bn = reinterpret_cast<uint16_t *>(p);
+            p += static_cast<size_t>(grid) * j.ns * 2;
+            g.cand_act = reinterpret_cast<uint16_t *>(p);
+            p += static_cast<size_t>(grid) * j.ns * 2;
+            g.list_s = reinterpret_cast<uint16_t *>(p);
+        }
+        g.entries       = static_cast<uint4 *>(j.d_entries);
+        g.items         = static_cast<uint16_t *>(j.d_items);
+        g.item_cursor   = static_cast<unsigned long long *>(d_ctr);
+        g.item_capacity = j.capacity;
+        g.row_cursor    = reinterpret_cast<int32_t *>(static_cast<uint8_t *>(d_ctr) + 8);
+        g.overflow      = reinterpret_cast<int32_t *>(static_cast<uint8_t *>(d_ctr) + 16);
+        const size_t smem = static_cast<size_t>(nb) * (32 + 40 + 8 + 32);
+        if (cudaFuncSetAttribute(beam_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
+            return false;
+        beam_build_kernel<<<grid, kThreads, smem, sk>>>(g);
+        if (cudaGetLastError() != cudaSuccess || cudaMemcpyAsync(h_ctr + 8 * set, d_ctr, 64, cudaMemcpyDeviceToHost, sk) != cudaSuccess ||
+            cudaEventRecord(ev_kernel[set], sk) != cudaSuccess)
+            return false;
+        j.launched = true;
+        return true;
+    };
+    // stage 2 of track i (while the kernel of track i + 1 runs): size, allocate, assemble on stream sc
+    auto finish = [&](size_t i) {
+        Job &j = jobs[i];
+        if (!j.launched)
+            return;
+        const int set = static_cast<int>(i & 1);
+        if (cudaEventSynchronize(ev_kernel[set]) != cudaSuccess)
+            return;
+        const unsigned long long used     = h_ctr[8 * set];
+        const int32_t           *counters = reinterpret_cast<const int32_t *>(h_ctr + 8 * set + 2);
+        if (counters[1] != 0 || used > j.capacity)
+            return; // item array full: the caller's one-track build retries with a larger one
+        BeamHeader hdr{};
+        if (!beam_layout(j.pl, cfg, used, j.ns, hdr, err))
+            return;
+        uint8_t *d_blob = nullptr;
+        if (cudaMalloc(reinterpret_cast<void **>(&d_blob), hdr.bytes) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return;
+        }
+        // the header and the rows go through a staging copy the driver makes at the call (pageable source): safe to let go of
+        bool ok = cudaMemsetAsync(d_blob + hdr.off_entries - 16, 0, 16, sc) == cudaSuccess && cudaMemsetAsync(d_blob + hdr.bytes - 16, 0, 16, sc) == cudaSuccess &&
+                  cudaMemcpyAsync(d_blob, &hdr, sizeof hdr, cudaMemcpyHostToDevice, sc) == cudaSuccess &&
+                  cudaMemcpyAsync(d_blob + hdr.off_rows, j.pl.rows.data(), j.pl.rows.size() * 4, cudaMemcpyHostToDevice, sc) == cudaSuccess &&
+                  cudaMemcpyAsync(d_blob + hdr.off_entries, j.d_entries, 16 * j.n_rows * j.pl.nb, cudaMemcpyDeviceToDevice, sc) == cudaSuccess &&
+                  (!used || cudaMemcpyAsync(d_blob + hdr.off_items, j.d_items, 2 * used, cudaMemcpyDeviceToDevice, sc) == cudaSuccess) &&
+                  cudaEventRecord(ev_copy[set], sc) == cudaSuccess;
+        if (!ok)
+        {
+            cudaGetLastError();
+            cudaStreamSynchronize(sc);
+            cudaFree(d_blob);
+            return;
+        }
+        copy_pending[set] = true;
+        blobs[i] = d_blob, bytes[i] = hdr.bytes;
+    };
+    if (ready)
+    {
+        for (size_t i = 0; i < n; ++i)
+        {
+            launch(i);
+            if (i > 0)
+                finish(i - 1);
+        }
+        finish(n - 1);
+        cudaStreamSynchronize(sc);
+        cudaStreamSynchronize(sk);
+    }
+    if (std::getenv("OK_BEAM_VERBOSE"))
+    {
+        size_t built = 0, total = 0;
+        for (size_t i = 0; i < n; ++i)
+            built += blobs[i] != nullptr, total += bytes[i];
+        std::fprintf(stderr, "[ok_beam_gpu] pipelined build: %zu of %zu tables, %.1f MB, %.1f ms\n", built, n, total / 1e6,
+                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    }
+    for (int k = 0; k < 2; ++k)
+    {
+        if (ev_kernel[k])
+            cudaEventDestroy(ev_kernel[k]);
+        if (ev_copy[k])
+            cudaEventDestroy(ev_copy[k]);
+    }
+    if (sk)
+        cudaStreamDestroy(sk);
+    if (sc)
+        cudaStreamDestroy(sc);
+    if (h_ctr)
+        cudaFreeHost(h_ctr);
+    cudaGetLastError();
+    if (prev >= 0)
+        cudaSetDevice(prev);
 }
 
 } // namespace ok

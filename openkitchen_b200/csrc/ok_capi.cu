@@ -502,7 +502,33 @@ int ensure_arena(OkEnv *e)
     const bool verbose = std::getenv("OK_BEAM_VERBOSE") != nullptr;
     const auto t_0     = std::chrono::steady_clock::now();
     if (want_beams)
-    { // (host-built tables only) first every table nobody else is building, then the ones other ranks were busy with
+    {
+        { // the tables nobody has built yet in this process, all at once: the device builder pipelines them
+            const char *force = std::getenv("OK_BEAM_BUILDER");
+            std::vector<const ok::Track *> todo;
+            std::vector<std::string>       keys;
+            if (!(force && std::strcmp(force, "cpu") == 0))
+            {
+                std::lock_guard<std::mutex> lock(g_beam_mu);
+                for (size_t i = 0; i < e->tracks.size(); ++i)
+                {
+                    const std::string key = beam_key(e->tracks[i], beam_config(e)) + "@" + std::to_string(e->cfg.device);
+                    if (!e->beams_dev[i] && !g_beam_dev_cache.count(key) && std::find(keys.begin(), keys.end(), key) == keys.end())
+                        todo.push_back(&e->tracks[i]), keys.push_back(key);
+                }
+            }
+            if (todo.size() > 1)
+            {
+                std::vector<uint8_t *> blobs;
+                std::vector<size_t>    sizes;
+                ok::build_beam_tables_device(todo, beam_config(e), e->cfg.device, blobs, sizes);
+                std::lock_guard<std::mutex> lock(g_beam_mu);
+                for (size_t k = 0; k < todo.size(); ++k)
+                    if (blobs[k])
+                        g_beam_dev_cache[keys[k]] = std::make_shared<DeviceBlob>(blobs[k], sizes[k], e->cfg.device);
+            }
+        }
+        // (host-built tables only) first every table nobody else is building, then the ones other ranks were busy with
         for (int pass = 0; pass < 2; ++pass)
             for (size_t i = 0; i < e->tracks.size(); ++i)
                 if (!e->beams_dev[i])
