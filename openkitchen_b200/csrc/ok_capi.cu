@@ -722,6 +722,34 @@ std::vector<ok::Tile> cost_balanced_tiles(std::vector<OkEnv::TileRun> &runs, int
     return out;
 }
 
+// The CTAs' first tiles with their track records side by side (ok::FirstTile), rebuilt whenever the tiling or the arena
+// changes.  Synchronises `s`: a launch in flight may still read the old records.
+int upload_first_tiles(OkEnv *e, cudaStream_t s)
+{
+    const int32_t nf = std::min<int32_t>(e->grid_beam, static_cast<int32_t>(e->h_tiles_beam.size()));
+    if (nf <= 0 || e->h_track_refs.empty())
+        return OK_SUCCESS;
+    OK_CUDA(cudaStreamSynchronize(s));
+    if (nf > e->first_capacity)
+    {
+        if (e->d_first_beam)
+            cudaFree(e->d_first_beam);
+        e->d_first_beam = nullptr, e->first_capacity = 0;
+        OK_CUDA(cudaMalloc(&e->d_first_beam, sizeof(ok::FirstTile) * static_cast<size_t>(nf)));
+        e->first_capacity = nf;
+    }
+    std::vector<ok::FirstTile> first(static_cast<size_t>(nf));
+    for (int32_t i = 0; i < nf; ++i)
+    {
+        first[i].tile = e->h_tiles_beam[i];
+        first[i].ref  = e->h_track_refs[e->h_tiles_beam[i].track];
+        std::memset(first[i].pad, 0, sizeof first[i].pad);
+    }
+    OK_CUDA(cudaMemcpy(e->d_first_beam, first.data(), sizeof(ok::FirstTile) * first.size(), cudaMemcpyHostToDevice));
+    e->first_dirty = false;
+    return OK_SUCCESS;
+}
+
 // Re-cuts the beam tiling from the per-tile times the last launch on `s` left in d_tile_ns.  Results do not depend on the
 // tiling (tests/test_gpu_properties.py); only the finish times of the SMs do.  Synchronises `s`.
 int rebalance_beam_tiles(OkEnv *e, cudaStream_t s)
@@ -781,7 +809,8 @@ int rebalance_beam_tiles(OkEnv *e, cudaStream_t s)
     e->first_dirty  = true;
     e->n_tiles_beam = static_cast<int32_t>(e->h_tiles_beam.size());
     e->grid_beam    = std::max(1, std::min(e->num_sms * e->ctas_per_sm_beam, e->n_tiles_beam));
-    return OK_SUCCESS;
+    // at once, not at the next launch: a CUDA graph captured earlier reads both arrays at every replay, and they must agree
+    return e->d_first_beam ? upload_first_tiles(e, s) : OK_SUCCESS;
 }
 
 int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
@@ -817,28 +846,8 @@ int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
             {
                 cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
                 if (cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone)
-                {
-                    const int32_t nf = std::min<int32_t>(grid, static_cast<int32_t>(e->h_tiles_beam.size()));
-                    if (nf > e->first_capacity)
-                    {
-                        OK_CUDA(cudaStreamSynchronize(s));
-                        if (e->d_first_beam)
-                            cudaFree(e->d_first_beam);
-                        e->d_first_beam = nullptr, e->first_capacity = 0;
-                        OK_CUDA(cudaMalloc(&e->d_first_beam, sizeof(ok::FirstTile) * static_cast<size_t>(nf)));
-                        e->first_capacity = nf;
-                    }
-                    std::vector<ok::FirstTile> first(static_cast<size_t>(nf));
-                    for (int32_t i = 0; i < nf; ++i)
-                    {
-                        first[i].tile = e->h_tiles_beam[i];
-                        first[i].ref  = e->h_track_refs[e->h_tiles_beam[i].track];
-                        std::memset(first[i].pad, 0, sizeof first[i].pad);
-                    }
-                    OK_CUDA(cudaStreamSynchronize(s)); // (a launch in flight may still read the old records)
-                    OK_CUDA(cudaMemcpy(e->d_first_beam, first.data(), sizeof(ok::FirstTile) * first.size(), cudaMemcpyHostToDevice));
-                    e->first_dirty = false;
-                }
+                    if (int rc2 = upload_first_tiles(e, s))
+                        return rc2;
             }
             if (!e->first_dirty)
                 p.first = e->d_first_beam;

@@ -123,3 +123,44 @@ def test_feedback_tiling_changes_the_schedule_not_the_bits(monkeypatch, kernel):
         for name in ok.BUFFERS:
             assert np.array_equal(a.read(name).view(np.uint8), env.read(name).view(np.uint8)), name
     assert len(before) == len(a.debug_tiles())
+
+
+def test_feedback_tiling_under_a_captured_graph(monkeypatch):
+    """a CUDA graph captured BEFORE a re-balancing keeps replaying correctly after it: the graph reads the tile table and
+    the first-tile records at every replay, the re-balancing rewrites both together.  Several tiles per CTA
+    (OK_BEAM_WAVES=3), where a CTA mixes its first-tile record with later tiles from the table."""
+    import torch
+
+    monkeypatch.setenv("OK_BEAM_WAVES", "3")
+    monkeypatch.setenv("OK_AUTO_BALANCE", "0")
+    ticks_per_replay, replays = 4, 6
+
+    def make():
+        env = ok.Env(device=0, movement_mode=ok.MOVE_VELOCITY, reward_mode=ok.REWARD_CMAES_PROGRESS, auto_reset=1)
+        bench.build_workload(ok, env, N)
+        return env
+
+    ref = make()
+    ref.launch_steps_random(0, 2)  # (the graphed env's two warm-up ticks)
+    env = make()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        env.launch_steps_random(0, 2, bench.SEED, side.cuda_stream)
+    side.synchronize()
+    assert env.launch_stats().tiles > 2 * env.launch_stats().grid_blocks
+    graph = torch.cuda.CUDAGraph()
+    # the graph replays the SAME tick numbers every time (the step counter is baked in): compare with a reference that does too
+    with torch.cuda.graph(graph, stream=side):
+        env.launch_steps_random(1000, ticks_per_replay, bench.SEED, side.cuda_stream)
+    before = env.debug_tiles().copy()
+    for r in range(replays):
+        graph.replay()
+        torch.cuda.synchronize()
+        if r in (1, 3):
+            env.balance_schedule()
+        ref.launch_steps_random(1000, ticks_per_replay)
+    ref.sync()
+    torch.cuda.synchronize()
+    assert not np.array_equal(before, env.debug_tiles()), "the tiling never changed"
+    for name in ok.BUFFERS:
+        assert np.array_equal(env.read(name).view(np.uint8), ref.read(name).view(np.uint8)), name

@@ -12,5 +12,5 @@ timeout 900 python tools/bench_configs.py > gpurun_out/cfg_$tag.jsonl 2> gpurun_
 timeout 300 python tools/trace_timeline.py > gpurun_out/timeline_$tag.json 2> gpurun_out/timeline_$tag.err; echo "timeline exit $?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 200 --csv --log-file gpurun_out/launches_$tag.csv \
   python bench.py --steps 40 --warmup 10 --no-cpu > gpurun_out/launches_$tag.log 2>&1; echo "launch list exit $?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 40 -c 1 -o gpurun_out/prof_$tag -f \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 90 -c 1 -o gpurun_out/prof_$tag -f \
   python bench.py --steps 20 --warmup 30 --no-cpu > gpurun_out/prof_$tag.log 2>&1; echo "ncu exit $?"

@@ -35,7 +35,7 @@ for rep in range(5):
     used = tr[:, :, 1] > 0
     t0 = tr[:, :, 1][used].min()
     t = (tr[:, :, 1:].astype(np.int64) - int(t0)) / 1e3  # us
-    start, p1, pa, pb, p4 = (t[:, :, k] for k in range(5))
+    start, p1, pa, pb, p4 = (t[:, :, k] for k in range(5))  # pa: thread 0's own phase 1 done (before the wait for the staged track and the barrier)
     smid = (tr[:, :, 0] >> np.uint64(32)).astype(np.int64)
     tiles_per_cta = used.sum(1)
     last_end = np.where(used, p4, 0).max(1)  # per CTA
@@ -70,13 +70,13 @@ for c in range(tr.shape[0]):
     for k in range(tr.shape[1]):
         if used[c, k]:
             trk, cnt, _ = tiles[tile_id[c, k]]
-            per_track.setdefault(int(trk), []).append((int(cnt), float(p1[c, k] - start[c, k]), float(pa[c, k] - p1[c, k]), float(pb[c, k] - pa[c, k]),
+            per_track.setdefault(int(trk), []).append((int(cnt), float(p1[c, k] - start[c, k]), float(pb[c, k] - p1[c, k]),
                                                        float(p4[c, k] - pb[c, k]), float(p4[c, k])))
 names = ok.track_names()
 res[-1]["per_track"] = {names[t]: {"tiles": len(v), "agents_per_tile": round(float(np.mean([x[0] for x in v])), 1),
-                                   "phase1_us": round(float(np.mean([x[1] for x in v])), 1), "passA_us": round(float(np.mean([x[2] for x in v])), 1),
-                                   "passB_tail_us": round(float(np.mean([x[3] for x in v])), 1), "phase4_us": round(float(np.mean([x[4] for x in v])), 1),
-                                   "end_us_mean": round(float(np.mean([x[5] for x in v])), 1), "end_us_max": round(float(np.max([x[5] for x in v])), 1)}
+                                   "phase1_us": round(float(np.mean([x[1] for x in v])), 1), "rays_us": round(float(np.mean([x[2] for x in v])), 1),
+                                   "phase4_us": round(float(np.mean([x[3] for x in v])), 1),
+                                   "end_us_mean": round(float(np.mean([x[4] for x in v])), 1), "end_us_max": round(float(np.max([x[4] for x in v])), 1)}
                         for t, v in sorted(per_track.items())}
 print(json.dumps(res[-1], indent=1))
 print(json.dumps({"event_ms_all": [r["event_ms"] for r in res], "span_us_all": [r["span_us"] for r in res]}))
