@@ -173,6 +173,12 @@ struct OkEnv
     // ok_step_host's tiling: several tiles per CTA, so that a tile's observations cross PCIe while the next one is computed
     ok::Tile            *d_tiles_e2e{nullptr};
     int32_t              n_tiles_e2e{0}, grid_e2e{0};
+    // ... with flusher CTAs (obs_flush_kernel) on SMs of their own: flags, epoch, the side stream and its fork / join events
+    int32_t              e2e_flushers{0};
+    uint32_t            *d_tile_flag{nullptr};
+    uint32_t             flag_epoch{0};
+    cudaStream_t         flush_stream{nullptr};
+    cudaEvent_t          ev_fork{nullptr}, ev_join{nullptr};
     int32_t              batch_agents_beam{0};
     int32_t              grid_beam{0};
     int32_t              ctas_per_sm_beam{1};
@@ -221,6 +227,9 @@ void free_agents(OkEnv *e)
         cudaFree(e->d_tiles_beam);
     if (e->d_tiles_e2e)
         cudaFree(e->d_tiles_e2e);
+    if (e->d_tile_flag)
+        cudaFree(e->d_tile_flag);
+    e->d_tile_flag = nullptr;
     e->d_tiles_beam = nullptr, e->n_tiles_beam = 0, e->d_tiles_e2e = nullptr, e->n_tiles_e2e = 0;
     if (e->d_tile_ns)
         cudaFree(e->d_tile_ns);
@@ -858,6 +867,18 @@ int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
             p.n_tiles = e->n_tiles_e2e;
             grid      = e->grid_e2e;
         }
+        const bool flushers = e2e && e->e2e_flushers > 0 && e->d_tile_flag && e->beam_staged && !e->beam_seg;
+        if (flushers)
+        { // fork: the flusher CTAs start next to the step kernel, on the side stream
+            p.tile_flag  = e->d_tile_flag;
+            p.flag_epoch = ++e->flag_epoch;
+            OK_CUDA(cudaEventRecord(e->ev_fork, s));
+            OK_CUDA(cudaStreamWaitEvent(e->flush_stream, e->ev_fork, 0));
+            ok::obs_flush_kernel<<<e->e2e_flushers, 1024, 0, e->flush_stream>>>(e->d_tiles_e2e, e->n_tiles_e2e, e->d_tile_flag, p.flag_epoch,
+                                                                                static_cast<const float *>(e->d_buf[OK_BUF_OBS]), p.host_obs, e->rays);
+            OK_CUDA(cudaGetLastError());
+            OK_CUDA(cudaEventRecord(e->ev_join, e->flush_stream));
+        }
         if (e->beam_seg)
             OK_CUDA(ok::launch_step_segstaged(p, grid, e->smem_beam, s));
         else if (e->beam_staged)
@@ -868,6 +889,8 @@ int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
     else
         ok::step_kernel<kBlock, false><<<e->grid, kBlock, e->smem, s>>>(p);
     OK_CUDA(cudaGetLastError());
+    if (p.tile_flag) // join: the tick is complete when the last tile has reached the host
+        OK_CUDA(cudaStreamWaitEvent(s, e->ev_join, 0));
     e->launches++;
     return OK_SUCCESS;
 }
@@ -974,6 +997,11 @@ int ok_create(const OkConfig *cfg, OkEnv **out)
         cudaDeviceGetAttribute(&e->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c.device);
         cudaDeviceGetAttribute(&e->smem_reserved, cudaDevAttrReservedSharedMemoryPerBlock, c.device);
         e->max_blob   = optin > 65536 ? static_cast<size_t>(optin) - 40960 : 0; // room for the batch scratch
+        if (const char *env = std::getenv("OK_L2_FETCH")) // experiment: cudaLimitMaxL2FetchGranularity (32 / 64 / 128 bytes), a device-wide hint
+        {
+            cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, static_cast<size_t>(std::max(32, std::atoi(env))));
+            cudaGetLastError();
+        }
     }
     else
     {
@@ -1024,6 +1052,12 @@ void ok_destroy(OkEnv *e)
             cudaFree(e->d_track_refs);
         if (e->d_stage)
             cudaFree(e->d_stage);
+        if (e->flush_stream)
+            cudaStreamDestroy(e->flush_stream);
+        if (e->ev_fork)
+            cudaEventDestroy(e->ev_fork);
+        if (e->ev_join)
+            cudaEventDestroy(e->ev_join);
     }
     delete e;
 }
@@ -1376,9 +1410,28 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
         int per_cta = e->beam_seg ? 2 : 4;
         if (const char *env = std::getenv("OK_E2E_TILES"))
             per_cta = std::max(1, std::atoi(env));
-        if (int rc = build_tiles_balanced(e->batch_agents_beam, e->num_sms * e->ctas_per_sm_beam, &e->d_tiles_e2e, &e->n_tiles_e2e, per_cta))
+        // OK_E2E_FLUSHERS = F > 0: F SMs are left to obs_flush_kernel, which moves finished tiles to the host while the
+        // step kernel's CTAs carry on
+        e->e2e_flushers = 0;
+        if (const char *env = std::getenv("OK_E2E_FLUSHERS"))
+            e->e2e_flushers = std::max(0, std::min(std::atoi(env), e->num_sms / 2));
+        if (e->beam_seg)
+            e->e2e_flushers = 0;
+        const int e2e_ctas = (e->num_sms - e->e2e_flushers) * e->ctas_per_sm_beam;
+        if (int rc = build_tiles_balanced(e->batch_agents_beam, e2e_ctas, &e->d_tiles_e2e, &e->n_tiles_e2e, per_cta))
             return rc;
-        e->grid_e2e = std::max(1, std::min(e->num_sms * e->ctas_per_sm_beam, e->n_tiles_e2e));
+        e->grid_e2e = std::max(1, std::min(e2e_ctas, e->n_tiles_e2e));
+        if (e->e2e_flushers > 0)
+        {
+            OK_CUDA(cudaMalloc(&e->d_tile_flag, sizeof(uint32_t) * static_cast<size_t>(e->n_tiles_e2e)));
+            OK_CUDA(cudaMemset(e->d_tile_flag, 0, sizeof(uint32_t) * static_cast<size_t>(e->n_tiles_e2e)));
+            if (!e->flush_stream)
+            {
+                OK_CUDA(cudaStreamCreateWithFlags(&e->flush_stream, cudaStreamNonBlocking));
+                OK_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+                OK_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+            }
+        }
     }
     if (e->beam_seg)
     { // both tilings are built: the launch's dynamic shared memory is the largest tile's need; two CTAs must fit an SM
@@ -2007,13 +2060,16 @@ int ok_pcie_probe(int32_t device, size_t bytes, int32_t iters, int32_t mode, dou
     {
         std::memset(h, 0, bytes);
         cudaMemsetAsync(d, 1, bytes, s);
+        int probe_grid = 296; // (OK_PROBE_GRID: how many CTAs it takes to fill the link with stores)
+        if (const char *env = std::getenv("OK_PROBE_GRID"))
+            probe_grid = std::max(1, std::atoi(env));
         auto once = [&]() {
             if (mode == 0)
                 cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s);
             else if (mode == 2)
                 cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s);
             else
-                ok::probe_store_kernel<<<296, 512, 0, s>>>(static_cast<const float4 *>(d), static_cast<float4 *>(h), bytes / 16);
+                ok::probe_store_kernel<<<probe_grid, 512, 0, s>>>(static_cast<const float4 *>(d), static_cast<float4 *>(h), bytes / 16);
         };
         for (int i = 0; i < 3; ++i)
             once();

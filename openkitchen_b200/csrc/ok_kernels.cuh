@@ -125,6 +125,10 @@ struct StepParams
     // produced, so the device->host transfer overlaps the tick instead of following it
     float   *host_obs, *host_reward;
     uint8_t *host_done;
+    // ok_step_host with flusher CTAs (obs_flush_kernel, launched next to this kernel): instead of copying a finished tile's
+    // observations to the host itself, a CTA publishes flag[tile] = epoch and moves on to its next tile
+    uint32_t *tile_flag;
+    uint32_t  flag_epoch;
     // configuration
     int32_t  movement_mode, reward_mode, raycast_mode, auto_reset, auto_reset_stride;
     float    sensor_range, speed_limit, dt, collision_dist2, sensor_offset, standstill_thr2;
@@ -1771,7 +1775,16 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
         OK_TRACE(4);
         if (kBeam && p.tile_ns && tid == 0)
             s_tns[2] = global_timer();
-        if (kBeam && p.host_obs)
+        if (kBeam && p.tile_flag)
+        { // (every thread's stores of this tile happened before the barrier above; the fence makes them visible device-wide
+          // before the flag, PTX fences being cumulative)
+            if (tid == 0)
+            {
+                __threadfence();
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.tile_flag + tile), "r"(p.flag_epoch) : "memory");
+            }
+        }
+        else if (kBeam && p.host_obs)
         { // End-to-end path (ok_step_host): this tile's observations are complete in device memory; they go to the pinned
           // HOST buffer now, as full 16-byte-per-lane stores through the mapping.  (The second ray pass finishes rays in
           // no particular order: storing them one by one reached the host as scattered 4-byte PCIe writes, 0.39 ms per
@@ -2058,6 +2071,42 @@ __global__ void track_query_kernel(const StepParams p, const QueryParams q)
 }
 
 // measurement only (ok_pcie_probe): full-warp 16-byte stores of a device buffer through a host mapping
+// ok_step_host's flusher: a few CTAs on SMs of their own, launched next to the step kernel.  CTA f takes the tiles f, f + F,
+// ... in list order, waits until the step kernel has published a tile (flag[tile] == epoch) and copies its observations
+// from device memory (L2) to the pinned host buffer through the mapping, 16 bytes per lane.  The step kernel's CTAs never
+// wait for the host link: they publish and move on.
+__global__ void __launch_bounds__(1024, 1) obs_flush_kernel(const Tile *__restrict__ tiles, const int n_tiles, const uint32_t *flags, const uint32_t epoch,
+                                                            const float *obs, float *host_obs, const int R)
+{
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x)
+    {
+        if (threadIdx.x == 0)
+        {
+            uint32_t v;
+            for (;;)
+            {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + t) : "memory");
+                if (v == epoch)
+                    break;
+                __nanosleep(200);
+            }
+        }
+        __syncthreads();
+        const Tile    tl   = tiles[t];
+        const int64_t base = tl.begin * R;
+        const int     n    = tl.count * R;
+        const float  *src  = obs + base;
+        float        *dst  = host_obs + base;
+        if (((base | n) & 3) == 0)
+            for (int i = threadIdx.x; i < (n >> 2); i += blockDim.x)
+                reinterpret_cast<float4 *>(dst)[i] = __ldcg(reinterpret_cast<const float4 *>(src) + i);
+        else
+            for (int i = threadIdx.x; i < n; i += blockDim.x)
+                dst[i] = __ldcg(src + i);
+        __syncthreads(); // (thread 0 must not run ahead into the next wait while others still read `tl`: harmless, but keep the CTA together)
+    }
+}
+
 __global__ void probe_store_kernel(const float4 *__restrict__ src, float4 *__restrict__ dst, size_t n)
 {
     for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)

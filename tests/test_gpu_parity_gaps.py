@@ -246,11 +246,14 @@ def test_envs_of_different_sizes_interleave():
     assert_same(small, ora_s, ctx="small env")
 
 
+@pytest.mark.parametrize("flushers", [0, 6])
 @pytest.mark.parametrize("n,rays", [(6000, 32), (2500, 15), (300, 32)])
-def test_host_step_delivers_every_buffer(n, rays):
+def test_host_step_delivers_every_buffer(monkeypatch, n, rays, flushers):
     """ok_step_host with pinned buffers: the kernel reads the actions and writes obs / reward / done through the host
-    mapping (obs as whole tiles, several tiles per CTA); what arrives must be the device buffers, bit for bit, and the
-    tiling used for this path must not change any result (compared with the same actions through ok_launch_step)."""
+    mapping (obs as whole tiles, several tiles per CTA -- or, with OK_E2E_FLUSHERS, by flusher CTAs next to the step
+    kernel that wait for a tile's flag); what arrives must be the device buffers, bit for bit, and the tiling used for
+    this path must not change any result (compared with the same actions through ok_launch_step)."""
+    monkeypatch.setenv("OK_E2E_FLUSHERS", str(flushers))
     names = ["Monza", "Sepang", "Spa"]
     tid = (np.arange(n) * len(names) // n).astype(np.int32)
     envs = []
