@@ -997,11 +997,6 @@ int ok_create(const OkConfig *cfg, OkEnv **out)
         cudaDeviceGetAttribute(&e->smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, c.device);
         cudaDeviceGetAttribute(&e->smem_reserved, cudaDevAttrReservedSharedMemoryPerBlock, c.device);
         e->max_blob   = optin > 65536 ? static_cast<size_t>(optin) - 40960 : 0; // room for the batch scratch
-        if (const char *env = std::getenv("OK_L2_FETCH")) // experiment: cudaLimitMaxL2FetchGranularity (32 / 64 / 128 bytes), a device-wide hint
-        {
-            cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, static_cast<size_t>(std::max(32, std::atoi(env))));
-            cudaGetLastError();
-        }
     }
     else
     {
