@@ -803,10 +803,9 @@ int rebalance_beam_tiles(OkEnv *e, cudaStream_t s)
         e->balance_before = sum > 0 ? static_cast<float>(worst * e->h_tiles_beam.size() / sum) : 1.0f;
     }
     for (size_t r = 0; r < e->beam_runs.size(); ++r)
-    { // damped: half way from the weight in use to the measured one (a tile's time also depends on who shares its SM)
+    { // the first measurement as it is; later ones damped, half way from the weight in use to the measured one
         const double measured = agents[r] > 0 ? ray_ns[r] / agents[r] : w_mean;
-        const double prev     = e->beam_launches_weighted ? e->beam_runs[r].w : w_mean;
-        e->beam_runs[r].w     = 0.5 * (prev + measured);
+        e->beam_runs[r].w     = e->beam_launches_weighted ? 0.5 * (e->beam_runs[r].w + measured) : measured;
     }
     e->beam_launches_weighted = true;
     std::vector<ok::Tile> tiles = cost_balanced_tiles(e->beam_runs, e->tiles_beam_target, c0, &e->balance_after);

@@ -164,3 +164,31 @@ def test_feedback_tiling_under_a_captured_graph(monkeypatch):
     assert not np.array_equal(before, env.debug_tiles()), "the tiling never changed"
     for name in ok.BUFFERS:
         assert np.array_equal(env.read(name).view(np.uint8), ref.read(name).view(np.uint8)), name
+
+
+@pytest.mark.parametrize("raycast,n", [(ok.RAYCAST_BEAM, 300), (ok.RAYCAST_GRID, 4096), (ok.RAYCAST_BEAM, 4096)])
+def test_balance_schedule_is_harmless_everywhere(raycast, n):
+    """ok_balance_schedule before any launch, on the unstaged shape (no feedback there), in grid mode, and repeatedly on a
+    staged population with a single track: never an error, never a changed result"""
+    names = ["Monza"] if n == 4096 and raycast == ok.RAYCAST_BEAM else ["Monza", "Spa", "Sochi"]
+    tid = (np.arange(n) * len(names) // n).astype(np.int32)
+
+    def make():
+        env = ok.Env(device=0, reward_mode=ok.REWARD_CMAES_PROGRESS, auto_reset=1, raycast_mode=raycast)
+        for nm in names:
+            env.add_named_track(nm)
+        env.alloc_agents(n, ok.ray_fan(32), tid)
+        return env
+
+    a, b = make(), make()
+    b.balance_schedule()  # nothing measured yet
+    for t in range(40):
+        a.launch_steps_random(t, 1)
+        b.launch_steps_random(t, 1)
+        if t % 7 == 3:
+            before, after = b.balance_schedule()
+            assert before >= 0.0 and after >= 0.0
+    a.sync()
+    b.sync()
+    for name in ok.BUFFERS:
+        assert np.array_equal(a.read(name).view(np.uint8), b.read(name).view(np.uint8)), name
