@@ -1520,7 +1520,12 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
             float4             *w_ray = s_wray + (tid & ~31);
             unsigned long long *w_key = s_wkey + (tid & ~31);
             // tile-local ray q: agent, angle and its table entry
-            auto locate = [&](const int q, const bool valid, int &al, float &ang, bool &active, bool &cov, uint4 &ent) {
+            // (`need_rest` = the caller reads ent.z, the rest's first chunk.  Pass A does not, and must not load it: left a
+            // dead quarter of a 128-bit load, ptxas recycles that register for the packed active / cov flags RIGHT BEHIND the
+            // load, and the write waits for the very load it was meant to run ahead of -- 12 % of all stall samples on that
+            // one PRMT, ncu.  Two loads from the same sector, every destination live.)
+            auto locate = [&](const int q, const bool valid, int &al, float &ang, bool &active, bool &cov, uint4 &ent,
+                              const bool need_rest) {
                 active = false, cov = false;
                 al  = 0;
                 ang = 0.0f;
@@ -1536,8 +1541,15 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                     {
                         const int bin = __float2int_rd(fmul(ang, ld_hot(s_hot.bin_scale))) & ld_hot(s_hot.nb_mask);
                         OK_CHECK(static_cast<uint32_t>(rec.row) < bv.n_rows);
-                        ent           = __ldg(ld_hot(s_hot.entries) + static_cast<size_t>(rec.row) * ld_hot(s_hot.nb) + bin);
-                        OK_CHECK((ent.w >> 24) == 0 || ent.z + (ent.w >> 24) <= bv.n_chunks);
+                        const uint4 *ep = ld_hot(s_hot.entries) + static_cast<size_t>(rec.row) * ld_hot(s_hot.nb) + bin;
+                        if (need_rest)
+                            ent = __ldg(ep);
+                        else
+                        {
+                            const uint2 c4 = __ldg(reinterpret_cast<const uint2 *>(ep));
+                            ent            = make_uint4(c4.x, c4.y, 0u, __ldg(reinterpret_cast<const uint32_t *>(ep) + 3));
+                        }
+                        OK_CHECK(!need_rest || (ent.w >> 24) == 0 || ent.z + (ent.w >> 24) <= bv.n_chunks);
                         cov           = true;
                     }
                 }
@@ -1549,7 +1561,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                 float ang;
                 bool  active, cov;
                 uint4 ent;
-                locate(q, has, al, ang, active, cov, ent);
+                locate(q, has, al, ang, active, cov, ent, true);
                 float dx = 0.0f, dy = 0.0f;
                 if (active)
                     sincosf(ang, dy, dx); // cosf/sinf of CollisionChecker.cu:47-48
@@ -1654,7 +1666,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
             float ang;
             bool  active, cov;
             uint4 ent;
-            locate((g << 5) + lane, g < n_groups && (g << 5) + lane < n_rays, al, ang, active, cov, ent);
+            locate((g << 5) + lane, g < n_groups && (g << 5) + lane < n_rays, al, ang, active, cov, ent, false);
             while (g < n_groups)
             {
                 const int g_next = g + kWarps;
@@ -1662,7 +1674,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                 float ang_n;
                 bool  active_n, cov_n;
                 uint4 ent_n;
-                locate((g_next << 5) + lane, g_next < n_groups && (g_next << 5) + lane < n_rays, al_n, ang_n, active_n, cov_n, ent_n);
+                locate((g_next << 5) + lane, g_next < n_groups && (g_next << 5) + lane < n_rays, al_n, ang_n, active_n, cov_n, ent_n, false);
 
                 const int  q   = (g << 5) + lane;
                 const bool has = q < n_rays;
