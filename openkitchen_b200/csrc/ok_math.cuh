@@ -50,55 +50,46 @@ __device__ __constant__ uint32_t kInvPio4[24] = {
     0x441529fc, 0x1529fc27, 0x29fc2757, 0xfc2757d1, 0x2757d1f5, 0x57d1f534, 0xd1f534dd, 0xf534ddc0,
     0x34ddc0db, 0xddc0db62, 0xc0db6295, 0xdb629599, 0x6295993c, 0x95993c43, 0x993c4390, 0x3c439041};
 
-// polynomial core: x = reduced argument (already multiplied by the quadrant sign), x2 = x*x of the
-// UNSIGNED reduced argument, n = quadrant, flip = use the negated-cosine table
-__device__ __forceinline__ void sincos_core(double x, double x2, int n, bool flip, float &sin_out, float &cos_out)
+// polynomial core: x = reduced argument WITHOUT the quadrant sign, q = quadrant that selects sign and table (glibc's
+// sign[q & 3] = {1,-1,-1,1} and "negated-cosine table for q & 2"), n = quadrant that swaps sine and cosine.
+// glibc multiplies x by the sign and negates the cosine coefficients BEFORE the polynomials; both polynomials are
+// odd / even in exactly the operands that change sign and every step rounds to nearest, so negating the two binary32
+// results instead gives the same bits (a zero result, where -(+0) would differ, needs x = 0, which only the
+// |y| < 2^-12 shortcut sees) -- checked against libm on all 2^32 inputs (tools/sincosf_unified_exhaustive.c).  One
+// path, no binary64 selects or sign products: the warp's lanes no longer split between "|y| < pi/4" and the rest.
+__device__ __forceinline__ void sincos_core(double x, int n, int q, float &sin_out, float &cos_out)
 {
-    const double sg = flip ? -1.0 : 1.0;
+    const double x2 = x * x;
     const double x4 = x2 * x2;
     const double x3 = x2 * x;
-    const double c2 = fma(x2, sg * OK_SC_C4, sg * OK_SC_C3);
+    const double c2 = fma(x2, OK_SC_C4, OK_SC_C3);
     const double s1 = fma(x2, OK_SC_S3, OK_SC_S2);
-    const double c1 = fma(x2, sg * OK_SC_C1, sg * OK_SC_C0);
+    const double c1 = fma(x2, OK_SC_C1, OK_SC_C0);
     const double x5 = x3 * x2;
     const double x6 = x4 * x2;
     const double s  = fma(x3, OK_SC_S1, x);
-    const double c  = fma(x4, sg * OK_SC_C2, c1);
-    const float  sv = __double2float_rn(fma(x5, s1, s));
-    const float  cv = __double2float_rn(fma(x6, c2, c));
-    if (n & 1)
-    {
-        sin_out = cv;
-        cos_out = sv;
-    }
-    else
-    {
-        sin_out = sv;
-        cos_out = cv;
-    }
+    const double c  = fma(x4, OK_SC_C2, c1);
+    const uint32_t sv = __float_as_uint(__double2float_rn(fma(x5, s1, s))) ^ ((static_cast<uint32_t>(q + 1) & 2u) << 30);
+    const uint32_t cv = __float_as_uint(__double2float_rn(fma(x6, c2, c))) ^ ((static_cast<uint32_t>(q) & 2u) << 30);
+    sin_out           = __uint_as_float((n & 1) ? cv : sv);
+    cos_out           = __uint_as_float((n & 1) ? sv : cv);
 }
 
 __device__ __forceinline__ void sincosf(float y, float &sin_out, float &cos_out)
 {
     const uint32_t top = (__float_as_uint(y) >> 20) & 0x7ffu;
     double         x   = static_cast<double>(y);
-    if (top < 0x3f4u)
-    { // |y| < pi/4
-        if (top < 0x398u)
-        { // |y| < 2^-12
-            sin_out = y;
-            cos_out = 1.0f;
-            return;
-        }
-        sincos_core(x, x * x, 0, false, sin_out, cos_out);
-    }
-    else if (top < 0x42fu)
-    { // |y| < 120: n = round(x * 2/pi) via a 2^24-scaled truncation
+    if (top < 0x42fu)
+    { // |y| < 120: n = round(x * 2/pi) via a 2^24-scaled truncation.  glibc's separate branch for |y| < 0.75 is this one
+      // with n = 0 (x - 0 * pi/2 = x exactly, sign +1, table 0); its |y| < 2^-12 shortcut is applied on top.
         const double r = x * 0x1.45F306DC9C883p+23;
         const int    n = (__double2int_rz(r) + 0x800000) >> 24;
         x              = fma(-static_cast<double>(n), 0x1.921FB54442D18p0, x);
-        const double s = ((n + 1) & 2) ? -1.0 : 1.0; // sign table {1,-1,-1,1}[n & 3]
-        sincos_core(x * s, x * x, n, (n & 2) != 0, sin_out, cos_out);
+        float sv, cv;
+        sincos_core(x, n, n, sv, cv);
+        const bool tiny = top < 0x398u; // |y| < 2^-12
+        sin_out         = tiny ? y : sv;
+        cos_out         = tiny ? 1.0f : cv;
     }
     else if (top < 0x7f8u)
     { // finite, large: Payne-Hanek style reduction with 4/pi in fixed point
@@ -115,11 +106,9 @@ __device__ __forceinline__ void sincosf(float y, float &sin_out, float &cos_out)
         res0 += res1;
         const uint64_t nn = (res0 + (1ULL << 61)) >> 62;
         res0 -= nn << 62;
-        x               = static_cast<double>(static_cast<int64_t>(res0)) * 0x1.921FB54442D18p-62;
-        const int    n  = static_cast<int>(nn);
-        const int    q  = n + sign;
-        const double s  = ((q + 1) & 2) ? -1.0 : 1.0;
-        sincos_core(x * s, x * x, n, (q & 2) != 0, sin_out, cos_out);
+        x           = static_cast<double>(static_cast<int64_t>(res0)) * 0x1.921FB54442D18p-62;
+        const int n = static_cast<int>(nn);
+        sincos_core(x, n, n + sign, sin_out, cos_out);
     }
     else
     {
