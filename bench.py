@@ -552,6 +552,21 @@ def main():
     e2e_ms = max(e0.elapsed_time(e1), 1e3 * tw) / e2e_steps  # host-synchronous path: the wall clock is the honest one
     h2d = 2 * 4 * n
     d2h = n * N_RAYS * 4 + n * 4 + n
+    # the same loop with the opt-in, LOSSY 16-bit fixed-point observations (ok_step_host_q16): half the bytes on the link
+    # that bounds this path.  Reported next to `e2e`, never as it.
+    q16_ms = None
+    try:
+        obs_q = ok.pinned_array((n, N_RAYS), np.uint16)
+        for i in range(3):
+            env.step_host(thr[i], steer[i], obs_q, rew, done, sp)
+        barrier()
+        tq = time.perf_counter()
+        for i in range(e2e_steps):
+            env.step_host(thr[i], steer[i], obs_q, rew, done, sp)
+        barrier()
+        q16_ms = 1e3 * (time.perf_counter() - tq) / e2e_steps
+    except Exception as ex:  # an experiment build (OK_B200_LIB) without the entry point
+        print(f"e2e q16 leg skipped: {ex}", file=sys.stderr)
     # what the host link gives this rank while EVERY rank is moving the same bytes (a bare 8.7 MB device->host transfer
     # per step, nothing else): the ceiling of any end-to-end path on this box
     barrier()
@@ -571,6 +586,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_per_step, e2e_ms, ms_tick, gen_ms = float(t[0]), float(t[1]), float(t[2]), float(t[3])
         link["d2h"], link["store"] = -float(t[4]), -float(t[5])  # the slowest rank's share
+        tq = torch.tensor([q16_ms if q16_ms is not None else float("inf")], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+        q16_ms = float(tq[0]) if float(tq[0]) != float("inf") else None
 
     c5 = None
     if args.config5 or (dist is not None and os.environ.get("OK_BENCH_CONFIG5", "1") != "0"):
@@ -622,7 +640,12 @@ def main():
                     "host_link": {"d2h_copy_GBps_slowest_rank": link.get("d2h"), "mapped_store_GBps_slowest_rank": link.get("store"),
                                   "what": "a bare transfer of d2h_bytes_per_step, all ranks at once (ok_pcie_probe)",
                                   "ceiling_ms_per_step": ceiling_ms,
-                                  "e2e_over_ceiling": (e2e_ms / ceiling_ms) if ceiling_ms else None}},
+                                  "e2e_over_ceiling": (e2e_ms / ceiling_ms) if ceiling_ms else None},
+                    "q16_opt_in": None if q16_ms is None else {
+                        "value": total_agents / (q16_ms * 1e-3), "ms_per_step": q16_ms,
+                        "d2h_bytes_per_step": n * N_RAYS * 2 + n * 4 + n,
+                        "what": "ok_step_host_q16: observations as 16-bit fixed point, rn(obs * 65535) -- LOSSY (<= 7.7e-6 of the "
+                                "sensor range), opt-in, not the headline"}},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if dist is not None:

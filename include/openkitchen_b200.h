@@ -264,6 +264,13 @@ int ok_discounted_returns(OkEnv *env, const float *d_rewards, const uint8_t *d_d
  * nullable), then a stream synchronise.  Host buffers should be pinned (ok_host_alloc). */
 int ok_step_host(OkEnv *env, const float *h_act_throttle, const float *h_act_steer, float *h_obs, float *h_reward,
                  uint8_t *h_done, void *stream);
+/* ok_step_host with the observations as 16-bit fixed point -- OPT-IN AND LOSSY: h_obs_q16[a][r] =
+ * round-to-nearest-even(clamp(obs, 0, 1) * 65535), obs being the binary32 value ok_step_host delivers
+ * (|error| <= 0.5 / 65535 = 7.7e-6 of the sensor range, 0.0015 px at 200 px).  Half the bytes on the host link, which bounds the
+ * end-to-end tick.  The device-side buffers (OK_BUF_OBS ...) keep the exact values; h_obs_q16 must be
+ * pinned.  No counterpart in the reference (its consumers read Agent::sensor_hits_, Agent.h:66, as float). */
+int ok_step_host_q16(OkEnv *env, const float *h_act_throttle, const float *h_act_steer, uint16_t *h_obs_q16, float *h_reward,
+                     uint8_t *h_done, void *stream);
 /* The object-model tick in ONE upload, one launch and two downloads (what the C++ shim's Environment::step and
  * CollisionChecker::checkCollision use; round 1 made ~24 synchronous buffer copies per tick).  The env's first thirteen
  * buffers (OK_BUF_POS_X .. OK_BUF_SS_Y: pose, speed, acceleration, action, flags, standstill record) are adjacent in

@@ -122,6 +122,7 @@ SIGNATURES = {
     "ok_fill_random_actions": (C.c_int, [_P, C.c_uint64, C.c_uint32, _P]),
     "ok_genetic_policy": (C.c_int, [_P, _P, _P, C.c_int32, _P]),
     "ok_step_host": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "ok_step_host_q16": (C.c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "ok_packed_layout": (C.c_int, [_P, C.POINTER(OkPackedLayout)]),
     "ok_step_packed": (C.c_int, [_P, _P, _P, C.c_int32, _P]),
     "ok_host_alloc": (C.c_int, [C.POINTER(_P), C.c_size_t]),

@@ -7,6 +7,8 @@
 #include "ok_kernels.cuh"
 #include "ok_track.hpp"
 
+#include <cuda.h> // types of the one driver entry point used (cuStreamWriteValue32), looked up at run time: libcuda is not linked
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -173,10 +175,20 @@ struct OkEnv
     // ok_step_host's tiling: several tiles per CTA, so that a tile's observations cross PCIe while the next one is computed
     ok::Tile            *d_tiles_e2e{nullptr};
     int32_t              n_tiles_e2e{0}, grid_e2e{0};
+    ok::Tile            *d_tiles_q16{nullptr}; // ok_step_host_q16's tiling: half the bytes per tile, fewer and larger tiles pay
+    int32_t              n_tiles_q16{0}, grid_q16{0};
     // ... with flusher CTAs (obs_flush_kernel) on SMs of their own: flags, epoch, the side stream and its fork / join events
     int32_t              e2e_flushers{0};
     uint32_t            *d_tile_flag{nullptr};
     uint32_t             flag_epoch{0};
+    // ok_step_host: device stage of the caller's two mapped action arrays, filled by the copy engine on act_stream next to
+    // the running kernel, + the word the stream sets to this launch's target when both copies have landed
+    float               *d_act_stage{nullptr};
+    uint32_t            *d_act_ready{nullptr};
+    uint32_t             act_ready_target{0};
+    cudaStream_t         act_stream{nullptr};
+    cudaEvent_t          ev_act{nullptr};
+    bool                 act_stage_on{true}; // OK_ACT_STAGE=0: every tile reads the mapping (A/B)
     cudaStream_t         flush_stream{nullptr};
     cudaEvent_t          ev_fork{nullptr}, ev_join{nullptr};
     int32_t              batch_agents_beam{0};
@@ -227,9 +239,17 @@ void free_agents(OkEnv *e)
         cudaFree(e->d_tiles_beam);
     if (e->d_tiles_e2e)
         cudaFree(e->d_tiles_e2e);
+    if (e->d_tiles_q16)
+        cudaFree(e->d_tiles_q16);
+    e->d_tiles_q16 = nullptr, e->n_tiles_q16 = 0;
     if (e->d_tile_flag)
         cudaFree(e->d_tile_flag);
     e->d_tile_flag = nullptr;
+    if (e->d_act_stage)
+        cudaFree(e->d_act_stage);
+    if (e->d_act_ready)
+        cudaFree(e->d_act_ready);
+    e->d_act_stage = nullptr, e->d_act_ready = nullptr, e->act_ready_target = 0;
     e->d_tiles_beam = nullptr, e->n_tiles_beam = 0, e->d_tiles_e2e = nullptr, e->n_tiles_e2e = 0;
     if (e->d_tile_ns)
         cudaFree(e->d_tile_ns);
@@ -821,6 +841,23 @@ int rebalance_beam_tiles(OkEnv *e, cudaStream_t s)
     return e->d_first_beam ? upload_first_tiles(e, s) : OK_SUCCESS;
 }
 
+// cuStreamWriteValue32 through the runtime's driver-entry-point lookup (the library does not link libcuda); nullptr if absent
+using StreamWriteValue32Fn = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+StreamWriteValue32Fn stream_write_value32()
+{
+    static const StreamWriteValue32Fn fn = [] {
+        void                            *f  = nullptr;
+        cudaDriverEntryPointQueryResult  qr = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &f, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess)
+        {
+            cudaGetLastError();
+            f = nullptr;
+        }
+        return reinterpret_cast<StreamWriteValue32Fn>(f);
+    }();
+    return fn;
+}
+
 int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
 {
     int rc = ensure_arena(e);
@@ -830,7 +867,7 @@ int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
     p.tracks     = e->d_track_refs;
     if (e->cfg.raycast_mode == OK_RAYCAST_BEAM)
     {
-        const bool e2e = p.host_obs && e->d_tiles_e2e;
+        const bool e2e = (p.host_obs || p.host_obs_q16) && e->d_tiles_e2e;
         if (!e2e && e->auto_balance && e->d_tile_ns)
         { // feedback tiling: re-cut the tiles from the measured tile times, a few times early on, then now and then
             const uint64_t k = e->beam_launches++;
@@ -865,8 +902,17 @@ int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
             p.tiles   = e->d_tiles_e2e;
             p.n_tiles = e->n_tiles_e2e;
             grid      = e->grid_e2e;
+            if (p.host_obs_q16 && e->d_tiles_q16)
+                p.tiles = e->d_tiles_q16, p.n_tiles = e->n_tiles_q16, grid = e->grid_q16;
+            if (p.ext_host && e->d_act_stage && p.n_tiles > grid && e->act_stage_on && stream_write_value32())
+            { // tiles after a CTA's first read the actions from a device copy (StepParams::act_ready)
+                p.act_stage_thr    = e->d_act_stage;
+                p.act_stage_steer  = e->d_act_stage + e->n_agents;
+                p.act_ready        = e->d_act_ready;
+                p.act_ready_target = ++e->act_ready_target;
+            }
         }
-        const bool flushers = e2e && e->e2e_flushers > 0 && e->d_tile_flag && e->beam_staged && !e->beam_seg;
+        const bool flushers = e2e && p.host_obs && e->e2e_flushers > 0 && e->d_tile_flag && e->beam_staged && !e->beam_seg;
         if (flushers)
         { // fork: the flusher CTAs start next to the step kernel, on the side stream
             p.tile_flag  = e->d_tile_flag;
@@ -888,6 +934,16 @@ int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
     else
         ok::step_kernel<kBlock, false><<<e->grid, kBlock, e->smem, s>>>(p);
     OK_CUDA(cudaGetLastError());
+    if (p.act_ready)
+    { // enqueued AFTER the launch: the kernel is already running its first tiles while the host issues these
+        const size_t bytes = sizeof(float) * static_cast<size_t>(e->n_agents);
+        OK_CUDA(cudaMemcpyAsync(p.act_stage_thr, p.ext_thr, bytes, cudaMemcpyHostToDevice, e->act_stream));
+        OK_CUDA(cudaMemcpyAsync(p.act_stage_steer, p.ext_steer, bytes, cudaMemcpyHostToDevice, e->act_stream));
+        if (stream_write_value32()(e->act_stream, reinterpret_cast<CUdeviceptr>(e->d_act_ready), p.act_ready_target, 0) != CUDA_SUCCESS)
+            return fail(OK_ERR_CUDA, "cuStreamWriteValue32 failed");
+        OK_CUDA(cudaEventRecord(e->ev_act, e->act_stream));
+        OK_CUDA(cudaStreamWaitEvent(s, e->ev_act, 0)); // join: nothing of this tick outlives the caller's stream
+    }
     if (p.tile_flag) // join: the tick is complete when the last tile has reached the host
         OK_CUDA(cudaStreamWaitEvent(s, e->ev_join, 0));
     e->launches++;
@@ -1048,6 +1104,10 @@ void ok_destroy(OkEnv *e)
             cudaFree(e->d_stage);
         if (e->flush_stream)
             cudaStreamDestroy(e->flush_stream);
+        if (e->act_stream)
+            cudaStreamDestroy(e->act_stream);
+        if (e->ev_act)
+            cudaEventDestroy(e->ev_act);
         if (e->ev_fork)
             cudaEventDestroy(e->ev_fork);
         if (e->ev_join)
@@ -1415,6 +1475,28 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
         if (int rc = build_tiles_balanced(e->batch_agents_beam, e2e_ctas, &e->d_tiles_e2e, &e->n_tiles_e2e, per_cta))
             return rc;
         e->grid_e2e = std::max(1, std::min(e2e_ctas, e->n_tiles_e2e));
+        { // ok_step_host_q16: measured at the C3 shape 0.164 / 0.157 / 0.171 / 0.199 ms per tick with 2 / 3 / 4 / 6 tiles per CTA
+            int per_cta_q16 = e->beam_seg ? 2 : 3;
+            if (const char *env = std::getenv("OK_E2E_TILES_Q16"))
+                per_cta_q16 = std::max(1, std::atoi(env));
+            else if (std::getenv("OK_E2E_TILES"))
+                per_cta_q16 = per_cta;
+            const int q16_ctas = e->num_sms * e->ctas_per_sm_beam;
+            if (int rc = build_tiles_balanced(e->batch_agents_beam, q16_ctas, &e->d_tiles_q16, &e->n_tiles_q16, per_cta_q16))
+                return rc;
+            e->grid_q16 = std::max(1, std::min(q16_ctas, e->n_tiles_q16));
+        }
+        OK_CUDA(cudaMalloc(&e->d_act_stage, sizeof(float) * 2 * static_cast<size_t>(n)));
+        OK_CUDA(cudaMalloc(&e->d_act_ready, sizeof(uint32_t)));
+        OK_CUDA(cudaMemset(e->d_act_ready, 0, sizeof(uint32_t)));
+        e->act_ready_target = 0;
+        if (!e->act_stream)
+        {
+            OK_CUDA(cudaStreamCreateWithFlags(&e->act_stream, cudaStreamNonBlocking));
+            OK_CUDA(cudaEventCreateWithFlags(&e->ev_act, cudaEventDisableTiming));
+        }
+        if (const char *env = std::getenv("OK_ACT_STAGE"))
+            e->act_stage_on = std::atoi(env) != 0;
         if (e->e2e_flushers > 0)
         {
             OK_CUDA(cudaMalloc(&e->d_tile_flag, sizeof(uint32_t) * static_cast<size_t>(e->n_tiles_e2e)));
@@ -1760,9 +1842,14 @@ int ok_track_query_host(OkEnv *e, const float *h_x, const float *h_y, const int3
     return OK_SUCCESS;
 }
 
-int ok_step_host(OkEnv *e, const float *h_thr, const float *h_steer, float *h_obs, float *h_reward, uint8_t *h_done,
-                 void *stream)
+} // extern "C"
+namespace
 {
+// ok_step_host / ok_step_host_q16: `h_obs` is float[N][R], or uint16_t[N][R] when `q16`
+int step_host_impl(OkEnv *e, const float *h_thr, const float *h_steer, void *h_obs_any, const bool q16, float *h_reward, uint8_t *h_done,
+                   void *stream)
+{
+    float *h_obs = q16 ? nullptr : static_cast<float *>(h_obs_any);
     int rc = check_ready(e);
     if (rc)
         return rc;
@@ -1786,6 +1873,7 @@ int ok_step_host(OkEnv *e, const float *h_thr, const float *h_steer, float *h_ob
         {
             p.ext_thr   = a_thr;
             p.ext_steer = a_steer;
+            p.ext_host  = 1;
         }
         else
         {
@@ -1808,7 +1896,13 @@ int ok_step_host(OkEnv *e, const float *h_thr, const float *h_steer, float *h_ob
     p.host_obs    = obs_by_copy ? nullptr : pinned_alias(h_obs);
     p.host_reward = (obs_by_copy || small_by_copy) ? nullptr : pinned_alias(h_reward);
     p.host_done   = (obs_by_copy || small_by_copy) ? nullptr : pinned_alias(h_done);
-    rc            = launch_step(e, p, s);
+    if (q16 && h_obs_any)
+    { // the fixed-point observations exist only as what the kernel stores through the mapping: no staged fallback
+        p.host_obs_q16 = pinned_alias(static_cast<uint16_t *>(h_obs_any));
+        if (!p.host_obs_q16)
+            return fail(OK_ERR_INVALID_ARG, "ok_step_host_q16: h_obs_q16 must be pinned host memory (ok_host_alloc / cudaHostRegister)");
+    }
+    rc = launch_step(e, p, s);
     if (rc)
         return rc;
     if (h_obs && !p.host_obs)
@@ -1819,6 +1913,19 @@ int ok_step_host(OkEnv *e, const float *h_thr, const float *h_steer, float *h_ob
         OK_CUDA(cudaMemcpyAsync(h_done, e->d_buf[OK_BUF_DONE], n, cudaMemcpyDeviceToHost, s));
     OK_CUDA(cudaStreamSynchronize(s));
     return OK_SUCCESS;
+}
+} // namespace
+extern "C"
+{
+int ok_step_host(OkEnv *e, const float *h_thr, const float *h_steer, float *h_obs, float *h_reward, uint8_t *h_done, void *stream)
+{
+    return step_host_impl(e, h_thr, h_steer, h_obs, false, h_reward, h_done, stream);
+}
+
+int ok_step_host_q16(OkEnv *e, const float *h_thr, const float *h_steer, uint16_t *h_obs_q16, float *h_reward, uint8_t *h_done,
+                     void *stream)
+{
+    return step_host_impl(e, h_thr, h_steer, h_obs_q16, true, h_reward, h_done, stream);
 }
 
 int ok_packed_layout(const OkEnv *e, OkPackedLayout *out)

@@ -116,6 +116,7 @@ struct StepParams
     uint32_t           *tile_ns;     // nullable (beam kernel): per tile {ns in the ray phase, ns in the rest of the tile}: feedback for the host's tiling
     // this launch
     const float *ext_thr, *ext_steer; // nullable: actions supplied by the caller
+    int32_t      ext_host;            // (host side only) they are pinned HOST arrays read through the mapping
     int32_t      action_source;       // 0 stored/ext, 1 philox
     uint32_t     seed;
     uint64_t     step;
@@ -125,6 +126,16 @@ struct StepParams
     // produced, so the device->host transfer overlaps the tick instead of following it
     float   *host_obs, *host_reward;
     uint8_t *host_done;
+    // ok_step_host_q16 (opt-in, lossy): the observations as 16-bit fixed point, q = rn(clamp(obs, 0, 1) * 65535), half the
+    // bytes on the host link.  Excludes host_obs.
+    uint16_t *host_obs_q16;
+    // ok_step_host: a CTA's FIRST tile reads the caller's two action arrays through the host mapping; meanwhile the copy engine
+    // brings both arrays to act_stage (device memory) on a side stream and then sets *act_ready = act_ready_target (a stream
+    // memory operation), and every later tile reads the stage.  A mapped read issued after a tile's observations have been
+    // flushed queues behind those posted writes (PCIe reads do not pass writes): 16-30 us per tile instead of 8, measured.
+    float    *act_stage_thr, *act_stage_steer;
+    uint32_t *act_ready;
+    uint32_t  act_ready_target;
     // ok_step_host with flusher CTAs (obs_flush_kernel, launched next to this kernel): instead of copying a finished tile's
     // observations to the host itself, a CTA publishes flag[tile] = epoch and moves on to its next tile
     uint32_t *tile_flag;
@@ -832,6 +843,12 @@ static __device__ __noinline__ int beam_walk_fallback(const uint8_t *blob, float
 // segment is `seg` (-1 = none); returns the squared norm of the relative hit
 // t_known != 0: the winner's exact t is already at hand (the beam key holds it; a zero is recomputed because the
 // key does not keep its sign)
+// ok_step_host_q16's fixed point: round-to-nearest-even of clamp(obs, 0, 1) * 65535 (a NaN becomes 0)
+__device__ __forceinline__ uint32_t obs_q16(const float ob)
+{
+    return __float2uint_rn(fmul(fminf(fmaxf(ob, 0.0f), 1.0f), 65535.0f));
+}
+
 template <bool kHostStore = true, typename Rec>
 __device__ __forceinline__ float finish_ray(const StepParams &p, const float4 *segs, const Rec &rec, const int64_t gi,
                                             const float dx, const float dy, const int seg, const float t_known = 0.0f)
@@ -860,6 +877,8 @@ __device__ __forceinline__ float finish_ray(const StepParams &p, const float4 *s
     p.obs[gi]      = ob;
     if (kHostStore && p.host_obs) // (the beam kernel copies a whole tile's observations at once, see its tile flush)
         p.host_obs[gi] = ob;
+    if (kHostStore && p.host_obs_q16)
+        p.host_obs_q16[gi] = static_cast<uint16_t>(obs_q16(ob));
     return sq;
 }
 
@@ -878,7 +897,8 @@ __host__ __device__ inline size_t beam_smem_bytes(int agents)
 // returns the record the ray and reward phases work from.
 // `gblob` is the track's blob in the GLOBAL arena: only a crashed agent's auto-reset reads it (centre line, headings),
 // so phase 1 does not have to wait for the blob to be staged in shared memory.
-__device__ __forceinline__ AgentRec agent_pre(const StepParams &p, const uint8_t *gblob, const TrackRef &tr, const BeamView &bv, const int64_t a)
+__device__ __forceinline__ AgentRec agent_pre(const StepParams &p, const uint8_t *gblob, const TrackRef &tr, const BeamView &bv, const int64_t a,
+                                              const bool act_staged = false)
 {
     float    x = p.x[a], y = p.y[a], rot = p.rot[a], speed = p.speed[a], accel = p.accel[a];
     bool     crashed = p.crashed[a] != 0, timed_out = p.timed_out[a] != 0;
@@ -928,6 +948,11 @@ __device__ __forceinline__ AgentRec agent_pre(const StepParams &p, const uint8_t
                 thr   = fmul(100.0f, fmul(static_cast<float>(o[0] >> 8), 0x1p-24f));
                 steer = fsub(fmul(10.0f, fmul(static_cast<float>(o[1] >> 8), 0x1p-24f)), 5.0f);
             }
+        }
+        else if (p.ext_thr && act_staged)
+        { // this launch's copy of the caller's arrays in device memory (see StepParams::act_ready)
+            thr   = __ldcg(p.act_stage_thr + a);
+            steer = __ldcg(p.act_stage_steer + a);
         }
         else if (p.ext_thr)
         {
@@ -1240,7 +1265,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint16_t                      s_order[kBeam ? 1 : 1024]; // pool order of the rays (p.ray_order)
     __shared__ __align__(8) uint64_t         bar;
-    __shared__ int                           s_tile, s_pool, s_pool2, s_npend, s_adone;
+    __shared__ int                           s_tile, s_pool, s_pool2, s_npend, s_adone, s_actdev;
     __shared__ int                           s_ready[kBeam ? kPendCap / 32 : 1]; // entries written, per 32-ray chunk of the queue
     __shared__ uint16_t                      s_pend[kBeam ? kPendCap : 1]; // tile-local indices of the rays pass A left open
 
@@ -1274,7 +1299,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
 #endif
     const bool single_wave = OK_SINGLE_WAVE && p.n_tiles <= static_cast<int>(gridDim.x);
     if (tid == 0)
-        s_tile = static_cast<int>(blockIdx.x);
+        s_tile = static_cast<int>(blockIdx.x), s_actdev = 0;
 
     for (;;)
     {
@@ -1332,7 +1357,7 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
         // phase 1 -- one thread per agent: optional reset, kinematics, standstill (Environment.cpp:128-143)
         // =====================================================================================
         if (tid < count)
-            recs[tid] = agent_pre(p, gblob, tr, bv, tl.begin + tid);
+            recs[tid] = agent_pre(p, gblob, tr, bv, tl.begin + tid, kBeam && n_done > 0 && s_actdev != 0);
         if (tid == 0)
         {
             s_pool = 0, s_pool2 = 0, s_npend = 0, s_adone = 0;
@@ -1485,6 +1510,8 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
                 p.obs[gi]      = ob;
                 if (p.host_obs)
                     p.host_obs[gi] = ob;
+                if (p.host_obs_q16)
+                    p.host_obs_q16[gi] = static_cast<uint16_t>(obs_q16(ob));
             }
             // min_dist2 of CollisionChecker.cu:150,162-165: `if (sq < min) min = sq` skips NaN, and so
             // does a signed-int min over the bit patterns of values >= +0 (a NaN made here is 0x7fffffff)
@@ -1781,7 +1808,15 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
             // claim the next batch now: late enough to keep the schedule dynamic (see the loop top), early enough
             // for the atomic's latency to hide behind the other warps' last groups and phase 4
             if (tid == 0)
+            {
                 s_tile = single_wave ? p.n_tiles : static_cast<int>(gridDim.x) + atomicAdd(p.sched, 1); // every thread read the old value before phase 1
+                if (p.act_ready)
+                { // have the staged actions arrived?  (Long since, normally; if not, the next tile reads the mapping.)
+                    uint32_t c;
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(c) : "l"(p.act_ready) : "memory");
+                    s_actdev = static_cast<int32_t>(c - p.act_ready_target) >= 0;
+                }
+            }
         }
         __syncthreads();
         OK_TRACE(4);
@@ -1810,6 +1845,26 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
             else
                 for (int i = tid; i < n_rays; i += kBlock)
                     dst[i] = __ldcg(src + i);
+        }
+        else if (kBeam && p.host_obs_q16)
+        { // the same flush at half width: eight observations per lane become one 16-byte store of 16-bit fixed point
+            const float *src = p.obs + ray_base;
+            uint16_t    *dst = p.host_obs_q16 + ray_base;
+            if (((ray_base | n_rays) & 7) == 0)
+                for (int i = tid; i < (n_rays >> 3); i += kBlock)
+                {
+                    const float4 a = __ldcg(reinterpret_cast<const float4 *>(src) + 2 * i);
+                    const float4 b = __ldcg(reinterpret_cast<const float4 *>(src) + 2 * i + 1);
+                    uint4        o;
+                    o.x = obs_q16(a.x) | (obs_q16(a.y) << 16);
+                    o.y = obs_q16(a.z) | (obs_q16(a.w) << 16);
+                    o.z = obs_q16(b.x) | (obs_q16(b.y) << 16);
+                    o.w = obs_q16(b.z) | (obs_q16(b.w) << 16);
+                    reinterpret_cast<uint4 *>(dst)[i] = o;
+                }
+            else
+                for (int i = tid; i < n_rays; i += kBlock)
+                    dst[i] = static_cast<uint16_t>(obs_q16(__ldcg(src + i)));
         }
         if (kBeam && p.stats && tid == 0)
         {

@@ -225,8 +225,12 @@ class Env:
         check(self.lib.ok_discounted_returns(self.h, d_rewards, d_done, d_out, steps, n, gamma, stream))
 
     def step_host(self, thr=None, steer=None, obs=None, reward=None, done=None, stream=None):
-        """End-to-end tick with HOST buffers (H2D actions, kernel, D2H results, sync)."""
-        check(self.lib.ok_step_host(self.h, _vp(thr), _vp(steer), _vp(obs), _vp(reward), _vp(done), stream))
+        """End-to-end tick with HOST buffers (H2D actions, kernel, D2H results, sync).  An `obs` array of dtype uint16
+        selects the opt-in, LOSSY 16-bit fixed-point observations (ok_step_host_q16: rn(clamp(obs, 0, 1) * 65535))."""
+        if obs is not None and getattr(obs, "dtype", None) == np.uint16:
+            check(self.lib.ok_step_host_q16(self.h, _vp(thr), _vp(steer), _vp(obs), _vp(reward), _vp(done), stream))
+        else:
+            check(self.lib.ok_step_host(self.h, _vp(thr), _vp(steer), _vp(obs), _vp(reward), _vp(done), stream))
 
     def track_query(self, x, y, track_id=None, stream=None):
         """RaceTrack::findNearestTrackIndexBruteForce / getDistanceToLaneCenter / getNearestDistanceToTrackBoundary

@@ -283,6 +283,56 @@ def test_host_step_delivers_every_buffer(monkeypatch, n, rays, flushers):
     assert (a.read("reset_pt") != 3).any() or n < 1000, "nobody ever crashed: test too weak"
 
 
+@pytest.mark.parametrize("raycast", [ok.RAYCAST_BEAM, ok.RAYCAST_GRID])
+@pytest.mark.parametrize("n,rays", [(6000, 32), (2500, 15), (300, 5)])
+def test_host_step_q16_is_the_rounded_float_observation(n, rays, raycast):
+    """ok_step_host_q16 (opt-in, lossy): what arrives is rn(clamp(obs, 0, 1) * 65535) of the SAME binary32 observation
+    ok_step_host delivers -- the quantisation is the only difference, and the device state stays exact (every buffer
+    compared with an env stepped through ok_launch_step on the same actions).  Whole-tile flush (rays a multiple of 8),
+    the ragged fallback (15 and 5 rays) and the per-ray stores of the grid kernel."""
+    names = ["Monza", "Sepang", "Spa"]
+    tid = (np.arange(n) * len(names) // n).astype(np.int32)
+    envs = []
+    for _ in range(2):
+        env = ok.Env(device=0, reward_mode=ok.REWARD_CMAES_PROGRESS, auto_reset=1, raycast_mode=raycast)
+        for nm in names:
+            env.add_named_track(nm)
+        env.alloc_agents(n, ok.ray_fan(rays), tid)
+        envs.append(env)
+    a, b = envs
+    rng = np.random.default_rng(6)
+    thr, steer = ok.pinned_array((n,), np.float32), ok.pinned_array((n,), np.float32)
+    q, rew, done = ok.pinned_array((n, rays), np.uint16), ok.pinned_array((n,), np.float32), ok.pinned_array((n,), np.uint8)
+    worst = 0.0
+    for step in range(20):
+        thr[:] = rng.random(n, dtype=np.float32) * 100.0
+        steer[:] = rng.random(n, dtype=np.float32) * 10.0 - 5.0
+        q[:], rew[:], done[:] = 12345, -1.0, 7
+        a.step_host(thr, steer, q, rew, done)
+        b.write("act_throttle", thr)
+        b.write("act_steer", steer)
+        b.launch_step()
+        obs = b.read("obs")
+        assert np.isfinite(obs).all()
+        want = np.rint(np.clip(obs, np.float32(0), np.float32(1)) * np.float32(65535.0)).astype(np.uint16)
+        assert np.array_equal(q, want), f"q16 obs, step {step}: {(q != want).sum()} differ"
+        worst = max(worst, float(np.abs(q.astype(np.float64) / 65535.0 - obs).max()))
+        assert np.array_equal(rew.view(np.uint32), b.read("reward").view(np.uint32)), f"reward, step {step}"
+        assert np.array_equal(done, b.read("done")), f"done, step {step}"
+    assert worst <= 0.5 / 65535.0 + 2.0**-23, worst  # half a step of the fixed point + the binary32 rounding of obs * 65535
+    for name in ok.BUFFERS:
+        assert np.array_equal(a.read(name).view(np.uint8), b.read(name).view(np.uint8)), name
+
+
+def test_host_step_q16_rejects_pageable_memory():
+    env = ok.Env(device=0)
+    env.add_named_track("Monza")
+    env.alloc_agents(64, ok.ray_fan(8), np.zeros(64, np.int32))
+    q = np.zeros((64, 8), np.uint16)
+    with pytest.raises(ok.OkError):
+        env.step_host(None, None, q, None, None)
+
+
 @pytest.mark.parametrize("kernel", ["staged", "unstaged", "segstaged"])
 @pytest.mark.parametrize("mode", [ok.MOVE_VELOCITY, ok.MOVE_ACCELERATION])
 def test_both_beam_kernel_shapes_match_the_oracle(monkeypatch, kernel, mode):
