@@ -38,6 +38,22 @@ doc = {
     "launch_list": "profiles/r2_launches.csv",
     "time_share_ns": dict(share), "launches": dict(count),
 }
+# the sentence bench.py prints next to the roofline numbers, from this capture's own metrics
+stalls = {}
+try:
+    for ln in open(f"profiles/{summary}"):
+        if ln.startswith("stall_"):
+            k, v = ln.split()
+            stalls[k] = float(v.rstrip("%"))
+except OSError:
+    pass
+top = sorted(stalls.items(), key=lambda kv: -kv[1])[:3]
+pipe = lambda k: round(get(f"sm__inst_executed_pipe_{k}.avg.pct_of_peak_sustained_active"))  # noqa: E731
+doc["note"] = (f"not HBM bound: warp-issue bound (ncu: {doc['issue_active_pct']:.1f} % of issue slots busy while a scheduler has work, "
+               f"{doc['active_threads_per_instruction']} active threads per instruction, ALU pipe ~{pipe('alu')} %, FMA ~{pipe('fma')} %, "
+               f"XU ~{pipe('xu')} %, FP64 ~{pipe('fp64')} %, top stalls " + ", ".join(f"{k[6:]} {v:.1f} %" for k, v in top) +
+               f"); DRAM traffic ({(rd + wr) / 1e6:.0f} MB) exceeds the algorithmic 22.8 MB because every ray fetches one 16-byte table entry as a "
+               f"random sector of a 5.7 GB table -- profiles/{summary}, profiles/r2_step_kernel_phases.txt, profiles/r2_timeline.json")
 for o in outs:
     json.dump(doc, open(o, "w"), indent=1)
 print(json.dumps(doc, indent=1))
