@@ -236,7 +236,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 class NvmlSampler:
@@ -673,7 +673,7 @@ def main():
             except Exception as ex:  # the bench line must still print
                 line["cpu_baseline"] = {"value": None, "unit": "agent-steps/s", "cores": None, "kind": "port",
                                         "sample": f"failed: {ex}"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -724,5 +724,17 @@ def config5_leg(ok, torch, dist, rank, world, local, mode, extra, n=1 << 20, tic
             "l2": "not flushed (state of 1M agents = 1.4 GB per tick, far larger than L2)"}
 
 
+def emit(line):
+    """the ONE JSON line of the contract, on the process's real stdout"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
+    # Libraries write to file descriptor 1 behind Python's back (NCCL prints "NCCL version ..." there when NCCL_DEBUG is set):
+    # keep the real stdout for the one JSON line and point fd 1 at stderr for everything else.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     main()
