@@ -253,6 +253,12 @@ typedef struct OkActorIO {
     uint8_t     *d_prev_done;
 } OkActorIO;
 int ok_ppo_actor(OkEnv *env, const OkActorIO *io, uint64_t step, uint32_t seed, void *stream);
+/* ok_ppo_actor and the tick that consumes its actions (ok_launch_step with the stored actions) as ONE launch: the policy
+ * step runs as phase 0 of every tile of the step kernel (ppo_sim.cpp:61-89's updateAction + env.step per tick).  At a few
+ * thousand agents a tick is launch-to-completion latency, and two kernels pay it twice.  Same results as the two calls; falls
+ * back to them when the env's kernel shape has no fused instantiation (grid / brute-force modes; the staged shapes of
+ * populations of 65,536 rays per tick and more, whose tick is not latency). */
+int ok_ppo_actor_step(OkEnv *env, const OkActorIO *io, uint64_t step, uint32_t seed, void *stream);
 /* ExperienceBuffer::calculateDiscountedRewards (RLRacers/PPO/ExperienceBuffer.hpp:45-62) for all agents: d_rewards
  * f32[steps][N] -> d_out f32[steps][N], ret[t] = r[t] + gamma * ret[t + 1] in binary32 with the reference's operation
  * order; d_done u8[steps][N] (nullable) restarts the sum where an episode ended.  No env needed beyond its device. */

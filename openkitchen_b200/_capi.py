@@ -145,6 +145,7 @@ SIGNATURES = {
     "ok_release_caches": (None, []),
     "ok_cmaes_controller": (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.c_float, C.c_float, _P]),
     "ok_ppo_actor": (C.c_int, [_P, C.POINTER(OkActorIO), C.c_uint64, C.c_uint32, _P]),
+    "ok_ppo_actor_step": (C.c_int, [_P, C.POINTER(OkActorIO), C.c_uint64, C.c_uint32, _P]),
     "ok_discounted_returns": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int64, C.c_float, _P]),
     "ok_track_query": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P, _P, _P]),
     "ok_track_query_host": (C.c_int, [_P, _P, _P, _P, C.c_int64, _P, _P, _P, _P]),

@@ -189,6 +189,7 @@ struct OkEnv
     cudaStream_t         act_stream{nullptr};
     cudaEvent_t          ev_act{nullptr};
     bool                 act_stage_on{true}; // OK_ACT_STAGE=0: every tile reads the mapping (A/B)
+    int                  actor_dyn_max{0};   // dynamic shared memory the fused actor + step kernel may use
     cudaStream_t         flush_stream{nullptr};
     cudaEvent_t          ev_fork{nullptr}, ev_join{nullptr};
     int32_t              batch_agents_beam{0};
@@ -696,6 +697,7 @@ int arm_shared_memory_limit(OkEnv *e)
     OK_CUDA(cudaFuncSetAttribute(ok::step_kernel<ok::kBeamBlockStaged, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  e->smem_optin - static_cast<int>(fa.sharedSizeBytes)));
     OK_CUDA(ok::arm_step_segstaged(e->smem_optin));
+    OK_CUDA(ok::arm_step_actor(e->smem_optin, &e->actor_dyn_max));
     return OK_SUCCESS;
 }
 
@@ -858,7 +860,7 @@ StreamWriteValue32Fn stream_write_value32()
     return fn;
 }
 
-int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
+int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s, const ok::ActorParams *actor = nullptr, size_t actor_smem = 0)
 {
     int rc = ensure_arena(e);
     if (rc)
@@ -924,15 +926,20 @@ int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s)
             OK_CUDA(cudaGetLastError());
             OK_CUDA(cudaEventRecord(e->ev_join, e->flush_stream));
         }
-        if (e->beam_seg)
+        if (actor)
+        { // the policy step as phase 0 of every tile (ok_ppo_actor_step): its weights sit behind the kernel's own shared memory
+            p.actor_smem_off = static_cast<uint32_t>((e->smem_beam + 15) & ~static_cast<size_t>(15));
+            OK_CUDA(ok::launch_step_actor(p, *actor, e->grid_beam, p.actor_smem_off + actor_smem, s));
+        }
+        else if (e->beam_seg)
             OK_CUDA(ok::launch_step_segstaged(p, grid, e->smem_beam, s));
         else if (e->beam_staged)
-            ok::step_kernel<ok::kBeamBlockStaged, true, true><<<grid, ok::kBeamBlockStaged, e->smem_beam, s>>>(p);
+            ok::step_kernel<ok::kBeamBlockStaged, true, true><<<grid, ok::kBeamBlockStaged, e->smem_beam, s>>>(p, ok::NoActor{});
         else
             OK_CUDA(ok::launch_step_unstaged(p, e->grid_beam, e->smem_beam, s));
     }
     else
-        ok::step_kernel<kBlock, false><<<e->grid, kBlock, e->smem, s>>>(p);
+        ok::step_kernel<kBlock, false><<<e->grid, kBlock, e->smem, s>>>(p, ok::NoActor{});
     OK_CUDA(cudaGetLastError());
     if (p.act_ready)
     { // enqueued AFTER the launch: the kernel is already running its first tiles while the host issues these
@@ -1270,7 +1277,10 @@ int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg,
         // beam kernel: one 64-byte record per agent; phases 1 / 4 run a thread per agent, so at most one block of agents.
         // Which shape (ok_kernels.cuh): the staged one for throughput, the unstaged one when the population is too small
         // to give every SM a worthwhile tile (OK_BEAM_KERNEL = staged | unstaged overrides).
-        e->beam_staged = n >= 2048; // measured (tools/bench_small.py): the unstaged shape is ahead only below ~2,000 agents
+        // measured (tools/bench_small.py, tools/bench_c4.py): the unstaged shape is ahead below ~2,000 agents of 32 rays, and at
+        // 4,096 agents of 5 rays (a PPO rollout tick: 0.0289 vs 0.0300 ms, 0.0262 with the policy step fused in), behind at
+        // 8,192 agents of 5 rays (0.0376 vs 0.0318 ms)
+        e->beam_staged = n >= 2048 && n * rays > 24576;
         e->beam_seg = false; // opt-in (OK_BEAM_KERNEL=segstaged): 1 % ahead at 65,536 agents with tiles of equal agent counts, but its tile times
                              // depend on the CTA that shares the SM, so the feedback tiling gains nothing there (0.092 vs 0.085 ms per tick)
         if (const char *env = std::getenv("OK_BEAM_KERNEL"))
@@ -1705,14 +1715,16 @@ int ok_cmaes_controller(OkEnv *e, const float *d_params, int32_t n_params, int32
     return OK_SUCCESS;
 }
 
-int ok_ppo_actor(OkEnv *e, const OkActorIO *io, uint64_t step, uint32_t seed, void *stream)
+} // extern "C"
+namespace
 {
-    int rc = check_ready(e);
-    if (rc)
-        return rc;
+// OkActorIO -> kernel parameters; *skip = nothing to do (no weights and nothing to record)
+int actor_params(const OkActorIO *io, ok::ActorParams &q, bool *skip)
+{
+    *skip = false;
     if (!io)
         return fail(OK_ERR_INVALID_ARG, "io is NULL");
-    ok::ActorParams q{};
+    q     = ok::ActorParams{};
     q.act = io->d_w1 != nullptr;
     if (q.act)
     {
@@ -1722,19 +1734,37 @@ int ok_ppo_actor(OkEnv *e, const OkActorIO *io, uint64_t step, uint32_t seed, vo
             return fail(OK_ERR_INVALID_ARG, "1 <= hidden <= 1024 and 1 <= n_actions <= 8");
     }
     else if (!io->d_prev_reward && !io->d_prev_done)
-        return OK_SUCCESS;
+        *skip = true;
     q.w1 = io->d_w1, q.b1 = io->d_b1, q.w2 = io->d_w2, q.b2 = io->d_b2;
     q.hidden = io->hidden, q.n_actions = io->n_actions;
     q.table = io->d_action_table, q.uniform = io->d_uniform, q.greedy = io->greedy;
     q.action_out = io->d_action, q.log_prob_out = io->d_log_prob, q.probs_out = io->d_probs, q.obs_out = io->d_obs;
     q.prev_reward_out = io->d_prev_reward, q.prev_done_out = io->d_prev_done;
+    return OK_SUCCESS;
+}
+
+size_t actor_weight_bytes(const ok::ActorParams &q, int rays)
+{
+    return q.act ? sizeof(float) * (static_cast<size_t>(q.hidden) * rays + q.hidden + static_cast<size_t>(q.n_actions) * q.hidden + q.n_actions) : 0;
+}
+} // namespace
+extern "C"
+{
+int ok_ppo_actor(OkEnv *e, const OkActorIO *io, uint64_t step, uint32_t seed, void *stream)
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    ok::ActorParams q;
+    bool            skip = false;
+    rc                   = actor_params(io, q, &skip);
+    if (rc || skip)
+        return rc;
     DeviceGuard    g(e->cfg.device);
     ok::StepParams p = base_params(e);
     p.step           = step;
     p.seed           = seed;
-    const size_t smem = q.act ? sizeof(float) * (static_cast<size_t>(q.hidden) * e->rays + q.hidden +
-                                                 static_cast<size_t>(q.n_actions) * q.hidden + q.n_actions)
-                              : 0;
+    const size_t smem = actor_weight_bytes(q, e->rays);
     if (smem > static_cast<size_t>(e->smem_optin))
         return fail(OK_ERR_CAPACITY, "the actor's weights do not fit in shared memory");
     if (smem > 48 * 1024)
@@ -1745,6 +1775,36 @@ int ok_ppo_actor(OkEnv *e, const OkActorIO *io, uint64_t step, uint32_t seed, vo
     OK_CUDA(cudaGetLastError());
     e->launches++;
     return OK_SUCCESS;
+}
+
+int ok_ppo_actor_step(OkEnv *e, const OkActorIO *io, uint64_t step, uint32_t seed, void *stream)
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    ok::ActorParams q;
+    bool            skip = false;
+    rc                   = actor_params(io, q, &skip);
+    if (rc)
+        return rc;
+    DeviceGuard  g(e->cfg.device);
+    const size_t wbytes = actor_weight_bytes(q, e->rays);
+    // one launch when the env runs the unstaged beam kernel (the shape of small populations, where a tick is latency) and the
+    // weights fit behind its shared memory; otherwise the same tick as two launches
+    const bool fused = q.act && e->cfg.raycast_mode == OK_RAYCAST_BEAM && !e->beam_staged &&
+                       ((e->smem_beam + 15) & ~static_cast<size_t>(15)) + wbytes <= static_cast<size_t>(std::max(0, e->actor_dyn_max));
+    if (!fused)
+    {
+        if (!skip)
+            if ((rc = ok_ppo_actor(e, io, step, seed, stream)) != OK_SUCCESS)
+                return rc;
+        return ok_launch_step(e, nullptr, nullptr, stream);
+    }
+    ok::StepParams p = base_params(e);
+    p.do_move        = 1;
+    p.step           = step; // (stored actions: the Philox counter and key are the actor's draw)
+    p.seed           = seed;
+    return launch_step(e, p, static_cast<cudaStream_t>(stream), &q, wbytes);
 }
 
 int ok_discounted_returns(OkEnv *e, const float *d_rewards, const uint8_t *d_done, float *d_out, int32_t steps, int64_t n,

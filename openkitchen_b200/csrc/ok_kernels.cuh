@@ -108,6 +108,7 @@ struct StepParams
     int32_t        rays;
     int32_t        batch_agents;    // agents per tile (shared-memory scratch is sized for this many)
     uint32_t       smem_blob_bytes; // offset of the batch scratch behind the staged track
+    uint32_t       actor_smem_off;  // kActor: offset of the policy weights in dynamic shared memory
     const uint16_t *ray_order;      // ray indices sorted by |angle|: pool order, long (central) rays first
     int32_t       *sched;           // {next tile, CTAs finished}: dynamic tile scheduler
     unsigned long long *stats;      // nullable: {rays cast, rays queued for pass B, rays sent to the grid walk} (beam kernel)
@@ -1256,10 +1257,182 @@ __device__ __forceinline__ unsigned long long global_timer()
             p.trace[(static_cast<size_t>(blockIdx.x) * p.trace_tiles + n_done) * 6 + (slot)] = global_timer();         \
     } while (0)
 
-template <int kBlock, bool kBeam, bool kStaged = true, bool kSegOnly = false>
-__global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS : (kSegOnly ? 1024 / kBlock : 1)) step_kernel(const StepParams p)
+// PPOAgent::updateAction + Actor::forward for every agent (RLRacers/PPO/PPOAgent.hpp:79-102, Actor.hpp:9-26): ONE
+// kernel per tick does observation -> Linear(R, H) -> relu -> Linear(H, A) -> softmax -> clamp [1e-8, 1 - 1e-8] ->
+// sample an action (torch::multinomial's distribution: inverse CDF of the clamped probabilities on a uniform draw) ->
+// log-probability -> kActionMap lookup into the action buffers.  The weights are shared by all agents and staged in
+// shared memory; kActorLanes lanes share an agent (each takes every kActorLanes-th hidden unit), logits meet by shuffles.
+// It also records: the observation the action was chosen from, and the PREVIOUS tick's reward / done (so a rollout costs
+// two launches per tick: this kernel and the step kernel).
+struct ActorParams
+{
+    const float *w1, *b1, *w2, *b2; // torch Linear layouts: w1 [H][R], w2 [A][H]
+    int32_t      hidden, n_actions;
+    const float *table;   // [A][2] = (throttle, steering) per action, PPOAgent::kActionMap
+    const float *uniform; // nullable: explicit draws in [0, 1), one per agent (tests); else Philox (id_base + a, step)
+    int32_t      greedy;  // != 0: argmax instead of sampling
+    int32_t     *action_out; // nullable outputs, one row of a rollout buffer each
+    float       *log_prob_out, *probs_out, *obs_out;
+    float       *prev_reward_out; // nullable: reward / done of the tick BEFORE this call (the env's buffers as they are)
+    uint8_t     *prev_done_out;
+    int32_t      act; // 0: only record prev_reward / prev_done (the flush after the last tick)
+};
+constexpr int kActorLanes   = 8;
+constexpr int kActorMaxActs = 8;
+
+// the weights of the actor, global -> shared memory (w1 | b1 | w2 | b2); the caller synchronises the CTA afterwards
+__device__ __forceinline__ void actor_stage_weights(const ActorParams &q, const int R, float *s_w, const int tid, const int n_threads)
+{
+    const int H = q.hidden, A = q.n_actions;
+    float    *s_w1 = s_w, *s_b1 = s_w1 + H * R, *s_w2 = s_b1 + H, *s_b2 = s_w2 + A * H;
+    for (int i = tid; i < H * R; i += n_threads)
+        s_w1[i] = q.w1[i];
+    for (int i = tid; i < H; i += n_threads)
+        s_b1[i] = q.b1[i];
+    for (int i = tid; i < A * H; i += n_threads)
+        s_w2[i] = q.w2[i];
+    for (int i = tid; i < A; i += n_threads)
+        s_b2[i] = q.b2[i];
+}
+
+// One agent's policy step by the kActorLanes lanes that share it (`sub` = the lane's place among them; `has` = the group holds
+// an agent).  Warp-collective: all 32 lanes of a warp call it together.
+__device__ __forceinline__ void actor_agent(const StepParams &p, const ActorParams &q, const float *s_w, const int64_t a, const bool has,
+                                            const int sub)
+{
+    const int    R = p.rays, H = q.hidden, A = q.n_actions;
+    const float *s_w1 = s_w, *s_b1 = s_w1 + H * R, *s_w2 = s_b1 + H, *s_b2 = s_w2 + A * H;
+    const int64_t ac  = has ? a : 0;
+    if (has && sub == 0)
+    { // the tick before this call
+        if (q.prev_reward_out)
+            q.prev_reward_out[a] = p.reward[a];
+        if (q.prev_done_out)
+            q.prev_done_out[a] = p.done[a];
+    }
+    if (!q.act)
+        return;
+    const float *obs = p.obs + ac * R;
+    float        logit[kActorMaxActs];
+#pragma unroll
+    for (int k = 0; k < kActorMaxActs; ++k)
+        logit[k] = 0.0f;
+    for (int h = sub; h < H; h += kActorLanes)
+    {
+        float        acc = s_b1[h];
+        const float *row = s_w1 + h * R;
+        for (int r = 0; r < R; ++r)
+            acc = fmaf(row[r], obs[r], acc); // (a plain load: the fused instantiation rewrites p.obs later in the same launch)
+        acc = fmaxf(acc, 0.0f); // relu
+#pragma unroll
+        for (int k = 0; k < kActorMaxActs; ++k)
+            if (k < A)
+                logit[k] = fmaf(s_w2[k * H + h], acc, logit[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < kActorMaxActs; ++k)
+#pragma unroll
+        for (int o = kActorLanes >> 1; o > 0; o >>= 1)
+            logit[k] += __shfl_xor_sync(0xffffffffu, logit[k], o);
+    if (!has || sub != 0)
+        return;
+    // softmax (max-subtracted, as torch::softmax), clamp of PPOAgent.hpp:82-83 (the bounds narrow to float: 1e-8f, 1.0f)
+    float mx = -FLT_MAX;
+#pragma unroll
+    for (int k = 0; k < kActorMaxActs; ++k)
+        if (k < A)
+        {
+            logit[k] += s_b2[k];
+            mx = fmaxf(mx, logit[k]);
+        }
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kActorMaxActs; ++k)
+        if (k < A)
+        {
+            logit[k] = expf(logit[k] - mx);
+            sum += logit[k];
+        }
+    float total = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kActorMaxActs; ++k)
+        if (k < A)
+        {
+            logit[k] = fminf(fmaxf(__fdiv_rn(logit[k], sum), 1e-8f), 1.0f);
+            total += logit[k];
+            if (q.probs_out)
+                q.probs_out[a * A + k] = logit[k];
+        }
+    int act = 0;
+    if (q.greedy)
+    {
+#pragma unroll
+        for (int k = 1; k < kActorMaxActs; ++k)
+            if (k < A && logit[k] > logit[act])
+                act = k;
+    }
+    else
+    { // torch::multinomial(probs, 1): index k with probability probs[k] / sum(probs)
+        float u;
+        if (q.uniform)
+            u = q.uniform[a];
+        else
+        {
+            uint32_t       o[4];
+            const uint64_t id = p.id_base + static_cast<uint64_t>(a);
+            philox4x32_10(static_cast<uint32_t>(id), static_cast<uint32_t>(id >> 32), static_cast<uint32_t>(p.step),
+                          static_cast<uint32_t>(p.step >> 32), p.seed, 0x50504fu /* "PPO": a stream of its own */, o);
+            u = static_cast<float>(o[0] >> 8) * 0x1p-24f;
+        }
+        const float target = u * total;
+        float       cum    = 0.0f;
+        act                = A - 1;
+#pragma unroll
+        for (int k = 0; k < kActorMaxActs; ++k)
+            if (k < A)
+            {
+                cum += logit[k];
+                if (target < cum && act == A - 1 && k < A - 1)
+                    act = k;
+            }
+    }
+    float pa = logit[0];
+#pragma unroll
+    for (int k = 1; k < kActorMaxActs; ++k)
+        pa = (k == act) ? logit[k] : pa;
+    if (q.action_out)
+        q.action_out[a] = act;
+    if (q.log_prob_out)
+        q.log_prob_out[a] = logf(pa);
+    if (q.obs_out)
+        for (int r = 0; r < R; ++r)
+            q.obs_out[a * R + r] = obs[r];
+    p.act_thr[a]   = q.table[2 * act];     // PPOAgent.hpp:95-96
+    p.act_steer[a] = q.table[2 * act + 1];
+}
+
+// the second kernel argument of step_kernel: the actor's parameters in the fused instantiation (kActor), nothing otherwise
+struct NoActor
+{
+};
+template <bool kActor> struct ActorArg
+{
+    using type = NoActor;
+};
+template <> struct ActorArg<true>
+{
+    using type = ActorParams;
+};
+
+// kActor (ok_ppo_actor_step): the PPO racers' policy step runs as phase 0 of every tile -- the tile's agents choose their
+// actions from last tick's observations (actor_agent) and the kinematics read them from the action buffers -- so that a
+// rollout tick is ONE launch: at a few thousand agents a tick is latency, and two kernels pay it twice.
+template <int kBlock, bool kBeam, bool kStaged = true, bool kSegOnly = false, bool kActor = false>
+__global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS : (kSegOnly ? 1024 / kBlock : 1))
+    step_kernel(const StepParams p, const typename ActorArg<kActor>::type q)
 {
     static_assert(!kSegOnly || (kBeam && kStaged), "the segment-staged shape is a beam kernel");
+    static_assert(!kActor || kBeam, "the fused actor is built for the beam kernels");
     constexpr bool kStage   = !kBeam || kStaged; // the track (kSegOnly: its header + segments) is staged in shared memory with one TMA bulk copy
     constexpr int  kPendCap = beam_pend_cap(kStaged, kSegOnly);
     extern __shared__ __align__(128) uint8_t smem[];
@@ -1300,6 +1473,12 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
     const bool single_wave = OK_SINGLE_WAVE && p.n_tiles <= static_cast<int>(gridDim.x);
     if (tid == 0)
         s_tile = static_cast<int>(blockIdx.x), s_actdev = 0;
+    float *s_actor_w = nullptr; // kActor: the policy's weights, behind everything else in dynamic shared memory
+    if constexpr (kActor)
+    {
+        s_actor_w = reinterpret_cast<float *>(smem + p.actor_smem_off);
+        actor_stage_weights(q, R, s_actor_w, tid, kBlock); // (visible after the loop-top barrier)
+    }
 
     for (;;)
     {
@@ -1356,6 +1535,15 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
         // =====================================================================================
         // phase 1 -- one thread per agent: optional reset, kinematics, standstill (Environment.cpp:128-143)
         // =====================================================================================
+        if constexpr (kActor)
+        { // phase 0: kActorLanes lanes per agent, every warp whole (the logits meet by shuffles)
+            for (int base = 0; base < count; base += kBlock / kActorLanes)
+            {
+                const int al = base + tid / kActorLanes;
+                actor_agent(p, q, s_actor_w, tl.begin + (al < count ? al : 0), al < count, tid & (kActorLanes - 1));
+            }
+            __syncthreads(); // the actions are in p.act_thr / p.act_steer: the agents' own threads read them next
+        }
         if (tid < count)
             recs[tid] = agent_pre(p, gblob, tr, bv, tl.begin + tid, kBeam && n_done > 0 && s_actdev != 0);
         if (tid == 0)
@@ -2301,156 +2489,14 @@ __global__ void __launch_bounds__(256) cmaes_controller_kernel(const StepParams 
     }
 }
 
-// PPOAgent::updateAction + Actor::forward for every agent (RLRacers/PPO/PPOAgent.hpp:79-102, Actor.hpp:9-26): ONE
-// kernel per tick does observation -> Linear(R, H) -> relu -> Linear(H, A) -> softmax -> clamp [1e-8, 1 - 1e-8] ->
-// sample an action (torch::multinomial's distribution: inverse CDF of the clamped probabilities on a uniform draw) ->
-// log-probability -> kActionMap lookup into the action buffers.  The weights are shared by all agents and staged in
-// shared memory; kActorLanes lanes share an agent (each takes every kActorLanes-th hidden unit), logits meet by shuffles.
-// It also records: the observation the action was chosen from, and the PREVIOUS tick's reward / done (so a rollout costs
-// two launches per tick: this kernel and the step kernel).
-struct ActorParams
-{
-    const float *w1, *b1, *w2, *b2; // torch Linear layouts: w1 [H][R], w2 [A][H]
-    int32_t      hidden, n_actions;
-    const float *table;   // [A][2] = (throttle, steering) per action, PPOAgent::kActionMap
-    const float *uniform; // nullable: explicit draws in [0, 1), one per agent (tests); else Philox (id_base + a, step)
-    int32_t      greedy;  // != 0: argmax instead of sampling
-    int32_t     *action_out; // nullable outputs, one row of a rollout buffer each
-    float       *log_prob_out, *probs_out, *obs_out;
-    float       *prev_reward_out; // nullable: reward / done of the tick BEFORE this call (the env's buffers as they are)
-    uint8_t     *prev_done_out;
-    int32_t      act; // 0: only record prev_reward / prev_done (the flush after the last tick)
-};
-constexpr int kActorLanes   = 8;
-constexpr int kActorMaxActs = 8;
-
 __global__ void __launch_bounds__(256) ppo_actor_kernel(const StepParams p, const ActorParams q, const int64_t n_agents)
 {
     extern __shared__ float s_w[]; // w1 | b1 | w2 | b2
-    const int R = p.rays, H = q.hidden, A = q.n_actions;
-    float    *s_w1 = s_w, *s_b1 = s_w1 + H * R, *s_w2 = s_b1 + H, *s_b2 = s_w2 + A * H;
     if (q.act)
-    {
-        for (int i = threadIdx.x; i < H * R; i += blockDim.x)
-            s_w1[i] = q.w1[i];
-        for (int i = threadIdx.x; i < H; i += blockDim.x)
-            s_b1[i] = q.b1[i];
-        for (int i = threadIdx.x; i < A * H; i += blockDim.x)
-            s_w2[i] = q.w2[i];
-        for (int i = threadIdx.x; i < A; i += blockDim.x)
-            s_b2[i] = q.b2[i];
-    }
+        actor_stage_weights(q, p.rays, s_w, threadIdx.x, blockDim.x);
     __syncthreads();
-    const int     sub = threadIdx.x & (kActorLanes - 1);
-    const int64_t a   = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / kActorLanes;
-    const bool    has = a < n_agents;
-    const int64_t ac  = has ? a : 0;
-    if (has && sub == 0)
-    { // the tick before this call
-        if (q.prev_reward_out)
-            q.prev_reward_out[a] = p.reward[a];
-        if (q.prev_done_out)
-            q.prev_done_out[a] = p.done[a];
-    }
-    if (!q.act)
-        return;
-    const float *obs = p.obs + ac * R;
-    float        logit[kActorMaxActs];
-#pragma unroll
-    for (int k = 0; k < kActorMaxActs; ++k)
-        logit[k] = 0.0f;
-    for (int h = sub; h < H; h += kActorLanes)
-    {
-        float        acc = s_b1[h];
-        const float *row = s_w1 + h * R;
-        for (int r = 0; r < R; ++r)
-            acc = fmaf(row[r], __ldg(obs + r), acc);
-        acc = fmaxf(acc, 0.0f); // relu
-#pragma unroll
-        for (int k = 0; k < kActorMaxActs; ++k)
-            if (k < A)
-                logit[k] = fmaf(s_w2[k * H + h], acc, logit[k]);
-    }
-#pragma unroll
-    for (int k = 0; k < kActorMaxActs; ++k)
-#pragma unroll
-        for (int o = kActorLanes >> 1; o > 0; o >>= 1)
-            logit[k] += __shfl_xor_sync(0xffffffffu, logit[k], o);
-    if (!has || sub != 0)
-        return;
-    // softmax (max-subtracted, as torch::softmax), clamp of PPOAgent.hpp:82-83 (the bounds narrow to float: 1e-8f, 1.0f)
-    float mx = -FLT_MAX;
-#pragma unroll
-    for (int k = 0; k < kActorMaxActs; ++k)
-        if (k < A)
-        {
-            logit[k] += s_b2[k];
-            mx = fmaxf(mx, logit[k]);
-        }
-    float sum = 0.0f;
-#pragma unroll
-    for (int k = 0; k < kActorMaxActs; ++k)
-        if (k < A)
-        {
-            logit[k] = expf(logit[k] - mx);
-            sum += logit[k];
-        }
-    float total = 0.0f;
-#pragma unroll
-    for (int k = 0; k < kActorMaxActs; ++k)
-        if (k < A)
-        {
-            logit[k] = fminf(fmaxf(__fdiv_rn(logit[k], sum), 1e-8f), 1.0f);
-            total += logit[k];
-            if (q.probs_out)
-                q.probs_out[a * A + k] = logit[k];
-        }
-    int act = 0;
-    if (q.greedy)
-    {
-#pragma unroll
-        for (int k = 1; k < kActorMaxActs; ++k)
-            if (k < A && logit[k] > logit[act])
-                act = k;
-    }
-    else
-    { // torch::multinomial(probs, 1): index k with probability probs[k] / sum(probs)
-        float u;
-        if (q.uniform)
-            u = q.uniform[a];
-        else
-        {
-            uint32_t       o[4];
-            const uint64_t id = p.id_base + static_cast<uint64_t>(a);
-            philox4x32_10(static_cast<uint32_t>(id), static_cast<uint32_t>(id >> 32), static_cast<uint32_t>(p.step),
-                          static_cast<uint32_t>(p.step >> 32), p.seed, 0x50504fu /* "PPO": a stream of its own */, o);
-            u = static_cast<float>(o[0] >> 8) * 0x1p-24f;
-        }
-        const float target = u * total;
-        float       cum    = 0.0f;
-        act                = A - 1;
-#pragma unroll
-        for (int k = 0; k < kActorMaxActs; ++k)
-            if (k < A)
-            {
-                cum += logit[k];
-                if (target < cum && act == A - 1 && k < A - 1)
-                    act = k;
-            }
-    }
-    float pa = logit[0];
-#pragma unroll
-    for (int k = 1; k < kActorMaxActs; ++k)
-        pa = (k == act) ? logit[k] : pa;
-    if (q.action_out)
-        q.action_out[a] = act;
-    if (q.log_prob_out)
-        q.log_prob_out[a] = logf(pa);
-    if (q.obs_out)
-        for (int r = 0; r < R; ++r)
-            q.obs_out[a * R + r] = obs[r];
-    p.act_thr[a]   = q.table[2 * act];     // PPOAgent.hpp:95-96
-    p.act_steer[a] = q.table[2 * act + 1];
+    const int64_t a = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) / kActorLanes;
+    actor_agent(p, q, s_w, a, a < n_agents, threadIdx.x & (kActorLanes - 1));
 }
 
 // ExperienceBuffer::calculateDiscountedRewards (RLRacers/PPO/ExperienceBuffer.hpp:45-62) for every agent: one thread per
@@ -2513,6 +2559,9 @@ __global__ void fill_actions_kernel(const StepParams p, int64_t n)
 
 // the unstaged beam kernel's launcher, occupancy and self-check counter (ok_step_unstaged.cu)
 cudaError_t launch_step_unstaged(const StepParams &p, int grid, size_t smem_bytes, cudaStream_t stream);
+// ok_step_actor.cu: the unstaged beam kernel with the policy step fused in
+cudaError_t launch_step_actor(const StepParams &p, const ActorParams &q, int grid, size_t smem_bytes, cudaStream_t stream);
+cudaError_t arm_step_actor(int smem_optin, int *max_dynamic);
 cudaError_t occupancy_step_unstaged(size_t smem_bytes, int *ctas_per_sm);
 cudaError_t violations_step_unstaged(unsigned long long *count);
 // the segment-staged beam kernel's (ok_step_segstaged.cu)

@@ -9,7 +9,7 @@ namespace ok
 {
 cudaError_t launch_step_segstaged(const StepParams &p, int grid, size_t smem_bytes, cudaStream_t stream)
 {
-    step_kernel<kBeamBlockSeg, true, true, true><<<grid, kBeamBlockSeg, smem_bytes, stream>>>(p);
+    step_kernel<kBeamBlockSeg, true, true, true><<<grid, kBeamBlockSeg, smem_bytes, stream>>>(p, NoActor{});
     return cudaGetLastError();
 }
 

@@ -221,6 +221,10 @@ class Env:
         """obs -> actor MLP -> softmax -> sample -> action buffers, one kernel (io: _capi.OkActorIO of device pointers)"""
         check(self.lib.ok_ppo_actor(self.h, C.byref(io), step, seed, stream))
 
+    def ppo_actor_step(self, io, step: int = 0, seed: int = 0x0C17C4E2, stream=None):
+        """ppo_actor + the tick that consumes its actions as ONE launch (ok_ppo_actor_step)"""
+        check(self.lib.ok_ppo_actor_step(self.h, C.byref(io), step, seed, stream))
+
     def discounted_returns(self, d_rewards, d_done, d_out, steps: int, n: int, gamma: float = 0.99, stream=None):
         check(self.lib.ok_discounted_returns(self.h, d_rewards, d_done, d_out, steps, n, gamma, stream))
 

@@ -128,18 +128,22 @@ class FusedActorRollout:
     """The PPO racers' rollout with the policy step as ONE hand-written kernel per tick (ok_ppo_actor) instead of ~10
     torch kernels: observation -> Linear(R, H) -> relu -> Linear(H, A) -> softmax -> clamp -> sample -> log-prob ->
     kActionMap -> action buffers, plus the recording of obs / action / log-prob and of the previous tick's reward / done
-    (RLRacers/PPO/PPOAgent.hpp:79-102, Actor.hpp:9-26, ppo_sim.cpp:61-89).  Two launches per tick (actor, step), all
-    ``steps`` ticks captured as one CUDA graph.
+    (RLRacers/PPO/PPOAgent.hpp:79-102, Actor.hpp:9-26, ppo_sim.cpp:61-89).  One launch per tick (the policy step is phase 0
+    of the step kernel's tiles; ``one_launch=False``: two launches, actor then step), all ``steps`` ticks captured as one
+    CUDA graph.
 
     l1, l2: ``torch.nn.Linear`` modules (the reference's ``Actor::l1`` / ``l2``); their parameters are read in place,
     so an optimizer step between rollouts is picked up by the next replay.  After ``run()``: ``obs`` f32[T, N, R],
     ``actions`` i32[T, N], ``log_prob`` f32[T, N], ``rewards`` f32[T, N], ``dones`` u8[T, N]."""
 
     def __init__(self, env: BatchEnv, l1: torch.nn.Linear, l2: torch.nn.Linear, action_table: torch.Tensor, steps: int,
-                 sample: bool = True, seed: int = 0x0C17C4E2):
+                 sample: bool = True, seed: int = 0x0C17C4E2, one_launch: bool = True):
         from ._capi import OkActorIO
 
         self.env, self.steps, self.sample, self.seed = env, int(steps), sample, int(seed)
+        # one_launch: the policy step runs as phase 0 of the step kernel's tiles (ok_ppo_actor_step) -- a tick of a few
+        # thousand agents is latency, and two kernels pay it twice; False = the two launches (ok_ppo_actor, then the step)
+        self.one_launch = bool(one_launch)
         dev, n, r = env.device, env.n_agents, env.n_rays
         for m in (l1, l2):
             if m.weight.device != dev or m.weight.dtype != torch.float32 or not m.weight.is_contiguous() or m.bias is None:
@@ -161,7 +165,7 @@ class FusedActorRollout:
         self._tick0 = 0
         self.graph: torch.cuda.CUDAGraph | None = None
 
-    def _actor(self, t: int, act: bool = True):
+    def _io_for(self, t: int, act: bool = True):
         io = self._io()
         if act:
             io.d_w1, io.d_b1 = self.l1.weight.data_ptr(), self.l1.bias.data_ptr()
@@ -174,12 +178,24 @@ class FusedActorRollout:
             io.d_probs, io.d_obs = self.probs[t].data_ptr(), self.obs[t].data_ptr()
         if t > 0:
             io.d_prev_reward, io.d_prev_done = self.rewards[t - 1].data_ptr(), self.dones[t - 1].data_ptr()
-        self.env.env.ppo_actor(io, self._tick0 + t, self.seed, self.env._stream())
+        return io
+
+    def _actor(self, t: int, act: bool = True):
+        """the policy step alone (ok_ppo_actor): actions into the env's buffers, records of tick t"""
+        self.env.env.ppo_actor(self._io_for(t, act), self._tick0 + t, self.seed, self.env._stream())
+
+    def _tick(self, t: int):
+        """policy step + the tick that consumes its actions"""
+        if self.one_launch:
+            self.env.env.ppo_actor_step(self._io_for(t), self._tick0 + t, self.seed, self.env._stream())
+            self.env._step_count += 1
+        else:
+            self._actor(t)
+            self.env.step()  # the actions the kernel left in the env's buffers
 
     def run_eager(self):
         for t in range(self.steps):
-            self._actor(t)
-            self.env.step()  # the actions the kernel left in the env's buffers
+            self._tick(t)
         self._actor(self.steps, act=False)  # the last tick's reward / done
         return self
 

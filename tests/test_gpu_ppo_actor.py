@@ -87,9 +87,11 @@ def test_philox_sampling_follows_the_probabilities():
     assert 0.2 < (first != r.actions[0]).float().mean() < 0.9  # another tick, another draw
 
 
+@pytest.mark.parametrize("one_launch", [True, False])
 @pytest.mark.parametrize("kind", ["port", "reference"])
-def test_fused_rollout_replayed_through_the_oracle(kind):
-    """Config 4's loop (ppo_sim.cpp:61-89) as one CUDA graph of 2 launches per tick.  The recorded actions are replayed
+def test_fused_rollout_replayed_through_the_oracle(kind, one_launch):
+    """Config 4's loop (ppo_sim.cpp:61-89) as one CUDA graph of one launch per tick (the policy step as phase 0 of the step
+    kernel's tiles, ok_ppo_actor_step) or two (ok_ppo_actor, then the step).  The recorded actions are replayed
     through the CPU oracle (kind = "reference": the reference's own Agent / RaceTrack objects): observations, rewards
     and done flags the rollout recorded must be the oracle's, bit for bit."""
     if kind == "reference" and not have_ref():
@@ -108,7 +110,7 @@ def test_fused_rollout_replayed_through_the_oracle(kind):
     ora.cast_rays()
     l1, l2 = _actor(seed=1)
     table = torch.tensor(TABLE, device="cuda")
-    r = FusedActorRollout(env, l1, l2, table, steps=steps, sample=True)
+    r = FusedActorRollout(env, l1, l2, table, steps=steps, sample=True, one_launch=one_launch)
     r.run()
     torch.cuda.synchronize()
     acts = r.actions.cpu().numpy()
@@ -149,3 +151,36 @@ def test_discounted_return_kernel_is_the_reference_loop():
             assert np.array_equal(got[:, a].view(np.uint32), want.view(np.uint32)), (use_done, a)
         ref = discounted_returns(torch.from_numpy(rew).cuda(), 0.99, torch.from_numpy(done).cuda() if use_done else None)
         assert torch.equal(torch.from_numpy(got).cuda(), ref)
+
+
+@pytest.mark.parametrize("kernel,n", [("staged", 4096), ("unstaged", 700), ("segstaged", 4096)])
+def test_one_launch_tick_equals_the_two_launches(monkeypatch, kernel, n):
+    """ok_ppo_actor_step (policy step fused into the step kernel) against ok_ppo_actor + ok_launch_step on twin envs: every
+    rollout record and every env buffer, bit for bit, in the beam kernel shape that has a fused instantiation (unstaged) and
+    in those that fall back to the two launches."""
+    monkeypatch.setenv("OK_BEAM_KERNEL", kernel)
+    l1, l2 = _actor(seed=3)
+    table = torch.tensor(TABLE, device="cuda")
+    outs = []
+    for one_launch in (True, False):
+        env = ok.BatchEnv(["Monza", "Zandvoort"], n, rays=FAN, reward_mode=ok.REWARD_CONSTANT, auto_reset=1)
+        pts = (np.arange(n) * 53 % 600).astype(np.int32)
+        env.reset(None, torch.from_numpy(pts).cuda())
+        env.cast_rays()
+        r = FusedActorRollout(env, l1, l2, table, steps=40, sample=True, one_launch=one_launch)
+        before = env.env.launch_stats().kernel_launches
+        r.run_eager()
+        launched = env.env.launch_stats().kernel_launches - before
+        # 40 ticks + the record of the last tick's reward / done: one launch per tick where a fused instantiation exists
+        assert launched == (41 if one_launch and kernel == "unstaged" else 81), launched
+        env.reset(None, torch.from_numpy(pts).cuda())
+        env.cast_rays()
+        r.run()
+        torch.cuda.synchronize()
+        outs.append((r, env))
+    (a, ea), (b, eb) = outs
+    for name in ("obs", "actions", "log_prob", "probs", "rewards", "dones"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert a.dones.sum() > 0
+    for name in ok.BUFFERS:
+        assert np.array_equal(ea.env.read(name).view(np.uint8), eb.env.read(name).view(np.uint8)), name
