@@ -1317,12 +1317,28 @@ __device__ __forceinline__ void actor_agent(const StepParams &p, const ActorPara
 #pragma unroll
     for (int k = 0; k < kActorMaxActs; ++k)
         logit[k] = 0.0f;
+    // (plain loads of the observation: the fused instantiation rewrites p.obs later in the same launch.)  Fans of up to eight
+    // rays -- the PPO racers' five -- are kept in registers: read in the loop they are eighty dependent L1 round trips per lane
+    constexpr int kObsRegs = 8;
+    const bool    in_regs  = R <= kObsRegs;
+    float         ob[kObsRegs];
+#pragma unroll
+    for (int r = 0; r < kObsRegs; ++r)
+        ob[r] = (in_regs && r < R) ? obs[r] : 0.0f;
     for (int h = sub; h < H; h += kActorLanes)
     {
         float        acc = s_b1[h];
         const float *row = s_w1 + h * R;
-        for (int r = 0; r < R; ++r)
-            acc = fmaf(row[r], obs[r], acc); // (a plain load: the fused instantiation rewrites p.obs later in the same launch)
+        if (in_regs)
+        {
+#pragma unroll
+            for (int r = 0; r < kObsRegs; ++r)
+                if (r < R)
+                    acc = fmaf(row[r], ob[r], acc);
+        }
+        else
+            for (int r = 0; r < R; ++r)
+                acc = fmaf(row[r], obs[r], acc);
         acc = fmaxf(acc, 0.0f); // relu
 #pragma unroll
         for (int k = 0; k < kActorMaxActs; ++k)
@@ -1331,9 +1347,10 @@ __device__ __forceinline__ void actor_agent(const StepParams &p, const ActorPara
     }
 #pragma unroll
     for (int k = 0; k < kActorMaxActs; ++k)
+        if (k < A) // (uniform)
 #pragma unroll
-        for (int o = kActorLanes >> 1; o > 0; o >>= 1)
-            logit[k] += __shfl_xor_sync(0xffffffffu, logit[k], o);
+            for (int o = kActorLanes >> 1; o > 0; o >>= 1)
+                logit[k] += __shfl_xor_sync(0xffffffffu, logit[k], o);
     if (!has || sub != 0)
         return;
     // softmax (max-subtracted, as torch::softmax), clamp of PPOAgent.hpp:82-83 (the bounds narrow to float: 1e-8f, 1.0f)
