@@ -172,7 +172,7 @@ def c4():
                               "crashed_fraction": float(ro.dones.float().mean())})
 
 
-    # the policy step as ONE hand-written kernel (ok_ppo_actor) + the step kernel: two launches per tick in one graph,
+    # the policy step as phase 0 of the step kernel's tiles (ok_ppo_actor_step): ONE launch per tick, all ticks in one graph,
     # returns by the discounted-return kernel (openkitchen_b200.rollout.FusedActorRollout)
     from openkitchen_b200.rollout import FusedActorRollout, discounted_returns_fused
 
@@ -192,7 +192,7 @@ def c4():
     e1.record()
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / reps
-    report("C4 PPO rollout 4096 envs x 256 steps, fused actor kernel + step kernel as one CUDA graph (FusedActorRollout) + return kernel",
+    report("C4 PPO rollout 4096 envs x 256 steps, policy step fused into the step kernel: one launch per tick, one CUDA graph (FusedActorRollout) + return kernel",
            n, rays, 1e3 * dt / steps, {"env_steps": n * steps, "env_steps_per_sec": n * steps / dt, "wall_s": dt,
                                        "device_ms_per_tick": e0.elapsed_time(e1) / reps / steps,
                                        "crashed_fraction": float(fr.dones.float().mean())})
