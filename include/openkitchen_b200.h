@@ -305,6 +305,13 @@ int ok_write_buffer(OkEnv *env, int32_t which, const void *h_src, size_t bytes, 
 int ok_sync(OkEnv *env, void *stream);
 
 /* ---- introspection (bench / profiling) ----------------------------------------------------- */
+/* Population counters (metrics: what the reference's apps print per episode -- colony averages, how many
+ * agents are still driving -- needs these): agents alive (= not crashed) / crashed / timed out / done in the env's buffers as
+ * they are now, counted on the device.  Synchronises `stream`. */
+typedef struct OkPopulationCounters {
+    uint64_t agents, alive, crashed, timed_out, done;
+} OkPopulationCounters;
+int ok_population_counters(OkEnv *env, OkPopulationCounters *out, void *stream);
 typedef struct OkLaunchStats {
     uint64_t kernel_launches; /* kernels launched by this env since creation */
     int32_t  grid_blocks, block_threads, smem_bytes, tiles;

@@ -70,6 +70,10 @@ class OkTrackInfo(C.Structure):
     ]
 
 
+class OkPopulationCounters(C.Structure):
+    _fields_ = [("agents", C.c_uint64), ("alive", C.c_uint64), ("crashed", C.c_uint64), ("timed_out", C.c_uint64), ("done", C.c_uint64)]
+
+
 class OkLaunchStats(C.Structure):
     _fields_ = [
         ("kernel_launches", C.c_uint64),
@@ -132,6 +136,7 @@ SIGNATURES = {
     "ok_write_buffer": (C.c_int, [_P, C.c_int32, _P, C.c_size_t, _P]),
     "ok_sync": (C.c_int, [_P, _P]),
     "ok_launch_stats": (C.c_int, [_P, C.POINTER(OkLaunchStats)]),
+    "ok_population_counters": (C.c_int, [_P, C.POINTER(OkPopulationCounters), _P]),
     "ok_debug_stats": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_int32]),
     "ok_debug_violations": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
     "ok_debug_trace": (C.c_int64, [_P, _P, C.c_int64, C.c_int32]),

@@ -7,6 +7,7 @@
 #include "ok_kernels.cuh"
 #include "ok_track.hpp"
 
+#include <nvtx3/nvToolsExt.h> // header-only; ranges only with OK_NVTX=1
 #include <cuda.h> // types of the one driver entry point used (cuStreamWriteValue32), looked up at run time: libcuda is not linked
 
 #include <algorithm>
@@ -42,6 +43,29 @@ int fail(int code, const std::string &msg)
         if (err__ != cudaSuccess)                                                                                      \
             return fail(OK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__));                           \
     } while (0)
+
+// NVTX range around a library call (tracing): visible in Nsight Systems / Compute timelines; OK_NVTX=1 turns it on
+struct NvtxRange
+{
+    bool on;
+    explicit NvtxRange(const char *name)
+    {
+        static const bool enabled = [] {
+            const char *v = std::getenv("OK_NVTX");
+            return v && std::atoi(v) != 0;
+        }();
+        on = enabled;
+        if (on)
+            nvtxRangePushA(name);
+    }
+    ~NvtxRange()
+    {
+        if (on)
+            nvtxRangePop();
+    }
+    NvtxRange(const NvtxRange &)            = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 struct DeviceGuard
 {
@@ -190,6 +214,7 @@ struct OkEnv
     cudaEvent_t          ev_act{nullptr};
     bool                 act_stage_on{true}; // OK_ACT_STAGE=0: every tile reads the mapping (A/B)
     int                  actor_dyn_max{0};   // dynamic shared memory the fused actor + step kernel may use
+    unsigned long long  *d_counters{nullptr}; // ok_population_counters
     cudaStream_t         flush_stream{nullptr};
     cudaEvent_t          ev_fork{nullptr}, ev_join{nullptr};
     int32_t              batch_agents_beam{0};
@@ -862,6 +887,7 @@ StreamWriteValue32Fn stream_write_value32()
 
 int launch_step(OkEnv *e, ok::StepParams &p, cudaStream_t s, const ok::ActorParams *actor = nullptr, size_t actor_smem = 0)
 {
+    NvtxRange range(actor ? "ok::step (actor + tick)" : "ok::step");
     int rc = ensure_arena(e);
     if (rc)
         return rc;
@@ -1111,6 +1137,8 @@ void ok_destroy(OkEnv *e)
             cudaFree(e->d_stage);
         if (e->flush_stream)
             cudaStreamDestroy(e->flush_stream);
+        if (e->d_counters)
+            cudaFree(e->d_counters);
         if (e->act_stream)
             cudaStreamDestroy(e->act_stream);
         if (e->ev_act)
@@ -1246,6 +1274,7 @@ namespace
 {
 int alloc_agents_impl(OkEnv *e, int64_t n, int32_t rays, const float *h_ray_deg, const int32_t *h_track_id)
 {
+    NvtxRange range("ok_alloc_agents (tiling, buffers)");
     e->n_agents = n;
     e->rays     = rays;
     // the segment-staged shape (two 512-thread CTAs per SM): populations that give every CTA a worthwhile tile, tracks
@@ -1909,6 +1938,7 @@ namespace
 int step_host_impl(OkEnv *e, const float *h_thr, const float *h_steer, void *h_obs_any, const bool q16, float *h_reward, uint8_t *h_done,
                    void *stream)
 {
+    NvtxRange range(q16 ? "ok_step_host_q16" : "ok_step_host");
     float *h_obs = q16 ? nullptr : static_cast<float *>(h_obs_any);
     int rc = check_ready(e);
     if (rc)
@@ -2363,6 +2393,34 @@ int64_t ok_debug_trace(OkEnv *e, uint64_t *h_out, int64_t capacity_words, int32_
         e->trace_tiles = tiles_per_cta;
     }
     return got;
+}
+
+int ok_population_counters(OkEnv *e, OkPopulationCounters *out, void *stream)
+{
+    int rc = check_ready(e);
+    if (rc)
+        return rc;
+    if (!out)
+        return fail(OK_ERR_INVALID_ARG, "out is NULL");
+    NvtxRange    range("ok_population_counters");
+    DeviceGuard  g(e->cfg.device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!e->d_counters)
+        OK_CUDA(cudaMalloc(&e->d_counters, 4 * sizeof(unsigned long long)));
+    OK_CUDA(cudaMemsetAsync(e->d_counters, 0, 4 * sizeof(unsigned long long), s));
+    const int threads = 256;
+    const int blocks  = static_cast<int>(std::min<int64_t>((e->n_agents + threads - 1) / threads, 4 * e->num_sms));
+    ok::population_counters_kernel<<<blocks, threads, 0, s>>>(static_cast<const uint8_t *>(e->d_buf[OK_BUF_CRASHED]),
+                                                               static_cast<const uint8_t *>(e->d_buf[OK_BUF_TIMED_OUT]),
+                                                               static_cast<const uint8_t *>(e->d_buf[OK_BUF_DONE]), e->n_agents, e->d_counters);
+    OK_CUDA(cudaGetLastError());
+    e->launches++;
+    unsigned long long h[4];
+    OK_CUDA(cudaMemcpyAsync(h, e->d_counters, sizeof h, cudaMemcpyDeviceToHost, s));
+    OK_CUDA(cudaStreamSynchronize(s));
+    out->agents = static_cast<uint64_t>(e->n_agents);
+    out->alive = h[0], out->crashed = h[1], out->timed_out = h[2], out->done = h[3];
+    return OK_SUCCESS;
 }
 
 int ok_launch_stats(const OkEnv *e, OkLaunchStats *out)

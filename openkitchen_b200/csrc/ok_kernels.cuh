@@ -2536,6 +2536,26 @@ __global__ void discounted_returns_kernel(const float *__restrict__ rewards, con
     }
 }
 
+// metrics ("per-step device counters"): how many agents are alive / crashed / timed out / done right now.
+// out[4] must be zero; one atomic per warp and counter.
+__global__ void population_counters_kernel(const uint8_t *__restrict__ crashed, const uint8_t *__restrict__ timed_out,
+                                           const uint8_t *__restrict__ done, const int64_t n, unsigned long long *out)
+{
+    unsigned c[4] = {0u, 0u, 0u, 0u};
+    for (int64_t a = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; a < n; a += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    {
+        const bool cr = crashed[a] != 0;
+        c[0] += !cr, c[1] += cr, c[2] += timed_out[a] != 0, c[3] += done[a] != 0;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        const unsigned w = __reduce_add_sync(0xffffffffu, c[k]);
+        if ((threadIdx.x & 31) == 0 && w)
+            atomicAdd(out + k, static_cast<unsigned long long>(w));
+    }
+}
+
 __global__ void sincosf_kernel(const float *in, float *s_out, float *c_out, int64_t n)
 {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;

@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 from . import _capi
-from ._capi import BUF, OkConfig, OkLaunchStats, OkTrackInfo, check
+from ._capi import BUF, OkConfig, OkLaunchStats, OkPopulationCounters, OkTrackInfo, check
 
 _NP_DTYPES = {_capi.DTYPE_F32: np.float32, _capi.DTYPE_I32: np.int32, _capi.DTYPE_U32: np.uint32, _capi.DTYPE_U8: np.uint8}
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "tracks_f32.npz")
@@ -320,6 +320,12 @@ class Env:
         buf = np.zeros((max(n, 1), 3), dtype=np.int64)
         check(self.lib.ok_debug_tiles(self.h, _vp(buf), n))
         return buf[:n]
+
+    def population_counters(self, stream=None) -> dict:
+        """agents / alive / crashed / timed_out / done right now, counted on the device (ok_population_counters)"""
+        c = OkPopulationCounters()
+        check(self.lib.ok_population_counters(self.h, C.byref(c), stream))
+        return {k: int(getattr(c, k)) for k, _ in c._fields_}
 
     def launch_stats(self) -> OkLaunchStats:
         s = OkLaunchStats()

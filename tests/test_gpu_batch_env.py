@@ -98,3 +98,26 @@ def test_views_outlive_close_and_keep_their_memory():
     gc.collect()
     torch.cuda.synchronize()
     assert dlpack.live_exports(inner) == 0 and inner.h is None, "released with its last view"
+
+
+def test_population_counters_are_the_buffer_sums():
+    """ok_population_counters (per-step device counters) against the flag buffers themselves, with NVTX ranges on
+    (OK_NVTX is read once per process: set here for whatever library calls come first in this process)."""
+    import os
+
+    os.environ.setdefault("OK_NVTX", "1")
+    n = 5000
+    env = ok.Env(device=0, auto_reset=0)
+    for nm in ("Monza", "Spa"):
+        env.add_named_track(nm)
+    env.alloc_agents(n, ok.ray_fan(7), (np.arange(n) % 2).astype(np.int32))
+    seen = []
+    for k in range(6):
+        env.launch_steps_random(8 * k, 8, 7)
+        c = env.population_counters()
+        seen.append(c["crashed"])
+        crashed, timed_out, done = env.read("crashed"), env.read("timed_out"), env.read("done")
+        assert c == {"agents": n, "alive": int((crashed == 0).sum()), "crashed": int((crashed != 0).sum()),
+                     "timed_out": int((timed_out != 0).sum()), "done": int((done != 0).sum())}, (k, c)
+        assert c["alive"] + c["crashed"] == n
+    assert seen == sorted(seen) and seen[-1] > 0 and seen[0] < n, seen  # nobody is reset here: crashes only accumulate
