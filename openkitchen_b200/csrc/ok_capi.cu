@@ -1774,7 +1774,8 @@ int actor_params(const OkActorIO *io, ok::ActorParams &q, bool *skip)
 
 size_t actor_weight_bytes(const ok::ActorParams &q, int rays)
 {
-    return q.act ? sizeof(float) * (static_cast<size_t>(q.hidden) * rays + q.hidden + static_cast<size_t>(q.n_actions) * q.hidden + q.n_actions) : 0;
+    // w1 | b1 | w2 | b2 | action table
+    return q.act ? sizeof(float) * (static_cast<size_t>(q.hidden) * rays + q.hidden + static_cast<size_t>(q.n_actions) * q.hidden + 3 * static_cast<size_t>(q.n_actions)) : 0;
 }
 } // namespace
 extern "C"
@@ -1817,7 +1818,7 @@ int ok_ppo_actor_step(OkEnv *e, const OkActorIO *io, uint64_t step, uint32_t see
     if (rc)
         return rc;
     DeviceGuard  g(e->cfg.device);
-    const size_t wbytes = actor_weight_bytes(q, e->rays);
+    const size_t wbytes = actor_weight_bytes(q, e->rays) + sizeof(float) * 2 * static_cast<size_t>(e->batch_agents_beam); // + the tile's chosen actions
     // one launch when the env runs the unstaged beam kernel (the shape of small populations, where a tick is latency) and the
     // weights fit behind its shared memory; otherwise the same tick as two launches
     const bool fused = q.act && e->cfg.raycast_mode == OK_RAYCAST_BEAM && !e->beam_staged &&

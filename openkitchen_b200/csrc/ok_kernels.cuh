@@ -899,7 +899,7 @@ __host__ __device__ inline size_t beam_smem_bytes(int agents)
 // `gblob` is the track's blob in the GLOBAL arena: only a crashed agent's auto-reset reads it (centre line, headings),
 // so phase 1 does not have to wait for the blob to be staged in shared memory.
 __device__ __forceinline__ AgentRec agent_pre(const StepParams &p, const uint8_t *gblob, const TrackRef &tr, const BeamView &bv, const int64_t a,
-                                              const bool act_staged = false)
+                                              const bool act_staged = false, const float2 *s_action = nullptr)
 {
     float    x = p.x[a], y = p.y[a], rot = p.rot[a], speed = p.speed[a], accel = p.accel[a];
     bool     crashed = p.crashed[a] != 0, timed_out = p.timed_out[a] != 0;
@@ -959,6 +959,11 @@ __device__ __forceinline__ AgentRec agent_pre(const StepParams &p, const uint8_t
         {
             thr   = p.ext_thr[a];
             steer = p.ext_steer[a];
+        }
+        else if (s_action)
+        { // the fused policy phase left it in shared memory (and in the action buffers)
+            thr   = s_action->x;
+            steer = s_action->y;
         }
         else
         {
@@ -1280,7 +1285,7 @@ struct ActorParams
 constexpr int kActorLanes   = 8;
 constexpr int kActorMaxActs = 8;
 
-// the weights of the actor, global -> shared memory (w1 | b1 | w2 | b2); the caller synchronises the CTA afterwards
+// the weights of the actor, global -> shared memory (w1 | b1 | w2 | b2 | action table); the caller synchronises the CTA afterwards
 __device__ __forceinline__ void actor_stage_weights(const ActorParams &q, const int R, float *s_w, const int tid, const int n_threads)
 {
     const int H = q.hidden, A = q.n_actions;
@@ -1293,13 +1298,15 @@ __device__ __forceinline__ void actor_stage_weights(const ActorParams &q, const 
         s_w2[i] = q.w2[i];
     for (int i = tid; i < A; i += n_threads)
         s_b2[i] = q.b2[i];
+    for (int i = tid; i < 2 * A; i += n_threads) // kActionMap behind the biases
+        s_b2[A + i] = q.table[i];
 }
 
 // One agent's policy step by the kActorLanes lanes that share it (`sub` = the lane's place among them; `has` = the group holds
 // an agent).  Warp-collective: all 32 lanes of a warp call it together.
 __device__ __forceinline__ void actor_agent(const StepParams &p, const ActorParams &q, const float *s_w, const int64_t a, const bool has,
-                                            const int sub)
-{
+                                            const int sub, float2 *s_chosen = nullptr)
+{ // s_chosen (fused instantiation): where the agent's own thread of the kinematics phase picks the action up (shared memory)
     const int    R = p.rays, H = q.hidden, A = q.n_actions;
     const float *s_w1 = s_w, *s_b1 = s_w1 + H * R, *s_w2 = s_b1 + H, *s_b2 = s_w2 + A * H;
     const int64_t ac  = has ? a : 0;
@@ -1424,8 +1431,11 @@ __device__ __forceinline__ void actor_agent(const StepParams &p, const ActorPara
     if (q.obs_out)
         for (int r = 0; r < R; ++r)
             q.obs_out[a * R + r] = obs[r];
-    p.act_thr[a]   = q.table[2 * act];     // PPOAgent.hpp:95-96
-    p.act_steer[a] = q.table[2 * act + 1];
+    const float thr = s_b2[A + 2 * act], steer = s_b2[A + 2 * act + 1]; // PPOAgent.hpp:95-96
+    p.act_thr[a]   = thr;
+    p.act_steer[a] = steer;
+    if (s_chosen)
+        *s_chosen = make_float2(thr, steer);
 }
 
 // the second kernel argument of step_kernel: the actor's parameters in the fused instantiation (kActor), nothing otherwise
@@ -1490,10 +1500,12 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
     const bool single_wave = OK_SINGLE_WAVE && p.n_tiles <= static_cast<int>(gridDim.x);
     if (tid == 0)
         s_tile = static_cast<int>(blockIdx.x), s_actdev = 0;
-    float *s_actor_w = nullptr; // kActor: the policy's weights, behind everything else in dynamic shared memory
+    float  *s_actor_w   = nullptr; // kActor: the policy's weights, behind everything else in dynamic shared memory,
+    float2 *s_actor_act = nullptr; //         and in front of them the tile's chosen actions (batch_agents of them)
     if constexpr (kActor)
     {
-        s_actor_w = reinterpret_cast<float *>(smem + p.actor_smem_off);
+        s_actor_act = reinterpret_cast<float2 *>(smem + p.actor_smem_off);
+        s_actor_w   = reinterpret_cast<float *>(s_actor_act + p.batch_agents);
         actor_stage_weights(q, R, s_actor_w, tid, kBlock); // (visible after the loop-top barrier)
     }
 
@@ -1557,12 +1569,12 @@ __global__ void __launch_bounds__(kBlock, (kBeam && !kStaged) ? OK_BEAM_MIN_CTAS
             for (int base = 0; base < count; base += kBlock / kActorLanes)
             {
                 const int al = base + tid / kActorLanes;
-                actor_agent(p, q, s_actor_w, tl.begin + (al < count ? al : 0), al < count, tid & (kActorLanes - 1));
+                actor_agent(p, q, s_actor_w, tl.begin + (al < count ? al : 0), al < count, tid & (kActorLanes - 1), s_actor_act + (al < count ? al : 0));
             }
-            __syncthreads(); // the actions are in p.act_thr / p.act_steer: the agents' own threads read them next
+            __syncthreads(); // the chosen actions are in shared memory: the agents' own threads read them next
         }
         if (tid < count)
-            recs[tid] = agent_pre(p, gblob, tr, bv, tl.begin + tid, kBeam && n_done > 0 && s_actdev != 0);
+            recs[tid] = agent_pre(p, gblob, tr, bv, tl.begin + tid, kBeam && n_done > 0 && s_actdev != 0, kActor ? s_actor_act + tid : nullptr);
         if (tid == 0)
         {
             s_pool = 0, s_pool2 = 0, s_npend = 0, s_adone = 0;
