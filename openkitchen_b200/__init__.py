@@ -23,7 +23,18 @@ from ._capi import (  # noqa: F401
     OkError,
 )
 from . import dlpack  # noqa: F401
-from .env import Env, pcie_probe, pinned_array, ray_fan, release_caches, track_columns, track_names, write_track_csv  # noqa: F401
+from .env import (  # noqa: F401
+    Env,
+    dequantize_obs_q16,
+    pcie_probe,
+    pinned_array,
+    quantize_obs_q16,
+    ray_fan,
+    release_caches,
+    track_columns,
+    track_names,
+    write_track_csv,
+)
 
 __version__ = "0.1.0"
 

@@ -333,6 +333,18 @@ class Env:
         return s
 
 
+def quantize_obs_q16(obs) -> np.ndarray:
+    """the fixed point ok_step_host_q16 delivers, from float observations: rn(clamp(obs, 0, 1) * 65535) in binary32 -- the
+    host-side statement of the kernel's obs_q16 (tests compare the two)"""
+    o = np.clip(np.asarray(obs, dtype=np.float32), np.float32(0), np.float32(1))
+    return np.rint(o * np.float32(65535.0)).astype(np.uint16)
+
+
+def dequantize_obs_q16(q) -> np.ndarray:
+    """float32 observations (norm / sensor range, in [0, 1]) from ok_step_host_q16's uint16; |error| <= 0.5 / 65535 of the range"""
+    return (np.asarray(q, dtype=np.uint16).astype(np.float32) / np.float32(65535.0)).astype(np.float32)
+
+
 def pcie_probe(device: int, nbytes: int, iters: int = 50, mode: str = "d2h") -> float:
     """GB/s of `iters` transfers of `nbytes` between pinned host memory and `device` (measurement only):
     mode "d2h" = DMA copies, "store" = kernel stores through the host mapping, "h2d" = DMA copies the other way"""

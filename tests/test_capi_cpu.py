@@ -121,3 +121,19 @@ def test_shim_and_pybind_build_and_fail_loudly_without_gpu(tmp_path):
 
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         okp.Environment(str(csv))
+
+
+def test_q16_observation_helpers_round_trip():
+    """ok_step_host_q16's fixed point, host side: quantise is rn(clamp(obs) * 65535) in binary32 (ties to even), dequantise
+    brings every code back to within half a step, and the codes are a fixed point of the round trip."""
+    obs = np.array([0.0, 1.0, 0.5, 1.5, -0.25, 0.5 / 65535.0, 1.5 / 65535.0, 2.5 / 65535.0, 0.123456], dtype=np.float32)
+    q = ok.quantize_obs_q16(obs)
+    assert q.dtype == np.uint16 and list(q[:5]) == [0, 65535, 32768, 65535, 0]
+    assert list(q[5:8]) == [0, 2, 2]  # ties to even
+    codes = np.arange(65536, dtype=np.uint16)
+    back = ok.dequantize_obs_q16(codes)
+    assert back.dtype == np.float32 and back[0] == 0.0 and back[-1] == 1.0
+    assert np.array_equal(ok.quantize_obs_q16(back), codes)
+    rng = np.random.default_rng(0)
+    x = rng.random(100000, dtype=np.float32)
+    assert np.abs(ok.dequantize_obs_q16(ok.quantize_obs_q16(x)).astype(np.float64) - x).max() <= 0.5 / 65535.0 + 2.0**-22

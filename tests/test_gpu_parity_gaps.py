@@ -314,12 +314,12 @@ def test_host_step_q16_is_the_rounded_float_observation(n, rays, raycast):
         b.launch_step()
         obs = b.read("obs")
         assert np.isfinite(obs).all()
-        want = np.rint(np.clip(obs, np.float32(0), np.float32(1)) * np.float32(65535.0)).astype(np.uint16)
+        want = ok.quantize_obs_q16(obs)
         assert np.array_equal(q, want), f"q16 obs, step {step}: {(q != want).sum()} differ"
-        worst = max(worst, float(np.abs(q.astype(np.float64) / 65535.0 - obs).max()))
+        worst = max(worst, float(np.abs(ok.dequantize_obs_q16(q).astype(np.float64) - obs).max()))
         assert np.array_equal(rew.view(np.uint32), b.read("reward").view(np.uint32)), f"reward, step {step}"
         assert np.array_equal(done, b.read("done")), f"done, step {step}"
-    assert worst <= 0.5 / 65535.0 + 2.0**-23, worst  # half a step of the fixed point + the binary32 rounding of obs * 65535
+    assert worst <= 0.5 / 65535.0 + 2.0**-22, worst  # half a step of the fixed point + binary32 roundings (obs * 65535, q / 65535)
     for name in ok.BUFFERS:
         assert np.array_equal(a.read(name).view(np.uint8), b.read(name).view(np.uint8)), name
 
