@@ -94,3 +94,40 @@ def test_track_pack_matches_reference_csvs(tmp_path):
             ref = o.track_array(t_csv, a)
             assert same_bits(ref, o.track_array(t_pack, a)).all(), (nm, a)
             assert same_bits(ref, o.track_array(t_rt, a)).all(), (nm, a)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("offset", [3.0, -5.0])
+def test_oracle_vs_reference_objects_with_a_sensor_offset(mode, offset):
+    """Agent::sensor_offset_ (Agent.h:69, CollisionChecker.cu:122-126: the lidar origin is shifted along the heading) and the
+    crash threshold of CollisionChecker.cu:167 -- what the reference's objects let one vary (dt, speed limit, sensor range
+    and the standstill window are compile-time constants there: Agent.h:10-12, Environment.h:19-20) -- in the C restatement
+    against the reference's own objects.  The GPU tests compare the CUDA path with the restatement on the same settings
+    (tests/test_gpu_parity_gaps.py): this closes the chain CUDA == restatement == reference for them."""
+    names = ["Monza", "Sepang"]
+    cfg = dict(movement_mode=mode, reward_mode=1, auto_reset=1, sensor_offset=offset, collision_dist2=3.5)
+    pair = []
+    for kind in ("port", "reference"):
+        o = Oracle(kind, **cfg)
+        for nm in names:
+            o.add_track(ok.track_columns(nm))
+        o.alloc_agents(48, ok.ray_fan(9), (np.arange(48) % 2).astype(np.int32))
+        pair.append(o)
+    a, b = pair
+    rng = np.random.default_rng(11)
+    idx = np.arange(48, dtype=np.int64)
+    pts = np.array([rng.integers(0, a.track_points(int(i % 2))) for i in idx], dtype=np.int32)
+    for o in pair:
+        o.reset(idx, pts, None, None)
+    crashed_seen = False
+    ticks = 120 if mode == 0 else 400  # the acceleration mode's action set builds speed slowly
+    for step in range(ticks):
+        for o in pair:
+            o.fill_random_actions(step)
+            o.step()
+        if step % 20 == 0 or step == ticks - 1:
+            for name in BUF:
+                assert same_bits(a.buffer(name), b.buffer(name)).all(), (step, name)
+        crashed_seen = crashed_seen or bool(a.buffer("crashed").any())
+    assert crashed_seen, "nobody crashed: the changed threshold was never exercised"
