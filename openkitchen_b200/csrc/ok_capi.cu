@@ -1985,6 +1985,8 @@ int step_host_impl(OkEnv *e, const float *h_thr, const float *h_steer, void *h_o
         return v && std::strcmp(v, "copy") == 0;
     }();
     p.host_obs    = obs_by_copy ? nullptr : pinned_alias(h_obs);
+    if (reinterpret_cast<uintptr_t>(p.host_obs) & 15u)
+        p.host_obs = nullptr; // the tile flush stores 16 bytes per lane: a buffer that is not 16-byte aligned takes the staged copy
     p.host_reward = (obs_by_copy || small_by_copy) ? nullptr : pinned_alias(h_reward);
     p.host_done   = (obs_by_copy || small_by_copy) ? nullptr : pinned_alias(h_done);
     if (q16 && h_obs_any)
@@ -1992,6 +1994,8 @@ int step_host_impl(OkEnv *e, const float *h_thr, const float *h_steer, void *h_o
         p.host_obs_q16 = pinned_alias(static_cast<uint16_t *>(h_obs_any));
         if (!p.host_obs_q16)
             return fail(OK_ERR_INVALID_ARG, "ok_step_host_q16: h_obs_q16 must be pinned host memory (ok_host_alloc / cudaHostRegister)");
+        if (reinterpret_cast<uintptr_t>(p.host_obs_q16) & 15u)
+            return fail(OK_ERR_INVALID_ARG, "ok_step_host_q16: h_obs_q16 must be 16-byte aligned (the tile flush stores 16 bytes per lane)");
     }
     rc = launch_step(e, p, s);
     if (rc)
